@@ -1,0 +1,211 @@
+/*
+ * vo_b200.h — C ABI of libvo_b200.so: the B200 (sm_100a) hot path of the RGB-D
+ * visual-odometry pipeline: descriptor matching -> keypoint gather / depth
+ * back-projection -> PnP-RANSAC -> relative pose.
+ *
+ * Plain C, no CUDA or torch types in any signature.  Every pointer is a DEVICE
+ * pointer unless its name ends in `_h` (host) or the comment says "host".
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * No entry point synchronises the stream; no entry point throws.  Return value:
+ * 0 = VO_OK, <0 = hard error (see vo_last_error()), >0 never (soft outcomes such
+ * as "no model" are per-pair and written to the `status` output arrays).
+ *
+ * Each entry point cites the reference interface (file:line under the upstream
+ * repository) it replaces.
+ *
+ * Batch convention: B independent frame pairs are processed per call.  Pair b
+ * owns rows [b*n_stride, b*n_stride + n_ref[b]) of the reference-frame arrays and
+ * [b*m_stride, b*m_stride + n_cur[b]) of the current-frame arrays.  `n_ref` /
+ * `n_cur` are device int32[B]; NULL means "every pair uses the full stride".
+ */
+#ifndef VO_B200_H
+#define VO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VO_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VO_API __attribute__((visibility("default")))
+#else
+#define VO_API
+#endif
+
+/* ---- return codes ------------------------------------------------------- */
+#define VO_OK 0
+#define VO_ERR_ARG (-1)
+#define VO_ERR_CUDA (-2)
+#define VO_ERR_UNSUPPORTED (-3)
+
+/* ---- per-pair status bits (device int32 status arrays) ------------------ */
+#define VO_ST_OK 0
+#define VO_ST_NO_MODEL 1        /* no hypothesis reached min_inliers (reference: "NO IT IS A BAD PNP") */
+#define VO_ST_TOO_FEW_POINTS 2  /* fewer correspondences than a minimal sample */
+#define VO_ST_KP_OUT_OF_IMAGE 4 /* a matched keypoint truncates outside the depth map (reference: IndexError -> bad PnP) */
+
+/* ---- matcher configuration ---------------------------------------------- */
+/* byte descriptors (ORB) */
+#define VO_NORM_HAMMING 0 /* popcount(a xor b): cv2.NORM_HAMMING (north-star semantics)          */
+#define VO_NORM_L2_U8 1   /* sqrt(sum (a_k-b_k)^2) over byte VALUES: what ORB.py:8 really builds  */
+/* float descriptors */
+#define VO_METRIC_L2 0     /* d = sqrt(sum (a-b)^2)            : SIFT.py:11,27                    */
+#define VO_METRIC_COSINE 1 /* s = a.b, d = sqrt(2-2s)          : R2D2.py:56-59                    */
+/* acceptance rule applied to (top-2 of each ref row, top-1 of each cur column) */
+#define VO_MODE_RATIO 0         /* d1 <  ratio*d2 (compared in double)      SIFT.py:30 / ORB.py:28 */
+#define VO_MODE_MUTUAL 1        /* col_best[nn1[i]] == i                     cv2 crossCheck=True    */
+#define VO_MODE_RATIO_MUTUAL 2  /* d1/(d2+1e-8f) <= ratio  AND mutual        R2D2.py:53-66          */
+#define VO_MODE_THRESH_MUTUAL 3 /* s1 >= thr AND mutual                      R2D2.py:29-37          */
+#define VO_MODE_THRESH 4        /* s1 >= thr                                 R2D2.py:40-51          */
+#define VO_MODE_NN 5            /* every row keeps its nearest neighbour                            */
+/* float-matcher arithmetic */
+#define VO_PREC_TF32X3 0    /* tcgen05 kind::tf32, hi/lo split, 3 MMAs per k-step (fp32-grade)   */
+#define VO_PREC_TF32X1 1    /* tcgen05 kind::tf32, 1 MMA per k-step (exact for integer-valued SIFT) */
+#define VO_PREC_FP32_SIMT 2 /* CUDA-core FP32, direct (a-b)^2 / dot form (validation kernel)      */
+
+typedef struct vo_ctx vo_ctx;
+
+/* Context: one per (process, device).  Owns a growable device workspace and
+ * nothing else; all inputs and outputs are caller-owned. */
+VO_API int vo_create(int device, vo_ctx **out);
+VO_API void vo_destroy(vo_ctx *ctx);
+VO_API int vo_abi_version(void);
+/* Thread-local text of the last hard error ("" if none). */
+VO_API const char *vo_last_error(void);
+/* Number of this library's kernels launched through `ctx` since creation. */
+VO_API long long vo_launch_count(const vo_ctx *ctx);
+
+/* Optional raw k-NN outputs shared by both matchers (any pointer may be NULL).
+ *   row_idx  int32 [B][n_stride][2]  nearest / second-nearest cur index (-1 if absent)
+ *   row_val  float [B][n_stride][2]  their distances (VO_METRIC_COSINE: similarities)
+ *   col_idx  int32 [B][m_stride]     nearest ref index of each cur descriptor
+ */
+typedef struct vo_knn_out {
+    int32_t *row_idx;
+    float *row_val;
+    int32_t *col_idx;
+} vo_knn_out;
+
+/*
+ * Byte-descriptor matcher.  Replaces cv2.BFMatcher.knnMatch(k=2) + ratio loop
+ * (feature_extractors/ORB.py:23-32) and cv2.BFMatcher(NORM_HAMMING, crossCheck).
+ *   ref uint8 [B][n_stride][32], cur uint8 [B][m_stride][32]  (bytes must be 32)
+ *   out_pairs int32 [B][n_stride][2]  accepted (ref,cur) pairs, ascending ref index
+ *   out_dist  float [B][n_stride]     distance of each accepted pair (may be NULL)
+ *   out_count int32 [B]
+ * Ties resolve to the lowest index (pinned against cv2).
+ */
+VO_API int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, int n_stride, int m_stride,
+                const int32_t *n_ref, const int32_t *n_cur, int bytes, int norm, int mode, double ratio,
+                int32_t *out_pairs, float *out_dist, int32_t *out_count, const vo_knn_out *knn, void *stream);
+
+/*
+ * Float-descriptor matcher.  Replaces knnMatch + ratio (feature_extractors/SIFT.py:25-34)
+ * and the torch matchers R2D2.py:29-66 (sim = d1 @ d2.T, topk, max, masks).
+ *   ref float [B][n_stride][dim], cur float [B][m_stride][dim], dim == 128
+ *   param: ratio (RATIO, RATIO_MUTUAL) or similarity threshold (THRESH*); a double because the
+ *   reference compares fp32 distances against Python doubles (0.85, 0.90)
+ *   near_tie uint8 [B][n_stride] (may be NULL): 1 where the row's best and second best
+ *   are within 1e-5 relative, i.e. the arg-min is not robust to rounding.
+ */
+VO_API int vo_match_f32(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_stride, int m_stride,
+                 const int32_t *n_ref, const int32_t *n_cur, int dim, int metric, int mode, double param,
+                 int precision, int32_t *out_pairs, float *out_dist, int32_t *out_count,
+                 const vo_knn_out *knn, uint8_t *near_tie, void *stream);
+
+/*
+ * Dense back-projection.  Replaces cv2.rgbd.depthTo3d (VisualOdometry_Stereo.py:96).
+ *   depth float [B][H][W] metres; K_h host double[9] row-major; xyz float [B][H][W][3]
+ *   X = ((u-cx)*(1/fx))*z, Y = ((v-cy)*(1/fy))*z, Z = z, all in fp32.
+ */
+VO_API int vo_backproject_dense(vo_ctx *ctx, const float *depth, int B, int H, int W, const double *K_h, float *xyz,
+                         void *stream);
+
+/*
+ * Fused keypoint gather + min-flow filter + sparse back-projection + range gate +
+ * order-preserving compaction.  Replaces VisualOdometry_Stereo.py:257-264 and :96-105.
+ *   pairs int32 [B][pair_cap][2], n_pairs int32 [B]
+ *   ref_kp float [B][n_stride][kp_stride], cur_kp float [B][m_stride][kp_stride]  (x,y first)
+ *   depth float [B][H][W] of the REFERENCE frame
+ *   outputs (capacity pair_cap per pair, first n_out[b] valid, order of `pairs` kept):
+ *     xyz float [B][pair_cap][3], ref_uv/cur_uv float [B][pair_cap][2],
+ *     src int32 [B][pair_cap] index into `pairs` (may be NULL), n_out int32 [B],
+ *     status int32 [B] (VO_ST_KP_OUT_OF_IMAGE or 0)
+ */
+VO_API int vo_gather_backproject(vo_ctx *ctx, const int32_t *pairs, const int32_t *n_pairs, int B, int pair_cap,
+                          const float *ref_kp, const float *cur_kp, int n_stride, int m_stride, int kp_stride,
+                          const float *depth, int H, int W, const double *K_h, float min_flow_px, float z_min,
+                          float z_max, float *xyz, float *ref_uv, float *cur_uv, int32_t *src, int32_t *n_out,
+                          int32_t *status, void *stream);
+
+/*
+ * Hypothesis table: int32 [B][H][4] of distinct indices in [0, n_pts[b]) drawn from a
+ * counter-based generator keyed by (seed, pair0 + b, h, slot).  Rows of pairs with fewer
+ * than 4 points are filled with -1.  The CPU oracle implements the same integer recipe.
+ */
+VO_API int vo_hypotheses(vo_ctx *ctx, const int32_t *n_pts, int B, int H, uint64_t seed, int64_t pair0, int32_t *hyp,
+                  void *stream);
+
+/*
+ * PnP-RANSAC + refit.  Replaces the 3x cv2.solvePnPRansac loop, cv2.Rodrigues and the
+ * pose inversion (VisualOdometry_Stereo.py:120-144).
+ *   xyz float [B][cap][3], uv float [B][cap][2], n_pts int32 [B]
+ *   K_h host double[9];  hyp int32 [B][H][4] (P3P sample + 1 disambiguation point)
+ *   thr_px: inlier iff squared reprojection error <= thr_px^2 (fp32, OpenCV rule)
+ *   min_inliers: model accepted iff count > min_inliers (reference: > 20)
+ *   outputs: rt double [B][12] (R row-major, t) with X_cur = R X_ref + t, refined;
+ *            rvec_tvec double [B][6];  T_rel double [B][16] = inverse of [R|t] (the pose the
+ *            reference stores, :141-143);  n_inl, best_h, status int32 [B];
+ *            inlier_mask uint8 [B][cap] of the best MINIMAL model (OpenCV semantics);
+ *            hyp_counts int32 [B][H] inlier count of every hypothesis (may be NULL; tests use it).
+ *   Ties between hypotheses resolve to the lowest hypothesis index.
+ */
+VO_API int vo_pnp_ransac(vo_ctx *ctx, const float *xyz, const float *uv, const int32_t *n_pts, int B, int cap,
+                  const double *K_h, const int32_t *hyp, int H, float thr_px, int min_inliers, int refine_iters,
+                  double *rt, double *rvec_tvec, double *T_rel, int32_t *n_inl, int32_t *best_h,
+                  uint8_t *inlier_mask, int32_t *hyp_counts, int32_t *status, void *stream);
+
+/*
+ * Whole hot path for a batch of pairs on one stream (match -> gather/back-project ->
+ * hypotheses -> PnP-RANSAC -> pose).  Replaces lines 256-264 + computepose_3D_2D of
+ * VisualOdometry.process_frame (VisualOdometry_Stereo.py:223-297) for B pre-declared pairs.
+ */
+typedef struct vo_pipeline_args {
+    int B, n_stride, m_stride;
+    const int32_t *n_ref, *n_cur; /* device int32[B] or NULL */
+    /* descriptors: exactly one of (ref_u8,cur_u8) / (ref_f32,cur_f32) is non-NULL */
+    const uint8_t *ref_u8, *cur_u8;
+    const float *ref_f32, *cur_f32;
+    int norm_or_metric, mode, precision;
+    double match_param;
+    /* keypoints + depth */
+    const float *ref_kp, *cur_kp;
+    int kp_stride;
+    const float *depth;
+    int H, W;
+    const double *K_h; /* host double[9] */
+    float min_flow_px, z_min, z_max;
+    /* RANSAC */
+    int n_hyp;
+    uint64_t seed;
+    int64_t pair0;
+    float thr_px;
+    int min_inliers, refine_iters;
+    /* outputs (device) */
+    double *T_rel;      /* [B][16] */
+    double *rt;         /* [B][12]  (may be NULL) */
+    int32_t *n_matches; /* [B] raw matches             */
+    int32_t *n_corr;    /* [B] correspondences after gating ("common_pts") */
+    int32_t *n_inl;     /* [B] */
+    int32_t *status;    /* [B] */
+} vo_pipeline_args;
+
+VO_API int vo_pipeline(vo_ctx *ctx, const vo_pipeline_args *args, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VO_B200_H */

@@ -1,0 +1,178 @@
+// Depth back-projection (dense) and the fused sparse path: keypoint gather + min-flow filter +
+// depth lookup at truncated pixel + range gate + order-preserving compaction.
+//
+// Replaces cv2.rgbd.depthTo3d (VisualOdometry_Stereo.py:96), the fancy-index gather at :97,
+// the 0<Z<50 gate at :100-105 and the keypoint gather / 3 px flow filter at :257-264.
+// Arithmetic follows depthTo3d for float depth: intrinsics are cast to the depth dtype (fp32),
+// X = ((u - cx) * (1/fx)) * z, Y = ((v - cy) * (1/fy)) * z, Z = z, each operation rounded to
+// fp32 (explicit _rn intrinsics so the compiler cannot contract them into FMAs).
+#include "common.cuh"
+
+namespace vo {
+namespace {
+
+struct Intr {
+    float inv_fx, inv_fy, cx, cy;
+};
+
+__host__ Intr make_intr(const double *K) {
+    Intr k;
+    const float fx = (float)K[0], fy = (float)K[4];
+    k.cx = (float)K[2];
+    k.cy = (float)K[5];
+    k.inv_fx = 1.0f / fx;
+    k.inv_fy = 1.0f / fy;
+    return k;
+}
+
+__device__ __forceinline__ void backproject(const Intr k, int u, int v, float z, float &X, float &Y) {
+    X = __fmul_rn(__fmul_rn(__fsub_rn((float)u, k.cx), k.inv_fx), z);
+    Y = __fmul_rn(__fmul_rn(__fsub_rn((float)v, k.cy), k.inv_fy), z);
+}
+
+// Dense: one thread owns 4 consecutive pixels of the flattened [B*H*W] image: one 128-bit
+// load, three 128-bit stores (48 contiguous bytes).  HBM-bound: 16 B per pixel.
+__global__ void __launch_bounds__(256)
+backproject_dense_kernel(const float *__restrict__ depth, float *__restrict__ xyz, long long n_px, int H, int W,
+                         Intr k) {
+    const long long n_vec = n_px >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        const float4 z4 = __ldcs(reinterpret_cast<const float4 *>(depth) + i);
+        const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+        float o[12];
+        const long long p0 = i << 2;
+        int u = (int)(p0 % W);
+        int v = (int)((p0 / W) % H);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            backproject(k, u, v, z[q], o[3 * q], o[3 * q + 1]);
+            o[3 * q + 2] = z[q];
+            if (++u == W) { u = 0; if (++v == H) v = 0; }
+        }
+        float4 *dst = reinterpret_cast<float4 *>(xyz) + i * 3;
+        __stcs(dst + 0, make_float4(o[0], o[1], o[2], o[3]));
+        __stcs(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
+        __stcs(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
+    }
+    // tail (n_px not a multiple of 4)
+    if (blockIdx.x == 0 && threadIdx.x < (n_px & 3)) {
+        const long long p = (n_vec << 2) + threadIdx.x;
+        const int u = (int)(p % W), v = (int)((p / W) % H);
+        const float z = depth[p];
+        float X, Y;
+        backproject(k, u, v, z, X, Y);
+        xyz[p * 3 + 0] = X; xyz[p * 3 + 1] = Y; xyz[p * 3 + 2] = z;
+    }
+}
+
+constexpr int GB_THREADS = 512;
+
+// Sparse fused path: one CTA per frame pair, chunks of GB_THREADS matches, ballot + warp-count
+// scan keeps the surviving correspondences in match order (the reference's boolean-mask
+// compression is order preserving and the hypothesis table indexes that order).
+__global__ void __launch_bounds__(GB_THREADS)
+gather_backproject_kernel(const int32_t *__restrict__ pairs, const int32_t *__restrict__ n_pairs, int pair_cap,
+                          const float *__restrict__ ref_kp, const float *__restrict__ cur_kp, int n_stride, int m_stride,
+                          int kp_stride, const float *__restrict__ depth, int H, int W, Intr k, float min_flow,
+                          float z_min, float z_max, float *__restrict__ xyz, float *__restrict__ ref_uv,
+                          float *__restrict__ cur_uv, int32_t *__restrict__ src, int32_t *__restrict__ n_out,
+                          int32_t *__restrict__ status) {
+    const int b = blockIdx.x;
+    const int n = min(n_pairs[b], pair_cap);
+    __shared__ int warp_cnt[GB_THREADS / 32];
+    __shared__ int base_s, oob_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { base_s = 0; oob_s = 0; }
+    __syncthreads();
+    const float *dimg = depth + (size_t)b * H * W;
+    for (int m0 = 0; m0 < n; m0 += GB_THREADS) {
+        const int m = m0 + threadIdx.x;
+        bool keep = false;
+        float rx = 0, ry = 0, cx = 0, cy = 0, X = 0, Y = 0, Z = 0;
+        if (m < n) {
+            const int ir = pairs[((size_t)b * pair_cap + m) * 2 + 0];
+            const int ic = pairs[((size_t)b * pair_cap + m) * 2 + 1];
+            const float *pr = ref_kp + ((size_t)b * n_stride + ir) * kp_stride;
+            const float *pc = cur_kp + ((size_t)b * m_stride + ic) * kp_stride;
+            rx = pr[0]; ry = pr[1]; cx = pc[0]; cy = pc[1];
+            // np.linalg.norm(ref - cur, axis=1) in fp32, keep diff >= 3 (:260-264)
+            const float dx = __fsub_rn(rx, cx), dy = __fsub_rn(ry, cy);
+            const float diff = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+            if (diff >= min_flow) {
+                // .astype(np.int32): truncation toward zero; index [row = y, col = x] (:97)
+                const int u = (int)rx, v = (int)ry;
+                if (u < 0 || u >= W || v < 0 || v >= H) {
+                    oob_s = 1;  // reference: IndexError (or negative wrap) -> pair fails
+                } else {
+                    Z = __ldg(dimg + (size_t)v * W + u);
+                    backproject(k, u, v, Z, X, Y);
+                    keep = (Z > z_min) && (Z < z_max);  // NaN fails both
+                }
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int prefix = base_s;
+        for (int w = 0; w < warp; ++w) prefix += warp_cnt[w];
+        if (keep) {
+            const size_t o = (size_t)b * pair_cap + prefix + __popc(bal & ((1u << lane) - 1u));
+            xyz[o * 3 + 0] = X; xyz[o * 3 + 1] = Y; xyz[o * 3 + 2] = Z;
+            ref_uv[o * 2 + 0] = rx; ref_uv[o * 2 + 1] = ry;
+            cur_uv[o * 2 + 0] = cx; cur_uv[o * 2 + 1] = cy;
+            if (src) src[o] = m;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < GB_THREADS / 32; ++w) tot += warp_cnt[w];
+            base_s += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        n_out[b] = base_s;
+        if (status) status[b] = oob_s ? VO_ST_KP_OUT_OF_IMAGE : VO_ST_OK;
+    }
+}
+
+}  // namespace
+}  // namespace vo
+
+extern "C" int vo_backproject_dense(vo_ctx *ctx, const float *depth, int B, int H, int W, const double *K_h,
+                                    float *xyz, void *stream) {
+    using namespace vo;
+    VO_REQUIRE(ctx && depth && xyz && K_h, "vo_backproject_dense: null argument");
+    VO_REQUIRE(B >= 0 && H > 0 && W > 0, "vo_backproject_dense: bad shape");
+    VO_REQUIRE(((uintptr_t)depth % 16) == 0 && ((uintptr_t)xyz % 16) == 0, "vo_backproject_dense: buffers must be 16B aligned");
+    VO_REQUIRE(K_h[0] != 0.0 && K_h[4] != 0.0, "vo_backproject_dense: zero focal length");
+    if (B == 0) return VO_OK;
+    const long long n_px = (long long)B * H * W;
+    const long long n_vec = n_px >> 2;
+    // >= 4 CTAs of 256 threads per SM in flight, grid-stride beyond that
+    long long want = (n_vec + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 16;
+    int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    backproject_dense_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(depth, xyz, n_px, H, W, make_intr(K_h));
+    VO_LAUNCH_CHECK(ctx);
+    return VO_OK;
+}
+
+extern "C" int vo_gather_backproject(vo_ctx *ctx, const int32_t *pairs, const int32_t *n_pairs, int B, int pair_cap,
+                                     const float *ref_kp, const float *cur_kp, int n_stride, int m_stride,
+                                     int kp_stride, const float *depth, int H, int W, const double *K_h,
+                                     float min_flow_px, float z_min, float z_max, float *xyz, float *ref_uv,
+                                     float *cur_uv, int32_t *src, int32_t *n_out, int32_t *status, void *stream) {
+    using namespace vo;
+    VO_REQUIRE(ctx && pairs && n_pairs && ref_kp && cur_kp && depth && K_h && xyz && ref_uv && cur_uv && n_out,
+               "vo_gather_backproject: null argument");
+    VO_REQUIRE(B >= 0 && pair_cap >= 0 && H > 0 && W > 0 && kp_stride >= 2, "vo_gather_backproject: bad shape");
+    VO_REQUIRE(K_h[0] != 0.0 && K_h[4] != 0.0, "vo_gather_backproject: zero focal length");
+    if (B == 0) return VO_OK;
+    gather_backproject_kernel<<<B, GB_THREADS, 0, (cudaStream_t)stream>>>(
+        pairs, n_pairs, pair_cap, ref_kp, cur_kp, n_stride, m_stride, kp_stride, depth, H, W, make_intr(K_h),
+        min_flow_px, z_min, z_max, xyz, ref_uv, cur_uv, src, n_out, status);
+    VO_LAUNCH_CHECK(ctx);
+    return VO_OK;
+}

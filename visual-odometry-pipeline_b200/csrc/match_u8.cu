@@ -1,0 +1,194 @@
+// 256-bit binary-descriptor matcher (ORB): XOR + POPC (Hamming) or byte-wise squared L2.
+//
+// Replaces cv2.BFMatcher.knnMatch on uint8 descriptors (feature_extractors/ORB.py:8,25;
+// the reference's BFMatcher() is NORM_L2 over byte values) and
+// cv2.BFMatcher(NORM_HAMMING, crossCheck=True) (the north-star semantics).
+//
+// Layout: every thread keeps ROWS_PT reference descriptors in registers (8 words each) and
+// walks the current-frame descriptors, which the CTA stages in shared memory; all lanes of a
+// warp read the same staged descriptor (smem broadcast, 2 x LDS.128 per 32 x ROWS_PT
+// distances).  Row top-2 is therefore thread-private; the column arg-min is a warp REDUX.MIN
+// over a packed (distance << 9 | row-in-CTA) key, merged per CTA in shared memory and per
+// grid with one 64-bit atomicMin per (CTA, column).  The N x M distance matrix never exists.
+#include "common.cuh"
+
+namespace vo {
+namespace {
+
+constexpr int U8_THREADS = 256;
+constexpr int U8_ROWS_PT = 2;
+constexpr int U8_ROWS_CTA = U8_THREADS * U8_ROWS_PT;  // 512 -> row-in-CTA fits 9 bits
+constexpr int U8_CHUNK = 1024;                        // staged columns per pass (32 KB)
+
+template <int NORM>
+__device__ __forceinline__ uint32_t dist256(const uint32_t (&a)[8], const uint4 b0, const uint4 b1) {
+    const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint32_t d = 0;
+    if (NORM == VO_NORM_HAMMING) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) d += __popc(a[w] ^ b[w]);
+    } else {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            uint32_t ad = __vabsdiffu4(a[w], b[w]);
+            d = __dp4a(ad, ad, d);  // sum of squared byte differences, exact in u32
+        }
+    }
+    return d;
+}
+
+template <int NORM, bool SECOND>
+__global__ void __launch_bounds__(U8_THREADS)
+match_u8_kernel(const uint8_t *__restrict__ ref, const uint8_t *__restrict__ cur, int n_stride, int m_stride,
+                const int32_t *__restrict__ n_ref, const int32_t *__restrict__ n_cur, int n_split,
+                vo_row_partial *__restrict__ part, unsigned long long *__restrict__ colkey) {
+    __shared__ uint4 sdesc[U8_CHUNK * 2];
+    __shared__ uint32_t scol[U8_CHUNK];
+
+    const int b = blockIdx.z, split = blockIdx.y;
+    const int N = n_ref ? min(n_ref[b], n_stride) : n_stride;
+    const int M = n_cur ? min(n_cur[b], m_stride) : m_stride;
+    const int row_base = blockIdx.x * U8_ROWS_CTA;
+    const int cols_per_split = (M + n_split - 1) / n_split;
+    const int c_begin = split * cols_per_split;
+    const int c_end = min(M, c_begin + cols_per_split);
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    uint32_t a[U8_ROWS_PT][8];
+    bool valid[U8_ROWS_PT];
+    uint32_t s1[U8_ROWS_PT], s2[U8_ROWS_PT];
+    int32_t i1[U8_ROWS_PT], i2[U8_ROWS_PT];
+#pragma unroll
+    for (int r = 0; r < U8_ROWS_PT; ++r) {
+        const int row = row_base + r * U8_THREADS + tid;
+        valid[r] = row < N;
+        const uint4 *p = reinterpret_cast<const uint4 *>(ref + ((size_t)b * n_stride + (valid[r] ? row : 0)) * 32);
+        uint4 q0 = valid[r] ? p[0] : make_uint4(0, 0, 0, 0), q1 = valid[r] ? p[1] : make_uint4(0, 0, 0, 0);
+        a[r][0] = q0.x; a[r][1] = q0.y; a[r][2] = q0.z; a[r][3] = q0.w;
+        a[r][4] = q1.x; a[r][5] = q1.y; a[r][6] = q1.z; a[r][7] = q1.w;
+        s1[r] = s2[r] = 0xffffffffu;
+        i1[r] = i2[r] = -1;
+    }
+
+    const uint4 *cur4 = reinterpret_cast<const uint4 *>(cur + (size_t)b * m_stride * 32);
+    for (int c0 = c_begin; c0 < c_end; c0 += U8_CHUNK) {
+        const int cnt = min(U8_CHUNK, c_end - c0);
+        __syncthreads();  // previous chunk fully consumed
+        for (int t = tid; t < cnt * 2; t += U8_THREADS) sdesc[t] = cur4[(size_t)c0 * 2 + t];
+        for (int t = tid; t < cnt; t += U8_THREADS) scol[t] = 0xffffffffu;
+        __syncthreads();
+
+#pragma unroll 2
+        for (int j = 0; j < cnt; ++j) {
+            const uint4 b0 = sdesc[2 * j], b1 = sdesc[2 * j + 1];
+            uint32_t ckey = 0xffffffffu;
+#pragma unroll
+            for (int r = 0; r < U8_ROWS_PT; ++r) {
+                const uint32_t d = dist256<NORM>(a[r], b0, b1);
+                const int col = c0 + j;
+                if (valid[r]) {
+                    if (d < s1[r]) {
+                        if (SECOND) { s2[r] = s1[r]; i2[r] = i1[r]; }
+                        s1[r] = d; i1[r] = col;
+                    } else if (SECOND && d < s2[r]) {
+                        s2[r] = d; i2[r] = col;
+                    }
+                    ckey = min(ckey, (d << 9) | (uint32_t)(r * U8_THREADS + tid));
+                }
+            }
+            const uint32_t wmin = __reduce_min_sync(0xffffffffu, ckey);
+            if (lane == 0 && wmin != 0xffffffffu) atomicMin(&scol[j], wmin);
+        }
+        __syncthreads();
+        for (int t = tid; t < cnt; t += U8_THREADS) {
+            const uint32_t k = scol[t];
+            if (k != 0xffffffffu) {
+                const unsigned long long g =
+                    ((unsigned long long)(k >> 9) << 32) | (unsigned long long)(uint32_t)(row_base + (int)(k & 511u));
+                atomicMin(&colkey[(size_t)b * m_stride + c0 + t], g);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < U8_ROWS_PT; ++r) {
+        const int row = row_base + r * U8_THREADS + tid;
+        if (row < n_stride) {
+            vo_row_partial p;
+            p.s1 = s1[r]; p.s2 = s2[r]; p.i1 = i1[r]; p.i2 = i2[r];
+            part[((size_t)b * n_split + split) * n_stride + row] = p;
+        }
+    }
+}
+
+__global__ void fill_u64_kernel(unsigned long long *p, size_t n, unsigned long long v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+}  // namespace
+
+int fill_u64(vo_ctx *ctx, unsigned long long *p, size_t n, unsigned long long v, cudaStream_t st) {
+    if (n == 0) return VO_OK;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    fill_u64_kernel<<<blocks, 256, 0, st>>>(p, n, v);
+    VO_LAUNCH_CHECK(ctx);
+    return VO_OK;
+}
+
+}  // namespace vo
+
+extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, int n_stride, int m_stride,
+                           const int32_t *n_ref, const int32_t *n_cur, int bytes, int norm, int mode, double ratio,
+                           int32_t *out_pairs, float *out_dist, int32_t *out_count, const vo_knn_out *knn,
+                           void *stream) {
+    using namespace vo;
+    VO_REQUIRE(ctx, "vo_match_u8: null ctx");
+    VO_REQUIRE(bytes == 32, "vo_match_u8: only 32-byte (256-bit) descriptors are supported, got %d", bytes);
+    VO_REQUIRE(norm == VO_NORM_HAMMING || norm == VO_NORM_L2_U8, "vo_match_u8: bad norm %d", norm);
+    VO_REQUIRE(mode >= VO_MODE_RATIO && mode <= VO_MODE_NN, "vo_match_u8: bad mode %d", mode);
+    VO_REQUIRE(mode != VO_MODE_THRESH && mode != VO_MODE_THRESH_MUTUAL && mode != VO_MODE_RATIO_MUTUAL,
+               "vo_match_u8: similarity modes need float descriptors");
+    VO_REQUIRE(B >= 0 && n_stride >= 0 && m_stride >= 0, "vo_match_u8: negative size");
+    VO_REQUIRE(out_pairs && out_count, "vo_match_u8: null output");
+    VO_REQUIRE(((uintptr_t)ref % 16) == 0 && ((uintptr_t)cur % 16) == 0, "vo_match_u8: descriptors must be 16B aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) return VO_OK;
+    if (n_stride == 0 || m_stride == 0) {
+        VO_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t) * B, st));
+        return VO_OK;
+    }
+    const int row_blocks = ceil_div(n_stride, U8_ROWS_CTA);
+    // enough CTAs for >= 2 waves when the batch alone cannot fill the GPU; >= 256 columns per split
+    int n_split = 1;
+    {
+        const int want = 2 * ctx->sm_count;
+        const int have = B * row_blocks;
+        if (have < want) n_split = ceil_div(want, have);
+        const int max_split = m_stride / 256 > 0 ? m_stride / 256 : 1;
+        if (n_split > max_split) n_split = max_split;
+        if (n_split > 64) n_split = 64;
+    }
+    vo_row_partial *part;
+    unsigned long long *colkey;
+    int rc;
+    if ((rc = ws_get(ctx, WS_ROWPART, sizeof(vo_row_partial) * (size_t)B * n_split * n_stride, (void **)&part))) return rc;
+    if ((rc = ws_get(ctx, WS_COLKEY, sizeof(unsigned long long) * (size_t)B * m_stride, (void **)&colkey))) return rc;
+    if ((rc = fill_u64(ctx, colkey, (size_t)B * m_stride, ~0ull, st))) return rc;
+
+    const bool second = (mode == VO_MODE_RATIO) || (knn && (knn->row_idx || knn->row_val));
+    dim3 grid(row_blocks, n_split, B);
+#define LAUNCH_U8(NORM, SEC) \
+    match_u8_kernel<NORM, SEC><<<grid, U8_THREADS, 0, st>>>(ref, cur, n_stride, m_stride, n_ref, n_cur, n_split, part, colkey)
+    if (norm == VO_NORM_HAMMING) {
+        if (second) LAUNCH_U8(VO_NORM_HAMMING, true); else LAUNCH_U8(VO_NORM_HAMMING, false);
+    } else {
+        if (second) LAUNCH_U8(VO_NORM_L2_U8, true); else LAUNCH_U8(VO_NORM_L2_U8, false);
+    }
+#undef LAUNCH_U8
+    VO_LAUNCH_CHECK(ctx);
+    return match_finalize(ctx, part, n_split, colkey, B, n_stride, m_stride, n_ref, n_cur,
+                          norm == VO_NORM_HAMMING ? SCORE_HAMMING : SCORE_L2SQ_U32, mode, ratio, nullptr, out_pairs,
+                          out_dist, out_count, knn, nullptr, st);
+}

@@ -1,0 +1,453 @@
+// PnP-RANSAC on the GPU: hypothesis table -> P3P minimal solves -> one warp per hypothesis
+// inlier counting over correspondences staged in shared memory -> packed atomic arg-max ->
+// inlier mask of the winner -> Gauss-Newton refit on its inliers -> pose outputs.
+//
+// Replaces the 3x cv2.solvePnPRansac(iterationsCount=100, reprojectionError=1.5) loop,
+// cv2.Rodrigues and the pose inversion of VisualOdometry.computepose_3D_2D
+// (VisualOdometry_Stereo.py:120-144).  OpenCV semantics kept: inlier iff fp32 squared
+// reprojection error <= thr^2; the returned inlier set is that of the best MINIMAL model; the
+// final pose is a non-linear least-squares refit on exactly those inliers.
+//
+// Compile this file with -fmad=false (see pnp_math.cuh).
+#include "common.cuh"
+#include "pnp_math.cuh"
+
+namespace vo {
+namespace {
+
+struct IntrD {
+    double fx, fy, cx, cy;
+};
+
+// ---------------------------------------------------------------- hypothesis table
+__global__ void hypotheses_kernel(const int32_t *__restrict__ n_pts, int B, int H, uint64_t seed, int64_t pair0,
+                                  int32_t *__restrict__ hyp) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * H) return;
+    const int b = (int)(gid / H), h = (int)(gid % H);
+    const int n = n_pts[b];
+    int32_t idx[4] = {-1, -1, -1, -1};
+    if (n >= 4) draw_hypothesis(seed, pair0 + b, h, n, idx);
+    reinterpret_cast<int4 *>(hyp)[gid] = make_int4(idx[0], idx[1], idx[2], idx[3]);
+}
+
+// ---------------------------------------------------------------- minimal solves
+// One thread per (pair, hypothesis).  Writes the fp32 pose the scorer uses; an inadmissible
+// hypothesis gets a NaN pose, which can never count an inlier.
+__global__ void __launch_bounds__(128)
+p3p_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ n_pts, int B,
+           int cap, const int32_t *__restrict__ hyp, int H, IntrD k, float *__restrict__ poses) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * H) return;
+    const int b = (int)(gid / H);
+    const int n = min(n_pts[b], cap);
+    const int4 id = reinterpret_cast<const int4 *>(hyp)[gid];
+    const int ids[4] = {id.x, id.y, id.z, id.w};
+    bool ok = true;
+    for (int s = 0; s < 4; ++s) ok = ok && ids[s] >= 0 && ids[s] < n;
+    PoseD best;
+    if (ok) {
+        double P[4][3], q[4][2];
+        for (int s = 0; s < 4; ++s) {
+            const size_t o = (size_t)b * cap + ids[s];
+            P[s][0] = xyz[o * 3 + 0]; P[s][1] = xyz[o * 3 + 1]; P[s][2] = xyz[o * 3 + 2];
+            q[s][0] = uv[o * 2 + 0]; q[s][1] = uv[o * 2 + 1];
+        }
+        ok = p3p_solve4(P, q, k.fx, k.fy, k.cx, k.cy, best);
+    }
+    float *o = poses + gid * 12;
+    if (ok) {
+        for (int j = 0; j < 9; ++j) o[j] = (float)best.r[j];
+        for (int j = 0; j < 3; ++j) o[9 + j] = (float)best.t[j];
+    } else {
+        const float qnan = __int_as_float(0x7fc00000);
+        for (int j = 0; j < 12; ++j) o[j] = qnan;
+    }
+}
+
+// ---------------------------------------------------------------- scoring
+constexpr int SC_WARPS = 8;
+constexpr int SC_TILE = 2048;  // correspondences staged per pass: 5 x 2048 x 4 B = 40 KB
+
+__device__ __forceinline__ void stage_points(const float *__restrict__ xyz, const float *__restrict__ uv, int p0,
+                                             int cnt, float *sX, float *sY, float *sZ, float *sU, float *sV) {
+    // coalesced AoS reads, SoA in shared memory (conflict-free when lane l reads element i + l)
+    for (int t = threadIdx.x; t < cnt * 3; t += blockDim.x) {
+        const float v = xyz[(size_t)p0 * 3 + t];
+        const int i = t / 3, c = t - 3 * i;
+        (c == 0 ? sX : (c == 1 ? sY : sZ))[i] = v;
+    }
+    for (int t = threadIdx.x; t < cnt * 2; t += blockDim.x) {
+        const float v = uv[(size_t)p0 * 2 + t];
+        ((t & 1) ? sV : sU)[t >> 1] = v;
+    }
+}
+
+__global__ void __launch_bounds__(SC_WARPS * 32)
+score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ n_pts, int cap,
+             const float *__restrict__ poses, int H, IntrF k, float thr2, unsigned long long *__restrict__ bestkey,
+             int32_t *__restrict__ hyp_counts) {
+    __shared__ float sX[SC_TILE], sY[SC_TILE], sZ[SC_TILE], sU[SC_TILE], sV[SC_TILE];
+    const int b = blockIdx.y;
+    const int n = min(n_pts[b], cap);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x * SC_WARPS + warp;
+    PoseF p;
+    if (h < H) {
+        const float *src = poses + ((size_t)b * H + h) * 12;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) p.r[j] = __ldg(src + j);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) p.t[j] = __ldg(src + 9 + j);
+    }
+    int count = 0;
+    const float *pxyz = xyz + (size_t)b * cap * 3;
+    const float *puv = uv + (size_t)b * cap * 2;
+    for (int p0 = 0; p0 < n; p0 += SC_TILE) {
+        const int cnt = min(SC_TILE, n - p0);
+        __syncthreads();
+        stage_points(pxyz, puv, p0, cnt, sX, sY, sZ, sU, sV);
+        __syncthreads();
+        if (h < H) {
+            for (int i = lane; i < cnt; i += 32) {
+                const float e = reproj_err2(p, k, sX[i], sY[i], sZ[i], sU[i], sV[i]);
+                count += (e <= thr2) ? 1 : 0;
+            }
+        }
+    }
+    if (h < H) {
+        count = __reduce_add_sync(0xffffffffu, count);
+        if (lane == 0) {
+            if (hyp_counts) hyp_counts[(size_t)b * H + h] = count;
+            // larger count wins; ties -> lowest hypothesis index
+            const unsigned long long key =
+                ((unsigned long long)(uint32_t)count << 32) | (unsigned long long)(0xffffffffu - (uint32_t)h);
+            atomicMax(&bestkey[b], key);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- winner mask + refit + outputs
+constexpr int RF_THREADS = 256;
+constexpr int RF_ACC = 28;  // 21 (upper JtJ) + 6 (Jtr) + 1 (cost)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ void so3_exp(const double w[3], double R[9]) {
+    const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    const double th = sqrt(th2);
+    double A, Bc;
+    if (th < 1e-6) {
+        A = 1.0 - th2 / 6.0;
+        Bc = 0.5 - th2 / 24.0;
+    } else {
+        A = sin(th) / th;
+        Bc = (1.0 - cos(th)) / th2;
+    }
+    const double wx = w[0], wy = w[1], wz = w[2];
+    R[0] = 1.0 - Bc * (wy * wy + wz * wz); R[1] = -A * wz + Bc * wx * wy;      R[2] = A * wy + Bc * wx * wz;
+    R[3] = A * wz + Bc * wx * wy;          R[4] = 1.0 - Bc * (wx * wx + wz * wz); R[5] = -A * wx + Bc * wy * wz;
+    R[6] = -A * wy + Bc * wx * wz;         R[7] = A * wx + Bc * wy * wz;        R[8] = 1.0 - Bc * (wx * wx + wy * wy);
+}
+
+__device__ void so3_log(const double R[9], double w[3]) {
+    double c = 0.5 * (R[0] + R[4] + R[8] - 1.0);
+    c = fmin(1.0, fmax(-1.0, c));
+    const double ax = R[7] - R[5], ay = R[2] - R[6], az = R[3] - R[1];
+    const double s = 0.5 * sqrt(ax * ax + ay * ay + az * az);
+    const double th = atan2(s, c);
+    if (s < 1e-9) {
+        if (c > 0.0) {  // theta ~ 0
+            w[0] = 0.5 * ax; w[1] = 0.5 * ay; w[2] = 0.5 * az;
+        } else {  // theta ~ pi: axis from the diagonal (cv::Rodrigues does the same)
+            double x = sqrt(fmax((R[0] + 1.0) * 0.5, 0.0));
+            double y = sqrt(fmax((R[4] + 1.0) * 0.5, 0.0)) * (R[1] < 0.0 ? -1.0 : 1.0);
+            double z = sqrt(fmax((R[8] + 1.0) * 0.5, 0.0)) * (R[2] < 0.0 ? -1.0 : 1.0);
+            if (fabs(x) < fabs(y) && fabs(x) < fabs(z) && (R[5] > 0.0) != (y * z > 0.0)) z = -z;
+            const double nrm = sqrt(x * x + y * y + z * z);
+            const double f = nrm > 0.0 ? th / nrm : 0.0;
+            w[0] = f * x; w[1] = f * y; w[2] = f * z;
+        }
+        return;
+    }
+    const double f = 0.5 * th / s;
+    w[0] = f * ax; w[1] = f * ay; w[2] = f * az;
+}
+
+// 6x6 SPD solve by Cholesky, in place on the packed upper triangle (row-major i<=j).
+__device__ bool solve6(const double Hu[21], const double g[6], double x[6]) {
+    double L[6][6];
+    int idx = 0;
+    double A[6][6];
+    for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) { A[i][j] = Hu[idx]; A[j][i] = Hu[idx]; ++idx; }
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j <= i; ++j) {
+            double s = A[i][j];
+            for (int q = 0; q < j; ++q) s -= L[i][q] * L[j][q];
+            if (i == j) {
+                if (!(s > 0.0)) return false;
+                L[i][i] = sqrt(s);
+            } else {
+                L[i][j] = s / L[j][j];
+            }
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+        double s = g[i];
+        for (int q = 0; q < i; ++q) s -= L[i][q] * y[q];
+        y[i] = s / L[i][i];
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+        for (int q = i + 1; q < 6; ++q) s -= L[q][i] * x[q];
+        x[i] = s / L[i][i];
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(RF_THREADS)
+refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ n_pts, int cap,
+             const float *__restrict__ poses, int H, IntrF kf, IntrD kd, float thr2, int min_inliers, int iters,
+             const unsigned long long *__restrict__ bestkey, double *__restrict__ rt_out,
+             double *__restrict__ rvec_tvec, double *__restrict__ T_rel, int32_t *__restrict__ n_inl_out,
+             int32_t *__restrict__ best_h_out, uint8_t *__restrict__ mask_out, int32_t *__restrict__ status,
+             int accumulate_status) {
+    const int b = blockIdx.x;
+    const int n = min(n_pts[b], cap);
+    const unsigned long long key = bestkey[b];
+    const int count = (int)(uint32_t)(key >> 32);
+    const int h = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+    const bool have = (n >= 4) && (key != 0ull) && (count > min_inliers);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *pxyz = xyz + (size_t)b * cap * 3;
+    const float *puv = uv + (size_t)b * cap * 2;
+
+    __shared__ double sR[9], st[3];
+    __shared__ double sacc[RF_THREADS / 32][RF_ACC];
+    __shared__ int s_stop;
+
+    if (!have) {
+        if (mask_out)
+            for (int i = threadIdx.x; i < cap; i += RF_THREADS) mask_out[(size_t)b * cap + i] = 0;
+        if (threadIdx.x == 0) {
+            int stt = (status && accumulate_status) ? status[b] : 0;
+            stt |= (n < 4) ? VO_ST_TOO_FEW_POINTS : VO_ST_NO_MODEL;
+            if (status) status[b] = stt;
+            if (n_inl_out) n_inl_out[b] = (n >= 4 && key != 0ull) ? count : 0;
+            if (best_h_out) best_h_out[b] = (n >= 4 && key != 0ull) ? h : -1;
+            for (int j = 0; j < 16; ++j) {
+                if (T_rel) T_rel[(size_t)b * 16 + j] = (j % 5 == 0) ? 1.0 : 0.0;
+            }
+            for (int j = 0; j < 12; ++j)
+                if (rt_out) rt_out[(size_t)b * 12 + j] = (j == 0 || j == 4 || j == 8) ? 1.0 : 0.0;
+            for (int j = 0; j < 6; ++j)
+                if (rvec_tvec) rvec_tvec[(size_t)b * 6 + j] = 0.0;
+        }
+        return;
+    }
+
+    PoseF p;
+    {
+        const float *src = poses + ((size_t)b * H + h) * 12;
+        for (int j = 0; j < 9; ++j) p.r[j] = src[j];
+        for (int j = 0; j < 3; ++j) p.t[j] = src[9 + j];
+    }
+    if (threadIdx.x == 0) {
+        // f64 start: the winning fp32 pose, rotation re-orthonormalised by two Newton polar steps
+        double R[9];
+        for (int j = 0; j < 9; ++j) R[j] = (double)p.r[j];
+        for (int it = 0; it < 2; ++it) {
+            double G[9];  // G = R^T R
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) G[3 * i + j] = R[i] * R[j] + R[3 + i] * R[3 + j] + R[6 + i] * R[6 + j];
+            double N[9];  // R (3I - G) / 2
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    double s = 0.0;
+                    for (int q = 0; q < 3; ++q) s += R[3 * i + q] * ((q == j ? 3.0 : 0.0) - G[3 * q + j]);
+                    N[3 * i + j] = 0.5 * s;
+                }
+            for (int j = 0; j < 9; ++j) R[j] = N[j];
+        }
+        for (int j = 0; j < 9; ++j) sR[j] = R[j];
+        for (int j = 0; j < 3; ++j) st[j] = (double)p.t[j];
+        s_stop = 0;
+    }
+    // inlier mask of the winning minimal model: identical arithmetic to score_kernel
+    // (per-thread flags are recomputed in the refit loop instead of being stored per point)
+    if (mask_out) {
+        for (int i = threadIdx.x; i < cap; i += RF_THREADS) {
+            uint8_t m = 0;
+            if (i < n) {
+                const float e = reproj_err2(p, kf, pxyz[i * 3], pxyz[i * 3 + 1], pxyz[i * 3 + 2], puv[i * 2], puv[i * 2 + 1]);
+                m = (e <= thr2) ? 1 : 0;
+            }
+            mask_out[(size_t)b * cap + i] = m;
+        }
+    }
+    __syncthreads();
+
+    for (int it = 0; it < iters; ++it) {
+        double acc[RF_ACC];
+#pragma unroll
+        for (int j = 0; j < RF_ACC; ++j) acc[j] = 0.0;
+        double R[9], t[3];
+        for (int j = 0; j < 9; ++j) R[j] = sR[j];
+        for (int j = 0; j < 3; ++j) t[j] = st[j];
+        for (int i = threadIdx.x; i < n; i += RF_THREADS) {
+            const float Xf = pxyz[i * 3], Yf = pxyz[i * 3 + 1], Zf = pxyz[i * 3 + 2];
+            const float uf = puv[i * 2], vf = puv[i * 2 + 1];
+            if (!(reproj_err2(p, kf, Xf, Yf, Zf, uf, vf) <= thr2)) continue;
+            const double X = Xf, Y = Yf, Z = Zf;
+            const double xr = R[0] * X + R[1] * Y + R[2] * Z;
+            const double yr = R[3] * X + R[4] * Y + R[5] * Z;
+            const double zr = R[6] * X + R[7] * Y + R[8] * Z;
+            const double xc = xr + t[0], yc = yr + t[1], zc = zr + t[2];
+            const double iz = 1.0 / zc;
+            const double x = xc * iz, y = yc * iz;
+            const double ru = kd.fx * x + kd.cx - (double)uf;
+            const double rv = kd.fy * y + kd.cy - (double)vf;
+            const double a0 = kd.fx * iz, a2 = -kd.fx * x * iz;
+            const double b1 = kd.fy * iz, b2 = -kd.fy * y * iz;
+            const double ju[6] = {a2 * yr, a0 * zr - a2 * xr, -a0 * yr, a0, 0.0, a2};
+            const double jv[6] = {-b1 * zr + b2 * yr, -b2 * xr, b1 * xr, 0.0, b1, b2};
+            int q = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = r; c < 6; ++c) acc[q++] += ju[r] * ju[c] + jv[r] * jv[c];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) acc[21 + r] += ju[r] * ru + jv[r] * rv;
+            acc[27] += ru * ru + rv * rv;
+        }
+#pragma unroll
+        for (int j = 0; j < RF_ACC; ++j) {
+            const double s = warp_sum(acc[j]);
+            if (lane == 0) sacc[warp][j] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot[RF_ACC];
+            for (int j = 0; j < RF_ACC; ++j) {
+                double s = 0.0;
+                for (int w = 0; w < RF_THREADS / 32; ++w) s += sacc[w][j];
+                tot[j] = s;
+            }
+            double g[6], d[6];
+            for (int j = 0; j < 6; ++j) g[j] = -tot[21 + j];
+            // tiny relative damping keeps the factorisation defined for planar / weak geometry
+            int dq = 0;
+            for (int r = 0; r < 6; ++r) {
+                tot[dq] += 1e-12 * tot[dq] + 1e-300;
+                dq += 6 - r;
+            }
+            if (solve6(tot, g, d)) {
+                double dR[9], Rn[9];
+                so3_exp(d, dR);
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j)
+                        Rn[3 * i + j] = dR[3 * i] * sR[j] + dR[3 * i + 1] * sR[3 + j] + dR[3 * i + 2] * sR[6 + j];
+                for (int j = 0; j < 9; ++j) sR[j] = Rn[j];
+                for (int j = 0; j < 3; ++j) st[j] += d[3 + j];
+                double mx = 0.0;
+                for (int j = 0; j < 6; ++j) mx = fmax(mx, fabs(d[j]));
+                if (mx < 1e-11) s_stop = 1;
+            } else {
+                s_stop = 1;
+            }
+        }
+        __syncthreads();
+        if (s_stop) break;
+    }
+
+    if (threadIdx.x == 0) {
+        if (status && !accumulate_status) status[b] = VO_ST_OK;  // else: keep the soft bits set upstream
+        if (n_inl_out) n_inl_out[b] = count;
+        if (best_h_out) best_h_out[b] = h;
+        if (rt_out) {
+            for (int j = 0; j < 9; ++j) rt_out[(size_t)b * 12 + j] = sR[j];
+            for (int j = 0; j < 3; ++j) rt_out[(size_t)b * 12 + 9 + j] = st[j];
+        }
+        if (rvec_tvec) {
+            double w[3];
+            so3_log(sR, w);
+            for (int j = 0; j < 3; ++j) rvec_tvec[(size_t)b * 6 + j] = w[j];
+            for (int j = 0; j < 3; ++j) rvec_tvec[(size_t)b * 6 + 3 + j] = st[j];
+        }
+        if (T_rel) {  // inverse of [R|t]: [R^T | -R^T t]  (pose.pose = pose.inv_pose, :143)
+            double *T = T_rel + (size_t)b * 16;
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) T[4 * i + j] = sR[3 * j + i];
+                T[4 * i + 3] = -(sR[i] * st[0] + sR[3 + i] * st[1] + sR[6 + i] * st[2]);
+            }
+            T[12] = 0.0; T[13] = 0.0; T[14] = 0.0; T[15] = 1.0;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace vo
+
+extern "C" int vo_hypotheses(vo_ctx *ctx, const int32_t *n_pts, int B, int H, uint64_t seed, int64_t pair0,
+                             int32_t *hyp, void *stream) {
+    using namespace vo;
+    VO_REQUIRE(ctx && n_pts && hyp, "vo_hypotheses: null argument");
+    VO_REQUIRE(B >= 0 && H >= 0, "vo_hypotheses: negative size");
+    VO_REQUIRE(((uintptr_t)hyp % 16) == 0, "vo_hypotheses: table must be 16B aligned");
+    const long long total = (long long)B * H;
+    if (total == 0) return VO_OK;
+    hypotheses_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_pts, B, H, seed, pair0, hyp);
+    VO_LAUNCH_CHECK(ctx);
+    return VO_OK;
+}
+
+namespace vo {
+int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_t *n_pts, int B, int cap,
+                    const double *K_h, const int32_t *hyp, int H, float thr_px, int min_inliers, int refine_iters,
+                    double *rt, double *rvec_tvec, double *T_rel, int32_t *n_inl, int32_t *best_h,
+                    uint8_t *inlier_mask, int32_t *hyp_counts, int32_t *status, int accumulate_status,
+                    void *stream) {
+    VO_REQUIRE(ctx && xyz && uv && n_pts && K_h && hyp, "vo_pnp_ransac: null argument");
+    VO_REQUIRE(B >= 0 && cap >= 0 && H > 0, "vo_pnp_ransac: bad size");
+    VO_REQUIRE(((uintptr_t)hyp % 16) == 0, "vo_pnp_ransac: hypothesis table must be 16B aligned");
+    VO_REQUIRE(K_h[0] != 0.0 && K_h[4] != 0.0, "vo_pnp_ransac: zero focal length");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) return VO_OK;
+    float *poses;
+    unsigned long long *bestkey;
+    int rc;
+    if ((rc = ws_get(ctx, WS_POSES, sizeof(float) * 12 * (size_t)B * H, (void **)&poses))) return rc;
+    if ((rc = ws_get(ctx, WS_BESTKEY, sizeof(unsigned long long) * (size_t)B, (void **)&bestkey))) return rc;
+    VO_CUDA(cudaMemsetAsync(bestkey, 0, sizeof(unsigned long long) * (size_t)B, st));
+
+    IntrD kd{K_h[0], K_h[4], K_h[2], K_h[5]};
+    IntrF kf{(float)K_h[0], (float)K_h[4], (float)K_h[2], (float)K_h[5]};
+    const float thr2 = thr_px * thr_px;
+    const long long total = (long long)B * H;
+    p3p_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(xyz, uv, n_pts, B, cap, hyp, H, kd, poses);
+    VO_LAUNCH_CHECK(ctx);
+    dim3 grid(ceil_div(H, SC_WARPS), B);
+    score_kernel<<<grid, SC_WARPS * 32, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, thr2, bestkey, hyp_counts);
+    VO_LAUNCH_CHECK(ctx);
+    refit_kernel<<<B, RF_THREADS, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, kd, thr2, min_inliers, refine_iters,
+                                           bestkey, rt, rvec_tvec, T_rel, n_inl, best_h, inlier_mask, status,
+                                           accumulate_status);
+    VO_LAUNCH_CHECK(ctx);
+    return VO_OK;
+}
+}  // namespace vo
+
+extern "C" int vo_pnp_ransac(vo_ctx *ctx, const float *xyz, const float *uv, const int32_t *n_pts, int B, int cap,
+                             const double *K_h, const int32_t *hyp, int H, float thr_px, int min_inliers,
+                             int refine_iters, double *rt, double *rvec_tvec, double *T_rel, int32_t *n_inl,
+                             int32_t *best_h, uint8_t *inlier_mask, int32_t *hyp_counts, int32_t *status,
+                             void *stream) {
+    return vo::pnp_ransac_impl(ctx, xyz, uv, n_pts, B, cap, K_h, hyp, H, thr_px, min_inliers, refine_iters, rt,
+                               rvec_tvec, T_rel, n_inl, best_h, inlier_mask, hyp_counts, status, 0, stream);
+}
