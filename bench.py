@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — frame-pairs/sec of the hot path (match -> gather/back-project -> PnP-RANSAC -> pose).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3]
+
+A step = one pass of the hot path over `--pairs` synthetic frame pairs per GPU (weak scaling: every rank owns
+its own block of the pre-declared pair list), followed under N>1 by one NCCL all-gather of the
+4x4 relative poses.  Default workload c2 = BASELINE.json configs[1]: ORB 5k keypoints/frame, 256-bit Hamming
+mutual-NN + PnP-RANSAC (1024 hypotheses), 1000-pair sequence, KITTI-shaped frames.
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU path (oracle/reference_path.py:
+the same OpenCV calls the reference makes) on the host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (descriptor kind, keypoints, hypotheses, matcher description, cpu matcher)
+    "c1": dict(kind="sift", n_kp=2000, n_hyp=512, pairs=256, shape="kitti", cpu_matcher="knn_ratio",
+               desc="SIFT 2k kp, L2 kNN-2 + ratio 0.85, PnP-RANSAC 512 hyp, KITTI 1241x376"),
+    "c2": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, shape="kitti", cpu_matcher="hamming_mutual",
+               desc="ORB 5k kp, 256-bit Hamming mutual-NN, PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
+    "c3": dict(kind="r2d2", n_kp=10000, n_hyp=4096, pairs=64, shape="kitti", cpu_matcher="r2d2",
+               desc="R2D2 10k kp, cosine GEMM-argmin ratio+mutual, PnP-RANSAC 4096 hyp, KITTI 1241x376"),
+}
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def matcher_cfg(kind, ops):
+    if kind == "orb":
+        return dict(norm_or_metric=ops.VO_NORM_HAMMING, mode=ops.VO_MODE_MUTUAL, match_param=0.0, precision=0)
+    if kind == "sift":
+        return dict(norm_or_metric=ops.VO_METRIC_L2, mode=ops.VO_MODE_RATIO, match_param=0.85, precision=ops.VO_PREC_TF32X1)
+    return dict(norm_or_metric=ops.VO_METRIC_COSINE, mode=ops.VO_MODE_RATIO_MUTUAL, match_param=0.90, precision=ops.VO_PREC_TF32X3)
+
+
+def make_host_batch(wl, unique, first_index):
+    from vo_b200 import synthetic
+    K, wh = (synthetic.KITTI_K, synthetic.KITTI_WH) if wl["shape"] == "kitti" else (synthetic.ZED_K, synthetic.ZED_WH)
+    return synthetic.make_batch(first_index, unique, n_kp=wl["n_kp"], kind=wl["kind"], K=K, wh=wh)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------- CPU reference arm
+def time_cpu_pairs(wl, n_pairs, first_index=0, warm=1):
+    """Runs the reference's CPU path over `n_pairs` synthetic pairs; returns (pairs/s, seconds, threads)."""
+    from oracle import reference_path as rp
+    threads = rp.set_threads(os.cpu_count() or 1)
+    batch = make_host_batch(wl, n_pairs + warm, first_index)
+    rng = np.random.RandomState(8214)          # vo_stereo_runner.py:20-24
+    def run(i):
+        p = batch["pairs"][i]
+        return rp.process_pair(p["ref_desc"], p["cur_desc"], p["ref_kp"], p["cur_kp"], p["depth"], p["K"],
+                               matcher=wl["cpu_matcher"], rng=rng)
+    for i in range(warm):
+        run(i)
+    t0 = time.perf_counter()
+    ok = 0
+    for i in range(warm, warm + n_pairs):
+        ok += bool(run(i)[0])
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, dt, threads, ok
+
+
+def run_reference(args, wl):
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    sample = args.cpu_pairs or {"c1": 24, "c2": 16, "c3": 4}[args.workload]
+    vals, secs = [], []
+    for s in range(args.warmup + args.steps):
+        v, dt, threads, ok = time_cpu_pairs(wl, sample, first_index=s * (sample + 1))
+        if s >= args.warmup:
+            vals.append(v); secs.append(dt)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "frame-pairs/sec (match+PnP)", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs) * 1e3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_of(wl), "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "pairs_per_step": sample,
+                   "path": "cv2.BFMatcher + depthTo3d restatement + 3x cv2.solvePnPRansac(100, 1.5) (oracle/reference_path.py)"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} pairs/step x {args.steps} steps of the same synthetic workload"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def dtype_of(wl):
+    return {"orb": "u8 (XOR+POPC) / f32+f64 PnP", "sift": "tf32 (1x, exact on integer SIFT) / f32+f64 PnP",
+            "r2d2": "tf32x3 / f32+f64 PnP"}[wl["kind"]]
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import vo_b200  # noqa: F401
+    from vo_b200 import ops, sequence
+
+    rank, local_rank, world = env_rank()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    P = args.pairs or wl["pairs"]                      # pairs per GPU per step
+    unique = min(args.unique, P)
+    reps = (P + unique - 1) // unique
+    host = make_host_batch(wl, unique, first_index=rank * P)
+    batch_full = sequence.PairBatch.from_numpy(host, dev, repeat=reps)
+    batch = batch_full.slice(0, P)                     # distinct memory per pair: inputs >> L2
+    mc = matcher_cfg(wl["kind"], ops)
+    if args.precision is not None:
+        mc["precision"] = args.precision
+    cfg = sequence.PipelineConfig(n_hyp=wl["n_hyp"], **mc)
+    chunk = min(args.chunk, P)
+    out = ops.PipelineBuffers(P, dev)
+
+    def step():
+        sequence.run_resident(batch, cfg, pair0=rank * P, chunk=chunk, out=out)
+        if world > 1:
+            return sequence.all_gather_poses(out.T_rel, out.status, world)
+        return out.T_rel, out.status
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = ops.launch_count()
+    ops.profile_enable(True)
+    ops.profile_collect()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        T_all, st_all = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    stages = ops.profile_collect()
+    ops.profile_enable(False)
+    launches = ops.launch_count() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * P * args.steps / (ms / 1e3)
+
+    # sanity of the work done inside the timed region (not a parity test: tests/ does that)
+    st = out.status.cpu().numpy()
+    ok_frac = float((st == 0).mean())
+    n_inl = out.n_inl.cpu().numpy()
+    from vo_b200 import synthetic
+    Tn = out.T_rel.cpu().numpy()
+    errs = [synthetic.pose_errors(Tn[i], host["pairs"][i % unique]["T_rel"]) for i in range(min(P, unique))]
+    chain = sequence.chain_poses(T_all.cpu().numpy(), sequence.gate_poses(T_all.cpu().numpy(), st_all.cpu().numpy()))
+
+    # ---- e2e: host buffers in, poses out, H2D/D2H inside the timed region
+    host_rep = {k: np.concatenate([host[k]] * reps, 0)[:P] for k in ("ref_desc", "cur_desc", "ref_kp", "cur_kp", "depth")}
+    host_rep["K"] = host["K"]
+    runner = sequence.HostPairRunner(host_rep, cfg, chunk=min(args.e2e_chunk, P), device=dev)
+    del host_rep
+
+    def e2e_step():
+        T_h, st_h, inl_h = runner.run(pair0=rank * P)
+        if world > 1:
+            sequence.all_gather_poses(runner.out.T_rel, runner.out.status, world)
+        torch.cuda.synchronize()
+        return T_h, st_h
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        T_h, st_h = e2e_step()
+        sequence.chain_poses(T_h.numpy(), sequence.gate_poses(T_h.numpy(), st_h.numpy()))
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * args.steps / (float(t.item()) / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, from the per-stage event times of the timed region
+    hbm_peak, bf16_peak, peak_kind = peaks()
+    N = M = wl["n_kp"]
+    stage_ms = {k: v[0] / max(v[1], 1) for k, v in stages.items() if v[1]}
+    total_stage = sum(v[0] for v in stages.values())
+    share = {k: (v[0] / total_stage if total_stage else 0.0) for k, v in stages.items() if v[1]}
+    launches_match = stages["match"][1]
+    pairs_per_launch = P * args.steps / max(launches_match, 1)
+    match_s = stage_ms.get("match", float("nan")) / 1e3
+    if wl["kind"] == "orb":
+        alg_bytes = pairs_per_launch * (32.0 * (N + M) + 16.0 * N + 8.0 * M)      # descriptors + row partials + column keys
+        roof = {"kernel": "match_u8_kernel (XOR+POPC Hamming, fused row/column arg-min)", "bound": "hbm",
+                "achieved": alg_bytes / match_s / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                "note": "structurally << 1: all-pairs Hamming is POPC-pipe bound, not HBM bound (SURVEY D5); see binding_pipe"}
+        popc = pairs_per_launch * N * M * 8.0
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        popc_peak = 16.0 * 148 * sm_mhz * 1e6                                        # 16 POPC lanes/clk/SM, nominal
+        roof["binding_pipe"] = {"pipe": "popc", "achieved": popc / match_s / 1e12, "peak": popc_peak / 1e12,
+                                "unit": "Tpopc/s", "frac": popc / match_s / popc_peak,
+                                "peak_source": "16 lanes/clk/SM x 148 SM x sampled SM clock (nominal rate)"}
+    else:
+        passes = 3 if mc["precision"] == ops.VO_PREC_TF32X3 else 1
+        flops = pairs_per_launch * 2.0 * N * M * 128 * (passes if mc["precision"] != ops.VO_PREC_FP32_SIMT else 1)
+        tf32_peak = bf16_peak / 2.0
+        roof = {"kernel": "match_f32 fused GEMM-argmin", "bound": "tensor", "achieved": flops / match_s / 1e12,
+                "peak": tf32_peak, "unit": "TFLOP/s", "traffic": None,
+                "peak_source": f"0.5 x bf16 cuBLAS peak in MEASURED_PEAKS.json ({peak_kind}); TF32 not separately measured",
+                "issued_passes": passes}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["avg_launch_ms"] = stage_ms.get("match")
+    roof["share_of_step"] = share.get("match")
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sample = args.cpu_pairs or {"c1": 48, "c2": 24, "c3": 6}[args.workload]
+        v, dt, threads, okc = time_cpu_pairs(wl, sample, first_index=0)
+        cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+               "sample": f"first {sample} pairs of the same synthetic workload, {dt:.1f} s, reference CPU path "
+                         f"(cv2 {wl['cpu_matcher']} + 3x solvePnPRansac), {okc}/{sample} poses found"}
+
+    line = {
+        "metric": "frame-pairs/sec (match+PnP)", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": dtype_of(wl), "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "pairs_per_gpu_per_step": P, "unique_pairs": unique,
+                   "chunk": chunk, "l2": "inputs larger than L2 (every pair has its own HBM copy: "
+                   f"{batch.nbytes() / 1e6:.0f} MB per GPU per step)", "parallelism": f"pairs sharded over {world} GPU(s), "
+                   "1 NCCL all-gather of 4x4 poses per step" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": runner.h2d_bytes,
+                "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "stages_ms_per_launch": stage_ms,
+        "stage_share": share,
+        "check": {"pairs_ok_frac": ok_frac, "median_inliers": float(np.median(n_inl)),
+                  "median_rot_err_rad": float(np.median([e[0] for e in errs])),
+                  "median_trans_err_m": float(np.median([e[1] for e in errs])),
+                  "chained_poses": int(chain.shape[0])},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: workload's)")
+    ap.add_argument("--unique", type=int, default=40, help="distinct synthetic pairs generated per rank (tiled to --pairs)")
+    ap.add_argument("--chunk", type=int, default=250, help="pairs per vo_pipeline call")
+    ap.add_argument("--e2e-chunk", type=int, default=125)
+    ap.add_argument("--precision", type=int, default=None)
+    ap.add_argument("--cpu-pairs", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

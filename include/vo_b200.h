@@ -169,6 +169,26 @@ VO_API int vo_pnp_ransac(vo_ctx *ctx, const float *xyz, const float *uv, const i
                   uint8_t *inlier_mask, int32_t *hyp_counts, int32_t *status, void *stream);
 
 /*
+ * Per-stage device timing (CUDA events recorded on the caller's stream around each kernel launch).
+ * Used by bench.py for the per-kernel roofline; off by default (no events recorded).
+ * vo_profile_collect synchronises the device, adds up the intervals recorded since the last collect
+ * and writes, per stage id, total milliseconds and interval count (arrays of VO_STAGE_COUNT).
+ */
+#define VO_STAGE_FILL 0     /* column-key reset                  */
+#define VO_STAGE_PREP 1     /* tf32 hi/lo split + norms (float)  */
+#define VO_STAGE_MATCH 2    /* distance kernel (u8 / f32)        */
+#define VO_STAGE_FINALIZE 3 /* merge + acceptance rule + compact */
+#define VO_STAGE_GATHER 4   /* gather + back-project + gate      */
+#define VO_STAGE_HYP 5      /* hypothesis table                  */
+#define VO_STAGE_P3P 6      /* minimal solves                    */
+#define VO_STAGE_SCORE 7    /* inlier counting                   */
+#define VO_STAGE_REFIT 8    /* winner mask + Gauss-Newton        */
+#define VO_STAGE_DENSE 9    /* dense back-projection             */
+#define VO_STAGE_COUNT 10
+VO_API int vo_profile_enable(vo_ctx *ctx, int on);
+VO_API int vo_profile_collect(vo_ctx *ctx, double *ms, long long *counts);
+
+/*
  * Whole hot path for a batch of pairs on one stream (match -> gather/back-project ->
  * hypotheses -> PnP-RANSAC -> pose).  Replaces lines 256-264 + computepose_3D_2D of
  * VisualOdometry.process_frame (VisualOdometry_Stereo.py:223-297) for B pre-declared pairs.

@@ -1,0 +1,24 @@
+// Host build of the device math header (csrc/pnp_math.cuh) so the CPU-only container can check, bit for bit,
+// that the code the kernels run equals the oracle's restatement.  Test infrastructure only.
+#include "../visual-odometry-pipeline_b200/csrc/pnp_math.cuh"
+extern "C" {
+int hm_p3p4(const double *P, const double *uv, const double *K, double *out) {
+    double Pm[4][3], uvm[4][2];
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 3; ++j) Pm[i][j] = P[3 * i + j];
+        uvm[i][0] = uv[2 * i]; uvm[i][1] = uv[2 * i + 1];
+    }
+    vo::PoseD best;
+    if (!vo::p3p_solve4(Pm, uvm, K[0], K[1], K[2], K[3], best)) return 0;
+    for (int j = 0; j < 9; ++j) out[j] = best.r[j];
+    for (int j = 0; j < 3; ++j) out[9 + j] = best.t[j];
+    return 1;
+}
+void hm_draw(unsigned long long seed, long long pair, int h, int n, int *out) { vo::draw_hypothesis(seed, pair, h, n, out); }
+float hm_err2(const float *pose, const float *k, float X, float Y, float Z, float u, float v) {
+    vo::PoseF p; vo::IntrF kk{k[0], k[1], k[2], k[3]};
+    for (int j = 0; j < 9; ++j) p.r[j] = pose[j];
+    for (int j = 0; j < 3; ++j) p.t[j] = pose[9 + j];
+    return vo::reproj_err2(p, kk, X, Y, Z, u, v);
+}
+}

@@ -1,0 +1,96 @@
+"""CUDA byte-descriptor matcher (through the C ABI) vs golden vectors and the CPU oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _pairs(res, b=0):
+    return res.numpy(b)
+
+
+def test_golden_hamming_knn_and_crosscheck(golden):
+    from vo_b200 import ops
+    g = golden("match_u8.npz")
+    r = ops.match_u8(_gpu(g["ref"]), _gpu(g["cur"]), ops.VO_NORM_HAMMING, ops.VO_MODE_MUTUAL, want_knn=True)
+    assert np.array_equal(r.knn_idx[0].cpu().numpy(), g["ham_idx"])
+    assert np.array_equal(r.knn_val[0].cpu().numpy(), g["ham_dist"])
+    assert np.array_equal(r.col_idx[0].cpu().numpy(), g["col_idx"])
+    assert np.array_equal(_pairs(r), g["cc_pairs"])
+    r2 = ops.match_u8(_gpu(g["ref2"]), _gpu(g["cur2"]), ops.VO_NORM_HAMMING, ops.VO_MODE_MUTUAL)
+    assert np.array_equal(_pairs(r2), g["cc_pairs2"])
+
+
+def test_golden_reference_orb_get_matches_l2_bytes(golden):
+    from vo_b200 import ops
+    g = golden("match_u8.npz")
+    r = ops.match_u8(_gpu(g["ref"]), _gpu(g["cur"]), ops.VO_NORM_L2_U8, ops.VO_MODE_RATIO, 0.85, want_knn=True)
+    assert np.array_equal(r.knn_idx[0].cpu().numpy(), g["l2_idx"])
+    assert np.array_equal(r.knn_val[0].cpu().numpy(), g["l2_dist"])
+    assert np.array_equal(_pairs(r), g["ref_orb_pairs"].reshape(-1, 2))
+    r2 = ops.match_u8(_gpu(g["ref2"]), _gpu(g["cur2"]), ops.VO_NORM_L2_U8, ops.VO_MODE_RATIO, 0.85)
+    assert np.array_equal(_pairs(r2), g["ref_orb_pairs2"].reshape(-1, 2))
+
+
+@pytest.mark.parametrize("n,m", [(5000, 5000), (1237, 3001), (513, 255), (1, 700), (700, 1)])
+def test_vs_oracle_sizes(orc, n, m):
+    from vo_b200 import ops, synthetic
+    p = synthetic.make_pair(n + m, n_kp=max(n, 8), n_cur=max(m, 8), kind="orb")
+    ref, cur = p["ref_desc"][:n], p["cur_desc"][:m]
+    for norm, mode, param in ((ops.VO_NORM_HAMMING, ops.VO_MODE_MUTUAL, 0.0), (ops.VO_NORM_HAMMING, ops.VO_MODE_RATIO, 0.85),
+                              (ops.VO_NORM_L2_U8, ops.VO_MODE_RATIO, 0.85), (ops.VO_NORM_HAMMING, ops.VO_MODE_NN, 0.0)):
+        r = ops.match_u8(_gpu(ref), _gpu(cur), norm, mode, param, want_knn=True)
+        ridx, rval, cidx = orc.knn_u8(ref, cur, norm)
+        assert np.array_equal(r.knn_idx[0].cpu().numpy(), ridx)
+        assert np.array_equal(r.knn_val[0].cpu().numpy(), rval)
+        assert np.array_equal(r.col_idx[0].cpu().numpy(), cidx)
+        want, wd = orc.accept(ridx, rval, cidx, mode, param)
+        assert np.array_equal(_pairs(r), want)
+        k = len(want)
+        assert np.array_equal(r.dist[0, :k].cpu().numpy(), wd)
+
+
+def test_ragged_batch_with_counts(orc):
+    import torch
+    from vo_b200 import ops, synthetic
+    B, N, M = 5, 640, 600
+    ps = [synthetic.make_pair(40 + b, n_kp=N, n_cur=M, kind="orb") for b in range(B)]
+    ref = np.stack([p["ref_desc"] for p in ps])
+    cur = np.stack([p["cur_desc"] for p in ps])
+    n_ref = np.array([640, 1, 333, 0, 512], np.int32)
+    n_cur = np.array([600, 600, 17, 50, 0], np.int32)
+    r = ops.match_u8(_gpu(ref), _gpu(cur), ops.VO_NORM_HAMMING, ops.VO_MODE_MUTUAL, n_ref=_gpu(n_ref), n_cur=_gpu(n_cur))
+    for b in range(B):
+        want, _ = orc.match_u8(ref[b, :n_ref[b]], cur[b, :n_cur[b]], orc.NORM_HAMMING, orc.MODE_MUTUAL)
+        assert np.array_equal(_pairs(r, b), want), b
+    assert r.count.cpu().tolist() == [len(orc.match_u8(ref[b, :n_ref[b]], cur[b, :n_cur[b]], 0, 1)[0]) for b in range(B)]
+
+
+def test_empty_inputs_and_bad_arguments():
+    import torch
+    from vo_b200 import ops, _lib
+    e = torch.zeros((0, 32), dtype=torch.uint8, device="cuda")
+    d = torch.arange(64, dtype=torch.uint8, device="cuda").reshape(2, 32)
+    assert ops.match_u8(e, d).count.item() == 0
+    assert ops.match_u8(d, e).count.item() == 0
+    with pytest.raises(_lib.VoError):
+        ops.match_u8(torch.zeros((4, 16), dtype=torch.uint8, device="cuda"), torch.zeros((4, 16), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(_lib.VoError):
+        ops.match_u8(d, d, mode=ops.VO_MODE_THRESH)
+
+
+def test_self_match_is_identity_at_full_size():
+    """size-independent property at the c2 size: matching a frame against itself gives i -> i with distance 0."""
+    import torch
+    from vo_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    d = torch.randint(0, 256, (5000, 32), dtype=torch.uint8, device="cuda", generator=g)
+    r = ops.match_u8(d, d, ops.VO_NORM_HAMMING, ops.VO_MODE_MUTUAL)
+    pairs = r.numpy()
+    assert np.array_equal(pairs[:, 0], np.arange(5000)) and np.array_equal(pairs[:, 1], np.arange(5000))
+    assert float(r.dist[0].abs().max()) == 0.0

@@ -1,0 +1,63 @@
+"""csrc/pnp_math.cuh compiled for the host (g++ -ffp-contract=off) must equal the oracle bit for bit: same
+hypothesis table, same P3P poses, same fp32 errors.  This is the CPU-side half of the "inlier sets bit-exact
+under a shared hypothesis set" claim; tests/test_gpu_pnp.py is the device half."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hm():
+    so = os.path.join(tempfile.gettempdir(), "libvo_host_math_test.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so,
+                           os.path.join(HERE, "host_math_shim.cpp")])
+    lib = ctypes.CDLL(so)
+    lib.hm_err2.restype = ctypes.c_float
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_hypothesis_generator_equals_oracle(hm, orc):
+    for n, pair in ((4, 0), (57, 3), (5000, 999)):
+        want = orc.hypotheses(n, 256, 8214, pair)
+        got = np.zeros((256, 4), np.int32)
+        for h in range(256):
+            hm.hm_draw(ctypes.c_ulonglong(8214), ctypes.c_longlong(pair), h, n, _p(got[h]))
+        assert np.array_equal(got, want)
+
+
+def test_p3p_and_scoring_bit_exact(hm, orc, golden):
+    g = golden("pnp.npz")
+    xyz, uv, K = g["xyz"], g["uv"], g["K"]
+    hyp = orc.hypotheses(len(xyz), 128, 8214, 0)
+    poses, counts = orc.solve_and_score(xyz, uv, K, hyp)
+    kv = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]])
+    kf = kv.astype(np.float32)
+    nvalid = 0
+    for h in range(128):
+        P = np.ascontiguousarray(xyz[hyp[h]].astype(np.float64))
+        q = np.ascontiguousarray(uv[hyp[h]].astype(np.float64))
+        out = np.zeros(12)
+        ok = hm.hm_p3p4(_p(P), _p(q), _p(kv), _p(out))
+        if not ok:
+            assert np.isnan(poses[h]).all()
+            continue
+        nvalid += 1
+        assert np.array_equal(out.astype(np.float32), poses[h])          # identical bits after the fp32 cast
+        p32 = np.ascontiguousarray(poses[h])
+        cnt = 0
+        for i in range(0, len(xyz), 7):
+            e = hm.hm_err2(_p(p32), _p(kf), *(ctypes.c_float(float(x)) for x in (*xyz[i], *uv[i])))
+            cnt += e <= np.float32(2.25)
+        m = orc.inlier_mask(xyz, uv, K, poses[h])
+        assert cnt == int(m[::7].sum())
+    assert nvalid > 100

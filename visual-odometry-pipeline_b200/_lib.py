@@ -73,7 +73,11 @@ PROTOTYPES = {
                               c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p]),
     "vo_pipeline": (c_int, [c_void_p, ctypes.POINTER(PipelineArgs), c_void_p]),
+    "vo_profile_enable": (c_int, [c_void_p, c_int]),
+    "vo_profile_collect": (c_int, [c_void_p, c_void_p, c_void_p]),
 }
+
+STAGES = ("fill", "prep", "match", "finalize", "gather", "hyp", "p3p", "score", "refit", "dense")
 
 _lib = None
 _lock = threading.Lock()

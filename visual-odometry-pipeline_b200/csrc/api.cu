@@ -1,6 +1,7 @@
 // Context, error plumbing, float-matcher entry point and the batched whole-path pipeline.
 #include "common.cuh"
 #include <stdlib.h>
+#include <vector>
 
 namespace vo {
 
@@ -33,6 +34,26 @@ int ws_get(vo_ctx *ctx, int slot, size_t bytes, void **out) {
     }
     *out = ctx->ws[slot];
     return VO_OK;
+}
+
+struct Profiler {
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> stage;  // stage opened by pool[i]
+    size_t used = 0;
+};
+
+void prof_mark(vo_ctx *ctx, cudaStream_t st, int stage) {
+    Profiler *p = (Profiler *)ctx->prof;
+    if (!p) return;
+    if (p->used == p->pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        p->pool.push_back(e);
+        p->stage.push_back(-1);
+    }
+    p->stage[p->used] = stage;
+    cudaEventRecord(p->pool[p->used], st);
+    p->used++;
 }
 
 int pick_split(vo_ctx *ctx, int B, int row_blocks, int col_tiles, int min_tiles_per_split) {
@@ -76,10 +97,43 @@ extern "C" int vo_create(int device, vo_ctx **out) {
     return VO_OK;
 }
 
+extern "C" int vo_profile_enable(vo_ctx *ctx, int on) {
+    using namespace vo;
+    VO_REQUIRE(ctx, "vo_profile_enable: null ctx");
+    if (on && !ctx->prof) ctx->prof = new Profiler();
+    ctx->prof_on = on ? 1 : 0;
+    return VO_OK;
+}
+
+extern "C" int vo_profile_collect(vo_ctx *ctx, double *ms, long long *counts) {
+    using namespace vo;
+    VO_REQUIRE(ctx && ms && counts, "vo_profile_collect: null argument");
+    for (int i = 0; i < VO_STAGE_COUNT; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    Profiler *p = (Profiler *)ctx->prof;
+    if (!p) return VO_OK;
+    VO_CUDA(cudaDeviceSynchronize());
+    for (size_t i = 0; i + 1 < p->used; ++i) {
+        const int sg = p->stage[i];
+        if (sg < 0 || sg >= VO_STAGE_COUNT) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, p->pool[i], p->pool[i + 1]) == cudaSuccess) {
+            ms[sg] += t;
+            counts[sg] += 1;
+        }
+    }
+    p->used = 0;
+    return VO_OK;
+}
+
 extern "C" void vo_destroy(vo_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->prof) {
+        vo::Profiler *p = (vo::Profiler *)ctx->prof;
+        for (cudaEvent_t e : p->pool) cudaEventDestroy(e);
+        delete p;
+    }
     for (int i = 0; i < 8; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     free(ctx);
@@ -108,6 +162,7 @@ extern "C" int vo_match_f32(vo_ctx *ctx, const float *ref, const float *cur, int
     int rc;
     unsigned long long *colkey;
     if ((rc = ws_get(ctx, WS_COLKEY, sizeof(unsigned long long) * (size_t)B * m_stride, (void **)&colkey))) return rc;
+    VO_PROF(ctx, st, VO_STAGE_FILL);
     if ((rc = fill_u64(ctx, colkey, (size_t)B * m_stride, ~0ull, st))) return rc;
     vo_row_partial *part;
     const float *row_norm = nullptr;
@@ -115,6 +170,7 @@ extern "C" int vo_match_f32(vo_ctx *ctx, const float *ref, const float *cur, int
     if (precision == VO_PREC_FP32_SIMT) {
         n_split = pick_split(ctx, B, ceil_div(n_stride, 64), ceil_div(m_stride, 64), 4);
         if ((rc = ws_get(ctx, WS_ROWPART, sizeof(vo_row_partial) * (size_t)B * n_split * n_stride, (void **)&part))) return rc;
+        VO_PROF(ctx, st, VO_STAGE_MATCH);
         if ((rc = match_f32_simt(ctx, ref, cur, B, n_stride, m_stride, dim, n_ref, n_cur, metric, part, n_split, colkey, st)))
             return rc;
     } else {

@@ -20,5 +20,5 @@ done
 fail=0
 for p in "${pids[@]}"; do wait "$p" || fail=1; done
 [ "$fail" = 0 ] || { echo "build failed"; exit 1; }
-"${NVCC}" -shared -o "${out}" "${obj}"/*.o -cudart static -Xlinker --exclude-libs=ALL
+"${NVCC}" -gencode arch=compute_100a,code=sm_100a -shared -o "${out}" "${obj}"/*.o -cudart static -Xlinker --exclude-libs=ALL
 echo "built ${out}"

@@ -89,6 +89,8 @@ struct vo_ctx {
     size_t ws_bytes[8];
     int tc_ready;  // tcgen05 path initialised (driver entry point resolved)
     void *encode_tiled;  // PFN_cuTensorMapEncodeTiled
+    void *prof;          // vo::Profiler* when profiling was ever enabled
+    int prof_on;
 };
 
 namespace vo {
@@ -96,6 +98,13 @@ enum WsSlot { WS_ROWPART = 0, WS_COLKEY = 1, WS_POSES = 2, WS_BESTKEY = 3, WS_SP
 // Returns a device buffer of at least `bytes` for `slot`, reallocating (stream-ordered
 // free of the old block) only when it must grow.
 int ws_get(vo_ctx *ctx, int slot, size_t bytes, void **out);
+
+// stage timing: record an event on `st` that opens stage `stage` (-1 closes the current one)
+void prof_mark(vo_ctx *ctx, cudaStream_t st, int stage);
+#define VO_PROF(ctx, st, stage)                       \
+    do {                                              \
+        if ((ctx)->prof_on) vo::prof_mark((ctx), (st), (stage)); \
+    } while (0)
 
 // stages (defined in the .cu files)
 int match_finalize(vo_ctx *ctx, const vo_row_partial *part, int n_split, const unsigned long long *colkey, int B,

@@ -154,8 +154,10 @@ extern "C" int vo_backproject_dense(vo_ctx *ctx, const float *depth, int B, int 
     long long want = (n_vec + 255) / 256;
     const long long cap = (long long)ctx->sm_count * 16;
     int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    VO_PROF(ctx, (cudaStream_t)stream, VO_STAGE_DENSE);
     backproject_dense_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(depth, xyz, n_px, H, W, make_intr(K_h));
     VO_LAUNCH_CHECK(ctx);
+    VO_PROF(ctx, (cudaStream_t)stream, -1);
     return VO_OK;
 }
 
@@ -170,9 +172,11 @@ extern "C" int vo_gather_backproject(vo_ctx *ctx, const int32_t *pairs, const in
     VO_REQUIRE(B >= 0 && pair_cap >= 0 && H > 0 && W > 0 && kp_stride >= 2, "vo_gather_backproject: bad shape");
     VO_REQUIRE(K_h[0] != 0.0 && K_h[4] != 0.0, "vo_gather_backproject: zero focal length");
     if (B == 0) return VO_OK;
+    VO_PROF(ctx, (cudaStream_t)stream, VO_STAGE_GATHER);
     gather_backproject_kernel<<<B, GB_THREADS, 0, (cudaStream_t)stream>>>(
         pairs, n_pairs, pair_cap, ref_kp, cur_kp, n_stride, m_stride, kp_stride, depth, H, W, make_intr(K_h),
         min_flow_px, z_min, z_max, xyz, ref_uv, cur_uv, src, n_out, status);
     VO_LAUNCH_CHECK(ctx);
+    VO_PROF(ctx, (cudaStream_t)stream, -1);
     return VO_OK;
 }

@@ -143,11 +143,13 @@ int match_finalize(vo_ctx *ctx, const vo_row_partial *part, int n_split, const u
                    int n_stride, int m_stride, const int32_t *n_ref, const int32_t *n_cur, int score_kind, int mode,
                    double param, const float *row_norm, int32_t *out_pairs, float *out_dist, int32_t *out_count,
                    const vo_knn_out *knn, uint8_t *near_tie, cudaStream_t st) {
+    VO_PROF(ctx, st, VO_STAGE_FINALIZE);
     finalize_kernel<<<B, FIN_THREADS, 0, st>>>(part, n_split, colkey, n_stride, m_stride, n_ref, n_cur, score_kind, mode,
                                                 param, row_norm, out_pairs, out_dist, out_count,
                                                 knn ? knn->row_idx : nullptr, knn ? knn->row_val : nullptr,
                                                 knn ? knn->col_idx : nullptr, near_tie);
     VO_LAUNCH_CHECK(ctx);
+    VO_PROF(ctx, st, -1);
     return VO_OK;
 }
 

@@ -175,10 +175,12 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
     int rc;
     if ((rc = ws_get(ctx, WS_ROWPART, sizeof(vo_row_partial) * (size_t)B * n_split * n_stride, (void **)&part))) return rc;
     if ((rc = ws_get(ctx, WS_COLKEY, sizeof(unsigned long long) * (size_t)B * m_stride, (void **)&colkey))) return rc;
+    VO_PROF(ctx, st, VO_STAGE_FILL);
     if ((rc = fill_u64(ctx, colkey, (size_t)B * m_stride, ~0ull, st))) return rc;
 
     const bool second = (mode == VO_MODE_RATIO) || (knn && (knn->row_idx || knn->row_val));
     dim3 grid(row_blocks, n_split, B);
+    VO_PROF(ctx, st, VO_STAGE_MATCH);
 #define LAUNCH_U8(NORM, SEC) \
     match_u8_kernel<NORM, SEC><<<grid, U8_THREADS, 0, st>>>(ref, cur, n_stride, m_stride, n_ref, n_cur, n_split, part, colkey)
     if (norm == VO_NORM_HAMMING) {

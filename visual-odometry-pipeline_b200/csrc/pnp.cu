@@ -402,8 +402,10 @@ extern "C" int vo_hypotheses(vo_ctx *ctx, const int32_t *n_pts, int B, int H, ui
     VO_REQUIRE(((uintptr_t)hyp % 16) == 0, "vo_hypotheses: table must be 16B aligned");
     const long long total = (long long)B * H;
     if (total == 0) return VO_OK;
+    VO_PROF(ctx, (cudaStream_t)stream, VO_STAGE_HYP);
     hypotheses_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_pts, B, H, seed, pair0, hyp);
     VO_LAUNCH_CHECK(ctx);
+    VO_PROF(ctx, (cudaStream_t)stream, -1);
     return VO_OK;
 }
 
@@ -430,15 +432,19 @@ int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_
     IntrF kf{(float)K_h[0], (float)K_h[4], (float)K_h[2], (float)K_h[5]};
     const float thr2 = thr_px * thr_px;
     const long long total = (long long)B * H;
+    VO_PROF(ctx, st, VO_STAGE_P3P);
     p3p_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(xyz, uv, n_pts, B, cap, hyp, H, kd, poses);
     VO_LAUNCH_CHECK(ctx);
     dim3 grid(ceil_div(H, SC_WARPS), B);
+    VO_PROF(ctx, st, VO_STAGE_SCORE);
     score_kernel<<<grid, SC_WARPS * 32, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, thr2, bestkey, hyp_counts);
     VO_LAUNCH_CHECK(ctx);
+    VO_PROF(ctx, st, VO_STAGE_REFIT);
     refit_kernel<<<B, RF_THREADS, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, kd, thr2, min_inliers, refine_iters,
                                            bestkey, rt, rvec_tvec, T_rel, n_inl, best_h, inlier_mask, status,
                                            accumulate_status);
     VO_LAUNCH_CHECK(ctx);
+    VO_PROF(ctx, st, -1);
     return VO_OK;
 }
 }  // namespace vo

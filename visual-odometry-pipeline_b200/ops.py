@@ -30,6 +30,20 @@ def launch_count(device=None):
     return context(device).launch_count()
 
 
+def profile_enable(on=True, device=None):
+    ctx = context(device)
+    check(ctx.lib.vo_profile_enable(ctx.handle, 1 if on else 0), "vo_profile_enable")
+
+
+def profile_collect(device=None):
+    """{stage: (total_ms, intervals)} since the last collect (synchronises the device)."""
+    ctx = context(device)
+    ms = (ctypes.c_double * len(_lib.STAGES))()
+    cnt = (ctypes.c_longlong * len(_lib.STAGES))()
+    check(ctx.lib.vo_profile_collect(ctx.handle, ms, cnt), "vo_profile_collect")
+    return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.STAGES)}
+
+
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 

@@ -1,0 +1,159 @@
+"""Throughput mode: a pre-declared list of frame pairs, sharded across GPUs.
+
+Each rank runs vo_pipeline over its contiguous block of pairs; one all-gather of the 4x4 relative poses
+(+ status) follows; the host chains them with a prefix product in which failed or implausible pairs
+contribute the identity, mirroring VisualOdometry.process_frame (VisualOdometry_Stereo.py:270-274, 283, 290).
+There is no other collective: pairs are independent.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def shard_range(n_pairs, rank, world):
+    """Contiguous block [lo, hi) of the pair list owned by `rank`."""
+    base, rem = divmod(int(n_pairs), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gate_poses(T_rel, status, max_step_m=1.5):
+    """Host-side a9 gate: a pair is used iff PnP succeeded and ||t|| <= 1.5 m (consecutive frames)."""
+    T_rel = np.asarray(T_rel, np.float64).reshape(-1, 4, 4)
+    ok = (np.asarray(status).reshape(-1) == 0) & (np.linalg.norm(T_rel[:, :3, 3], axis=1) <= max_step_m)
+    return ok
+
+
+def chain_poses(T_rel, ok=None):
+    """Global poses G_0 = I, G_k = prod_{i<k} T_i (failed pairs -> identity).  Vectorised log-depth scan:
+    ceil(log2 P) batched 4x4 products instead of P sequential ones.  Returns (P+1, 4, 4) f64."""
+    T = np.array(T_rel, np.float64).reshape(-1, 4, 4)
+    P = T.shape[0]
+    if ok is not None:
+        T[~np.asarray(ok, bool)] = np.eye(4)
+    acc = T.copy()
+    shift = 1
+    while shift < P:
+        nxt = acc.copy()
+        nxt[shift:] = acc[:-shift] @ acc[shift:]     # inclusive scan, left-to-right products
+        acc = nxt
+        shift *= 2
+    out = np.empty((P + 1, 4, 4), np.float64)
+    out[0] = np.eye(4)
+    out[1:] = acc
+    return out
+
+
+def all_gather_poses(T_rel, status, world=None):
+    """One all-gather of [T_rel | status] over the default process group (NCCL on GPUs, gloo in CPU tests).
+    T_rel [P_local,4,4] f64, status [P_local] int32 -> concatenated over ranks in rank order.  Every rank
+    must contribute the same P_local (pad the tail rank)."""
+    import torch.distributed as dist
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    packed = torch.cat([T_rel.reshape(T_rel.shape[0], 16), status.to(torch.float64).reshape(-1, 1)], dim=1).contiguous()
+    if world == 1:
+        return T_rel.reshape(-1, 4, 4), status
+    out = torch.empty((world * packed.shape[0], 17), dtype=torch.float64, device=packed.device)
+    dist.all_gather_into_tensor(out, packed)
+    return out[:, :16].reshape(-1, 4, 4), out[:, 16].to(torch.int32)
+
+
+class PairBatch:
+    """Device-resident inputs of a block of frame pairs (what a front-end would have produced)."""
+
+    def __init__(self, ref_desc, cur_desc, ref_kp, cur_kp, depth, K):
+        self.ref_desc, self.cur_desc, self.ref_kp, self.cur_kp, self.depth = ref_desc, cur_desc, ref_kp, cur_kp, depth
+        self.K = np.asarray(K, np.float64)
+        self.B = ref_desc.shape[0]
+
+    @staticmethod
+    def from_numpy(batch, device="cuda", repeat=1):
+        def up(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+            return t.repeat((repeat,) + (1,) * (t.dim() - 1)) if repeat > 1 else t
+        return PairBatch(up(batch["ref_desc"]), up(batch["cur_desc"]), up(batch["ref_kp"]), up(batch["cur_kp"]),
+                         up(batch["depth"]), batch["K"])
+
+    def slice(self, lo, hi):
+        return PairBatch(self.ref_desc[lo:hi], self.cur_desc[lo:hi], self.ref_kp[lo:hi], self.cur_kp[lo:hi],
+                         self.depth[lo:hi], self.K)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.ref_desc, self.cur_desc, self.ref_kp, self.cur_kp, self.depth))
+
+
+class PipelineConfig:
+    def __init__(self, norm_or_metric, mode, match_param=0.85, precision=ops.VO_PREC_TF32X3, n_hyp=1024, seed=8214,
+                 thr_px=1.5, min_inliers=20, refine_iters=10):
+        self.kw = dict(norm_or_metric=norm_or_metric, mode=mode, match_param=match_param, precision=precision,
+                       n_hyp=n_hyp, seed=seed, thr_px=thr_px, min_inliers=min_inliers, refine_iters=refine_iters)
+
+
+def run_resident(batch, cfg, pair0=0, chunk=None, out=None):
+    """vo_pipeline over device-resident pairs, in chunks; returns a PipelineBuffers covering the whole block."""
+    B = batch.B
+    chunk = chunk or B
+    out = out or ops.PipelineBuffers(B, batch.ref_desc.device)
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        sub = batch.slice(lo, hi)
+        view = ops.PipelineBuffers.__new__(ops.PipelineBuffers)
+        view.T_rel, view.rt = out.T_rel[lo:hi], out.rt[lo:hi]
+        view.n_matches, view.n_corr = out.n_matches[lo:hi], out.n_corr[lo:hi]
+        view.n_inl, view.status = out.n_inl[lo:hi], out.status[lo:hi]
+        ops.pipeline(sub.ref_desc, sub.cur_desc, sub.ref_kp, sub.cur_kp, sub.depth, batch.K, pair0=pair0 + lo,
+                     out=view, **cfg.kw)
+    return out
+
+
+class HostPairRunner:
+    """End-to-end path for HOST inputs: pinned host buffers -> H2D on a copy stream, double-buffered against
+    vo_pipeline on the compute stream -> D2H of poses / status.  This is the call a user with frames in host
+    memory makes; bench.py times it as `e2e`."""
+
+    def __init__(self, host_batch, cfg, chunk, device="cuda"):
+        self.cfg, self.chunk, self.device = cfg, chunk, torch.device(device)
+        self.K = np.asarray(host_batch["K"], np.float64)
+        keys = ("ref_desc", "cur_desc", "ref_kp", "cur_kp", "depth")
+        self.host = {k: torch.from_numpy(np.ascontiguousarray(host_batch[k])).pin_memory() for k in keys}
+        self.B = self.host["ref_desc"].shape[0]
+        self.stage = [{k: torch.empty((chunk,) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device)
+                       for k, v in self.host.items()} for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.out = ops.PipelineBuffers(self.B, self.device)
+        self.host_T = torch.empty((self.B, 4, 4), dtype=torch.float64).pin_memory()
+        self.host_status = torch.empty((self.B,), dtype=torch.int32).pin_memory()
+        self.host_inl = torch.empty((self.B,), dtype=torch.int32).pin_memory()
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.d2h_bytes = self.host_T.numel() * 8 + self.host_status.numel() * 4 + self.host_inl.numel() * 4
+
+    def run(self, pair0=0):
+        """One pass over all pairs.  Returns after the D2H copies were enqueued; caller synchronises."""
+        compute = torch.cuda.current_stream(self.device)
+        n_chunks = (self.B + self.chunk - 1) // self.chunk
+        for c in range(n_chunks):
+            lo, hi = c * self.chunk, min(self.B, (c + 1) * self.chunk)
+            buf = c % 2
+            with torch.cuda.stream(self.copy_stream):
+                if c >= 2:
+                    self.copy_stream.wait_event(self.consumed[buf])
+                for k, v in self.host.items():
+                    self.stage[buf][k][: hi - lo].copy_(v[lo:hi], non_blocking=True)
+                self.copied[buf].record(self.copy_stream)
+            compute.wait_event(self.copied[buf])
+            s = self.stage[buf]
+            view = ops.PipelineBuffers.__new__(ops.PipelineBuffers)
+            view.T_rel, view.rt = self.out.T_rel[lo:hi], self.out.rt[lo:hi]
+            view.n_matches, view.n_corr = self.out.n_matches[lo:hi], self.out.n_corr[lo:hi]
+            view.n_inl, view.status = self.out.n_inl[lo:hi], self.out.status[lo:hi]
+            ops.pipeline(s["ref_desc"][: hi - lo], s["cur_desc"][: hi - lo], s["ref_kp"][: hi - lo], s["cur_kp"][: hi - lo],
+                         s["depth"][: hi - lo], self.K, pair0=pair0 + lo, out=view, **self.cfg.kw)
+            self.consumed[buf].record(compute)
+        self.host_T.copy_(self.out.T_rel, non_blocking=True)
+        self.host_status.copy_(self.out.status, non_blocking=True)
+        self.host_inl.copy_(self.out.n_inl, non_blocking=True)
+        return self.host_T, self.host_status, self.host_inl

@@ -148,6 +148,7 @@ def make_batch(first_index, count, **kw):
 
 def pose_errors(T_est, T_gt):
     """(rotation error rad, translation error m) between two 4x4 poses."""
-    dR = T_est[:3, :3].T @ T_gt[:3, :3]
-    ang = np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1))
+    # ||Ra - Rb||_F = 2 sqrt(2) |sin(theta/2)|: accurate for tiny angles, unlike arccos((tr-1)/2)
+    f = np.linalg.norm(T_est[:3, :3] - T_gt[:3, :3])
+    ang = 2.0 * np.arcsin(min(1.0, f / (2.0 * np.sqrt(2.0))))
     return float(ang), float(np.linalg.norm(T_est[:3, 3] - T_gt[:3, 3]))
