@@ -1,0 +1,199 @@
+"""RGB-D visual-odometry state machine with the interface of the reference's VisualOdometry_Stereo.py:
+`VisualOdometry(camera_intrinsics, seq=0)`, `.process_frame(img, depth_img, midpoint, frame_no) -> SE3`
+(:223-297), `.computepose_3D_2D(framepair) -> (retval, framepair, n_common, best_inlier)` (:87-149),
+`.global_poses`, `.save_poses`.
+
+What changed is where the arithmetic runs: descriptor matching (feature plug-ins), the keypoint back-projection
+with its 0<Z<50 gate and the PnP-RANSAC + refit all execute as sm_100a kernels behind libvo_b200's C ABI; the
+keyframe policy, the 1.5 m motion gate and pose chaining stay on the host in fp64, unchanged (:270-296).
+"""
+import os
+import pickle
+
+import numpy as np
+import torch
+import yaml
+
+import _bootstrap  # noqa: F401
+from vo_b200 import ops
+
+np.set_printoptions(suppress=True, precision=2)
+
+with open("config/vo_params.yaml") as _f:
+    vo_params = yaml.load(_f, Loader=yaml.FullLoader)
+
+_fe = str(vo_params.get("feature_extractor", "orb")).lower()
+if _fe == "sift":
+    from feature_extractors.SIFT import *  # noqa: F401,F403
+elif _fe == "orb":
+    import feature_extractors.ORB as _orb_mod
+    _orb_mod.MATCHER = vo_params.get("orb_matcher", _orb_mod.MATCHER)
+    from feature_extractors.ORB import *  # noqa: F401,F403
+elif _fe == "r2d2":
+    from R2D2 import *  # noqa: F401,F403
+else:
+    raise ValueError(f"feature_extractor must be sift, orb or r2d2 (got {_fe!r})")
+
+from Utils.frame_utils import Frame, FramePair  # noqa: E402
+from Utils.SE3_utils import SE3  # noqa: E402
+
+
+def append_to_list(lst, ele, listlen=1):
+    lst.append(ele)
+    return lst[-listlen:]
+
+
+class VisualOdometry:
+    MIN_INLIERS = 20          # model accepted iff inliers > 20            (:132)
+    REPROJ_PX = 1.5           # solvePnPRansac(reprojectionError=1.5)      (:129)
+    Z_RANGE = (0.0, 50.0)     # keep 0 < Z < 50 m                          (:100)
+    MIN_FLOW_PX = 3.0         # drop matches that moved < 3 px             (:263-264)
+    MAX_STEP_M = 1.5          # reject > 1.5 m per frame of baseline       (:271)
+
+    def __init__(self, camera_intrinsics, seq=0):
+        self.cam_intr = np.asarray(camera_intrinsics, np.float64).copy()
+        self.ref_data = []
+        self.global_poses = {0: SE3().pose}
+        self.global_pose = SE3()
+        self.pose_ctr = 0
+        self.cur_data = None
+        self.frame_pairs = []
+        self.img_id = 0
+        self.bad_pnp = 0
+        self.seq = seq
+        self.method = "r2d2"
+        self.find_ps_homography = False
+        self.midpoint_3D = None
+        self.n_hyp = int(vo_params.get("ransac_hypotheses", 512))
+        self.seed = int(vo_params.get("ransac_seed", 8214))
+        self.device = torch.device("cuda", int(vo_params.get("device", 0)))
+        self._pair_ctr = 0
+        ops.context(self.device)  # fail now, loudly, if there is no B200 / no library
+        if not os.path.exists(self.method):  # the reference creates this directory as a side effect (:78-79)
+            os.mkdir(self.method)
+
+    # ---------------------------------------------------------------------------------------------
+    def update_global_pose(self, poss):
+        self.global_pose.t += self.global_pose.R @ poss.t
+        self.global_pose.R = self.global_pose.R @ poss.R
+
+    def _depth_on_device(self, frame):
+        cache = getattr(frame, "device_cache", None)
+        if cache is None:
+            cache = frame.device_cache = {}
+        if "depth" not in cache:
+            d = np.ascontiguousarray(frame.depth, dtype=np.float32)
+            cache["depth"] = torch.from_numpy(d).to(self.device)[None]
+        return cache["depth"]
+
+    def computepose_3D_2D(self, framepair):
+        """3D-2D pose of frame2 relative to frame1 from matched keypoints and frame1's depth.
+
+        left_kp / right_kp are (K,2) float32 pixel coordinates.  Steps (all on the GPU): gather depth at the
+        truncated left keypoints, back-project, keep 0<Z<50, draw the hypothesis table, P3P + inlier counting +
+        Gauss-Newton refit.  The stored pose is the inverse of the PnP solution, as in the reference (:141-143)."""
+        left_kp, right_kp = framepair.getkeypts()
+        left_kp = np.ascontiguousarray(left_kp, dtype=np.float32).reshape(-1, 2)
+        right_kp = np.ascontiguousarray(right_kp, dtype=np.float32).reshape(-1, 2)
+        K = left_kp.shape[0]
+        dev = self.device
+        cap = max(K, 1)
+        lk = torch.zeros((1, cap, 2), dtype=torch.float32, device=dev)
+        rk = torch.zeros((1, cap, 2), dtype=torch.float32, device=dev)
+        if K:
+            lk[0, :K] = torch.from_numpy(left_kp).to(dev)
+            rk[0, :K] = torch.from_numpy(right_kp).to(dev)
+        ident = torch.arange(cap, dtype=torch.int32, device=dev)
+        pairs = torch.stack([ident, ident], 1)[None].contiguous()
+        n_pairs = torch.tensor([K], dtype=torch.int32, device=dev)
+        corr = ops.gather_backproject(pairs, n_pairs, lk, rk, self._depth_on_device(framepair.frame1), self.cam_intr,
+                                      min_flow_px=-1.0, z_min=self.Z_RANGE[0], z_max=self.Z_RANGE[1])
+        hyp = ops.hypotheses(corr.count, self.n_hyp, self.seed, self._pair_ctr)
+        self._pair_ctr += 1
+        res = ops.pnp_ransac(corr.xyz, corr.cur_uv, corr.count, self.cam_intr, hyp, self.REPROJ_PX, self.MIN_INLIERS, 10)
+        status = int(corr.status.item()) | int(res.status.item())   # one small D2H round trip per pair
+        n_common = int(corr.count.item())
+        best_inlier = int(res.n_inl.item())
+        keep = corr.src[0, :n_common].cpu().numpy()
+        framepair.left_kp = left_kp[keep].copy()
+        framepair.right_kp = right_kp[keep].copy()
+        framepair.left_kp_og = framepair.left_kp.copy()
+        framepair.right_kp_og = framepair.right_kp.copy()
+        if status != 0:
+            print("NO IT IS A BAD PNP")
+            self.bad_pnp += 1
+            return False, framepair, n_common, best_inlier
+        pose = SE3()
+        pose.pose = res.T_rel[0].cpu().numpy().copy()
+        framepair.pose = pose
+        framepair.inlier_pts_ct = best_inlier
+        return True, framepair, n_common, best_inlier
+
+    # ---------------------------------------------------------------------------------------------
+    def update_frames_data(self, framepair):
+        self.ref_data = append_to_list(self.ref_data, self.cur_data, 2)
+
+    def update_framepairs(self, fp):
+        self.frame_pairs = append_to_list(self.frame_pairs, fp, 4)
+
+    def get_midpoint(self, d_img, midpoint):
+        """3-D position of a tracked image point (parking add-on of the reference, :187-216): depth lookup +
+        pinhole back-projection in fp64."""
+        z = float(d_img[midpoint[1], midpoint[0]])
+        fx, fy, cx, cy = self.cam_intr[0, 0], self.cam_intr[1, 1], self.cam_intr[0, 2], self.cam_intr[1, 2]
+        self.midpoint_3D = np.array([[(midpoint[0] - cx) / fx * z, (midpoint[1] - cy) / fy * z, z]])
+
+    def save_poses(self, save_name="r2d2parking.pkl"):
+        with open(save_name, "wb") as f:
+            pickle.dump(self.global_poses, f)
+
+    def process_frame(self, img, depth_img, midpoint, frame_no):
+        """One frame of the keyframe-based VO loop.  Returns the frame's global pose (SE3)."""
+        if frame_no == 0:
+            kp, desc = extract_features_and_desc(img)  # noqa: F405
+            first = Frame(id=0, img=img, kps=kp, desc=desc, fil="%06d" % frame_no, pose=SE3(), depth=depth_img)
+            self.ref_data = append_to_list(self.ref_data, first)
+            self.get_midpoint(depth_img, midpoint)
+            return SE3()
+
+        self.img_id = frame_no
+        cur_kp, cur_desc = extract_features_and_desc(img)  # noqa: F405
+        frame1 = self.ref_data[-1]                          # the KEYFRAME, not the previous frame (:251)
+        ref_kp, ref_desc = frame1.get_kp_desc()
+        frame2 = Frame(id=frame_no, img=img, kps=cur_kp, desc=cur_desc, fil="%06d" % frame_no, pose=SE3(), depth=depth_img)
+        self.cur_data = frame2
+
+        matches = np.asarray(get_matches(ref_kp, ref_desc, cur_kp, cur_desc, img.shape)).reshape(-1, 2)  # noqa: F405
+        ref_pts = np.asarray(ref_kp)[matches[:, 0], :2].astype(np.float32)
+        cur_pts = np.asarray(cur_kp)[matches[:, 1], :2].astype(np.float32)
+        moved = np.linalg.norm(ref_pts - cur_pts, axis=1) >= self.MIN_FLOW_PX
+        framepair = FramePair(frame1, frame2, matches, ref_pts[moved], cur_pts[moved], matches)
+
+        to_update = False
+        common_pts = best_inliers = 0
+        dist_scale = 0.0
+        try:
+            retval, framepair, common_pts, best_inliers = self.computepose_3D_2D(framepair)
+            dist_scale = float(np.linalg.norm(framepair.pose.t))
+            if dist_scale > self.MAX_STEP_M * (frame2.id - frame1.id):
+                retval = False
+                self.bad_pnp += 1
+                print("Inside false PnP condition")
+        except Exception as exc:  # same blanket policy as the reference (:275-279)
+            print(exc)
+            print("Inside bad PnP")
+            self.bad_pnp += 1
+            retval = False
+
+        if retval:
+            self.bad_pnp = 0
+            frame2.pose._pose = frame1.pose._pose @ framepair.pose._pose.copy()
+            to_update = common_pts < 200 or best_inliers < 100 or dist_scale > 1.5
+        else:
+            frame2.pose._pose = frame1.pose._pose.copy()
+
+        self.pose_ctr += 1
+        self.global_poses[self.pose_ctr] = frame2.pose._pose
+        if to_update or self.bad_pnp > 3:
+            self.update_frames_data(framepair)
+        return frame2.pose

@@ -15,11 +15,12 @@ constexpr int FIN_THREADS = 512;
 
 __device__ __forceinline__ void top2_insert(uint32_t s, int32_t i, uint32_t &s1, int32_t &i1, uint32_t &s2,
                                             int32_t &i2) {
-    // strict '<' keeps the earlier (lower-index) candidate on ties: cv2 knnMatch order
+    // ties resolve to the lower column index (cv2 knnMatch order), whatever order the partials arrive in:
+    // the tcgen05 kernel's two epilogue groups own interleaved column tiles
     if (i < 0) return;
-    if (s < s1) {
+    if (s < s1 || (s == s1 && i < i1)) {
         s2 = s1; i2 = i1; s1 = s; i1 = i;
-    } else if (s < s2) {
+    } else if (s < s2 || (s == s2 && (i2 < 0 || i < i2))) {
         s2 = s; i2 = i;
     }
 }

@@ -1,0 +1,32 @@
+"""SIFT plug-in — same module-level interface as the reference's feature_extractors/SIFT.py
+(`extract_features_and_desc(image) -> (kp, desc)` :14-23, `get_matches(...) -> int[K,2]` :25-34).
+
+Detection / description stays on OpenCV (the front-end is outside the accelerated path); matching —
+brute-force 2-NN in L2 plus Lowe's 0.85 ratio test — runs on the tensor cores through vo_match_f32.
+"""
+import cv2
+import numpy as np
+
+from feature_extractors import _gpu_match
+
+_sift = None
+
+
+def _detector():
+    global _sift
+    if _sift is None:
+        make = getattr(getattr(cv2, "xfeatures2d", None), "SIFT_create", None) or cv2.SIFT_create
+        _sift = make()
+    return _sift
+
+
+def extract_features_and_desc(image):
+    gray = cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)
+    kps, desc = _detector().detectAndCompute(gray, None)
+    return np.asarray([[k.pt[0], k.pt[1]] for k in kps]), desc
+
+
+def get_matches(ref_kp, ref_desc, cur_kp, cur_desc, img_shape, pix_rad=100, flag=2):
+    if flag != 2:
+        return None  # the reference defines flag == 2 only (SIFT.py:26)
+    return _gpu_match.knn_ratio_f32(ref_desc, cur_desc, 0.85, tag="sift")

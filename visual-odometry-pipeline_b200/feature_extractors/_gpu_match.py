@@ -1,0 +1,39 @@
+"""Shared glue of the SIFT / ORB plug-ins: numpy descriptors in, (K,2) int64 matches out, all distance work and
+the acceptance rule on the GPU through libvo_b200 (vo_match_u8 / vo_match_f32)."""
+import numpy as np
+import torch
+
+import _bootstrap  # noqa: F401
+from vo_b200 import ops
+
+_int_valued = {}
+
+
+def _dev(a, dtype):
+    if isinstance(a, torch.Tensor):
+        return a.to(device="cuda", dtype=dtype).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype={torch.uint8: np.uint8, torch.float32: np.float32}[dtype])).cuda()
+
+
+def knn_ratio_u8(ref_desc, cur_desc, ratio=0.85, norm=ops.VO_NORM_L2_U8):
+    res = ops.match_u8(_dev(ref_desc, torch.uint8), _dev(cur_desc, torch.uint8), norm, ops.VO_MODE_RATIO, ratio,
+                       want_dist=False)
+    return res.numpy()
+
+
+def mutual_u8(ref_desc, cur_desc, norm=ops.VO_NORM_HAMMING):
+    res = ops.match_u8(_dev(ref_desc, torch.uint8), _dev(cur_desc, torch.uint8), norm, ops.VO_MODE_MUTUAL, 0.0,
+                       want_dist=False)
+    return res.numpy()
+
+
+def knn_ratio_f32(ref_desc, cur_desc, ratio=0.85, tag="sift"):
+    a, b = _dev(ref_desc, torch.float32), _dev(cur_desc, torch.float32)
+    if tag not in _int_valued:
+        # OpenCV SIFT descriptors are integer-valued in [0,255]: one TF32 pass is then exact.  Checked once.
+        _int_valued[tag] = bool(((a == a.round()) & (a.abs() <= 2047)).all().item())
+    prec = ops.VO_PREC_TF32X1 if _int_valued[tag] else ops.VO_PREC_TF32X3
+    if a.shape[-1] != 128:
+        prec = ops.VO_PREC_FP32_SIMT
+    res = ops.match_f32(a, b, ops.VO_METRIC_L2, ops.VO_MODE_RATIO, ratio, precision=prec, want_dist=False)
+    return res.numpy()
