@@ -5,21 +5,25 @@
 // distance matrix of cv2.BFMatcher.knnMatch (feature_extractors/SIFT.py:27).  Here the N x M similarity
 // matrix lives only in tensor memory:
 //
-//   * one CTA owns a 128-row block of the reference descriptors (A, resident in shared memory for the whole
-//     CTA lifetime, loaded once by TMA) and streams 128-column tiles of the current-frame descriptors (B)
-//     through a 5-stage TMA/mbarrier ring;
+//   * one CTA owns a 128-row block of the reference descriptors (A).  A is written ONCE into tensor memory
+//     (tcgen05.st, 128 columns for the tf32 "hi" part, 128 for the "lo" part) and stays there: the MMAs take
+//     A from TMEM, so shared memory holds nothing but the B ring and the MMA reads only B from it;
+//   * 128-column x 32-k boxes of the current-frame descriptors (B) stream through a 13-stage TMA/mbarrier
+//     ring (208 KB in flight per SM).  Two CTAs (adjacent row blocks) form a cluster and each issues every other
+//     box with .multicast::cluster, so each box crosses L2 -> SM once per pair of SMs;
 //   * a single thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) into one of two
-//     128-column fp32 accumulators in TMEM.  3xTF32: operands are pre-split into tf32 hi/lo parts and every
-//     k-step issues lo*hi, hi*hi and hi*lo, which restores fp32-grade products; for integer-valued SIFT
-//     descriptors one pass is already exact (every product and partial sum is an integer < 2^24);
+//     128-column fp32 accumulators.  3xTF32: every k-step issues lo*hi, hi*hi and hi*lo, which restores
+//     fp32-grade products; for integer-valued SIFT descriptors one pass is already exact (every product and
+//     partial sum is an integer < 2^24);
 //   * two groups of four epilogue warps (one group per accumulator) read the tile with tcgen05.ld and fold it
 //     into a running top-2 per row (thread-private, one row per thread) and a per-column arg-max
-//     (redux.sync.max.f32 across the 32 rows of a warp, 4 warps merged in shared memory, one 64-bit
+//     (redux.sync.max.f32 + ballot across the 32 rows of a warp, 4 warps merged in shared memory, one 64-bit
 //     atomicMin per column and CTA), while the MMA thread already fills the other accumulator.
 //
 // L2 mode uses the GEMM form -|a_i - b_j|^2 = (2 a_i.b_j - |b_j|^2) - |a_i|^2, evaluated per element in the
 // epilogue (the row norm matters for the column arg-min, the column norm for the row arg-min).
 #include "common.cuh"
+#include <stdlib.h>
 #include <cuda.h>  // CUtensorMap & enums only; cuTensorMapEncodeTiled is resolved at run time
 
 namespace vo {
@@ -30,20 +34,18 @@ constexpr int TC_BN = 128;      // columns per B tile (= accumulator columns)
 constexpr int TC_D = 128;       // descriptor length
 constexpr int TC_KB = 32;       // k elements per swizzle-128B row (32 fp32 = 128 B)
 constexpr int TC_NKB = TC_D / TC_KB;
-constexpr int TC_STAGES = 5;
+constexpr int TC_STAGES = 13;
 constexpr int TC_BLOCK_BYTES = TC_BN * 128;  // one [128 rows x 32 k] fp32 box = 16 KB
 constexpr int TC_THREADS = 320;              // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int TC_TMEM_COLS = 256;            // 2 accumulators x 128 columns
+constexpr int TC_TMEM_COLS = 512;            // 2 accumulators x 128 | A_hi 128 | A_lo 128
+constexpr int TC_TMEM_A = 256;               // first column of A_hi (A_lo follows)
+constexpr int TC_CLUSTER = 2;
 
-struct TcSmem {
-    // offsets into the 1024-aligned dynamic shared memory
-    static constexpr int a_hi = 0;
-    static constexpr int a_lo = a_hi + TC_NKB * TC_BLOCK_BYTES;
-    static __host__ __device__ constexpr int b_stages(int passes) { return passes == 3 ? a_lo + TC_NKB * TC_BLOCK_BYTES : a_lo; }
-    static __host__ __device__ constexpr int scol(int passes) { return b_stages(passes) + TC_STAGES * TC_BLOCK_BYTES; }
-    static __host__ __device__ constexpr int bars(int passes) { return scol(passes) + 2 * 4 * TC_BN * 8; }
-    static __host__ __device__ constexpr int total(int passes) { return bars(passes) + 256 + 1024 /* alignment slack */; }
-};
+// shared memory map (offsets from the 1024-aligned base)
+constexpr int TC_OFF_B = 0;
+constexpr int TC_OFF_SCOL = TC_OFF_B + TC_STAGES * TC_BLOCK_BYTES;  // [2 groups][4 quarters][128] x (float, u32)
+constexpr int TC_OFF_BAR = TC_OFF_SCOL + 2 * 4 * TC_BN * 8;
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 512 + 1024;              // barriers + alignment slack
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -60,8 +62,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Bounded wait: a protocol bug must end in a trap (sticky error the host reports), never in a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    const long long t0 = clock64();
-    for (;;) {
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -70,13 +72,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 1.9 GHz
+        if ((spin & 255u) == 255u) {  // ~2 s at 1.9 GHz before giving up
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 4000000000ll) __trap();
+        }
     }
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar,
+                                               uint16_t mask) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+        "l"((uint64_t)map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -84,12 +91,18 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor], tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
@@ -107,12 +120,35 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
 __device__ __forceinline__ float warp_max_f32(float v) {
     float m;
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
     return m;
 }
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) = 1 (unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B (8 rows x 128 B)
@@ -153,14 +189,60 @@ prep_kernel(const float *__restrict__ x, long long rows, float *__restrict__ hi,
     }
 }
 
+// ---------------------------------------------------------------- epilogue: one 32-column chunk
+// v[] = 32 accumulator columns of this thread's row.  Updates the row top-2 and leaves, per column, the warp's
+// maximum and the ballot of the lanes that attain it (lane 0 stores both; they are warp-uniform).
+template <int METRIC, bool MASK_COLS>
+__device__ __forceinline__ void epi_chunk(const float (&v)[32], int cbase, int M, bool row_ok, float na,
+                                          const float *__restrict__ cn, int lane, float *cv_out, uint32_t *cb_out,
+                                          float &s1, float &s2, int32_t &i1, int32_t &i2) {
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 8) {
+        float sc[8];
+        float m8 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = cbase + j0 + j;
+            float s = v[j0 + j];
+            if (METRIC == VO_METRIC_L2) {
+                const float nb = MASK_COLS ? ((col < M) ? __ldg(cn + col) : 0.0f) : __ldg(cn + col);
+                s = __fsub_rn(__fmaf_rn(2.0f, s, -nb), na);
+            }
+            if (MASK_COLS) s = (col < M) ? s : -INFINITY;
+            sc[j] = s;
+            m8 = fmaxf(m8, s);
+            const float sr = row_ok ? s : -INFINITY;
+            const float wm = warp_max_f32(sr);
+            const unsigned bal = __ballot_sync(0xffffffffu, sr == wm);
+            if (lane == 0) {
+                cv_out[j0 + j] = wm;
+                cb_out[j0 + j] = bal;
+            }
+        }
+        if (row_ok && m8 > s2) {  // rare after the first tiles; sequential update keeps the lowest index on ties
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float s = sc[j];
+                const int col = cbase + j0 + j;
+                if (s > s1) {
+                    s2 = s1; i2 = i1; s1 = s; i1 = col;
+                } else if (s > s2) {
+                    s2 = s; i2 = col;
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- main kernel
 template <int PASSES, int METRIC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                    int n_stride, int m_stride, const int32_t *__restrict__ n_ref, const int32_t *__restrict__ n_cur,
+__global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1)
+match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                    const float *__restrict__ a_hi, const float *__restrict__ a_lo, int n_stride, int m_stride,
+                    const int32_t *__restrict__ n_ref, const int32_t *__restrict__ n_cur,
                     const float *__restrict__ row_norm, const float *__restrict__ col_norm, int n_split,
-                    vo_row_partial *__restrict__ part, unsigned long long *__restrict__ colkey) {
+                    vo_row_partial *__restrict__ part, unsigned long long *__restrict__ colkey,
+                    long long *__restrict__ dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - smem_u32(smem_raw));
@@ -173,26 +255,35 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const int tiles_per_split = (tiles_total + n_split - 1) / n_split;
     const int t_begin = min(tiles_total, split * tiles_per_split);
     const int t_end = min(tiles_total, t_begin + tiles_per_split);
-    const int n_tiles = t_end - t_begin;
+    const int n_tiles = t_end - t_begin;  // identical in both CTAs of the cluster (same pair, same split)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_rank();
+    // optional cycle accounting of CTA (0,0,0) for bring-up / tuning (dbg == nullptr in production)
+    const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    const long long t_kernel0 = dbg_on ? clock64() : 0;
+#define TC_DBG_BEGIN() const long long _t0 = dbg_on ? clock64() : 0
+#define TC_DBG_END(slot) do { if (dbg_on) dbg_acc[slot] += clock64() - _t0; } while (0)
+    long long dbg_acc[4] = {0, 0, 0, 0};
 
     constexpr int ITEMS = (PASSES == 3) ? 2 * TC_NKB : TC_NKB;  // B boxes streamed per tile
-    const uint32_t s_a_hi = base + TcSmem::a_hi, s_a_lo = base + TcSmem::a_lo;
-    const uint32_t s_b = base + TcSmem::b_stages(PASSES);
-    float *scol_v = reinterpret_cast<float *>(smem + TcSmem::scol(PASSES));          // [2][4][128]
-    int *scol_r = reinterpret_cast<int *>(smem + TcSmem::scol(PASSES) + 2 * 4 * TC_BN * 4);
-    const uint32_t s_bar = base + TcSmem::bars(PASSES);
-    // barrier slots (8 B each): full[5] empty[5] a_full tmem_full[2] tmem_empty[2]; then the TMEM base word
+    const uint32_t s_b = base + TC_OFF_B;
+    float *scol_v = reinterpret_cast<float *>(smem + TC_OFF_SCOL);                       // [2][4][128]
+    uint32_t *scol_b = reinterpret_cast<uint32_t *>(smem + TC_OFF_SCOL + 2 * 4 * TC_BN * 4);
+    const uint32_t s_bar = base + TC_OFF_BAR;
+    // barrier slots (8 B each): full[S] empty[S] a_full tmem_full[2] tmem_empty[2]; then the TMEM base word
     auto bar_full = [&](int s) { return s_bar + 8u * s; };
     auto bar_empty = [&](int s) { return s_bar + 8u * (TC_STAGES + s); };
     const uint32_t bar_a = s_bar + 8u * (2 * TC_STAGES);
     auto bar_tfull = [&](int g) { return s_bar + 8u * (2 * TC_STAGES + 1 + g); };
     auto bar_tempty = [&](int g) { return s_bar + 8u * (2 * TC_STAGES + 3 + g); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::bars(PASSES) + 8 * (2 * TC_STAGES + 5));
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TC_OFF_BAR + 8 * (2 * TC_STAGES + 5));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        mbar_init(bar_a, 1);
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(bar_full(s), 1);            // this CTA's producer arms it; TMA bytes complete it
+            mbar_init(bar_empty(s), TC_CLUSTER);  // one commit from each CTA of the cluster
+        }
+        mbar_init(bar_a, PASSES == 3 ? 8 : 4);
         for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull(g), 1); mbar_init(bar_tempty(g), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -204,50 +295,48 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();  // the peer's barriers exist before anything multicasts into this CTA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0 && n_tiles > 0) {
-            const int arow = b * n_stride + row0;
-            mbar_expect_tx(bar_a, (PASSES == 3 ? 2 : 1) * TC_NKB * TC_BLOCK_BYTES);
-            for (int kb = 0; kb < TC_NKB; ++kb) {
-                tma_load_2d(s_a_hi + kb * TC_BLOCK_BYTES, &map_a_hi, kb * TC_KB, arow, bar_a);
-                if (PASSES == 3) tma_load_2d(s_a_lo + kb * TC_BLOCK_BYTES, &map_a_lo, kb * TC_KB, arow, bar_a);
-            }
+        if (lane == 0) {
             int it = 0;
             for (int t = t_begin; t < t_end; ++t) {
                 const int brow = b * m_stride + t * TC_BN;
                 for (int item = 0; item < ITEMS; ++item, ++it) {
                     const int stage = it % TC_STAGES;
                     const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
-                    mbar_wait(bar_empty(stage), phase ^ 1u);
-                    mbar_expect_tx(bar_full(stage), TC_BLOCK_BYTES);
-                    const int kb = (PASSES == 3) ? (item >> 1) : item;
-                    const bool is_lo = (PASSES == 3) && (item & 1);
-                    tma_load_2d(s_b + stage * TC_BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * TC_KB, brow,
-                                bar_full(stage));
+                    { TC_DBG_BEGIN(); mbar_wait(bar_empty(stage), phase ^ 1u); TC_DBG_END(0); }  // both CTAs consumed the slot
+                    mbar_expect_tx(bar_full(stage), TC_BLOCK_BYTES);  // bytes arrive by multicast, whoever issues
+                    if ((uint32_t)(it & 1) == crank) {
+                        const int kb = (PASSES == 3) ? (item >> 1) : item;
+                        const bool is_lo = (PASSES == 3) && (item & 1);
+                        tma_load_2d_mc(s_b + stage * TC_BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * TC_KB, brow,
+                                       bar_full(stage), (uint16_t)((1u << TC_CLUSTER) - 1u));
+                    }
                 }
             }
+            if (dbg_on) dbg[4] = dbg_acc[0];
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0 && n_tiles > 0) {
-            mbar_wait(bar_a, 0);
+            mbar_wait(bar_a, 0);  // A is in tensor memory
             tc_fence_after();
             int it = 0;
             for (int lt = 0; lt < n_tiles; ++lt) {
                 const int buf = lt & 1;
                 const uint32_t use = (uint32_t)(lt >> 1);
-                mbar_wait(bar_tempty(buf), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+                { TC_DBG_BEGIN(); mbar_wait(bar_tempty(buf), (use & 1u) ^ 1u); TC_DBG_END(1); }  // accumulator drained
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * TC_BN);
                 uint32_t acc = 0;
                 for (int item = 0; item < ITEMS; ++item, ++it) {
                     const int stage = it % TC_STAGES;
                     const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
-                    mbar_wait(bar_full(stage), phase);
+                    { TC_DBG_BEGIN(); mbar_wait(bar_full(stage), phase); TC_DBG_END(0); }
                     tc_fence_after();
                     const int kb = (PASSES == 3) ? (item >> 1) : item;
                     const bool is_lo = (PASSES == 3) && (item & 1);
@@ -255,91 +344,84 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
                     for (int k8 = 0; k8 < TC_KB / 8; ++k8) {
                         const uint64_t bdesc = make_sdesc(sb + k8 * 32);
-                        const uint64_t ahi = make_sdesc(s_a_hi + kb * TC_BLOCK_BYTES + k8 * 32);
+                        const uint32_t ahi = tmem_base + (uint32_t)(TC_TMEM_A + kb * TC_KB + k8 * 8);
                         if (is_lo) {  // a_hi * b_lo
-                            tc_mma_tf32(d_tmem, ahi, bdesc, TC_IDESC, acc);
+                            tc_mma_tf32_ts(d_tmem, ahi, bdesc, TC_IDESC, acc);
                             acc = 1;
                         } else {
                             if (PASSES == 3) {  // a_lo * b_hi first (small term), then a_hi * b_hi
-                                const uint64_t alo = make_sdesc(s_a_lo + kb * TC_BLOCK_BYTES + k8 * 32);
-                                tc_mma_tf32(d_tmem, alo, bdesc, TC_IDESC, acc);
+                                tc_mma_tf32_ts(d_tmem, ahi + TC_D, bdesc, TC_IDESC, acc);
                                 acc = 1;
                             }
-                            tc_mma_tf32(d_tmem, ahi, bdesc, TC_IDESC, acc);
+                            tc_mma_tf32_ts(d_tmem, ahi, bdesc, TC_IDESC, acc);
                             acc = 1;
                         }
                     }
-                    tc_commit(bar_empty(stage));  // smem slot reusable once these MMAs retire
+                    // slot reusable (in BOTH CTAs' rings) once these MMAs retire
+                    tc_commit_mc(bar_empty(stage), (uint16_t)((1u << TC_CLUSTER) - 1u));
                 }
                 tc_commit(bar_tfull(buf));  // accumulator complete
             }
+            if (dbg_on) { dbg[1] = dbg_acc[0]; dbg[2] = dbg_acc[1]; dbg[3] = clock64() - t_kernel0; dbg[11] = n_tiles; }
         }
     } else {
         // ===================== epilogue: 2 groups x 4 warps =====================
         const int e = warp - 2;
         const int g = e >> 2;       // accumulator / tile parity served by this group
-        const int q = warp & 3;     // TMEM lane quarter this warp may read
+        const int q = warp & 3;     // TMEM lane quarter this warp may access
         const int row = row0 + q * 32 + lane;
         const bool row_ok = row < N;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+
+        // ---- A -> tensor memory, once: group 0 stores the tf32 hi part, group 1 the lo part
+        if (n_tiles > 0 && (g == 0 || PASSES == 3)) {
+            const float *src = (g == 0 ? a_hi : a_lo) + ((size_t)b * n_stride + min(row, n_stride - 1)) * TC_D;
+            const bool have = row < n_stride;
+#pragma unroll 1
+            for (int c = 0; c < TC_D / 32; ++c) {
+                float v[32];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 x = have ? __ldg(reinterpret_cast<const float4 *>(src + c * 32) + k) : make_float4(0, 0, 0, 0);
+                    v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+                }
+                tc_st32(lane_base + (uint32_t)(TC_TMEM_A + g * TC_D + c * 32), v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar_a);
+        }
+
         float s1 = -INFINITY, s2 = -INFINITY;  // running top-2 of -|a-b|^2 or a.b: larger is better
         int32_t i1 = -1, i2 = -1;
         float *my_cv = scol_v + (g * 4 + q) * TC_BN;
-        int *my_cr = scol_r + (g * 4 + q) * TC_BN;
+        uint32_t *my_cb = scol_b + (g * 4 + q) * TC_BN;
         const float *cn = (METRIC == VO_METRIC_L2) ? col_norm + (size_t)b * m_stride : nullptr;
         const float na = (METRIC == VO_METRIC_L2 && row_ok) ? row_norm[(size_t)b * n_stride + row] : 0.0f;
 
         for (int lt = g; lt < n_tiles; lt += 2) {
             const int col0 = (t_begin + lt) * TC_BN;
             const uint32_t use = (uint32_t)(lt >> 1);
-            mbar_wait(bar_tfull(g), use & 1u);
+            const bool full_tile = col0 + TC_BN <= M;
+            { TC_DBG_BEGIN(); mbar_wait(bar_tfull(g), use & 1u); TC_DBG_END(0); }
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * TC_BN);
+            const long long _tc0 = dbg_on ? clock64() : 0;
+            const uint32_t taddr = lane_base + (uint32_t)(g * TC_BN);
 #pragma unroll 1
             for (int c = 0; c < TC_BN / 32; ++c) {
                 float v[32];
                 tc_ld32(taddr + c * 32, v);
-                if (c == TC_BN / 32 - 1) {  // whole accumulator is in registers / consumed: hand it back
+                if (c == TC_BN / 32 - 1) {  // the whole accumulator has been read: hand it back to the MMA thread
                     tc_fence_before();
                     if (lane == 0) mbar_arrive(bar_tempty(g));
                 }
-                const int cbase = col0 + c * 32;
-                float cv = -INFINITY;
-                int cr = 0;
-#pragma unroll
-                for (int j0 = 0; j0 < 32; j0 += 8) {
-                    float sc[8];
-                    float m8 = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = cbase + j0 + j;
-                        float s = v[j0 + j];
-                        if (METRIC == VO_METRIC_L2)
-                            s = __fsub_rn(__fmaf_rn(2.0f, s, -__ldg(cn + min(col, m_stride - 1))), na);
-                        s = (col < M) ? s : -INFINITY;
-                        sc[j] = s;
-                        m8 = fmaxf(m8, s);
-                        // column arg-max over the 32 rows of this warp (lowest row on ties)
-                        const float sr = row_ok ? s : -INFINITY;
-                        const float wm = warp_max_f32(sr);
-                        const unsigned bal = __ballot_sync(0xffffffffu, sr == wm);
-                        if (lane == j0 + j) { cv = wm; cr = __ffs(bal) - 1; }
-                    }
-                    if (row_ok && m8 > s2) {  // rare after the first tiles: sequential update keeps lowest index on ties
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float s = sc[j];
-                            const int col = cbase + j0 + j;
-                            if (s > s1) {
-                                s2 = s1; i2 = i1; s1 = s; i1 = col;
-                            } else if (s > s2) {
-                                s2 = s; i2 = col;
-                            }
-                        }
-                    }
-                }
-                my_cv[c * 32 + lane] = cv;
-                my_cr[c * 32 + lane] = cr;
+                if (full_tile)
+                    epi_chunk<METRIC, false>(v, col0 + c * 32, M, row_ok, na, cn, lane, my_cv + c * 32, my_cb + c * 32, s1, s2, i1, i2);
+                else
+                    epi_chunk<METRIC, true>(v, col0 + c * 32, M, row_ok, na, cn, lane, my_cv + c * 32, my_cb + c * 32, s1, s2, i1, i2);
             }
+            if (dbg_on) dbg_acc[1] += clock64() - _tc0;
+            const long long _tm0 = dbg_on ? clock64() : 0;
             group_bar(1 + g);
             {   // 128 threads of the group: one column each, merge the 4 lane quarters (ascending rows)
                 const int j = (e & 3) * 32 + lane;
@@ -349,8 +431,8 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
                     const float val = scol_v[(g * 4 + qq) * TC_BN + j];
-                    const int r = scol_r[(g * 4 + qq) * TC_BN + j];
-                    if (r >= 0 && val > best) { best = val; brow = qq * 32 + r; }
+                    const uint32_t bal = scol_b[(g * 4 + qq) * TC_BN + j];
+                    if (bal != 0u && val > best) { best = val; brow = qq * 32 + __ffs(bal) - 1; }
                 }
                 if (col < M && brow >= 0 && row0 + brow < N) {
                     const unsigned long long key =
@@ -360,7 +442,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 }
             }
             group_bar(1 + g);
+            if (dbg_on) dbg_acc[2] += clock64() - _tm0;
         }
+        if (dbg_on && q == 0 && lane == 0) { dbg[5 + g] = dbg_acc[0]; dbg[7 + g] = dbg_acc[1]; dbg[9 + g] = dbg_acc[2]; }
         // the two groups saw disjoint tiles: each writes its own partial (finalize merges tie-aware)
         if (row < n_stride) {
             vo_row_partial p;
@@ -370,8 +454,10 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         }
     }
 
+    if (dbg_on && threadIdx.x == 0) dbg[0] = clock64() - t_kernel0;
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();  // nobody leaves while the peer can still multicast into / arrive on this CTA
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
@@ -399,16 +485,30 @@ int make_map(vo_ctx *ctx, CUtensorMap *map, const float *ptr, long long rows) {
 }
 
 template <int PASSES, int METRIC>
-int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh,
-              const CUtensorMap &bl, int n_stride, int m_stride, const int32_t *n_ref, const int32_t *n_cur,
-              const float *row_norm, const float *col_norm, int n_split, vo_row_partial *part,
-              unsigned long long *colkey, cudaStream_t st) {
+int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &bl, const float *a_hi, const float *a_lo,
+              int n_stride, int m_stride, const int32_t *n_ref, const int32_t *n_cur, const float *row_norm,
+              const float *col_norm, int n_split, vo_row_partial *part, unsigned long long *colkey, cudaStream_t st) {
     auto kern = match_f32_tc_kernel<PASSES, METRIC>;
-    const int smem = TcSmem::total(PASSES);
-    VO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(ah, al, bh, bl, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part,
-                                         colkey);
+    long long *dbg = nullptr;
+    if (getenv("VO_TC_DEBUG")) {  // bring-up only: cycle accounting of CTA (0,0,0), printed after a sync
+        static long long *dbg_dev = nullptr;
+        if (!dbg_dev) VO_CUDA(cudaMalloc(&dbg_dev, 16 * sizeof(long long)));
+        VO_CUDA(cudaMemsetAsync(dbg_dev, 0, 16 * sizeof(long long), st));
+        dbg = dbg_dev;
+    }
+    VO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(bh, bl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm,
+                                                  n_split, part, colkey, dbg);
     VO_LAUNCH_CHECK(ctx);
+    if (dbg) {
+        long long h[16];
+        VO_CUDA(cudaStreamSynchronize(st));
+        VO_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr,
+                "[vo tc dbg] passes=%d tiles=%lld cta_cycles=%lld | mma: wait_full=%lld wait_tempty=%lld total=%lld | "
+                "producer wait_empty=%lld | epi g0: wait_tfull=%lld chunks=%lld merge=%lld | g1: wait_tfull=%lld chunks=%lld merge=%lld\n",
+                PASSES, h[11], h[0], h[1], h[2], h[3], h[4], h[5], h[7], h[9], h[6], h[8], h[10]);
+    }
     return VO_OK;
 }
 
@@ -430,7 +530,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     }
     const long long rows_a = (long long)B * n_stride, rows_b = (long long)B * m_stride;
     const bool l2 = metric == VO_METRIC_L2;
-    // workspace: A_hi | A_lo | B_hi | B_lo  and  row norms | column norms
+    // workspace: A_hi | A_lo  and  B_hi | B_lo  and  row norms | column norms
     float *split_a, *split_b, *norms;
     int rc;
     const size_t per_a = (size_t)rows_a * TC_D * sizeof(float), per_b = (size_t)rows_b * TC_D * sizeof(float);
@@ -447,29 +547,28 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     prep_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b_hi, b_lo, l2 ? col_norm : nullptr);
     VO_LAUNCH_CHECK(ctx);
 
-    CUtensorMap mah, mal, mbh, mbl;
-    if ((rc = make_map(ctx, &mah, a_hi, rows_a))) return rc;
+    CUtensorMap mbh, mbl;
     if ((rc = make_map(ctx, &mbh, b_hi, rows_b))) return rc;
-    if ((rc = make_map(ctx, &mal, passes == 3 ? a_lo : a_hi, rows_a))) return rc;
     if ((rc = make_map(ctx, &mbl, passes == 3 ? b_lo : b_hi, rows_b))) return rc;
 
     const int row_blocks = ceil_div(n_stride, TC_BM);
-    const int n_split = pick_split(ctx, B, row_blocks, ceil_div(m_stride, TC_BN), 4);
+    const int grid_x = ceil_div(row_blocks, TC_CLUSTER) * TC_CLUSTER;  // clusters pair adjacent row blocks
+    const int n_split = pick_split(ctx, B, grid_x, ceil_div(m_stride, TC_BN), 4);
     vo_row_partial *part;
     if ((rc = ws_get(ctx, WS_ROWPART, sizeof(vo_row_partial) * (size_t)B * n_split * 2 * n_stride, (void **)&part))) return rc;
-    dim3 grid(row_blocks, n_split, B);
+    dim3 grid(grid_x, n_split, B);
     VO_PROF(ctx, st, VO_STAGE_MATCH);
     if (passes == 3) {
-        rc = l2 ? launch_tc<3, VO_METRIC_L2>(ctx, grid, mah, mal, mbh, mbl, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st)
-                : launch_tc<3, VO_METRIC_COSINE>(ctx, grid, mah, mal, mbh, mbl, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st);
+        rc = l2 ? launch_tc<3, VO_METRIC_L2>(ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st)
+                : launch_tc<3, VO_METRIC_COSINE>(ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st);
     } else {
-        rc = l2 ? launch_tc<1, VO_METRIC_L2>(ctx, grid, mah, mal, mbh, mbl, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st)
-                : launch_tc<1, VO_METRIC_COSINE>(ctx, grid, mah, mal, mbh, mbl, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st);
+        rc = l2 ? launch_tc<1, VO_METRIC_L2>(ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st)
+                : launch_tc<1, VO_METRIC_COSINE>(ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st);
     }
     if (rc) return rc;
     *part_out = part;
     *n_split_out = n_split * 2;  // two epilogue groups -> two partials per (row, split)
-    *row_norm_out = nullptr;  // scores already carry -|a-b|^2 in full
+    *row_norm_out = nullptr;     // scores already carry -|a-b|^2 in full
     return VO_OK;
 }
 
