@@ -36,7 +36,8 @@ constexpr int TC_KB = 32;       // k elements per swizzle-128B row (32 fp32 = 12
 constexpr int TC_NKB = TC_D / TC_KB;
 constexpr int TC_STAGES = 13;
 constexpr int TC_BLOCK_BYTES = TC_BN * 128;  // one [128 rows x 32 k] fp32 box = 16 KB
-constexpr int TC_THREADS = 320;              // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_THREADS = 576;              // warps 0..15 epilogue, warp 16 TMA, warp 17 MMA
+constexpr int TC_WARP_TMA = 16, TC_WARP_MMA = 17;
 constexpr int TC_TMEM_COLS = 512;            // 2 accumulators x 128 | A_hi 128 | A_lo 128
 constexpr int TC_TMEM_A = 256;               // first column of A_hi (A_lo follows)
 constexpr int TC_CLUSTER = 2;
@@ -120,6 +121,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -140,7 +150,16 @@ __device__ __forceinline__ float warp_max_f32(float v) {
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
     return m;
 }
-__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -156,6 +175,7 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+constexpr uint32_t TC_SDESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // upper word of make_sdesc()
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
 // A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -189,49 +209,57 @@ prep_kernel(const float *__restrict__ x, long long rows, float *__restrict__ hi,
     }
 }
 
-// ---------------------------------------------------------------- epilogue: one 32-column chunk
-// v[] = 32 accumulator columns of this thread's row.  Updates the row top-2 and leaves, per column, the warp's
-// maximum and the ballot of the lanes that attain it (lane 0 stores both; they are warp-uniform).
-template <int METRIC, bool MASK_COLS>
-__device__ __forceinline__ void epi_chunk(const float (&v)[32], int cbase, int M, bool row_ok, float na,
-                                          const float *__restrict__ cn, int lane, float *cv_out, uint32_t *cb_out,
-                                          float &s1, float &s2, int32_t &i1, int32_t &i2) {
+// ---------------------------------------------------------------- epilogue helpers
+// Fold 8 consecutive columns into the row's running top-2 (larger is better).  Ties go to the lower column index
+// explicitly, because column tiles are visited in a rotated order.
+__device__ __forceinline__ void row_update8(const float (&sc)[8], int col_first, float &s1, float &s2, int32_t &i1,
+                                            int32_t &i2) {
 #pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += 8) {
-        float sc[8];
-        float m8 = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int col = cbase + j0 + j;
-            float s = v[j0 + j];
-            if (METRIC == VO_METRIC_L2) {
-                const float nb = MASK_COLS ? ((col < M) ? __ldg(cn + col) : 0.0f) : __ldg(cn + col);
-                s = __fsub_rn(__fmaf_rn(2.0f, s, -nb), na);
-            }
-            if (MASK_COLS) s = (col < M) ? s : -INFINITY;
-            sc[j] = s;
-            m8 = fmaxf(m8, s);
-            const float sr = row_ok ? s : -INFINITY;
-            const float wm = warp_max_f32(sr);
-            const unsigned bal = __ballot_sync(0xffffffffu, sr == wm);
-            if (lane == 0) {
-                cv_out[j0 + j] = wm;
-                cb_out[j0 + j] = bal;
-            }
-        }
-        if (row_ok && m8 > s2) {  // rare after the first tiles; sequential update keeps the lowest index on ties
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float s = sc[j];
-                const int col = cbase + j0 + j;
-                if (s > s1) {
-                    s2 = s1; i2 = i1; s1 = s; i1 = col;
-                } else if (s > s2) {
-                    s2 = s; i2 = col;
-                }
-            }
+    for (int j = 0; j < 8; ++j) {
+        const float s = sc[j];
+        const int col = col_first + j;
+        if (s > s1 || (s == s1 && col < i1)) {
+            s2 = s1; i2 = i1; s1 = s; i1 = col;
+        } else if (s > s2 || (s == s2 && (i2 < 0 || col < i2))) {
+            if (s > -INFINITY) { s2 = s; i2 = col; }
         }
     }
+}
+
+// ---------------------------------------------------------------- epilogue: 8 accumulator columns
+// v[] = 8 accumulator columns of this thread's row.  Updates the row top-2 and leaves, per column, the warp's
+// maximum and the ballot of the lanes that attain it (both warp-uniform; lane 0 stores them as two vectors).
+// ROW_MASK is set only for the last, partial row block: elsewhere every lane holds a valid row.
+// Kept small on purpose (a rolled loop calls it 8 times per tile and warp): 16 warps share the instruction cache.
+template <int METRIC, bool MASK_COLS, bool ROW_MASK>
+__device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M, bool row_ok, float na,
+                                           const float *__restrict__ cn, int lane, float *cv_out, uint32_t *cb_out,
+                                           float &s1, float &s2, int32_t &i1, int32_t &i2) {
+    float sc[8], wm[8];
+    uint32_t bal[8];
+    float m8 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = cbase + j;
+        float s = v[j];
+        if (METRIC == VO_METRIC_L2) {
+            const float nb = MASK_COLS ? ((col < M) ? __ldg(cn + col) : 0.0f) : __ldg(cn + col);
+            s = __fsub_rn(__fmaf_rn(2.0f, s, -nb), na);
+        }
+        if (MASK_COLS) s = (col < M) ? s : -INFINITY;
+        sc[j] = s;
+        m8 = fmaxf(m8, s);
+        const float sr = ROW_MASK ? (row_ok ? s : -INFINITY) : s;
+        wm[j] = warp_max_f32(sr);
+        bal[j] = __ballot_sync(0xffffffffu, sr == wm[j]);
+    }
+    if (lane == 0) {
+        *reinterpret_cast<float4 *>(cv_out) = make_float4(wm[0], wm[1], wm[2], wm[3]);
+        *reinterpret_cast<float4 *>(cv_out + 4) = make_float4(wm[4], wm[5], wm[6], wm[7]);
+        *reinterpret_cast<uint4 *>(cb_out) = make_uint4(bal[0], bal[1], bal[2], bal[3]);
+        *reinterpret_cast<uint4 *>(cb_out + 4) = make_uint4(bal[4], bal[5], bal[6], bal[7]);
+    }
+    if ((!ROW_MASK || row_ok) && m8 >= s2) row_update8(sc, cbase, s1, s2, i1, i2);  // rare after the first tiles
 }
 
 // ---------------------------------------------------------------- main kernel
@@ -283,11 +311,11 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             mbar_init(bar_full(s), 1);            // this CTA's producer arms it; TMA bytes complete it
             mbar_init(bar_empty(s), TC_CLUSTER);  // one commit from each CTA of the cluster
         }
-        mbar_init(bar_a, PASSES == 3 ? 8 : 4);
-        for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull(g), 1); mbar_init(bar_tempty(g), 4); }
+        mbar_init(bar_a, PASSES == 3 ? 16 : 8);
+        for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull(g), 1); mbar_init(bar_tempty(g), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM allocation is warp-collective; this warp also frees it
+    if (warp == TC_WARP_MMA) {  // TMEM allocation is warp-collective; this warp also frees it
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
@@ -299,12 +327,14 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    auto tile_of = [&](int lt) { return t_begin + lt; };
+
+    if (warp == TC_WARP_TMA) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int it = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                const int brow = b * m_stride + t * TC_BN;
+            for (int lt = 0; lt < n_tiles; ++lt) {
+                const int brow = b * m_stride + tile_of(lt) * TC_BN;
                 for (int item = 0; item < ITEMS; ++item, ++it) {
                     const int stage = it % TC_STAGES;
                     const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
@@ -320,65 +350,73 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             }
             if (dbg_on) dbg[4] = dbg_acc[0];
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0 && n_tiles > 0) {
+    } else if (warp == TC_WARP_MMA) {
+        // ===================== MMA issuer =====================
+        // The warp stays converged (all lanes wait on the barriers); one elected lane issues.  Descriptors are a
+        // constant upper word plus (smem address >> 4): one integer add per MMA, nothing else on the issue path.
+        if (n_tiles > 0) {
             mbar_wait(bar_a, 0);  // A is in tensor memory
             tc_fence_after();
-            int it = 0;
+            uint32_t stage = 0, phase = 0;
+            long long mma_wait_full = 0, mma_wait_tempty = 0;
             for (int lt = 0; lt < n_tiles; ++lt) {
                 const int buf = lt & 1;
                 const uint32_t use = (uint32_t)(lt >> 1);
-                { TC_DBG_BEGIN(); mbar_wait(bar_tempty(buf), (use & 1u) ^ 1u); TC_DBG_END(1); }  // accumulator drained
+                { const long long _t0 = dbg_on ? clock64() : 0;
+                  mbar_wait(bar_tempty(buf), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+                  if (dbg_on) mma_wait_tempty += clock64() - _t0; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * TC_BN);
-                uint32_t acc = 0;
-                for (int item = 0; item < ITEMS; ++item, ++it) {
-                    const int stage = it % TC_STAGES;
-                    const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
-                    { TC_DBG_BEGIN(); mbar_wait(bar_full(stage), phase); TC_DBG_END(0); }
-                    tc_fence_after();
-                    const int kb = (PASSES == 3) ? (item >> 1) : item;
-                    const bool is_lo = (PASSES == 3) && (item & 1);
-                    const uint32_t sb = s_b + stage * TC_BLOCK_BYTES;
 #pragma unroll
-                    for (int k8 = 0; k8 < TC_KB / 8; ++k8) {
-                        const uint64_t bdesc = make_sdesc(sb + k8 * 32);
-                        const uint32_t ahi = tmem_base + (uint32_t)(TC_TMEM_A + kb * TC_KB + k8 * 8);
-                        if (is_lo) {  // a_hi * b_lo
-                            tc_mma_tf32_ts(d_tmem, ahi, bdesc, TC_IDESC, acc);
-                            acc = 1;
-                        } else {
-                            if (PASSES == 3) {  // a_lo * b_hi first (small term), then a_hi * b_hi
-                                tc_mma_tf32_ts(d_tmem, ahi + TC_D, bdesc, TC_IDESC, acc);
-                                acc = 1;
+                for (int item = 0; item < ITEMS; ++item) {
+                    { const long long _t0 = dbg_on ? clock64() : 0;
+                      mbar_wait(bar_full(stage), phase);
+                      if (dbg_on) mma_wait_full += clock64() - _t0; }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int kb = (PASSES == 3) ? (item >> 1) : item;       // compile-time after unrolling
+                        const bool is_lo = (PASSES == 3) && (item & 1);
+                        const uint32_t b_lo32 = (((s_b + stage * TC_BLOCK_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
+                        const uint32_t a_hi_t = tmem_base + (uint32_t)(TC_TMEM_A + kb * TC_KB);
+#pragma unroll
+                        for (int k8 = 0; k8 < TC_KB / 8; ++k8) {
+                            const uint64_t bdesc = ((uint64_t)TC_SDESC_HI << 32) | (uint64_t)(b_lo32 + k8 * 2);
+                            const uint32_t ahi = a_hi_t + k8 * 8;
+                            if (is_lo) {  // a_hi * b_lo
+                                tc_mma_tf32_ts(d_tmem, ahi, bdesc, TC_IDESC, 1u);
+                            } else {
+                                if (PASSES == 3)  // a_lo * b_hi first (small term), then a_hi * b_hi
+                                    tc_mma_tf32_ts(d_tmem, ahi + TC_D, bdesc, TC_IDESC, (item | k8) ? 1u : 0u);
+                                tc_mma_tf32_ts(d_tmem, ahi, bdesc, TC_IDESC, (PASSES == 3 || (item | k8)) ? 1u : 0u);
                             }
-                            tc_mma_tf32_ts(d_tmem, ahi, bdesc, TC_IDESC, acc);
-                            acc = 1;
                         }
+                        // slot reusable (in BOTH CTAs' rings) once these MMAs retire
+                        tc_commit_mc(bar_empty(stage), (uint16_t)((1u << TC_CLUSTER) - 1u));
+                        if (item == ITEMS - 1) tc_commit(bar_tfull(buf));  // accumulator complete
                     }
-                    // slot reusable (in BOTH CTAs' rings) once these MMAs retire
-                    tc_commit_mc(bar_empty(stage), (uint16_t)((1u << TC_CLUSTER) - 1u));
+                    __syncwarp();
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(bar_tfull(buf));  // accumulator complete
             }
-            if (dbg_on) { dbg[1] = dbg_acc[0]; dbg[2] = dbg_acc[1]; dbg[3] = clock64() - t_kernel0; dbg[11] = n_tiles; }
+            if (dbg_on && lane == 0) { dbg[1] = mma_wait_full; dbg[2] = mma_wait_tempty; dbg[3] = clock64() - t_kernel0; dbg[11] = n_tiles; }
         }
     } else {
-        // ===================== epilogue: 2 groups x 4 warps =====================
-        const int e = warp - 2;
-        const int g = e >> 2;       // accumulator / tile parity served by this group
-        const int q = warp & 3;     // TMEM lane quarter this warp may access
+        // ===================== epilogue: 2 groups (one per accumulator) x 8 warps =====================
+        // warp -> lane quarter q (hardware rule: warp w may touch TMEM lanes 32*(w%4)..), column half h, group g
+        const int g = warp >> 3;
+        const int h = (warp >> 2) & 1;
+        const int q = warp & 3;
         const int row = row0 + q * 32 + lane;
         const bool row_ok = row < N;
+        const bool partial_rows = row0 + TC_BM > N;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 
-        // ---- A -> tensor memory, once: group 0 stores the tf32 hi part, group 1 the lo part
+        // ---- A -> tensor memory, once: group 0 stores the tf32 hi part, group 1 the lo part; each warp 2 k-chunks
         if (n_tiles > 0 && (g == 0 || PASSES == 3)) {
             const float *src = (g == 0 ? a_hi : a_lo) + ((size_t)b * n_stride + min(row, n_stride - 1)) * TC_D;
             const bool have = row < n_stride;
 #pragma unroll 1
-            for (int c = 0; c < TC_D / 32; ++c) {
+            for (int c = 2 * h; c < 2 * h + 2; ++c) {
                 float v[32];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -392,7 +430,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             if (lane == 0) mbar_arrive(bar_a);
         }
 
-        float s1 = -INFINITY, s2 = -INFINITY;  // running top-2 of -|a-b|^2 or a.b: larger is better
+        float s1 = -INFINITY, s2 = -INFINITY;  // running top-2 of -|a-b|^2 or a.b over this warp's columns
         int32_t i1 = -1, i2 = -1;
         float *my_cv = scol_v + (g * 4 + q) * TC_BN;
         uint32_t *my_cb = scol_b + (g * 4 + q) * TC_BN;
@@ -400,31 +438,35 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         const float na = (METRIC == VO_METRIC_L2 && row_ok) ? row_norm[(size_t)b * n_stride + row] : 0.0f;
 
         for (int lt = g; lt < n_tiles; lt += 2) {
-            const int col0 = (t_begin + lt) * TC_BN;
+            const int col0 = tile_of(lt) * TC_BN;
             const uint32_t use = (uint32_t)(lt >> 1);
             const bool full_tile = col0 + TC_BN <= M;
             { TC_DBG_BEGIN(); mbar_wait(bar_tfull(g), use & 1u); TC_DBG_END(0); }
             tc_fence_after();
             const long long _tc0 = dbg_on ? clock64() : 0;
             const uint32_t taddr = lane_base + (uint32_t)(g * TC_BN);
+            if (full_tile && !partial_rows) {
 #pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
-                float v[32];
-                tc_ld32(taddr + c * 32, v);
-                if (c == TC_BN / 32 - 1) {  // the whole accumulator has been read: hand it back to the MMA thread
-                    tc_fence_before();
-                    if (lane == 0) mbar_arrive(bar_tempty(g));
+                for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 8) {
+                    float v[8];
+                    tc_ld8(taddr + j0, v);
+                    epi_group8<METRIC, false, false>(v, col0 + j0, M, row_ok, na, cn, lane, my_cv + j0, my_cb + j0, s1, s2, i1, i2);
                 }
-                if (full_tile)
-                    epi_chunk<METRIC, false>(v, col0 + c * 32, M, row_ok, na, cn, lane, my_cv + c * 32, my_cb + c * 32, s1, s2, i1, i2);
-                else
-                    epi_chunk<METRIC, true>(v, col0 + c * 32, M, row_ok, na, cn, lane, my_cv + c * 32, my_cb + c * 32, s1, s2, i1, i2);
+            } else {
+#pragma unroll 1
+                for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 8) {
+                    float v[8];
+                    tc_ld8(taddr + j0, v);
+                    epi_group8<METRIC, true, true>(v, col0 + j0, M, row_ok, na, cn, lane, my_cv + j0, my_cb + j0, s1, s2, i1, i2);
+                }
             }
+            tc_fence_before();  // this warp's share of the accumulator has been read: hand it back
+            if (lane == 0) mbar_arrive(bar_tempty(g));
             if (dbg_on) dbg_acc[1] += clock64() - _tc0;
             const long long _tm0 = dbg_on ? clock64() : 0;
             group_bar(1 + g);
-            {   // 128 threads of the group: one column each, merge the 4 lane quarters (ascending rows)
-                const int j = (e & 3) * 32 + lane;
+            if (h == 0) {  // 128 threads: one column each, merge the 4 lane quarters (ascending rows)
+                const int j = q * 32 + lane;
                 const int col = col0 + j;
                 float best = -INFINITY;
                 int brow = -1;
@@ -444,13 +486,13 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             group_bar(1 + g);
             if (dbg_on) dbg_acc[2] += clock64() - _tm0;
         }
-        if (dbg_on && q == 0 && lane == 0) { dbg[5 + g] = dbg_acc[0]; dbg[7 + g] = dbg_acc[1]; dbg[9 + g] = dbg_acc[2]; }
-        // the two groups saw disjoint tiles: each writes its own partial (finalize merges tie-aware)
+        if (dbg_on && q == 0 && h == 0 && lane == 0) { dbg[5 + g] = dbg_acc[0]; dbg[7 + g] = dbg_acc[1]; dbg[9 + g] = dbg_acc[2]; }
+        // four warps (2 groups x 2 column halves) saw disjoint columns of each row: four partials, merged by finalize
         if (row < n_stride) {
             vo_row_partial p;
             p.s1 = float_to_ordered(-s1); p.s2 = float_to_ordered(-s2);
             p.i1 = i1; p.i2 = i2;
-            part[((size_t)b * (n_split * 2) + split * 2 + g) * n_stride + row] = p;
+            part[((size_t)b * (n_split * 4) + split * 4 + g * 2 + h) * n_stride + row] = p;
         }
     }
 
@@ -458,7 +500,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // nobody leaves while the peer can still multicast into / arrive on this CTA
-    if (warp == 1) {
+    if (warp == TC_WARP_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
     }
@@ -555,7 +597,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     const int grid_x = ceil_div(row_blocks, TC_CLUSTER) * TC_CLUSTER;  // clusters pair adjacent row blocks
     const int n_split = pick_split(ctx, B, grid_x, ceil_div(m_stride, TC_BN), 4);
     vo_row_partial *part;
-    if ((rc = ws_get(ctx, WS_ROWPART, sizeof(vo_row_partial) * (size_t)B * n_split * 2 * n_stride, (void **)&part))) return rc;
+    if ((rc = ws_get(ctx, WS_ROWPART, sizeof(vo_row_partial) * (size_t)B * n_split * 4 * n_stride, (void **)&part))) return rc;
     dim3 grid(grid_x, n_split, B);
     VO_PROF(ctx, st, VO_STAGE_MATCH);
     if (passes == 3) {
@@ -567,7 +609,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     }
     if (rc) return rc;
     *part_out = part;
-    *n_split_out = n_split * 2;  // two epilogue groups -> two partials per (row, split)
+    *n_split_out = n_split * 4;  // 2 epilogue groups x 2 column halves -> four partials per (row, split)
     *row_norm_out = nullptr;     // scores already carry -|a-b|^2 in full
     return VO_OK;
 }
