@@ -45,7 +45,7 @@ constexpr int TC_CLUSTER = 2;
 // shared memory map (offsets from the 1024-aligned base)
 constexpr int TC_OFF_B = 0;
 constexpr int TC_OFF_SCOL = TC_OFF_B + TC_STAGES * TC_BLOCK_BYTES;  // [2 groups][4 quarters][128] x (float, u32)
-constexpr int TC_OFF_BAR = TC_OFF_SCOL + 2 * 4 * TC_BN * 8;
+constexpr int TC_OFF_BAR = TC_OFF_SCOL + 2 * 2 * 4 * TC_BN * 8;  // scol is double-buffered per group
 constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 512 + 1024;              // barriers + alignment slack
 
 // ---------------------------------------------------------------- PTX helpers
@@ -210,20 +210,17 @@ prep_kernel(const float *__restrict__ x, long long rows, float *__restrict__ hi,
 }
 
 // ---------------------------------------------------------------- epilogue helpers
-// Fold 8 consecutive columns into the row's running top-2 (larger is better).  Ties go to the lower column index
-// explicitly, because column tiles are visited in a rotated order.
-__device__ __forceinline__ void row_update8(const float (&sc)[8], int col_first, float &s1, float &s2, int32_t &i1,
-                                            int32_t &i2) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float s = sc[j];
-        const int col = col_first + j;
-        if (s > s1 || (s == s1 && col < i1)) {
-            s2 = s1; i2 = i1; s1 = s; i1 = col;
-        } else if (s > s2 || (s == s2 && (i2 < 0 || col < i2))) {
-            if (s > -INFINITY) { s2 = s; i2 = col; }
-        }
-    }
+// Fold one (score, column) into the row's running top-2 (larger is better), branch-free.  Ties go to the lower
+// column index explicitly (an unset slot is (-inf, -1): neither a -inf score nor an index comparison can take it).
+__device__ __forceinline__ void row_insert(float s, int col, float &s1, float &s2, int32_t &i1, int32_t &i2) {
+    const bool gt1 = (s > s1) | ((s == s1) & (col < i1));
+    const bool gt2 = (s > s2) | ((s == s2) & (col < i2));
+    const float ns2 = gt1 ? s1 : (gt2 ? s : s2);
+    const int32_t ni2 = gt1 ? i1 : (gt2 ? col : i2);
+    s1 = gt1 ? s : s1;
+    i1 = gt1 ? col : i1;
+    s2 = ns2;
+    i2 = ni2;
 }
 
 // ---------------------------------------------------------------- epilogue: 8 accumulator columns
@@ -237,7 +234,6 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
                                            float &s1, float &s2, int32_t &i1, int32_t &i2) {
     float sc[8], wm[8];
     uint32_t bal[8];
-    float m8 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int col = cbase + j;
@@ -248,7 +244,6 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
         }
         if (MASK_COLS) s = (col < M) ? s : -INFINITY;
         sc[j] = s;
-        m8 = fmaxf(m8, s);
         const float sr = ROW_MASK ? (row_ok ? s : -INFINITY) : s;
         wm[j] = warp_max_f32(sr);
         bal[j] = __ballot_sync(0xffffffffu, sr == wm[j]);
@@ -259,7 +254,17 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
         *reinterpret_cast<uint4 *>(cb_out) = make_uint4(bal[0], bal[1], bal[2], bal[3]);
         *reinterpret_cast<uint4 *>(cb_out + 4) = make_uint4(bal[4], bal[5], bal[6], bal[7]);
     }
-    if ((!ROW_MASK || row_ok) && m8 >= s2) row_update8(sc, cbase, s1, s2, i1, i2);  // rare after the first tiles
+    // Row top-2: a 4-wide max filter, then a branch-free insert of the 4 candidates.  The branch is taken by the
+    // whole warp if any lane needs it, so the filter is kept narrow (expected entries ~ 64/k per
+    // 4 columns once a row has seen k columns).
+#pragma unroll
+    for (int j0 = 0; j0 < 8; j0 += 4) {
+        const float m4 = fmaxf(fmaxf(sc[j0], sc[j0 + 1]), fmaxf(sc[j0 + 2], sc[j0 + 3]));
+        if ((!ROW_MASK || row_ok) && m4 >= s2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) row_insert(sc[j0 + j], cbase + j0 + j, s1, s2, i1, i2);
+        }
+    }
 }
 
 // ---------------------------------------------------------------- main kernel
@@ -295,8 +300,8 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
 
     constexpr int ITEMS = (PASSES == 3) ? 2 * TC_NKB : TC_NKB;  // B boxes streamed per tile
     const uint32_t s_b = base + TC_OFF_B;
-    float *scol_v = reinterpret_cast<float *>(smem + TC_OFF_SCOL);                       // [2][4][128]
-    uint32_t *scol_b = reinterpret_cast<uint32_t *>(smem + TC_OFF_SCOL + 2 * 4 * TC_BN * 4);
+    float *scol_v = reinterpret_cast<float *>(smem + TC_OFF_SCOL);                       // [2 groups][2 bufs][4][128]
+    uint32_t *scol_b = reinterpret_cast<uint32_t *>(smem + TC_OFF_SCOL + 2 * 2 * 4 * TC_BN * 4);
     const uint32_t s_bar = base + TC_OFF_BAR;
     // barrier slots (8 B each): full[S] empty[S] a_full tmem_full[2] tmem_empty[2]; then the TMEM base word
     auto bar_full = [&](int s) { return s_bar + 8u * s; };
@@ -432,8 +437,8 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
 
         float s1 = -INFINITY, s2 = -INFINITY;  // running top-2 of -|a-b|^2 or a.b over this warp's columns
         int32_t i1 = -1, i2 = -1;
-        float *my_cv = scol_v + (g * 4 + q) * TC_BN;
-        uint32_t *my_cb = scol_b + (g * 4 + q) * TC_BN;
+        float *grp_cv = scol_v + g * 2 * 4 * TC_BN;
+        uint32_t *grp_cb = scol_b + g * 2 * 4 * TC_BN;
         const float *cn = (METRIC == VO_METRIC_L2) ? col_norm + (size_t)b * m_stride : nullptr;
         const float na = (METRIC == VO_METRIC_L2 && row_ok) ? row_norm[(size_t)b * n_stride + row] : 0.0f;
 
@@ -441,6 +446,10 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             const int col0 = tile_of(lt) * TC_BN;
             const uint32_t use = (uint32_t)(lt >> 1);
             const bool full_tile = col0 + TC_BN <= M;
+            float *tile_cv = grp_cv + (use & 1u) * 4 * TC_BN;   // this tile's column scratch (alternates per use)
+            uint32_t *tile_cb = grp_cb + (use & 1u) * 4 * TC_BN;
+            float *my_cv = tile_cv + q * TC_BN;
+            uint32_t *my_cb = tile_cb + q * TC_BN;
             { TC_DBG_BEGIN(); mbar_wait(bar_tfull(g), use & 1u); TC_DBG_END(0); }
             tc_fence_after();
             const long long _tc0 = dbg_on ? clock64() : 0;
@@ -472,8 +481,8 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                 int brow = -1;
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
-                    const float val = scol_v[(g * 4 + qq) * TC_BN + j];
-                    const uint32_t bal = scol_b[(g * 4 + qq) * TC_BN + j];
+                    const float val = tile_cv[qq * TC_BN + j];
+                    const uint32_t bal = tile_cb[qq * TC_BN + j];
                     if (bal != 0u && val > best) { best = val; brow = qq * 32 + __ffs(bal) - 1; }
                 }
                 if (col < M && brow >= 0 && row0 + brow < N) {
@@ -483,7 +492,8 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                     if (key < *reinterpret_cast<volatile unsigned long long *>(dst)) atomicMin(dst, key);
                 }
             }
-            group_bar(1 + g);
+            // no second barrier: the next tile of this group writes the other scratch buffer, and the one after
+            // next cannot start before every warp has passed the barrier above again
             if (dbg_on) dbg_acc[2] += clock64() - _tm0;
         }
         if (dbg_on && q == 0 && h == 0 && lane == 0) { dbg[5 + g] = dbg_acc[0]; dbg[7 + g] = dbg_acc[1]; dbg[9 + g] = dbg_acc[2]; }
