@@ -25,11 +25,11 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (descriptor kind, keypoints, hypotheses, matcher description, cpu matcher)
-    "c1": dict(kind="sift", n_kp=2000, n_hyp=512, pairs=256, shape="kitti", cpu_matcher="knn_ratio",
+    "c1": dict(kind="sift", n_kp=2000, n_hyp=512, pairs=256, chunk=256, shape="kitti", cpu_matcher="knn_ratio",
                desc="SIFT 2k kp, L2 kNN-2 + ratio 0.85, PnP-RANSAC 512 hyp, KITTI 1241x376"),
-    "c2": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, shape="kitti", cpu_matcher="hamming_mutual",
+    "c2": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="hamming_mutual",
                desc="ORB 5k kp, 256-bit Hamming mutual-NN, PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
-    "c3": dict(kind="r2d2", n_kp=10000, n_hyp=4096, pairs=64, shape="kitti", cpu_matcher="r2d2",
+    "c3": dict(kind="r2d2", n_kp=10000, n_hyp=4096, pairs=64, chunk=64, shape="kitti", cpu_matcher="r2d2",
                desc="R2D2 10k kp, cosine GEMM-argmin ratio+mutual, PnP-RANSAC 4096 hyp, KITTI 1241x376"),
 }
 
@@ -107,6 +107,40 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def measure_tf32_peak(dev):
+    """cuBLAS TF32 GEMM throughput on this GPU (8192^3, best of 10) — the measuring stick for the matching GEMM,
+    taken outside every timed region.  MEASURED_PEAKS.json has no TF32 figure."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        best = float("inf")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(10):
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def ncu_traffic(kernel_key, pairs_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture, scaled to this
+    run's pairs per launch (profiles/traffic.json: bytes and pairs of the captured launch)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get(kernel_key)
+    if not d:
+        return None
+    return d["dram_bytes"] / d["pairs_per_launch"] * pairs_per_launch
+
+
 # --------------------------------------------------------------------------------------- CPU reference arm
 def time_cpu_pairs(wl, n_pairs, first_index=0, warm=1):
     """Runs the reference's CPU path over `n_pairs` synthetic pairs; returns (pairs/s, seconds, threads)."""
@@ -181,7 +215,7 @@ def run_ours(args, wl):
     if args.precision is not None:
         mc["precision"] = args.precision
     cfg = sequence.PipelineConfig(n_hyp=wl["n_hyp"], **mc)
-    chunk = min(args.chunk, P)
+    chunk = min(args.chunk or wl["chunk"], P)
     out = ops.PipelineBuffers(P, dev)
 
     def step():
@@ -234,7 +268,7 @@ def run_ours(args, wl):
     # ---- e2e: host buffers in, poses out, H2D/D2H inside the timed region
     host_rep = {k: np.concatenate([host[k]] * reps, 0)[:P] for k in ("ref_desc", "cur_desc", "ref_kp", "cur_kp", "depth")}
     host_rep["K"] = host["K"]
-    runner = sequence.HostPairRunner(host_rep, cfg, chunk=min(args.e2e_chunk, P), device=dev)
+    runner = sequence.HostPairRunner(host_rep, cfg, chunk=min(args.e2e_chunk or max(1, chunk // 2), P), device=dev)
     del host_rep
 
     def e2e_step():
@@ -277,7 +311,8 @@ def run_ours(args, wl):
     if wl["kind"] == "orb":
         alg_bytes = pairs_per_launch * (32.0 * (N + M) + 16.0 * N + 8.0 * M)      # descriptors + row partials + column keys
         roof = {"kernel": "match_u8_kernel (XOR+POPC Hamming, fused row/column arg-min)", "bound": "hbm",
-                "achieved": alg_bytes / match_s / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": None,
+                "achieved": alg_bytes / match_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "traffic": ncu_traffic("match_u8_kernel", pairs_per_launch), "algorithmic_bytes": alg_bytes,
                 "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "note": "structurally << 1: all-pairs Hamming is POPC-pipe bound, not HBM bound (SURVEY D5); see binding_pipe"}
         popc = pairs_per_launch * N * M * 8.0
@@ -289,11 +324,17 @@ def run_ours(args, wl):
     else:
         passes = 3 if mc["precision"] == ops.VO_PREC_TF32X3 else 1
         flops = pairs_per_launch * 2.0 * N * M * 128 * (passes if mc["precision"] != ops.VO_PREC_FP32_SIMT else 1)
-        tf32_peak = bf16_peak / 2.0
-        roof = {"kernel": "match_f32 fused GEMM-argmin", "bound": "tensor", "achieved": flops / match_s / 1e12,
-                "peak": tf32_peak, "unit": "TFLOP/s", "traffic": None,
-                "peak_source": f"0.5 x bf16 cuBLAS peak in MEASURED_PEAKS.json ({peak_kind}); TF32 not separately measured",
-                "issued_passes": passes}
+        tf32_half_bf16 = bf16_peak / 2.0
+        tf32_cublas = measure_tf32_peak(dev)
+        roof = {"kernel": "match_f32_tc_kernel (tcgen05 kind::tf32 fused GEMM + row top-2 / column arg-max)",
+                "bound": "tensor", "achieved": flops / match_s / 1e12, "peak": tf32_half_bf16, "unit": "TFLOP/s",
+                "traffic": ncu_traffic("match_f32_tc_kernel", pairs_per_launch),
+                "peak_source": f"0.5 x bf16 cuBLAS burst peak of MEASURED_PEAKS.json ({peak_kind}); MEASURED_PEAKS has no "
+                               "TF32 entry, so cuBLAS TF32 was also measured in this run: see peak_cublas_tf32",
+                "peak_cublas_tf32": tf32_cublas, "frac_of_cublas_tf32": flops / match_s / 1e12 / tf32_cublas,
+                "frac_of_nominal_1100": flops / match_s / 1e12 / 1100.0,
+                "issued_passes": passes, "algorithmic_flops": flops / passes,
+                "note": "achieved counts ISSUED tensor FLOPs (3 tf32 MMAs per k-step for 3xTF32), as BASELINE.md section 3 specifies"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["avg_launch_ms"] = stage_ms.get("match")
     roof["share_of_step"] = share.get("match")
@@ -342,8 +383,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: workload's)")
     ap.add_argument("--unique", type=int, default=40, help="distinct synthetic pairs generated per rank (tiled to --pairs)")
-    ap.add_argument("--chunk", type=int, default=250, help="pairs per vo_pipeline call")
-    ap.add_argument("--e2e-chunk", type=int, default=125)
+    ap.add_argument("--chunk", type=int, default=0, help="pairs per vo_pipeline call (default: workload's)")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="pairs per H2D/compute chunk of the e2e run (default: chunk/2)")
     ap.add_argument("--precision", type=int, default=None)
     ap.add_argument("--cpu-pairs", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

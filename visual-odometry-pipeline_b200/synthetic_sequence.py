@@ -64,7 +64,7 @@ def make_sequence(n_frames=30, n_kp=1500, kind="orb", K=KITTI_K, wh=KITTI_WH, no
             v = fy * Xc[:, 1] / z + cy
         vis = np.nonzero((z > 3.0) & (z < 48.0) & (u >= 2) & (u < W - 2) & (v >= 2) & (v < H - 2))[0]
         n_l = min(len(vis), int(n_kp * 0.85))
-        vis = rng.choice(vis, n_l, replace=False)
+        vis = vis[:n_l]  # lowest landmark ids first: a landmark stays tracked while it is visible (high overlap)
         kp = np.stack([u[vis], v[vis]], 1) + rng.normal(0, noise_px, (n_l, 2))
         kp[:, 0] = np.clip(kp[:, 0], 0, W - 1.001)
         kp[:, 1] = np.clip(kp[:, 1], 0, H - 1.001)
