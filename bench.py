@@ -31,6 +31,11 @@ WORKLOADS = {
                desc="ORB 5k kp, 256-bit Hamming mutual-NN, PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
     "c3": dict(kind="r2d2", n_kp=10000, n_hyp=4096, pairs=64, chunk=64, shape="kitti", cpu_matcher="r2d2",
                desc="R2D2 10k kp, cosine GEMM-argmin ratio+mutual, PnP-RANSAC 4096 hyp, KITTI 1241x376"),
+    # the two multi-GPU configurations of BASELINE.json (per-GPU block of the sharded sequence; weak scaling)
+    "c4": dict(kind="sift", n_kp=20000, n_hyp=16384, pairs=32, chunk=32, shape="kitti", cpu_matcher="knn_ratio", unique=8,
+               desc="SIFT 20k kp, L2 kNN-2 + ratio 0.85, PnP-RANSAC 16384 hyp, KITTI 1241x376"),
+    "c5": dict(kind="r2d2", n_kp=50000, n_hyp=4096, pairs=8, chunk=8, shape="zed", cpu_matcher="r2d2", unique=4,
+               desc="R2D2 50k kp, cosine GEMM-argmin ratio+mutual, PnP-RANSAC 4096 hyp, ZED-Mini-shaped 2208x1242"),
 }
 
 
@@ -166,7 +171,7 @@ def run_reference(args, wl):
     rank, _, world = env_rank()
     if rank != 0:
         return
-    sample = args.cpu_pairs or {"c1": 24, "c2": 16, "c3": 4}[args.workload]
+    sample = args.cpu_pairs or {"c1": 24, "c2": 16, "c3": 4, "c4": 2, "c5": 1}[args.workload]
     vals, secs = [], []
     for s in range(args.warmup + args.steps):
         v, dt, threads, ok = time_cpu_pairs(wl, sample, first_index=s * (sample + 1))
@@ -206,7 +211,7 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=dev)
 
     P = args.pairs or wl["pairs"]                      # pairs per GPU per step
-    unique = min(args.unique, P)
+    unique = min(args.unique or wl.get("unique", 40), P)
     reps = (P + unique - 1) // unique
     host = make_host_batch(wl, unique, first_index=rank * P)
     batch_full = sequence.PairBatch.from_numpy(host, dev, repeat=reps)
@@ -342,7 +347,7 @@ def run_ours(args, wl):
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
-        sample = args.cpu_pairs or {"c1": 48, "c2": 24, "c3": 6}[args.workload]
+        sample = args.cpu_pairs or {"c1": 48, "c2": 24, "c3": 6, "c4": 2, "c5": 1}[args.workload]
         v, dt, threads, okc = time_cpu_pairs(wl, sample, first_index=0)
         cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
                "sample": f"first {sample} pairs of the same synthetic workload, {dt:.1f} s, reference CPU path "
@@ -382,7 +387,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: workload's)")
-    ap.add_argument("--unique", type=int, default=40, help="distinct synthetic pairs generated per rank (tiled to --pairs)")
+    ap.add_argument("--unique", type=int, default=0, help="distinct synthetic pairs generated per rank, tiled to --pairs "
+                    "(default: 40; 8 / 4 for c4 / c5)")
     ap.add_argument("--chunk", type=int, default=0, help="pairs per vo_pipeline call (default: workload's)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="pairs per H2D/compute chunk of the e2e run (default: chunk/2)")
     ap.add_argument("--precision", type=int, default=None)

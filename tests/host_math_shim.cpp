@@ -15,10 +15,11 @@ int hm_p3p4(const double *P, const double *uv, const double *K, double *out) {
     return 1;
 }
 void hm_draw(unsigned long long seed, long long pair, int h, int n, int *out) { vo::draw_hypothesis(seed, pair, h, n, out); }
-float hm_err2(const float *pose, const float *k, float X, float Y, float Z, float u, float v) {
+int hm_is_inlier(const float *pose, const float *k, float thr, float X, float Y, float Z, float u, float v) {
     vo::PoseF p; vo::IntrF kk{k[0], k[1], k[2], k[3]};
     for (int j = 0; j < 9; ++j) p.r[j] = pose[j];
     for (int j = 0; j < 3; ++j) p.t[j] = pose[9 + j];
-    return vo::reproj_err2(p, kk, X, Y, Z, u, v);
+    const vo::ScoreModel m = vo::score_model(p, kk);
+    return vo::is_inlier(m, thr, X, Y, Z, u - kk.cx, v - kk.cy) ? 1 : 0;
 }
 }

@@ -18,7 +18,7 @@ def hm():
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so,
                            os.path.join(HERE, "host_math_shim.cpp")])
     lib = ctypes.CDLL(so)
-    lib.hm_err2.restype = ctypes.c_float
+    lib.hm_is_inlier.restype = ctypes.c_int
     return lib
 
 
@@ -56,8 +56,8 @@ def test_p3p_and_scoring_bit_exact(hm, orc, golden):
         p32 = np.ascontiguousarray(poses[h])
         cnt = 0
         for i in range(0, len(xyz), 7):
-            e = hm.hm_err2(_p(p32), _p(kf), *(ctypes.c_float(float(x)) for x in (*xyz[i], *uv[i])))
-            cnt += e <= np.float32(2.25)
+            cnt += hm.hm_is_inlier(_p(p32), _p(kf), ctypes.c_float(1.5),
+                                   *(ctypes.c_float(float(x)) for x in (*xyz[i], *uv[i])))
         m = orc.inlier_mask(xyz, uv, K, poses[h])
         assert cnt == int(m[::7].sum())
     assert nvalid > 100

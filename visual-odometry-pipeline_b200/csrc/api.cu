@@ -175,8 +175,11 @@ extern "C" int vo_match_f32(vo_ctx *ctx, const float *ref, const float *cur, int
             return rc;
     } else {
         VO_REQUIRE(dim == 128, "vo_match_f32: the tcgen05 path takes 128-d descriptors (got %d); use VO_PREC_FP32_SIMT", dim);
+        // the column arg-max feeds the mutual rules and the raw col_idx output only
+        const int need_cols = mode == VO_MODE_MUTUAL || mode == VO_MODE_RATIO_MUTUAL || mode == VO_MODE_THRESH_MUTUAL ||
+                              (knn && knn->col_idx);
         if ((rc = match_f32_tc(ctx, ref, cur, B, n_stride, m_stride, n_ref, n_cur, metric,
-                               precision == VO_PREC_TF32X3 ? 3 : 1, &part, &n_split, colkey, &row_norm, st)))
+                               precision == VO_PREC_TF32X3 ? 3 : 1, need_cols, &part, &n_split, colkey, &row_norm, st)))
             return rc;
     }
     return match_finalize(ctx, part, n_split, colkey, B, n_stride, m_stride, n_ref, n_cur,

@@ -117,8 +117,9 @@ int match_f32_simt(vo_ctx *ctx, const float *ref, const float *cur, int B, int n
 // tcgen05 path: owns its split choice and workspaces; returns the partial buffer, split count and
 // (L2 only) the per-row squared norms that finalize adds back.
 int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_stride, int m_stride,
-                 const int32_t *n_ref, const int32_t *n_cur, int metric, int passes, vo_row_partial **part_out,
-                 int *n_split_out, unsigned long long *colkey, const float **row_norm_out, cudaStream_t st);
+                 const int32_t *n_ref, const int32_t *n_cur, int metric, int passes, int need_cols,
+                 vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey, const float **row_norm_out,
+                 cudaStream_t st);
 int pick_split(vo_ctx *ctx, int B, int row_blocks, int col_tiles, int min_tiles_per_split);
 int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_t *n_pts, int B, int cap,
                     const double *K_h, const int32_t *hyp, int H, float thr_px, int min_inliers, int refine_iters,

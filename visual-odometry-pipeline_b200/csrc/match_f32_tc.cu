@@ -228,27 +228,42 @@ __device__ __forceinline__ void row_insert(float s, int col, float &s1, float &s
 // maximum and the ballot of the lanes that attain it (both warp-uniform; lane 0 stores them as two vectors).
 // ROW_MASK is set only for the last, partial row block: elsewhere every lane holds a valid row.
 // Kept small on purpose (a rolled loop calls it 8 times per tile and warp): 16 warps share the instruction cache.
-template <int METRIC, bool MASK_COLS, bool ROW_MASK>
+template <int METRIC, bool MASK_COLS, bool ROW_MASK, bool COLS>
 __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M, bool row_ok, float na,
-                                           const float *__restrict__ cn, int lane, float *cv_out, uint32_t *cb_out,
-                                           float &s1, float &s2, int32_t &i1, int32_t &i2) {
-    float sc[8], wm[8];
+                                           const float *__restrict__ cn, bool cn_vec, int lane, float *cv_out,
+                                           uint32_t *cb_out, float &s1, float &s2, int32_t &i1, int32_t &i2) {
+    float sc[8], wm[8], nb[8];
     uint32_t bal[8];
+    if (METRIC == VO_METRIC_L2) {
+        if (!MASK_COLS && cn_vec) {  // warp-uniform: two 128-bit broadcast loads instead of eight scalar ones
+            const float4 n0 = __ldg(reinterpret_cast<const float4 *>(cn + cbase));
+            const float4 n1 = __ldg(reinterpret_cast<const float4 *>(cn + cbase) + 1);
+            nb[0] = n0.x; nb[1] = n0.y; nb[2] = n0.z; nb[3] = n0.w;
+            nb[4] = n1.x; nb[5] = n1.y; nb[6] = n1.z; nb[7] = n1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nb[j] = (!MASK_COLS || cbase + j < M) ? __ldg(cn + cbase + j) : 0.0f;
+        }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int col = cbase + j;
         float s = v[j];
         if (METRIC == VO_METRIC_L2) {
-            const float nb = MASK_COLS ? ((col < M) ? __ldg(cn + col) : 0.0f) : __ldg(cn + col);
-            s = __fsub_rn(__fmaf_rn(2.0f, s, -nb), na);
+            // with a column arg-min the row norm orders rows inside a column; without one it is a per-row
+            // constant that the caller subtracts once, after the scan (same two roundings either way)
+            s = __fmaf_rn(2.0f, s, -nb[j]);
+            if (COLS) s = __fsub_rn(s, na);
         }
         if (MASK_COLS) s = (col < M) ? s : -INFINITY;
         sc[j] = s;
-        const float sr = ROW_MASK ? (row_ok ? s : -INFINITY) : s;
-        wm[j] = warp_max_f32(sr);
-        bal[j] = __ballot_sync(0xffffffffu, sr == wm[j]);
+        if (COLS) {
+            const float sr = ROW_MASK ? (row_ok ? s : -INFINITY) : s;
+            wm[j] = warp_max_f32(sr);
+            bal[j] = __ballot_sync(0xffffffffu, sr == wm[j]);
+        }
     }
-    if (lane == 0) {
+    if (COLS && lane == 0) {
         *reinterpret_cast<float4 *>(cv_out) = make_float4(wm[0], wm[1], wm[2], wm[3]);
         *reinterpret_cast<float4 *>(cv_out + 4) = make_float4(wm[4], wm[5], wm[6], wm[7]);
         *reinterpret_cast<uint4 *>(cb_out) = make_uint4(bal[0], bal[1], bal[2], bal[3]);
@@ -268,7 +283,9 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
 }
 
 // ---------------------------------------------------------------- main kernel
-template <int PASSES, int METRIC>
+// COLS = false drops the column arg-max (REDUX + ballot per column and warp, the per-tile merge and its barrier):
+// the ratio / threshold / plain-NN acceptance rules never read it.
+template <int PASSES, int METRIC, bool COLS>
 __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1)
 match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                     const float *__restrict__ a_hi, const float *__restrict__ a_lo, int n_stride, int m_stride,
@@ -441,6 +458,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         uint32_t *grp_cb = scol_b + g * 2 * 4 * TC_BN;
         const float *cn = (METRIC == VO_METRIC_L2) ? col_norm + (size_t)b * m_stride : nullptr;
         const float na = (METRIC == VO_METRIC_L2 && row_ok) ? row_norm[(size_t)b * n_stride + row] : 0.0f;
+        const bool cn_vec = (METRIC == VO_METRIC_L2) && ((reinterpret_cast<uintptr_t>(cn) & 15u) == 0);
 
         for (int lt = g; lt < n_tiles; lt += 2) {
             const int col0 = tile_of(lt) * TC_BN;
@@ -459,22 +477,22 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                 for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 8) {
                     float v[8];
                     tc_ld8(taddr + j0, v);
-                    epi_group8<METRIC, false, false>(v, col0 + j0, M, row_ok, na, cn, lane, my_cv + j0, my_cb + j0, s1, s2, i1, i2);
+                    epi_group8<METRIC, false, false, COLS>(v, col0 + j0, M, row_ok, na, cn, cn_vec, lane, my_cv + j0, my_cb + j0, s1, s2, i1, i2);
                 }
             } else {
 #pragma unroll 1
                 for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 8) {
                     float v[8];
                     tc_ld8(taddr + j0, v);
-                    epi_group8<METRIC, true, true>(v, col0 + j0, M, row_ok, na, cn, lane, my_cv + j0, my_cb + j0, s1, s2, i1, i2);
+                    epi_group8<METRIC, true, true, COLS>(v, col0 + j0, M, row_ok, na, cn, cn_vec, lane, my_cv + j0, my_cb + j0, s1, s2, i1, i2);
                 }
             }
             tc_fence_before();  // this warp's share of the accumulator has been read: hand it back
             if (lane == 0) mbar_arrive(bar_tempty(g));
             if (dbg_on) dbg_acc[1] += clock64() - _tc0;
             const long long _tm0 = dbg_on ? clock64() : 0;
-            group_bar(1 + g);
-            if (h == 0) {  // 128 threads: one column each, merge the 4 lane quarters (ascending rows)
+            if (COLS) group_bar(1 + g);
+            if (COLS && h == 0) {  // 128 threads: one column each, merge the 4 lane quarters (ascending rows)
                 const int j = q * 32 + lane;
                 const int col = col0 + j;
                 float best = -INFINITY;
@@ -498,6 +516,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         }
         if (dbg_on && q == 0 && h == 0 && lane == 0) { dbg[5 + g] = dbg_acc[0]; dbg[7 + g] = dbg_acc[1]; dbg[9 + g] = dbg_acc[2]; }
         // four warps (2 groups x 2 column halves) saw disjoint columns of each row: four partials, merged by finalize
+        if (METRIC == VO_METRIC_L2 && !COLS) {  // the deferred row norm (-inf stays -inf)
+            s1 = __fsub_rn(s1, na); s2 = __fsub_rn(s2, na);
+        }
         if (row < n_stride) {
             vo_row_partial p;
             p.s1 = float_to_ordered(-s1); p.s2 = float_to_ordered(-s2);
@@ -536,11 +557,11 @@ int make_map(vo_ctx *ctx, CUtensorMap *map, const float *ptr, long long rows) {
     return VO_OK;
 }
 
-template <int PASSES, int METRIC>
+template <int PASSES, int METRIC, bool COLS>
 int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &bl, const float *a_hi, const float *a_lo,
               int n_stride, int m_stride, const int32_t *n_ref, const int32_t *n_cur, const float *row_norm,
               const float *col_norm, int n_split, vo_row_partial *part, unsigned long long *colkey, cudaStream_t st) {
-    auto kern = match_f32_tc_kernel<PASSES, METRIC>;
+    auto kern = match_f32_tc_kernel<PASSES, METRIC, COLS>;
     long long *dbg = nullptr;
     if (getenv("VO_TC_DEBUG")) {  // bring-up only: cycle accounting of CTA (0,0,0), printed after a sync
         static long long *dbg_dev = nullptr;
@@ -567,8 +588,9 @@ int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &
 }  // namespace
 
 int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_stride, int m_stride,
-                 const int32_t *n_ref, const int32_t *n_cur, int metric, int passes, vo_row_partial **part_out,
-                 int *n_split_out, unsigned long long *colkey, const float **row_norm_out, cudaStream_t st) {
+                 const int32_t *n_ref, const int32_t *n_cur, int metric, int passes, int need_cols,
+                 vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey, const float **row_norm_out,
+                 cudaStream_t st) {
     if (!ctx->tc_ready) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -588,10 +610,11 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     const size_t per_a = (size_t)rows_a * TC_D * sizeof(float), per_b = (size_t)rows_b * TC_D * sizeof(float);
     if ((rc = ws_get(ctx, WS_SPLIT_A, per_a * (passes == 3 ? 2 : 1), (void **)&split_a))) return rc;
     if ((rc = ws_get(ctx, WS_SPLIT_B, per_b * (passes == 3 ? 2 : 1), (void **)&split_b))) return rc;
-    if ((rc = ws_get(ctx, WS_NORMS, sizeof(float) * (size_t)(rows_a + rows_b), (void **)&norms))) return rc;
+    const long long rows_a4 = (rows_a + 3) & ~3ll;  // column norms start 16 B aligned (vector loads in the epilogue)
+    if ((rc = ws_get(ctx, WS_NORMS, sizeof(float) * (size_t)(rows_a4 + rows_b), (void **)&norms))) return rc;
     float *a_hi = split_a, *a_lo = passes == 3 ? split_a + (size_t)rows_a * TC_D : nullptr;
     float *b_hi = split_b, *b_lo = passes == 3 ? split_b + (size_t)rows_b * TC_D : nullptr;
-    float *row_norm = norms, *col_norm = norms + rows_a;
+    float *row_norm = norms, *col_norm = norms + rows_a4;
 
     VO_PROF(ctx, st, VO_STAGE_PREP);
     prep_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, a_hi, a_lo, l2 ? row_norm : nullptr);
@@ -610,13 +633,12 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     if ((rc = ws_get(ctx, WS_ROWPART, sizeof(vo_row_partial) * (size_t)B * n_split * 4 * n_stride, (void **)&part))) return rc;
     dim3 grid(grid_x, n_split, B);
     VO_PROF(ctx, st, VO_STAGE_MATCH);
-    if (passes == 3) {
-        rc = l2 ? launch_tc<3, VO_METRIC_L2>(ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st)
-                : launch_tc<3, VO_METRIC_COSINE>(ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st);
-    } else {
-        rc = l2 ? launch_tc<1, VO_METRIC_L2>(ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st)
-                : launch_tc<1, VO_METRIC_COSINE>(ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st);
-    }
+#define TC_ARGS ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st
+#define TC_PICK(P, MET) (need_cols ? launch_tc<P, MET, true>(TC_ARGS) : launch_tc<P, MET, false>(TC_ARGS))
+    if (passes == 3) rc = l2 ? TC_PICK(3, VO_METRIC_L2) : TC_PICK(3, VO_METRIC_COSINE);
+    else rc = l2 ? TC_PICK(1, VO_METRIC_L2) : TC_PICK(1, VO_METRIC_COSINE);
+#undef TC_PICK
+#undef TC_ARGS
     if (rc) return rc;
     *part_out = part;
     *n_split_out = n_split * 4;  // 2 epilogue groups x 2 column halves -> four partials per (row, split)

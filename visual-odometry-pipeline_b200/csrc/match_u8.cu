@@ -8,42 +8,73 @@
 // walks the current-frame descriptors, which the CTA stages in shared memory; all lanes of a
 // warp read the same staged descriptor (smem broadcast, 2 x LDS.128 per 32 x ROWS_PT
 // distances).  Row top-2 is therefore thread-private; the column arg-min is a warp REDUX.MIN
-// over a packed (distance << 9 | row-in-CTA) key, merged per CTA in shared memory and per
+// over a packed (distance << 10 | row-in-CTA) key, merged per CTA in shared memory and per
 // grid with one 64-bit atomicMin per (CTA, column).  The N x M distance matrix never exists.
+//
+// Hamming arithmetic: the POPC pipe issues 16 lanes/clk/SM, a quarter of the logic pipe, so a
+// plain 8 x (XOR, POPC) distance is POPC-bound.  The eight XOR words are first compressed by a
+// carry-save adder tree (4 full adders = 8 LOP3: 3-input XOR 0x96 and majority 0xE8) into two
+// words of weight 1, one of weight 2 and one of weight 4, which leaves 4 POPC per distance and
+// moves the bound to the logic pipe (16 LOP3 per distance at 64 lanes/clk/SM).
 #include "common.cuh"
 
 namespace vo {
 namespace {
 
 constexpr int U8_THREADS = 256;
-constexpr int U8_ROWS_PT = 2;
-constexpr int U8_ROWS_CTA = U8_THREADS * U8_ROWS_PT;  // 512 -> row-in-CTA fits 9 bits
-constexpr int U8_CHUNK = 1024;                        // staged columns per pass (32 KB)
+constexpr int U8_ROWS_PT = 4;
+constexpr int U8_ROW_BITS = 10;
+constexpr int U8_ROWS_CTA = U8_THREADS * U8_ROWS_PT;  // 1024 -> row-in-CTA fits 10 bits
+constexpr int U8_CHUNK = 512;                         // staged columns per pass (16 KB + 16 KB of per-warp column minima)
+constexpr uint32_t U8_INVALID_ROW = 0x80000000u;      // added to the column key of rows >= N: never the minimum
+constexpr int U8_COL_BITS = 20;                       // Hamming row key = dist << 20 | column
+static_assert(U8_ROWS_CTA == (1 << U8_ROW_BITS), "row-in-CTA must fit the key");
+
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 template <int NORM>
 __device__ __forceinline__ uint32_t dist256(const uint32_t (&a)[8], const uint4 b0, const uint4 b1) {
     const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    uint32_t d = 0;
     if (NORM == VO_NORM_HAMMING) {
+        uint32_t x[8];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) d += __popc(a[w] ^ b[w]);
+        for (int w = 0; w < 8; ++w) x[w] = a[w] ^ b[w];
+        const uint32_t sa = xor3(x[0], x[1], x[2]), ca = maj3(x[0], x[1], x[2]);
+        const uint32_t sb = xor3(x[3], x[4], x[5]), cb = maj3(x[3], x[4], x[5]);
+        const uint32_t sc = xor3(sa, sb, x[6]), cc = maj3(sa, sb, x[6]);
+        const uint32_t t = xor3(ca, cb, cc), f = maj3(ca, cb, cc);
+        // ones: sc, x7; twos: t; fours: f
+        return (__popc(sc) + __popc(x[7])) + (2u * __popc(t) + 4u * __popc(f));
     } else {
+        uint32_t d = 0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
             uint32_t ad = __vabsdiffu4(a[w], b[w]);
             d = __dp4a(ad, ad, d);  // sum of squared byte differences, exact in u32
         }
+        return d;
     }
-    return d;
 }
 
 template <int NORM, bool SECOND>
-__global__ void __launch_bounds__(U8_THREADS)
+__global__ void __launch_bounds__(U8_THREADS, 3)
 match_u8_kernel(const uint8_t *__restrict__ ref, const uint8_t *__restrict__ cur, int n_stride, int m_stride,
                 const int32_t *__restrict__ n_ref, const int32_t *__restrict__ n_cur, int n_split,
                 vo_row_partial *__restrict__ part, unsigned long long *__restrict__ colkey) {
     __shared__ uint4 sdesc[U8_CHUNK * 2];
-    __shared__ uint32_t scol[U8_CHUNK];
+    __shared__ uint32_t swcol[U8_THREADS / 32][U8_CHUNK];  // per-warp column minima of the staged chunk
+    // Hamming distances are <= 256, so (dist << 20 | column) orders rows by distance, then by lowest column:
+    // the row top-2 is two integer minima per distance instead of compare/select chains.
+    constexpr bool PACKED = (NORM == VO_NORM_HAMMING);
 
     const int b = blockIdx.z, split = blockIdx.y;
     const int N = n_ref ? min(n_ref[b], n_stride) : n_stride;
@@ -52,60 +83,68 @@ match_u8_kernel(const uint8_t *__restrict__ ref, const uint8_t *__restrict__ cur
     const int cols_per_split = (M + n_split - 1) / n_split;
     const int c_begin = split * cols_per_split;
     const int c_end = min(M, c_begin + cols_per_split);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     uint32_t a[U8_ROWS_PT][8];
-    bool valid[U8_ROWS_PT];
-    uint32_t s1[U8_ROWS_PT], s2[U8_ROWS_PT];
+    uint32_t rowid[U8_ROWS_PT];                     // row-in-CTA, or that + INVALID for rows past N
+    uint32_t s1[U8_ROWS_PT], s2[U8_ROWS_PT];        // PACKED: keys; else distances
     int32_t i1[U8_ROWS_PT], i2[U8_ROWS_PT];
 #pragma unroll
     for (int r = 0; r < U8_ROWS_PT; ++r) {
         const int row = row_base + r * U8_THREADS + tid;
-        valid[r] = row < N;
-        const uint4 *p = reinterpret_cast<const uint4 *>(ref + ((size_t)b * n_stride + (valid[r] ? row : 0)) * 32);
-        uint4 q0 = valid[r] ? p[0] : make_uint4(0, 0, 0, 0), q1 = valid[r] ? p[1] : make_uint4(0, 0, 0, 0);
+        const bool valid = row < N;
+        const uint4 *p = reinterpret_cast<const uint4 *>(ref + ((size_t)b * n_stride + (valid ? row : 0)) * 32);
+        uint4 q0 = valid ? p[0] : make_uint4(0, 0, 0, 0), q1 = valid ? p[1] : make_uint4(0, 0, 0, 0);
         a[r][0] = q0.x; a[r][1] = q0.y; a[r][2] = q0.z; a[r][3] = q0.w;
         a[r][4] = q1.x; a[r][5] = q1.y; a[r][6] = q1.z; a[r][7] = q1.w;
+        rowid[r] = (uint32_t)(r * U8_THREADS + tid) + (valid ? 0u : U8_INVALID_ROW);
         s1[r] = s2[r] = 0xffffffffu;
         i1[r] = i2[r] = -1;
     }
 
     const uint4 *cur4 = reinterpret_cast<const uint4 *>(cur + (size_t)b * m_stride * 32);
-    for (int c0 = c_begin; c0 < c_end; c0 += U8_CHUNK) {
-        const int cnt = min(U8_CHUNK, c_end - c0);
-        __syncthreads();  // previous chunk fully consumed
-        for (int t = tid; t < cnt * 2; t += U8_THREADS) sdesc[t] = cur4[(size_t)c0 * 2 + t];
-        for (int t = tid; t < cnt; t += U8_THREADS) scol[t] = 0xffffffffu;
-        __syncthreads();
+    if (row_base < N) {
+        for (int c0 = c_begin; c0 < c_end; c0 += U8_CHUNK) {
+            const int cnt = min(U8_CHUNK, c_end - c0);
+            __syncthreads();  // previous chunk fully consumed
+            for (int t = tid; t < cnt * 2; t += U8_THREADS) sdesc[t] = cur4[(size_t)c0 * 2 + t];
+            __syncthreads();
 
 #pragma unroll 2
-        for (int j = 0; j < cnt; ++j) {
-            const uint4 b0 = sdesc[2 * j], b1 = sdesc[2 * j + 1];
-            uint32_t ckey = 0xffffffffu;
+            for (int j = 0; j < cnt; ++j) {
+                const uint4 b0 = sdesc[2 * j], b1 = sdesc[2 * j + 1];
+                const uint32_t col = (uint32_t)(c0 + j);
+                uint32_t ckey = 0xffffffffu;
 #pragma unroll
-            for (int r = 0; r < U8_ROWS_PT; ++r) {
-                const uint32_t d = dist256<NORM>(a[r], b0, b1);
-                const int col = c0 + j;
-                if (valid[r]) {
-                    if (d < s1[r]) {
-                        if (SECOND) { s2[r] = s1[r]; i2[r] = i1[r]; }
-                        s1[r] = d; i1[r] = col;
-                    } else if (SECOND && d < s2[r]) {
-                        s2[r] = d; i2[r] = col;
+                for (int r = 0; r < U8_ROWS_PT; ++r) {
+                    const uint32_t d = dist256<NORM>(a[r], b0, b1);
+                    if (PACKED) {
+                        const uint32_t k = (d << U8_COL_BITS) + col;
+                        if (SECOND) s2[r] = min(s2[r], max(s1[r], k));
+                        s1[r] = min(s1[r], k);
+                    } else {
+                        if (d < s1[r]) {
+                            if (SECOND) { s2[r] = s1[r]; i2[r] = i1[r]; }
+                            s1[r] = d; i1[r] = (int32_t)col;
+                        } else if (SECOND && d < s2[r]) {
+                            s2[r] = d; i2[r] = (int32_t)col;
+                        }
                     }
-                    ckey = min(ckey, (d << 9) | (uint32_t)(r * U8_THREADS + tid));
+                    ckey = min(ckey, (d << U8_ROW_BITS) + rowid[r]);
                 }
+                const uint32_t wmin = __reduce_min_sync(0xffffffffu, ckey);
+                if (lane == 0) swcol[warp][j] = wmin;  // warp-private slot: no atomics in the inner loop
             }
-            const uint32_t wmin = __reduce_min_sync(0xffffffffu, ckey);
-            if (lane == 0 && wmin != 0xffffffffu) atomicMin(&scol[j], wmin);
-        }
-        __syncthreads();
-        for (int t = tid; t < cnt; t += U8_THREADS) {
-            const uint32_t k = scol[t];
-            if (k != 0xffffffffu) {
-                const unsigned long long g =
-                    ((unsigned long long)(k >> 9) << 32) | (unsigned long long)(uint32_t)(row_base + (int)(k & 511u));
-                atomicMin(&colkey[(size_t)b * m_stride + c0 + t], g);
+            __syncthreads();
+            for (int t = tid; t < cnt; t += U8_THREADS) {
+                uint32_t k = swcol[0][t];
+#pragma unroll
+                for (int w = 1; w < U8_THREADS / 32; ++w) k = min(k, swcol[w][t]);
+                if (k < U8_INVALID_ROW) {
+                    const unsigned long long g = ((unsigned long long)(k >> U8_ROW_BITS) << 32) |
+                                                 (unsigned long long)(uint32_t)(row_base + (int)(k & (U8_ROWS_CTA - 1)));
+                    atomicMin(&colkey[(size_t)b * m_stride + c0 + t], g);
+                }
             }
         }
     }
@@ -114,7 +153,17 @@ match_u8_kernel(const uint8_t *__restrict__ ref, const uint8_t *__restrict__ cur
         const int row = row_base + r * U8_THREADS + tid;
         if (row < n_stride) {
             vo_row_partial p;
-            p.s1 = s1[r]; p.s2 = s2[r]; p.i1 = i1[r]; p.i2 = i2[r];
+            if (PACKED) {
+                const bool v1 = row < N && s1[r] != 0xffffffffu, v2 = row < N && SECOND && s2[r] != 0xffffffffu;
+                p.s1 = v1 ? (s1[r] >> U8_COL_BITS) : 0xffffffffu;
+                p.i1 = v1 ? (int32_t)(s1[r] & ((1u << U8_COL_BITS) - 1)) : -1;
+                p.s2 = v2 ? (s2[r] >> U8_COL_BITS) : 0xffffffffu;
+                p.i2 = v2 ? (int32_t)(s2[r] & ((1u << U8_COL_BITS) - 1)) : -1;
+            } else {
+                const bool v = row < N;
+                p.s1 = v ? s1[r] : 0xffffffffu; p.s2 = v ? s2[r] : 0xffffffffu;
+                p.i1 = v ? i1[r] : -1; p.i2 = v ? i2[r] : -1;
+            }
             part[((size_t)b * n_split + split) * n_stride + row] = p;
         }
     }
@@ -159,16 +208,25 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
         VO_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t) * B, st));
         return VO_OK;
     }
+    VO_REQUIRE(norm != VO_NORM_HAMMING || m_stride < (1 << U8_COL_BITS),
+               "vo_match_u8: Hamming matcher supports at most %d descriptors per frame", (1 << U8_COL_BITS) - 1);
     const int row_blocks = ceil_div(n_stride, U8_ROWS_CTA);
-    // enough CTAs for >= 2 waves when the batch alone cannot fill the GPU; >= 256 columns per split
+    // Column splits: every CTA costs the same, so pick the smallest split count whose CTA total fills the
+    // resident slots (3 CTAs per SM) to >= 94 % in its last wave, with >= 256 columns per split.
     int n_split = 1;
     {
-        const int want = 2 * ctx->sm_count;
-        const int have = B * row_blocks;
-        if (have < want) n_split = ceil_div(want, have);
-        const int max_split = m_stride / 256 > 0 ? m_stride / 256 : 1;
-        if (n_split > max_split) n_split = max_split;
-        if (n_split > 64) n_split = 64;
+        const int slots = 3 * ctx->sm_count;
+        const long long have = (long long)B * row_blocks;
+        int max_split = m_stride / 256 > 0 ? m_stride / 256 : 1;
+        if (max_split > 64) max_split = 64;
+        double best_eff = -1.0;
+        for (int s = 1; s <= max_split; ++s) {
+            const long long total = have * s;
+            const long long waves = (total + slots - 1) / slots;
+            const double eff = (double)total / (double)(waves * slots);
+            if (eff > best_eff + 1e-9) { best_eff = eff; n_split = s; }
+            if (eff >= 0.94) { n_split = s; break; }
+        }
     }
     vo_row_partial *part;
     unsigned long long *colkey;

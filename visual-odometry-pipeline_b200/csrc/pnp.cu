@@ -66,63 +66,72 @@ p3p_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const in
 }
 
 // ---------------------------------------------------------------- scoring
+// One warp owns SC_HPW hypotheses at a time (their scaled poses live in registers); its lanes stride over the
+// correspondences the CTA staged in shared memory, so every staged point (one LDS.128 + one LDS.32) feeds
+// SC_HPW independent inlier tests: 17 fp32 instructions each, no division, no branch (pnp_math.cuh).
 constexpr int SC_WARPS = 8;
-constexpr int SC_TILE = 2048;  // correspondences staged per pass: 5 x 2048 x 4 B = 40 KB
-
-__device__ __forceinline__ void stage_points(const float *__restrict__ xyz, const float *__restrict__ uv, int p0,
-                                             int cnt, float *sX, float *sY, float *sZ, float *sU, float *sV) {
-    // coalesced AoS reads, SoA in shared memory (conflict-free when lane l reads element i + l)
-    for (int t = threadIdx.x; t < cnt * 3; t += blockDim.x) {
-        const float v = xyz[(size_t)p0 * 3 + t];
-        const int i = t / 3, c = t - 3 * i;
-        (c == 0 ? sX : (c == 1 ? sY : sZ))[i] = v;
-    }
-    for (int t = threadIdx.x; t < cnt * 2; t += blockDim.x) {
-        const float v = uv[(size_t)p0 * 2 + t];
-        ((t & 1) ? sV : sU)[t >> 1] = v;
-    }
-}
+constexpr int SC_HPW = 4;      // hypotheses per warp
+constexpr int SC_TILE = 2048;  // correspondences staged per pass: 2048 x 20 B = 40 KB
 
 __global__ void __launch_bounds__(SC_WARPS * 32)
 score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ n_pts, int cap,
-             const float *__restrict__ poses, int H, IntrF k, float thr2, unsigned long long *__restrict__ bestkey,
+             const float *__restrict__ poses, int H, IntrF k, float thr, unsigned long long *__restrict__ bestkey,
              int32_t *__restrict__ hyp_counts) {
-    __shared__ float sX[SC_TILE], sY[SC_TILE], sZ[SC_TILE], sU[SC_TILE], sV[SC_TILE];
+    __shared__ float4 sP[SC_TILE];  // X, Y, Z, u - cx
+    __shared__ float sV[SC_TILE];   // v - cy
     const int b = blockIdx.y;
     const int n = min(n_pts[b], cap);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.x * SC_WARPS + warp;
-    PoseF p;
-    if (h < H) {
+    const int h0 = (blockIdx.x * SC_WARPS + warp) * SC_HPW;
+    ScoreModel m[SC_HPW];
+#pragma unroll
+    for (int q = 0; q < SC_HPW; ++q) {
+        PoseF p;
+        const int h = min(h0 + q, H - 1);
         const float *src = poses + ((size_t)b * H + h) * 12;
 #pragma unroll
         for (int j = 0; j < 9; ++j) p.r[j] = __ldg(src + j);
 #pragma unroll
         for (int j = 0; j < 3; ++j) p.t[j] = __ldg(src + 9 + j);
+        m[q] = score_model(p, k);
     }
-    int count = 0;
+    int count[SC_HPW];
+#pragma unroll
+    for (int q = 0; q < SC_HPW; ++q) count[q] = 0;
     const float *pxyz = xyz + (size_t)b * cap * 3;
     const float *puv = uv + (size_t)b * cap * 2;
     for (int p0 = 0; p0 < n; p0 += SC_TILE) {
         const int cnt = min(SC_TILE, n - p0);
         __syncthreads();
-        stage_points(pxyz, puv, p0, cnt, sX, sY, sZ, sU, sV);
+        for (int i = threadIdx.x; i < cnt; i += SC_WARPS * 32) {
+            const float *q3 = pxyz + (size_t)(p0 + i) * 3;
+            const float2 q2 = *reinterpret_cast<const float2 *>(puv + (size_t)(p0 + i) * 2);
+            sP[i] = make_float4(q3[0], q3[1], q3[2], VO_FSUBF(q2.x, k.cx));
+            sV[i] = VO_FSUBF(q2.y, k.cy);
+        }
         __syncthreads();
-        if (h < H) {
+        if (h0 < H) {
+#pragma unroll 2
             for (int i = lane; i < cnt; i += 32) {
-                const float e = reproj_err2(p, k, sX[i], sY[i], sZ[i], sU[i], sV[i]);
-                count += (e <= thr2) ? 1 : 0;
+                const float4 P = sP[i];
+                const float vc = sV[i];
+#pragma unroll
+                for (int q = 0; q < SC_HPW; ++q) count[q] += is_inlier(m[q], thr, P.x, P.y, P.z, P.w, vc) ? 1 : 0;
             }
         }
     }
-    if (h < H) {
-        count = __reduce_add_sync(0xffffffffu, count);
-        if (lane == 0) {
-            if (hyp_counts) hyp_counts[(size_t)b * H + h] = count;
-            // larger count wins; ties -> lowest hypothesis index
-            const unsigned long long key =
-                ((unsigned long long)(uint32_t)count << 32) | (unsigned long long)(0xffffffffu - (uint32_t)h);
-            atomicMax(&bestkey[b], key);
+#pragma unroll
+    for (int q = 0; q < SC_HPW; ++q) {
+        const int h = h0 + q;
+        if (h < H) {
+            const int c = __reduce_add_sync(0xffffffffu, count[q]);
+            if (lane == 0) {
+                if (hyp_counts) hyp_counts[(size_t)b * H + h] = c;
+                // larger count wins; ties -> lowest hypothesis index
+                const unsigned long long key =
+                    ((unsigned long long)(uint32_t)c << 32) | (unsigned long long)(0xffffffffu - (uint32_t)h);
+                atomicMax(&bestkey[b], key);
+            }
         }
     }
 }
@@ -213,7 +222,7 @@ __device__ bool solve6(const double Hu[21], const double g[6], double x[6]) {
 
 __global__ void __launch_bounds__(RF_THREADS)
 refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ n_pts, int cap,
-             const float *__restrict__ poses, int H, IntrF kf, IntrD kd, float thr2, int min_inliers, int iters,
+             const float *__restrict__ poses, int H, IntrF kf, IntrD kd, float thr, int min_inliers, int iters,
              const unsigned long long *__restrict__ bestkey, double *__restrict__ rt_out,
              double *__restrict__ rvec_tvec, double *__restrict__ T_rel, int32_t *__restrict__ n_inl_out,
              int32_t *__restrict__ best_h_out, uint8_t *__restrict__ mask_out, int32_t *__restrict__ status,
@@ -258,6 +267,7 @@ refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
         for (int j = 0; j < 9; ++j) p.r[j] = src[j];
         for (int j = 0; j < 3; ++j) p.t[j] = src[9 + j];
     }
+    const ScoreModel sm = score_model(p, kf);
     if (threadIdx.x == 0) {
         // f64 start: the winning fp32 pose, rotation re-orthonormalised by two Newton polar steps
         double R[9];
@@ -285,8 +295,8 @@ refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
         for (int i = threadIdx.x; i < cap; i += RF_THREADS) {
             uint8_t m = 0;
             if (i < n) {
-                const float e = reproj_err2(p, kf, pxyz[i * 3], pxyz[i * 3 + 1], pxyz[i * 3 + 2], puv[i * 2], puv[i * 2 + 1]);
-                m = (e <= thr2) ? 1 : 0;
+                m = is_inlier(sm, thr, pxyz[i * 3], pxyz[i * 3 + 1], pxyz[i * 3 + 2], VO_FSUBF(puv[i * 2], kf.cx),
+                              VO_FSUBF(puv[i * 2 + 1], kf.cy)) ? 1 : 0;
             }
             mask_out[(size_t)b * cap + i] = m;
         }
@@ -303,7 +313,7 @@ refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
         for (int i = threadIdx.x; i < n; i += RF_THREADS) {
             const float Xf = pxyz[i * 3], Yf = pxyz[i * 3 + 1], Zf = pxyz[i * 3 + 2];
             const float uf = puv[i * 2], vf = puv[i * 2 + 1];
-            if (!(reproj_err2(p, kf, Xf, Yf, Zf, uf, vf) <= thr2)) continue;
+            if (!is_inlier(sm, thr, Xf, Yf, Zf, VO_FSUBF(uf, kf.cx), VO_FSUBF(vf, kf.cy))) continue;
             const double X = Xf, Y = Yf, Z = Zf;
             const double xr = R[0] * X + R[1] * Y + R[2] * Z;
             const double yr = R[3] * X + R[4] * Y + R[5] * Z;
@@ -430,17 +440,16 @@ int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_
 
     IntrD kd{K_h[0], K_h[4], K_h[2], K_h[5]};
     IntrF kf{(float)K_h[0], (float)K_h[4], (float)K_h[2], (float)K_h[5]};
-    const float thr2 = thr_px * thr_px;
     const long long total = (long long)B * H;
     VO_PROF(ctx, st, VO_STAGE_P3P);
     p3p_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(xyz, uv, n_pts, B, cap, hyp, H, kd, poses);
     VO_LAUNCH_CHECK(ctx);
-    dim3 grid(ceil_div(H, SC_WARPS), B);
+    dim3 grid(ceil_div(H, SC_WARPS * SC_HPW), B);
     VO_PROF(ctx, st, VO_STAGE_SCORE);
-    score_kernel<<<grid, SC_WARPS * 32, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, thr2, bestkey, hyp_counts);
+    score_kernel<<<grid, SC_WARPS * 32, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, thr_px, bestkey, hyp_counts);
     VO_LAUNCH_CHECK(ctx);
     VO_PROF(ctx, st, VO_STAGE_REFIT);
-    refit_kernel<<<B, RF_THREADS, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, kd, thr2, min_inliers, refine_iters,
+    refit_kernel<<<B, RF_THREADS, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, kd, thr_px, min_inliers, refine_iters,
                                            bestkey, rt, rvec_tvec, T_rel, n_inl, best_h, inlier_mask, status,
                                            accumulate_status);
     VO_LAUNCH_CHECK(ctx);

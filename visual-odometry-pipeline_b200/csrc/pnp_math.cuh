@@ -5,8 +5,8 @@
 //  * P3P minimal solver (Grunert's distance formulation, quartic by Ferrari with a bracketed
 //    Newton resolvent root, rigid alignment of the two triangles, 4th point disambiguation —
 //    the same contract as OpenCV's SOLVEPNP_P3P inside solvePnPRansac: 3 points + 1 to choose)
-//  * fp32 reprojection error with OpenCV's inlier rule err^2 <= thr^2 (ptsetreg.cpp semantics,
-//    SURVEY 3.4.1)
+//  * fp32 inlier rule of OpenCV's RANSAC, err^2 <= thr^2 (ptsetreg.cpp semantics),
+//    in a division-free form
 //
 // The f64 solver uses only + - * / sqrt, and this translation unit is compiled with
 // -fmad=false, so the CPU oracle (gcc -ffp-contract=off) reproduces every bit of it.  The fp32
@@ -25,12 +25,10 @@
 #define VO_FMAF(a, b, c) __fmaf_rn((a), (b), (c))
 #define VO_FMULF(a, b) __fmul_rn((a), (b))
 #define VO_FSUBF(a, b) __fsub_rn((a), (b))
-#define VO_FRCPF(a) __fdiv_rn(1.0f, (a))
 #else
 #define VO_FMAF(a, b, c) fmaf((a), (b), (c))
 #define VO_FMULF(a, b) ((a) * (b))
 #define VO_FSUBF(a, b) ((a) - (b))
-#define VO_FRCPF(a) (1.0f / (a))
 #endif
 
 namespace vo {
@@ -70,17 +68,42 @@ struct IntrF {
     float fx, fy, cx, cy;
 };
 
-// squared reprojection error of one correspondence, OpenCV projectPoints order:
-// Xc = R X + t ; x = Xc.x / Xc.z ; u^ = fx x + cx ; err = (u - u^)^2 + (v - v^)^2
-VO_HD float reproj_err2(const PoseF &p, const IntrF &k, float X, float Y, float Z, float u, float v) {
-    const float xc = VO_FMAF(p.r[0], X, VO_FMAF(p.r[1], Y, VO_FMAF(p.r[2], Z, p.t[0])));
-    const float yc = VO_FMAF(p.r[3], X, VO_FMAF(p.r[4], Y, VO_FMAF(p.r[5], Z, p.t[1])));
-    const float zc = VO_FMAF(p.r[6], X, VO_FMAF(p.r[7], Y, VO_FMAF(p.r[8], Z, p.t[2])));
-    const float iz = (zc != 0.0f) ? VO_FRCPF(zc) : 1.0f;
-    const float uh = VO_FMAF(k.fx, VO_FMULF(xc, iz), k.cx);
-    const float vh = VO_FMAF(k.fy, VO_FMULF(yc, iz), k.cy);
-    const float du = VO_FSUBF(u, uh), dv = VO_FSUBF(v, vh);
-    return VO_FMAF(du, du, VO_FMULF(dv, dv));
+// Inlier rule of cv2.solvePnPRansac (ptsetreg.cpp / PnPRansacCallback::computeError):
+//   Xc = R X + t ; u^ = fx Xc.x / Xc.z + cx ; inlier iff (u - u^)^2 + (v - v^)^2 <= thr^2.
+// Evaluated division-free, multiplied through by Xc.z^2 (exact in real arithmetic, sign-independent):
+//   a = z (u - cx) - fx x,  b = z (v - cy) - fy y,  inlier iff a^2 + b^2 <= (thr z)^2
+// with fx, fy folded into the first two pose rows once per hypothesis (ScoreModel) and the principal
+// point removed once per correspondence (uc = u - cx, vc = v - cy).  17 fp32 instructions per
+// (hypothesis, point), every one an explicitly rounded mul / fma, so host and device agree bit for bit.
+// A point exactly on the camera plane (Xc.z == 0, which projectPoints maps as if z were 1) and any
+// NaN pose are never inliers.
+struct ScoreModel {
+    float m[12];  // rows 0,1 of [R|t] scaled by fx, fy; row 2 as is: m[0..2],m[9] | m[3..5],m[10] | m[6..8],m[11]
+};
+
+VO_HD ScoreModel score_model(const PoseF &p, const IntrF &k) {
+    ScoreModel s;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        s.m[j] = VO_FMULF(k.fx, p.r[j]);
+        s.m[3 + j] = VO_FMULF(k.fy, p.r[3 + j]);
+        s.m[6 + j] = p.r[6 + j];
+    }
+    s.m[9] = VO_FMULF(k.fx, p.t[0]);
+    s.m[10] = VO_FMULF(k.fy, p.t[1]);
+    s.m[11] = p.t[2];
+    return s;
+}
+
+// uc = u - cx, vc = v - cy (each rounded once); thr = reprojection threshold in pixels
+VO_HD bool is_inlier(const ScoreModel &s, float thr, float X, float Y, float Z, float uc, float vc) {
+    const float x = VO_FMAF(s.m[0], X, VO_FMAF(s.m[1], Y, VO_FMAF(s.m[2], Z, s.m[9])));
+    const float y = VO_FMAF(s.m[3], X, VO_FMAF(s.m[4], Y, VO_FMAF(s.m[5], Z, s.m[10])));
+    const float z = VO_FMAF(s.m[6], X, VO_FMAF(s.m[7], Y, VO_FMAF(s.m[8], Z, s.m[11])));
+    const float a = VO_FMAF(z, uc, -x);
+    const float b = VO_FMAF(z, vc, -y);
+    const float w = VO_FMULF(thr, z);
+    return VO_FMAF(a, a, VO_FMULF(b, b)) <= VO_FMULF(w, w);
 }
 
 // ---------------------------------------------------------------- quartic (f64, basic ops only)
