@@ -225,6 +225,52 @@ typedef struct vo_pipeline_args {
 
 VO_API int vo_pipeline(vo_ctx *ctx, const vo_pipeline_args *args, void *stream);
 
+/*
+ * Device-resident keyframe loop.  Replaces the host control flow of VisualOdometry.process_frame
+ * (VisualOdometry_Stereo.py:232-297) for a stream of frames whose features already exist: keyframe
+ * selection (:251, :285-296), the 1.5 m-per-frame plausibility gate (:270-274), the bad-PnP counter
+ * (:273, :279, :282, :295) and pose chaining T_cur = T_key @ T_rel (:283, :290) run in a one-thread
+ * policy kernel behind vo_pipeline, and a conditional device copy promotes the current frame to
+ * keyframe.  No host round trip per frame: vo_seq_push only enqueues work on `stream`.
+ *
+ *   vo_seq_push: desc (uint8 [n_kp][32] or float [n_kp][128]), kp float [n_kp][kp_stride] (x, y first),
+ *   depth float [H][W]; each may be a device pointer or a (pinned) host pointer — they are copied into
+ *   the loop's own frame slot with cudaMemcpyAsync on `stream`.  frame_id is the reference's frame_no
+ *   (the gate scales with frame_id - keyframe_id).  The first push only installs the keyframe.
+ *   vo_seq_read: synchronises `stream` and copies out, for frames [first, first+count):
+ *     poses_h  double [count][16]  global pose of each frame (frame 0 = identity), what the
+ *                                  reference stores in global_poses (:293)
+ *     info_h   int32  [count][6]   status bits | n_matches | n_corr ("common_pts") | n_inl |
+ *                                  keyframe id the frame was matched against | 1 if it became the keyframe
+ */
+typedef struct vo_seq vo_seq;
+typedef struct vo_seq_config {
+    int desc_is_f32;            /* 0: 256-bit byte descriptors, 1: 128-d float descriptors */
+    int n_cap;                  /* capacity: keypoints per frame */
+    int kp_stride;              /* floats per keypoint row (2: SIFT/ORB, 3: R2D2) */
+    int H, W;
+    double K[9];
+    int norm_or_metric, mode, precision;
+    double match_param;
+    float min_flow_px, z_min, z_max;
+    int n_hyp;
+    uint64_t seed;
+    float thr_px;
+    int min_inliers, refine_iters;
+    double max_step_m;          /* 1.5  (:271) */
+    int kf_min_common;          /* 200  (:286) */
+    int kf_min_inliers;         /* 100  (:286) */
+    double kf_max_dist;         /* 1.5  (:286) */
+    int bad_pnp_limit;          /* 3    (:295) */
+    int max_frames;             /* capacity of the pose / info history */
+} vo_seq_config;
+VO_API int vo_seq_create(vo_ctx *ctx, const vo_seq_config *cfg, vo_seq **out);
+VO_API void vo_seq_destroy(vo_seq *seq);
+VO_API int vo_seq_push(vo_seq *seq, const void *desc, const float *kp, int n_kp, const float *depth, int frame_id,
+                void *stream);
+VO_API int vo_seq_frames(const vo_seq *seq);
+VO_API int vo_seq_read(vo_seq *seq, int first, int count, double *poses_h, int32_t *info_h, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

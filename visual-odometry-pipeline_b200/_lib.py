@@ -53,6 +53,24 @@ class PipelineArgs(ctypes.Structure):
     ]
 
 
+class SeqConfig(ctypes.Structure):
+    _fields_ = [
+        ("desc_is_f32", c_int), ("n_cap", c_int), ("kp_stride", c_int), ("H", c_int), ("W", c_int),
+        ("K", c_double * 9),
+        ("norm_or_metric", c_int), ("mode", c_int), ("precision", c_int),
+        ("match_param", c_double),
+        ("min_flow_px", c_float), ("z_min", c_float), ("z_max", c_float),
+        ("n_hyp", c_int),
+        ("seed", c_u64),
+        ("thr_px", c_float),
+        ("min_inliers", c_int), ("refine_iters", c_int),
+        ("max_step_m", c_double),
+        ("kf_min_common", c_int), ("kf_min_inliers", c_int),
+        ("kf_max_dist", c_double),
+        ("bad_pnp_limit", c_int), ("max_frames", c_int),
+    ]
+
+
 PROTOTYPES = {
     "vo_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     "vo_destroy": (None, [c_void_p]),
@@ -73,6 +91,11 @@ PROTOTYPES = {
                               c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p]),
     "vo_pipeline": (c_int, [c_void_p, ctypes.POINTER(PipelineArgs), c_void_p]),
+    "vo_seq_create": (c_int, [c_void_p, ctypes.POINTER(SeqConfig), ctypes.POINTER(c_void_p)]),
+    "vo_seq_destroy": (None, [c_void_p]),
+    "vo_seq_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "vo_seq_frames": (c_int, [c_void_p]),
+    "vo_seq_read": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vo_profile_enable": (c_int, [c_void_p, c_int]),
     "vo_profile_collect": (c_int, [c_void_p, c_void_p, c_void_p]),
 }

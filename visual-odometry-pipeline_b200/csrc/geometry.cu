@@ -30,30 +30,59 @@ __device__ __forceinline__ void backproject(const Intr k, int u, int v, float z,
     Y = __fmul_rn(__fmul_rn(__fsub_rn((float)v, k.cy), k.inv_fy), z);
 }
 
-// Dense: one thread owns 4 consecutive pixels of the flattened [B*H*W] image: one 128-bit
-// load, three 128-bit stores (48 contiguous bytes).  HBM-bound: 16 B per pixel.
-__global__ void __launch_bounds__(256)
+// Dense: one thread owns 4 consecutive pixels of the flattened [B*H*W] image (one 128-bit streaming load).  Its 12
+// outputs go through a warp-private shared-memory tile so that every 128-bit streaming store of a warp covers 512
+// contiguous bytes (a direct store would put each lane's 16 B at a 48 B stride: half-filled sectors on every request).
+// HBM-bound: 16 B per pixel.
+constexpr int BD_THREADS = 256;
+
+__global__ void __launch_bounds__(BD_THREADS)
 backproject_dense_kernel(const float *__restrict__ depth, float *__restrict__ xyz, long long n_px, int H, int W,
                          Intr k) {
+    __shared__ float4 tile[BD_THREADS / 32][96];  // per warp: 128 pixels x 3 floats
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long n_vec = n_px >> 2;
+    const long long n_vec_warp = (n_vec + 31) & ~31ll;  // whole warps iterate together (shared-memory exchange)
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-        const float4 z4 = __ldcs(reinterpret_cast<const float4 *>(depth) + i);
-        const float z[4] = {z4.x, z4.y, z4.z, z4.w};
-        float o[12];
-        const long long p0 = i << 2;
-        int u = (int)(p0 % W);
-        int v = (int)((p0 / W) % H);
+    constexpr int UNROLL = 4;  // loads of UNROLL grid-strided vectors are issued before the first is consumed
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec_warp; i0 += UNROLL * stride) {
+        float4 zin[UNROLL];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            backproject(k, u, v, z[q], o[3 * q], o[3 * q + 1]);
-            o[3 * q + 2] = z[q];
-            if (++u == W) { u = 0; if (++v == H) v = 0; }
+        for (int r = 0; r < UNROLL; ++r) {
+            const long long i = i0 + r * stride;
+            zin[r] = (i < n_vec) ? __ldcs(reinterpret_cast<const float4 *>(depth) + i) : make_float4(0, 0, 0, 0);
         }
-        float4 *dst = reinterpret_cast<float4 *>(xyz) + i * 3;
-        __stcs(dst + 0, make_float4(o[0], o[1], o[2], o[3]));
-        __stcs(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
-        __stcs(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
+#pragma unroll
+        for (int r = 0; r < UNROLL; ++r) {
+            const long long i = i0 + r * stride;
+            const long long w0 = i - lane;  // first vector of this warp's 32
+            if (w0 >= n_vec) break;         // warp-uniform
+            if (i < n_vec) {
+                const float z[4] = {zin[r].x, zin[r].y, zin[r].z, zin[r].w};
+                float o[12];
+                const long long p0 = i << 2;
+                int u = (int)(p0 % W);
+                int v = (int)((p0 / W) % H);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    backproject(k, u, v, z[q], o[3 * q], o[3 * q + 1]);
+                    o[3 * q + 2] = z[q];
+                    if (++u == W) { u = 0; if (++v == H) v = 0; }
+                }
+                tile[warp][3 * lane + 0] = make_float4(o[0], o[1], o[2], o[3]);
+                tile[warp][3 * lane + 1] = make_float4(o[4], o[5], o[6], o[7]);
+                tile[warp][3 * lane + 2] = make_float4(o[8], o[9], o[10], o[11]);
+            }
+            __syncwarp();
+            const long long valid = min(32ll, n_vec - w0) * 3;  // float4 outputs this warp produced
+            float4 *dst = reinterpret_cast<float4 *>(xyz) + w0 * 3;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int j = q * 32 + lane;
+                if (j < valid) __stcs(dst + j, tile[warp][j]);
+            }
+            __syncwarp();
+        }
     }
     // tail (n_px not a multiple of 4)
     if (blockIdx.x == 0 && threadIdx.x < (n_px & 3)) {
@@ -150,9 +179,9 @@ extern "C" int vo_backproject_dense(vo_ctx *ctx, const float *depth, int B, int 
     if (B == 0) return VO_OK;
     const long long n_px = (long long)B * H * W;
     const long long n_vec = n_px >> 2;
-    // >= 4 CTAs of 256 threads per SM in flight, grid-stride beyond that
+    // 4 resident CTAs of 256 threads per SM (register-limited), 4 x 512 B loads in flight per warp, grid-stride beyond
     long long want = (n_vec + 255) / 256;
-    const long long cap = (long long)ctx->sm_count * 16;
+    const long long cap = (long long)ctx->sm_count * 4;
     int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     VO_PROF(ctx, (cudaStream_t)stream, VO_STAGE_DENSE);
     backproject_dense_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(depth, xyz, n_px, H, W, make_intr(K_h));
