@@ -273,7 +273,8 @@ def run_ours(args, wl):
     # ---- e2e: host buffers in, poses out, H2D/D2H inside the timed region
     host_rep = {k: np.concatenate([host[k]] * reps, 0)[:P] for k in ("ref_desc", "cur_desc", "ref_kp", "cur_kp", "depth")}
     host_rep["K"] = host["K"]
-    runner = sequence.HostPairRunner(host_rep, cfg, chunk=min(args.e2e_chunk or max(1, chunk // 2), P), device=dev)
+    runner = sequence.HostPairRunner(host_rep, cfg, chunk=min(args.e2e_chunk or max(1, chunk // 2), P), device=dev,
+                                     depth_mode=args.e2e_depth)
     del host_rep
 
     def e2e_step():
@@ -415,7 +416,8 @@ def run_ours(args, wl):
                    f"{batch.nbytes() / 1e6:.0f} MB per GPU per step)", "parallelism": f"pairs sharded over {world} GPU(s), "
                    "1 NCCL all-gather of 4x4 poses per step" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": runner.h2d_bytes,
-                "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
+                "depth": args.e2e_depth},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -445,6 +447,9 @@ def main():
                     "(default: 40; 8 / 4 for c4 / c5)")
     ap.add_argument("--chunk", type=int, default=0, help="pairs per vo_pipeline call (default: workload's)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="pairs per H2D/compute chunk of the e2e run (default: chunk/2)")
+    ap.add_argument("--e2e-depth", default="sampled", choices=["sampled", "dense"],
+                    help="e2e leg: copy whole depth maps (dense) or read depth at the reference keypoints zero-copy from "
+                         "pinned host memory (sampled, default)")
     ap.add_argument("--precision", type=int, default=None)
     ap.add_argument("--cpu-pairs", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

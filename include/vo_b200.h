@@ -142,6 +142,15 @@ VO_API int vo_gather_backproject(vo_ctx *ctx, const int32_t *pairs, const int32_
                           int32_t *status, void *stream);
 
 /*
+ * Depth at the truncated pixel of every keypoint, depth[int(y), int(x)] (VisualOdometry_Stereo.py:97), written
+ * as depth_kp float [B][n_stride] (rows past n_kp[b]: NaN; keypoints outside the image: a reserved NaN that makes
+ * the pair fail with VO_ST_KP_OUT_OF_IMAGE if such a keypoint is matched).  `depth` must be device-accessible: a
+ * pinned host image works (zero-copy), which moves 32 B per keypoint over PCIe instead of the whole map.
+ */
+VO_API int vo_sample_depth(vo_ctx *ctx, const float *kp, int B, int n_stride, int kp_stride, const int32_t *n_kp,
+                    const float *depth, int H, int W, float *depth_kp, void *stream);
+
+/*
  * Hypothesis table: int32 [B][H][4] of distinct indices in [0, n_pts[b]) drawn from a
  * counter-based generator keyed by (seed, pair0 + b, h, slot).  Rows of pairs with fewer
  * than 4 points are filled with -1.  The CPU oracle implements the same integer recipe.
@@ -221,6 +230,9 @@ typedef struct vo_pipeline_args {
     int32_t *n_corr;    /* [B] correspondences after gating ("common_pts") */
     int32_t *n_inl;     /* [B] */
     int32_t *status;    /* [B] */
+    /* optional: depth already sampled at every reference keypoint (vo_sample_depth), float [B][n_stride];
+     * when non-NULL it replaces the dense `depth` lookup */
+    const float *depth_kp;
 } vo_pipeline_args;
 
 VO_API int vo_pipeline(vo_ctx *ctx, const vo_pipeline_args *args, void *stream);

@@ -76,3 +76,58 @@ def test_gather_flags_out_of_image_keypoints():
     pairs = torch.tensor([[[0, 0], [1, 1]]], dtype=torch.int32, device="cuda")
     c = ops.gather_backproject(pairs, torch.tensor([2], dtype=torch.int32, device="cuda"), kp, kp + 5, depth, K)
     assert int(c.count.item()) == 1 and int(c.status.item()) == ops._lib.VO_ST_KP_OUT_OF_IMAGE
+
+
+def test_sampled_depth_equals_dense_lookup_device_and_pinned_host(orc):
+    import vo_b200
+    """vo_sample_depth + the depth_kp path of vo_pipeline give exactly what the dense-map path gives, whether the map
+    lives in HBM or stays in pinned host memory (zero-copy), including NaN / zero depth and the status of a keypoint
+    that truncates outside the image."""
+    import torch
+    from vo_b200 import ops, synthetic
+    B, N = 3, 1200
+    batch = synthetic.make_batch(700, B, n_kp=N, kind="orb")
+    g = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    ref_kp, cur_kp, depth = g(batch["ref_kp"]), g(batch["cur_kp"]), g(batch["depth"])
+    z_dev = ops.sample_depth(ref_kp, depth)
+    pinned = torch.from_numpy(np.ascontiguousarray(batch["depth"])).pin_memory()
+    z_host = ops.sample_depth(ref_kp, pinned)
+    torch.cuda.synchronize()
+    want = np.stack([batch["depth"][b][batch["ref_kp"][b, :, 1].astype(np.int32), batch["ref_kp"][b, :, 0].astype(np.int32)]
+                     for b in range(B)])
+    for z in (z_dev, z_host):
+        got = z.cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.array_equal(got[~np.isnan(want)], want[~np.isnan(want)])
+    kw = dict(norm_or_metric=ops.VO_NORM_HAMMING, mode=ops.VO_MODE_MUTUAL, n_hyp=256, pair0=700)
+    a = ops.pipeline(g(batch["ref_desc"]), g(batch["cur_desc"]), ref_kp, cur_kp, depth, batch["K"], **kw)
+    b = ops.pipeline(g(batch["ref_desc"]), g(batch["cur_desc"]), ref_kp, cur_kp, None, batch["K"], depth_kp=z_host,
+                     hw=depth.shape[1:], **kw)
+    for f in ("n_matches", "n_corr", "n_inl", "status"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+    assert torch.equal(a.T_rel, b.T_rel)
+    # a matched keypoint outside the image fails the pair on both paths
+    bad = batch["ref_kp"].copy()
+    bad[1, :, 0] += 5000.0
+    zb = ops.sample_depth(g(bad), pinned)
+    c = ops.pipeline(g(batch["ref_desc"]), g(batch["cur_desc"]), g(bad), cur_kp, None, batch["K"], depth_kp=zb,
+                     hw=depth.shape[1:], **kw)
+    d = ops.pipeline(g(batch["ref_desc"]), g(batch["cur_desc"]), g(bad), cur_kp, depth, batch["K"], **kw)
+    assert torch.equal(c.status, d.status) and int(c.status[1].item()) & vo_b200.VO_ST_KP_OUT_OF_IMAGE
+    assert int(c.status[0].item()) == 0
+
+
+def test_host_runner_sampled_equals_dense():
+    import torch
+    from vo_b200 import ops, sequence, synthetic
+    B = 12
+    batch = synthetic.make_batch(40, B, n_kp=800, kind="orb")
+    cfg = sequence.PipelineConfig(ops.VO_NORM_HAMMING, ops.VO_MODE_MUTUAL, 0.0, 0, n_hyp=256)
+    outs = []
+    for mode in ("dense", "sampled"):
+        r = sequence.HostPairRunner(batch, cfg, chunk=5, device="cuda", depth_mode=mode)
+        T, st, inl = r.run(pair0=40)
+        torch.cuda.synchronize()
+        outs.append((T.clone(), st.clone(), inl.clone(), r.h2d_bytes))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert outs[1][3] < outs[0][3] / 3

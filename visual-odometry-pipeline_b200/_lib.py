@@ -50,6 +50,7 @@ class PipelineArgs(ctypes.Structure):
         ("min_inliers", c_int), ("refine_iters", c_int),
         ("T_rel", c_void_p), ("rt", c_void_p),
         ("n_matches", c_void_p), ("n_corr", c_void_p), ("n_inl", c_void_p), ("status", c_void_p),
+        ("depth_kp", c_void_p),
     ]
 
 
@@ -86,6 +87,8 @@ PROTOTYPES = {
     "vo_gather_backproject": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                       c_int, c_void_p, c_int, c_int, c_void_p, c_float, c_float, c_float,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vo_sample_depth": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                c_void_p]),
     "vo_hypotheses": (c_int, [c_void_p, c_void_p, c_int, c_int, c_u64, c_i64, c_void_p, c_void_p]),
     "vo_pnp_ransac": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
                               c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -194,7 +194,7 @@ extern "C" int vo_pipeline(vo_ctx *ctx, const vo_pipeline_args *a, void *stream)
     const bool u8 = a->ref_u8 && a->cur_u8, f32 = a->ref_f32 && a->cur_f32;
     VO_REQUIRE(u8 != f32, "vo_pipeline: give exactly one descriptor pair (u8 or f32)");
     VO_REQUIRE(a->B >= 0 && a->n_stride > 0 && a->m_stride > 0 && a->n_hyp > 0, "vo_pipeline: bad size");
-    VO_REQUIRE(a->ref_kp && a->cur_kp && a->depth && a->K_h, "vo_pipeline: null geometry input");
+    VO_REQUIRE(a->ref_kp && a->cur_kp && (a->depth || a->depth_kp) && a->K_h, "vo_pipeline: null geometry input");
     VO_REQUIRE(a->T_rel && a->n_matches && a->n_corr && a->n_inl && a->status, "vo_pipeline: null output");
     if (a->B == 0) return VO_OK;
     const int B = a->B, cap = a->n_stride, H = a->n_hyp;
@@ -221,9 +221,10 @@ extern "C" int vo_pipeline(vo_ctx *ctx, const vo_pipeline_args *a, void *stream)
                           a->norm_or_metric, a->mode, a->match_param, a->precision, pairs, nullptr, a->n_matches,
                           nullptr, nullptr, stream);
     if (rc) return rc;
-    if ((rc = vo_gather_backproject(ctx, pairs, a->n_matches, B, cap, a->ref_kp, a->cur_kp, a->n_stride, a->m_stride,
-                                    a->kp_stride, a->depth, a->H, a->W, a->K_h, a->min_flow_px, a->z_min, a->z_max,
-                                    xyz, ruv, cuv, nullptr, a->n_corr, a->status, stream)))
+    if ((rc = gather_backproject_impl(ctx, pairs, a->n_matches, B, cap, a->ref_kp, a->cur_kp, a->n_stride, a->m_stride,
+                                      a->kp_stride, a->depth_kp ? nullptr : a->depth, a->depth_kp, a->H, a->W, a->K_h,
+                                      a->min_flow_px, a->z_min, a->z_max, xyz, ruv, cuv, nullptr, a->n_corr, a->status,
+                                      stream)))
         return rc;
     if ((rc = vo_hypotheses(ctx, a->n_corr, B, H, a->seed, a->pair0, hyp, stream))) return rc;
     return pnp_ransac_impl(ctx, xyz, cuv, a->n_corr, B, cap, a->K_h, hyp, H, a->thr_px, a->min_inliers,

@@ -126,6 +126,11 @@ int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_
                     double *rt, double *rvec_tvec, double *T_rel, int32_t *n_inl, int32_t *best_h,
                     uint8_t *inlier_mask, int32_t *hyp_counts, int32_t *status, int accumulate_status,
                     void *stream);
+int gather_backproject_impl(vo_ctx *ctx, const int32_t *pairs, const int32_t *n_pairs, int B, int pair_cap,
+                            const float *ref_kp, const float *cur_kp, int n_stride, int m_stride, int kp_stride,
+                            const float *depth, const float *depth_kp, int H, int W, const double *K_h,
+                            float min_flow_px, float z_min, float z_max, float *xyz, float *ref_uv, float *cur_uv,
+                            int32_t *src, int32_t *n_out, int32_t *status, void *stream);
 int fill_u64(vo_ctx *ctx, unsigned long long *p, size_t n, unsigned long long v, cudaStream_t st);
 
 // score kinds understood by match_finalize

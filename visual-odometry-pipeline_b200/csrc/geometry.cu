@@ -96,6 +96,27 @@ backproject_dense_kernel(const float *__restrict__ depth, float *__restrict__ xy
 }
 
 constexpr int GB_THREADS = 512;
+constexpr uint32_t VO_DEPTH_OOB_BITS = 0xffc0b200u;  // quiet NaN with a payload: "keypoint truncates outside the image"
+
+// Depth at every keypoint's truncated pixel, depth[int(y), int(x)] (VisualOdometry_Stereo.py:97), as a compact
+// [B][n_stride] array.  `depth` only has to be device-ACCESSIBLE: reading a pinned host image through the mapped
+// pointer moves one 32-byte sector per keypoint over PCIe instead of the whole H x W map (1.87 MB at 1241 x 376).
+__global__ void __launch_bounds__(256)
+sample_depth_kernel(const float *__restrict__ kp, int n_stride, int kp_stride, const int32_t *__restrict__ n_kp,
+                    const float *__restrict__ depth, int H, int W, long long total, float *__restrict__ z_kp) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int b = (int)(gid / n_stride), i = (int)(gid % n_stride);
+    const int n = n_kp ? min(n_kp[b], n_stride) : n_stride;
+    float z = __int_as_float(0x7fc00000);
+    if (i < n) {
+        const float *p = kp + (size_t)gid * kp_stride;
+        const int u = (int)p[0], v = (int)p[1];
+        if (u < 0 || u >= W || v < 0 || v >= H) z = __uint_as_float(VO_DEPTH_OOB_BITS);
+        else z = depth[(size_t)b * H * W + (size_t)v * W + u];
+    }
+    z_kp[gid] = z;
+}
 
 // Sparse fused path: one CTA per frame pair, chunks of GB_THREADS matches, ballot + warp-count
 // scan keeps the surviving correspondences in match order (the reference's boolean-mask
@@ -103,8 +124,9 @@ constexpr int GB_THREADS = 512;
 __global__ void __launch_bounds__(GB_THREADS)
 gather_backproject_kernel(const int32_t *__restrict__ pairs, const int32_t *__restrict__ n_pairs, int pair_cap,
                           const float *__restrict__ ref_kp, const float *__restrict__ cur_kp, int n_stride, int m_stride,
-                          int kp_stride, const float *__restrict__ depth, int H, int W, Intr k, float min_flow,
-                          float z_min, float z_max, float *__restrict__ xyz, float *__restrict__ ref_uv,
+                          int kp_stride, const float *__restrict__ depth, const float *__restrict__ depth_kp, int H,
+                          int W, Intr k, float min_flow, float z_min, float z_max, float *__restrict__ xyz,
+                          float *__restrict__ ref_uv,
                           float *__restrict__ cur_uv, int32_t *__restrict__ src, int32_t *__restrict__ n_out,
                           int32_t *__restrict__ status) {
     const int b = blockIdx.x;
@@ -114,7 +136,8 @@ gather_backproject_kernel(const int32_t *__restrict__ pairs, const int32_t *__re
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { base_s = 0; oob_s = 0; }
     __syncthreads();
-    const float *dimg = depth + (size_t)b * H * W;
+    const float *dimg = depth ? depth + (size_t)b * H * W : nullptr;
+    const float *dkp = depth_kp ? depth_kp + (size_t)b * n_stride : nullptr;  // depth already sampled per ref keypoint
     for (int m0 = 0; m0 < n; m0 += GB_THREADS) {
         const int m = m0 + threadIdx.x;
         bool keep = false;
@@ -131,10 +154,12 @@ gather_backproject_kernel(const int32_t *__restrict__ pairs, const int32_t *__re
             if (diff >= min_flow) {
                 // .astype(np.int32): truncation toward zero; index [row = y, col = x] (:97)
                 const int u = (int)rx, v = (int)ry;
-                if (u < 0 || u >= W || v < 0 || v >= H) {
+                const bool inside = !(u < 0 || u >= W || v < 0 || v >= H);
+                if (dkp) Z = __ldg(dkp + ir);
+                if (!inside || (dkp && __float_as_uint(Z) == VO_DEPTH_OOB_BITS)) {
                     oob_s = 1;  // reference: IndexError (or negative wrap) -> pair fails
                 } else {
-                    Z = __ldg(dimg + (size_t)v * W + u);
+                    if (!dkp) Z = __ldg(dimg + (size_t)v * W + u);
                     backproject(k, u, v, Z, X, Y);
                     keep = (Z > z_min) && (Z < z_max);  // NaN fails both
                 }
@@ -190,22 +215,47 @@ extern "C" int vo_backproject_dense(vo_ctx *ctx, const float *depth, int B, int 
     return VO_OK;
 }
 
-extern "C" int vo_gather_backproject(vo_ctx *ctx, const int32_t *pairs, const int32_t *n_pairs, int B, int pair_cap,
-                                     const float *ref_kp, const float *cur_kp, int n_stride, int m_stride,
-                                     int kp_stride, const float *depth, int H, int W, const double *K_h,
-                                     float min_flow_px, float z_min, float z_max, float *xyz, float *ref_uv,
-                                     float *cur_uv, int32_t *src, int32_t *n_out, int32_t *status, void *stream) {
+namespace vo {
+int gather_backproject_impl(vo_ctx *ctx, const int32_t *pairs, const int32_t *n_pairs, int B, int pair_cap,
+                            const float *ref_kp, const float *cur_kp, int n_stride, int m_stride, int kp_stride,
+                            const float *depth, const float *depth_kp, int H, int W, const double *K_h,
+                            float min_flow_px, float z_min, float z_max, float *xyz, float *ref_uv, float *cur_uv,
+                            int32_t *src, int32_t *n_out, int32_t *status, void *stream) {
     using namespace vo;
-    VO_REQUIRE(ctx && pairs && n_pairs && ref_kp && cur_kp && depth && K_h && xyz && ref_uv && cur_uv && n_out,
+    VO_REQUIRE(ctx && pairs && n_pairs && ref_kp && cur_kp && (depth || depth_kp) && K_h && xyz && ref_uv && cur_uv && n_out,
                "vo_gather_backproject: null argument");
     VO_REQUIRE(B >= 0 && pair_cap >= 0 && H > 0 && W > 0 && kp_stride >= 2, "vo_gather_backproject: bad shape");
     VO_REQUIRE(K_h[0] != 0.0 && K_h[4] != 0.0, "vo_gather_backproject: zero focal length");
     if (B == 0) return VO_OK;
     VO_PROF(ctx, (cudaStream_t)stream, VO_STAGE_GATHER);
     gather_backproject_kernel<<<B, GB_THREADS, 0, (cudaStream_t)stream>>>(
-        pairs, n_pairs, pair_cap, ref_kp, cur_kp, n_stride, m_stride, kp_stride, depth, H, W, make_intr(K_h),
+        pairs, n_pairs, pair_cap, ref_kp, cur_kp, n_stride, m_stride, kp_stride, depth, depth_kp, H, W, make_intr(K_h),
         min_flow_px, z_min, z_max, xyz, ref_uv, cur_uv, src, n_out, status);
     VO_LAUNCH_CHECK(ctx);
     VO_PROF(ctx, (cudaStream_t)stream, -1);
+    return VO_OK;
+}
+}  // namespace vo
+
+extern "C" int vo_gather_backproject(vo_ctx *ctx, const int32_t *pairs, const int32_t *n_pairs, int B, int pair_cap,
+                                     const float *ref_kp, const float *cur_kp, int n_stride, int m_stride, int kp_stride,
+                                     const float *depth, int H, int W, const double *K_h, float min_flow_px, float z_min,
+                                     float z_max, float *xyz, float *ref_uv, float *cur_uv, int32_t *src, int32_t *n_out,
+                                     int32_t *status, void *stream) {
+    return vo::gather_backproject_impl(ctx, pairs, n_pairs, B, pair_cap, ref_kp, cur_kp, n_stride, m_stride, kp_stride,
+                                       depth, nullptr, H, W, K_h, min_flow_px, z_min, z_max, xyz, ref_uv, cur_uv, src,
+                                       n_out, status, stream);
+}
+
+extern "C" int vo_sample_depth(vo_ctx *ctx, const float *kp, int B, int n_stride, int kp_stride, const int32_t *n_kp,
+                               const float *depth, int H, int W, float *depth_kp, void *stream) {
+    using namespace vo;
+    VO_REQUIRE(ctx && kp && depth && depth_kp, "vo_sample_depth: null argument");
+    VO_REQUIRE(B >= 0 && n_stride >= 0 && kp_stride >= 2 && H > 0 && W > 0, "vo_sample_depth: bad shape");
+    const long long total = (long long)B * n_stride;
+    if (total == 0) return VO_OK;
+    sample_depth_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kp, n_stride, kp_stride, n_kp, depth,
+                                                                                          H, W, total, depth_kp);
+    VO_LAUNCH_CHECK(ctx);
     return VO_OK;
 }

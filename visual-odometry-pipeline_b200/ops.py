@@ -157,6 +157,22 @@ def backproject_dense(depth, K):
     return out[0] if squeeze else out
 
 
+def sample_depth(kp, depth, n_kp=None, out=None):
+    """depth[int(y), int(x)] at every keypoint (vo_sample_depth).  kp [B,N,s] CUDA float32; depth [B,H,W] float32 on the
+    device OR in pinned host memory (read zero-copy through the mapped pointer).  Returns depth_kp [B,N] CUDA float32."""
+    _chk(kp, torch.float32, "kp")
+    if depth.dtype != torch.float32 or not depth.is_contiguous() or not (depth.is_cuda or depth.is_pinned()):
+        raise ValueError("sample_depth: depth must be contiguous float32 on the device or in pinned host memory")
+    B, N, s = kp.shape
+    if out is None:
+        out = torch.empty((B, N), dtype=torch.float32, device=kp.device)
+    ctx = context(kp.device)
+    with torch.cuda.device(kp.device):
+        check(ctx.lib.vo_sample_depth(ctx.handle, _ptr(kp), B, N, s, _ptr(n_kp), _ptr(depth), int(depth.shape[1]),
+                                      int(depth.shape[2]), _ptr(out), _stream()), "vo_sample_depth")
+    return out
+
+
 class Correspondences:
     def __init__(self, xyz, ref_uv, cur_uv, src, count, status):
         self.xyz, self.ref_uv, self.cur_uv, self.src, self.count, self.status = xyz, ref_uv, cur_uv, src, count, status
@@ -256,11 +272,18 @@ class PipelineBuffers:
 
 def pipeline(ref_desc, cur_desc, ref_kp, cur_kp, depth, K, *, norm_or_metric, mode, match_param=0.85,
              precision=VO_PREC_TF32X3, n_ref=None, n_cur=None, n_hyp=1024, seed=8214, pair0=0, thr_px=1.5,
-             min_inliers=20, refine_iters=10, min_flow_px=3.0, z_min=0.0, z_max=50.0, out=None):
-    """match -> gather/back-project -> hypotheses -> PnP-RANSAC -> T_rel for a batch of pairs (vo_pipeline)."""
+             min_inliers=20, refine_iters=10, min_flow_px=3.0, z_min=0.0, z_max=50.0, out=None, depth_kp=None, hw=None):
+    """match -> gather/back-project -> hypotheses -> PnP-RANSAC -> T_rel for a batch of pairs (vo_pipeline).
+    `depth` is the reference frames' dense map [B,H,W]; alternatively pass `depth_kp` [B,N] (sample_depth) and
+    `hw=(H, W)`."""
     _chk(ref_kp, torch.float32, "ref_kp")
     _chk(cur_kp, torch.float32, "cur_kp")
-    _chk(depth, torch.float32, "depth")
+    if depth_kp is not None:
+        _chk(depth_kp, torch.float32, "depth_kp")
+        if hw is None and depth is None:
+            raise ValueError("pipeline: depth_kp needs hw=(H, W)")
+    else:
+        _chk(depth, torch.float32, "depth")
     if not ref_desc.is_contiguous() or not cur_desc.is_contiguous():
         raise ValueError("pipeline: descriptors must be contiguous")
     B, N, M = ref_desc.shape[0], ref_desc.shape[1], cur_desc.shape[1]
@@ -278,7 +301,11 @@ def pipeline(ref_desc, cur_desc, ref_kp, cur_kp, depth, K, *, norm_or_metric, mo
         raise ValueError("pipeline: descriptors must be uint8 or float32")
     a.norm_or_metric, a.mode, a.precision, a.match_param = int(norm_or_metric), int(mode), int(precision), float(match_param)
     a.ref_kp, a.cur_kp, a.kp_stride = ref_kp.data_ptr(), cur_kp.data_ptr(), int(ref_kp.shape[2])
-    a.depth, a.H, a.W = depth.data_ptr(), int(depth.shape[1]), int(depth.shape[2])
+    if depth_kp is not None:
+        a.depth, a.depth_kp = None, depth_kp.data_ptr()
+        a.H, a.W = (int(hw[0]), int(hw[1])) if hw is not None else (int(depth.shape[1]), int(depth.shape[2]))
+    else:
+        a.depth, a.H, a.W = depth.data_ptr(), int(depth.shape[1]), int(depth.shape[2])
     a.K_h = kp.value
     a.min_flow_px, a.z_min, a.z_max = float(min_flow_px), float(z_min), float(z_max)
     a.n_hyp, a.seed, a.pair0 = int(n_hyp), int(seed), int(pair0)

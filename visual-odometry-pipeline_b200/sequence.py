@@ -113,14 +113,25 @@ class HostPairRunner:
     vo_pipeline on the compute stream -> D2H of poses / status.  This is the call a user with frames in host
     memory makes; bench.py times it as `e2e`."""
 
-    def __init__(self, host_batch, cfg, chunk, device="cuda"):
+    def __init__(self, host_batch, cfg, chunk, device="cuda", depth_mode="sampled"):
+        """depth_mode "dense": the whole depth map of every reference frame crosses PCIe (1.87 MB at 1241x376);
+        "sampled": the maps stay in pinned host memory and vo_sample_depth reads depth[int(y), int(x)] of the
+        reference keypoints through the mapped pointer on the copy stream (one 32 B sector per keypoint)."""
+        if depth_mode not in ("dense", "sampled"):
+            raise ValueError(depth_mode)
+        self.depth_mode = depth_mode
         self.cfg, self.chunk, self.device = cfg, chunk, torch.device(device)
         self.K = np.asarray(host_batch["K"], np.float64)
         keys = ("ref_desc", "cur_desc", "ref_kp", "cur_kp", "depth")
         self.host = {k: torch.from_numpy(np.ascontiguousarray(host_batch[k])).pin_memory() for k in keys}
         self.B = self.host["ref_desc"].shape[0]
-        self.stage = [{k: torch.empty((chunk,) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device)
-                       for k, v in self.host.items()} for _ in range(2)]
+        staged = [k for k in keys if not (k == "depth" and depth_mode == "sampled")]
+        self.stage = [{k: torch.empty((chunk,) + tuple(self.host[k].shape[1:]), dtype=self.host[k].dtype, device=self.device)
+                       for k in staged} for _ in range(2)]
+        self.hw = tuple(self.host["depth"].shape[1:])
+        if depth_mode == "sampled":
+            for st in self.stage:
+                st["depth_kp"] = torch.empty((chunk, self.host["ref_kp"].shape[1]), dtype=torch.float32, device=self.device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.copied = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
@@ -128,7 +139,9 @@ class HostPairRunner:
         self.host_T = torch.empty((self.B, 4, 4), dtype=torch.float64).pin_memory()
         self.host_status = torch.empty((self.B,), dtype=torch.int32).pin_memory()
         self.host_inl = torch.empty((self.B,), dtype=torch.int32).pin_memory()
-        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.h2d_bytes = sum(v.numel() * v.element_size() for k, v in self.host.items() if k in staged)
+        if depth_mode == "sampled":   # one 32-byte sector per reference keypoint crosses the bus
+            self.h2d_bytes += int(self.host["ref_kp"].shape[0]) * int(self.host["ref_kp"].shape[1]) * 32
         self.d2h_bytes = self.host_T.numel() * 8 + self.host_status.numel() * 4 + self.host_inl.numel() * 4
 
     def run(self, pair0=0):
@@ -142,7 +155,11 @@ class HostPairRunner:
                 if c >= 2:
                     self.copy_stream.wait_event(self.consumed[buf])
                 for k, v in self.host.items():
-                    self.stage[buf][k][: hi - lo].copy_(v[lo:hi], non_blocking=True)
+                    if k in self.stage[buf]:
+                        self.stage[buf][k][: hi - lo].copy_(v[lo:hi], non_blocking=True)
+                if self.depth_mode == "sampled":
+                    ops.sample_depth(self.stage[buf]["ref_kp"][: hi - lo], self.host["depth"][lo:hi],
+                                     out=self.stage[buf]["depth_kp"][: hi - lo])
                 self.copied[buf].record(self.copy_stream)
             compute.wait_event(self.copied[buf])
             s = self.stage[buf]
@@ -150,8 +167,13 @@ class HostPairRunner:
             view.T_rel, view.rt = self.out.T_rel[lo:hi], self.out.rt[lo:hi]
             view.n_matches, view.n_corr = self.out.n_matches[lo:hi], self.out.n_corr[lo:hi]
             view.n_inl, view.status = self.out.n_inl[lo:hi], self.out.status[lo:hi]
-            ops.pipeline(s["ref_desc"][: hi - lo], s["cur_desc"][: hi - lo], s["ref_kp"][: hi - lo], s["cur_kp"][: hi - lo],
-                         s["depth"][: hi - lo], self.K, pair0=pair0 + lo, out=view, **self.cfg.kw)
+            if self.depth_mode == "sampled":
+                ops.pipeline(s["ref_desc"][: hi - lo], s["cur_desc"][: hi - lo], s["ref_kp"][: hi - lo], s["cur_kp"][: hi - lo],
+                             None, self.K, pair0=pair0 + lo, out=view, depth_kp=s["depth_kp"][: hi - lo], hw=self.hw,
+                             **self.cfg.kw)
+            else:
+                ops.pipeline(s["ref_desc"][: hi - lo], s["cur_desc"][: hi - lo], s["ref_kp"][: hi - lo], s["cur_kp"][: hi - lo],
+                             s["depth"][: hi - lo], self.K, pair0=pair0 + lo, out=view, **self.cfg.kw)
             self.consumed[buf].record(compute)
         self.host_T.copy_(self.out.T_rel, non_blocking=True)
         self.host_status.copy_(self.out.status, non_blocking=True)
