@@ -45,3 +45,30 @@ def evaluate(gt, pred):
         trans.append(translation_error(e) / ld)
         rot.append(rotation_error(e))
     return ate / dist, float(np.mean(trans)), float(np.sum(rot) * 180 / np.pi) / dist, dist
+
+
+def sequence_errors(gt, pred, lengths=(100, 200, 300, 400, 500, 600, 700, 800), step=10):
+    """Plain-loop restatement of calc_sequence_errors (plot_utils/kittievalodom.py:181-233) with its helpers
+    trajectory_distances (:118-136) and last_frame_from_segment_length (:166-179): for every 10th first frame and
+    every segment length, the relative pose error between first frame and the first frame further than `length`
+    along the ground-truth path.  gt / pred: (N,4,4).  Returns rows [first, r_err/len, t_err/len, len, speed]."""
+    gt, pred = np.asarray(gt, np.float64), np.asarray(pred, np.float64)
+    dist = [0.0]
+    for i in range(len(gt) - 1):
+        d = gt[i, :3, 3] - gt[i + 1, :3, 3]
+        dist.append(dist[i] + np.sqrt(d[0] ** 2 + d[1] ** 2 + d[2] ** 2))
+    err = []
+    for first in range(0, len(gt), step):
+        for ln in lengths:
+            last = -1
+            for i in range(first, len(dist)):
+                if dist[i] > dist[first] + ln:
+                    last = i
+                    break
+            if last == -1 or last >= len(pred) or first >= len(pred):
+                continue
+            dg = np.dot(np.linalg.inv(gt[first]), gt[last])
+            dr = np.dot(np.linalg.inv(pred[first]), pred[last])
+            e = np.dot(np.linalg.inv(dr), dg)
+            err.append([first, rotation_error(e) / ln, translation_error(e) / ln, ln, ln / (0.1 * (last - first + 1.0))])
+    return err

@@ -14,6 +14,7 @@ Sources of each fixture (file:line under /root/reference):
   pnp.npz             cv2.solveP3P, cv2.projectPoints, cv2.solvePnP(ITERATIVE), cv2.solvePnPRansac
                       (VisualOdometry_Stereo.py:129 call signature)
   kitti03_eval.npz    plot_utils/kittievalodom.py:513-570 eval() on plot_utils/data (known-answer tuple)
+  kitti03_segments.npz  the evaluator's per-segment table and reductions on the same data (:181-233, :247-270, :361-469)
 """
 import ast
 import os
@@ -211,6 +212,25 @@ def gen_kitti_eval():
     pred = np.loadtxt(os.path.join(REF, "plot_utils", "data", "global_poses.npy.txt"))[:, :12]
     save("kitti03_eval.npz", gt=gt.astype(np.float64), pred=pred.astype(np.float64), expected=np.array(tup, np.float64))
     print("evaluator tuple:", tup)
+    # the per-segment table and its reductions on the same data (calc_sequence_errors :181-233, compute_overall_err
+    # :247-270, compute_segment_error :361-390, compute_ATE :392-427, compute_RPE :429-469), called directly
+    def to_dict(a):
+        P = np.tile(np.eye(4), (len(a), 1, 1))
+        P[:, :3, :] = a.reshape(-1, 3, 4)
+        return {i: P[i] for i in range(len(a))}
+    ev = kittievalodom.KittiEvalOdom()
+    pg, pr = to_dict(gt), to_dict(pred)
+    g0, p0 = np.linalg.inv(pg[0]), np.linalg.inv(pr[0])
+    for k in pr:
+        pr[k] = p0 @ pr[k]
+        pg[k] = g0 @ pg[k]
+    seq_err = ev.calc_sequence_errors(pg, pr)
+    overall = ev.compute_overall_err(seq_err)
+    seg = ev.compute_segment_error(seq_err)
+    seg_arr = np.array([seg[l] if len(seg[l]) else [np.nan, np.nan] for l in ev.lengths], np.float64)
+    save("kitti03_segments.npz", seq_err=np.asarray(seq_err, np.float64), overall=np.asarray(overall, np.float64),
+         segments=seg_arr, ate=np.float64(ev.compute_ATE(pg, pr)), rpe=np.asarray(ev.compute_RPE(pg, pr), np.float64),
+         dist=np.asarray(ev.trajectory_distances(pg), np.float64))
 
 
 if __name__ == "__main__":

@@ -54,9 +54,15 @@ def main():
             for i, (kp, d, z) in enumerate(pinned):
                 loop.push(kp, d, z, i)
             return loop.poses()
+        from vo_b200 import ops
         run_dev()
         torch.cuda.synchronize()
         t0 = time.perf_counter(); got, info = run_dev(); t_dev = time.perf_counter() - t0
+        ops.profile_enable(True); ops.profile_collect()
+        t0 = time.perf_counter(); run_dev(); t_prof = time.perf_counter() - t0
+        stages = {k: round(v[0] / max(v[1], 1), 4) for k, v in ops.profile_collect().items() if v[1]}
+        ops.profile_enable(False)
+        print(json.dumps({"kind": kind, "device_loop_stage_ms_per_frame": stages, "profiled_run_s": t_prof}), flush=True)
         print(json.dumps({"kind": kind, "n_kp": n_kp, "frames": n_frames, "host_policy_fps": n_frames / t_host,
                           "device_loop_fps": n_frames / t_dev, "max_abs_pose_diff": float(np.abs(got - want).max()),
                           "keyframes": int(info[:, 5].sum()), "bad_pnp": int((info[1:, 0] != 0).sum()),

@@ -28,3 +28,5 @@ if __name__ == "__main__":
     run(10000, 10000, B, ops.VO_PREC_TF32X3, ops.VO_METRIC_COSINE)
     run(10000, 10000, B, ops.VO_PREC_TF32X1, ops.VO_METRIC_COSINE)
     run(10000, 10000, B, ops.VO_PREC_TF32X1, ops.VO_METRIC_L2)
+    run(20000, 20000, max(1, B // 2), ops.VO_PREC_TF32X1, ops.VO_METRIC_L2)
+    run(2000, 2000, 256, ops.VO_PREC_TF32X1, ops.VO_METRIC_L2)

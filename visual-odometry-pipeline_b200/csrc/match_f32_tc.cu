@@ -121,14 +121,38 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
+// Asynchronous 8-column TMEM read: the registers may only be consumed after tc_ld_wait8() on the same array.  The
+// wait takes them as in/out operands so that the compiler cannot schedule a use above it.
+__device__ __forceinline__ void tc_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld_wait8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
 }
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
     asm volatile(
@@ -188,9 +212,11 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 
 // one warp per descriptor row (128 floats = 32 lanes x float4)
+// ext (optional, [rows][32]): -|x|^2 split into three tf32 pieces in columns 0..2, zeros elsewhere — the extra
+// K-step that lets the MMA itself subtract the column norm (single-pass L2 mode).
 __global__ void __launch_bounds__(256)
 prep_kernel(const float *__restrict__ x, long long rows, float *__restrict__ hi, float *__restrict__ lo,
-            float *__restrict__ norm2) {
+            float *__restrict__ norm2, float *__restrict__ ext) {
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -206,6 +232,15 @@ prep_kernel(const float *__restrict__ x, long long rows, float *__restrict__ hi,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
         if (lane == 0) norm2[row] = s;
+        if (ext) {
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane == 0) {
+                const float n1 = to_tf32(s), n2 = to_tf32(__fsub_rn(s, n1));
+                const float n3 = to_tf32(__fsub_rn(__fsub_rn(s, n1), n2));
+                e = make_float4(-n1, -n2, -n3, 0.f);
+            }
+            if (lane < 8) reinterpret_cast<float4 *>(ext)[row * 8 + lane] = e;
+        }
     }
 }
 
@@ -228,13 +263,13 @@ __device__ __forceinline__ void row_insert(float s, int col, float &s1, float &s
 // maximum and the ballot of the lanes that attain it (both warp-uniform; lane 0 stores them as two vectors).
 // ROW_MASK is set only for the last, partial row block: elsewhere every lane holds a valid row.
 // Kept small on purpose (a rolled loop calls it 8 times per tile and warp): 16 warps share the instruction cache.
-template <int METRIC, bool MASK_COLS, bool ROW_MASK, bool COLS>
+template <int METRIC, bool MASK_COLS, bool ROW_MASK, bool COLS, bool EXT>
 __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M, bool row_ok, float na,
                                            const float *__restrict__ cn, bool cn_vec, int lane, float *cv_out,
                                            uint32_t *cb_out, float &s1, float &s2, int32_t &i1, int32_t &i2) {
     float sc[8], wm[8], nb[8];
     uint32_t bal[8];
-    if (METRIC == VO_METRIC_L2) {
+    if (METRIC == VO_METRIC_L2 && !EXT) {
         if (!MASK_COLS && cn_vec) {  // warp-uniform: two 128-bit broadcast loads instead of eight scalar ones
             const float4 n0 = __ldg(reinterpret_cast<const float4 *>(cn + cbase));
             const float4 n1 = __ldg(reinterpret_cast<const float4 *>(cn + cbase) + 1);
@@ -252,7 +287,8 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
         if (METRIC == VO_METRIC_L2) {
             // with a column arg-min the row norm orders rows inside a column; without one it is a per-row
             // constant that the caller subtracts once, after the scan (same two roundings either way)
-            s = __fmaf_rn(2.0f, s, -nb[j]);
+            // EXT: the accumulator already holds 2 a.b - |b|^2 (A scaled by 2, norm folded in as one more K-step)
+            if (!EXT) s = __fmaf_rn(2.0f, s, -nb[j]);
             if (COLS) s = __fsub_rn(s, na);
         }
         if (MASK_COLS) s = (col < M) ? s : -INFINITY;
@@ -315,7 +351,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
 #define TC_DBG_END(slot) do { if (dbg_on) dbg_acc[slot] += clock64() - _t0; } while (0)
     long long dbg_acc[4] = {0, 0, 0, 0};
 
-    constexpr int ITEMS = (PASSES == 3) ? 2 * TC_NKB : TC_NKB;  // B boxes streamed per tile
+    // single-pass L2: one extra box per tile carries -|b|^2 (three tf32 pieces), multiplied by a column block of ones in A
+    constexpr bool EXT = (PASSES == 1) && (METRIC == VO_METRIC_L2);
+    constexpr int ITEMS = (PASSES == 3) ? 2 * TC_NKB : (EXT ? TC_NKB + 1 : TC_NKB);  // B boxes streamed per tile
     const uint32_t s_b = base + TC_OFF_B;
     float *scol_v = reinterpret_cast<float *>(smem + TC_OFF_SCOL);                       // [2 groups][2 bufs][4][128]
     uint32_t *scol_b = reinterpret_cast<uint32_t *>(smem + TC_OFF_SCOL + 2 * 2 * 4 * TC_BN * 4);
@@ -333,7 +371,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             mbar_init(bar_full(s), 1);            // this CTA's producer arms it; TMA bytes complete it
             mbar_init(bar_empty(s), TC_CLUSTER);  // one commit from each CTA of the cluster
         }
-        mbar_init(bar_a, PASSES == 3 ? 16 : 8);
+        mbar_init(bar_a, PASSES == 3 ? 16 : (EXT ? 12 : 8));
         for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull(g), 1); mbar_init(bar_tempty(g), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -363,8 +401,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                     { TC_DBG_BEGIN(); mbar_wait(bar_empty(stage), phase ^ 1u); TC_DBG_END(0); }  // both CTAs consumed the slot
                     mbar_expect_tx(bar_full(stage), TC_BLOCK_BYTES);  // bytes arrive by multicast, whoever issues
                     if ((uint32_t)(it & 1) == crank) {
-                        const int kb = (PASSES == 3) ? (item >> 1) : item;
-                        const bool is_lo = (PASSES == 3) && (item & 1);
+                        const bool is_ext = EXT && item == TC_NKB;  // map_b_lo is the extension map in that mode
+                        const int kb = is_ext ? 0 : ((PASSES == 3) ? (item >> 1) : item);
+                        const bool is_lo = is_ext || ((PASSES == 3) && (item & 1));
                         tma_load_2d_mc(s_b + stage * TC_BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * TC_KB, brow,
                                        bar_full(stage), (uint16_t)((1u << TC_CLUSTER) - 1u));
                     }
@@ -400,6 +439,10 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                         const bool is_lo = (PASSES == 3) && (item & 1);
                         const uint32_t b_lo32 = (((s_b + stage * TC_BLOCK_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
                         const uint32_t a_hi_t = tmem_base + (uint32_t)(TC_TMEM_A + kb * TC_KB);
+                        if (EXT && item == TC_NKB) {  // ones[128 x 8] * (-|b|^2 pieces)[8 x 128]
+                            const uint64_t bdesc = ((uint64_t)TC_SDESC_HI << 32) | (uint64_t)b_lo32;
+                            tc_mma_tf32_ts(d_tmem, tmem_base + (uint32_t)(TC_TMEM_A + TC_D), bdesc, TC_IDESC, 1u);
+                        } else
 #pragma unroll
                         for (int k8 = 0; k8 < TC_KB / 8; ++k8) {
                             const uint64_t bdesc = ((uint64_t)TC_SDESC_HI << 32) | (uint64_t)(b_lo32 + k8 * 2);
@@ -443,10 +486,19 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float4 x = have ? __ldg(reinterpret_cast<const float4 *>(src + c * 32) + k) : make_float4(0, 0, 0, 0);
-                    v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+                    const float sc2 = EXT ? 2.0f : 1.0f;  // exact
+                    v[4 * k] = sc2 * x.x; v[4 * k + 1] = sc2 * x.y; v[4 * k + 2] = sc2 * x.z; v[4 * k + 3] = sc2 * x.w;
                 }
                 tc_st32(lane_base + (uint32_t)(TC_TMEM_A + g * TC_D + c * 32), v);
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar_a);
+        }
+
+        if (EXT && n_tiles > 0 && g == 1 && h == 0) {  // the ones block of A (TMEM columns of the unused lo half)
+            const float ones[8] = {1.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            tc_st8(lane_base + (uint32_t)(TC_TMEM_A + TC_D), ones);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar_a);
@@ -472,20 +524,64 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             tc_fence_after();
             const long long _tc0 = dbg_on ? clock64() : 0;
             const uint32_t taddr = lane_base + (uint32_t)(g * TC_BN);
-            if (full_tile && !partial_rows) {
-#pragma unroll 1
-                for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 8) {
-                    float v[8];
-                    tc_ld8(taddr + j0, v);
-                    epi_group8<METRIC, false, false, COLS>(v, col0 + j0, M, row_ok, na, cn, cn_vec, lane, my_cv + j0, my_cb + j0, s1, s2, i1, i2);
-                }
+            // Three epilogue schedules.  3xTF32 is bound by the tensor pipe: plain load -> wait -> fold.  Single pass is
+            // bound by the epilogue, whose cost per 8 columns was the TMEM read latency, so the read of the next
+            // columns is kept in flight while the current ones are folded (two register buffers swapped by moves: the
+            // loops stay rolled with one or two epi_group8 bodies, 16 warps share the instruction cache); without the
+            // column arg-max there are registers to spare and the reads are 16 columns wide.
+            if (PASSES == 3) {
+#define TC_EPI_LOOP(MASKC, MASKR)                                                                                          \
+    _Pragma("unroll 1") for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 8) {                                                 \
+        uint32_t cur[8];                                                                                                   \
+        tc_ld8_issue(taddr + j0, cur);                                                                                     \
+        tc_ld_wait8(cur);                                                                                                  \
+        float v[8];                                                                                                        \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(cur[i]);                                      \
+        epi_group8<METRIC, MASKC, MASKR, COLS, EXT>(v, col0 + j0, M, row_ok, na, cn, cn_vec, lane, my_cv + j0, my_cb + j0, \
+                                                    s1, s2, i1, i2);                                                       \
+    }
+                if (full_tile && !partial_rows) { TC_EPI_LOOP(false, false) } else { TC_EPI_LOOP(true, true) }
+#undef TC_EPI_LOOP
+            } else if (COLS) {
+                uint32_t cur[8], nxt[8];
+                tc_ld8_issue(taddr + 64 * h, cur);
+                tc_ld_wait8(cur);
+#define TC_EPI_LOOP(MASKC, MASKR)                                                                                          \
+    _Pragma("unroll 1") for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 8) {                                                 \
+        const bool more = j0 + 8 < 64 * h + 64;                                                                            \
+        if (more) tc_ld8_issue(taddr + j0 + 8, nxt);                                                                       \
+        float v[8];                                                                                                        \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(cur[i]);                                      \
+        epi_group8<METRIC, MASKC, MASKR, COLS, EXT>(v, col0 + j0, M, row_ok, na, cn, cn_vec, lane, my_cv + j0, my_cb + j0, \
+                                                    s1, s2, i1, i2);                                                       \
+        if (more) {                                                                                                        \
+            tc_ld_wait8(nxt);                                                                                              \
+            _Pragma("unroll") for (int i = 0; i < 8; ++i) cur[i] = nxt[i];                                                 \
+        }                                                                                                                  \
+    }
+                if (full_tile && !partial_rows) { TC_EPI_LOOP(false, false) } else { TC_EPI_LOOP(true, true) }
+#undef TC_EPI_LOOP
             } else {
-#pragma unroll 1
-                for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 8) {
-                    float v[8];
-                    tc_ld8(taddr + j0, v);
-                    epi_group8<METRIC, true, true, COLS>(v, col0 + j0, M, row_ok, na, cn, cn_vec, lane, my_cv + j0, my_cb + j0, s1, s2, i1, i2);
-                }
+                uint32_t cur[16], nxt[16];
+                tc_ld16_issue(taddr + 64 * h, cur);
+                tc_ld_wait16(cur);
+#define TC_EPI_LOOP(MASKC, MASKR)                                                                                          \
+    _Pragma("unroll 1") for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 16) {                                                \
+        const bool more = j0 + 16 < 64 * h + 64;                                                                           \
+        if (more) tc_ld16_issue(taddr + j0 + 16, nxt);                                                                     \
+        _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                                                    \
+            float v[8];                                                                                                    \
+            _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(cur[8 * u + i]);                          \
+            epi_group8<METRIC, MASKC, MASKR, COLS, EXT>(v, col0 + j0 + 8 * u, M, row_ok, na, cn, cn_vec, lane,             \
+                                                        my_cv + j0 + 8 * u, my_cb + j0 + 8 * u, s1, s2, i1, i2);           \
+        }                                                                                                                  \
+        if (more) {                                                                                                        \
+            tc_ld_wait16(nxt);                                                                                             \
+            _Pragma("unroll") for (int i = 0; i < 16; ++i) cur[i] = nxt[i];                                                \
+        }                                                                                                                  \
+    }
+                if (full_tile && !partial_rows) { TC_EPI_LOOP(false, false) } else { TC_EPI_LOOP(true, true) }
+#undef TC_EPI_LOOP
             }
             tc_fence_before();  // this warp's share of the accumulator has been read: hand it back
             if (lane == 0) mbar_arrive(bar_tempty(g));
@@ -541,10 +637,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(vo_ctx *ctx, CUtensorMap *map, const float *ptr, long long rows) {
+int make_map(vo_ctx *ctx, CUtensorMap *map, const float *ptr, long long rows, int row_floats = TC_D) {
     PFN_encodeTiled fn = (PFN_encodeTiled)ctx->encode_tiled;
-    cuuint64_t dims[2] = {(cuuint64_t)TC_D, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)TC_D * sizeof(float)};
+    cuuint64_t dims[2] = {(cuuint64_t)row_floats, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_floats * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_BN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
@@ -609,22 +705,27 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     int rc;
     const size_t per_a = (size_t)rows_a * TC_D * sizeof(float), per_b = (size_t)rows_b * TC_D * sizeof(float);
     if ((rc = ws_get(ctx, WS_SPLIT_A, per_a * (passes == 3 ? 2 : 1), (void **)&split_a))) return rc;
-    if ((rc = ws_get(ctx, WS_SPLIT_B, per_b * (passes == 3 ? 2 : 1), (void **)&split_b))) return rc;
+    const bool ext = passes == 1 && l2;  // B extension rows [rows_b][32] live behind B_hi
+    const size_t per_ext = (size_t)rows_b * TC_KB * sizeof(float);
+    if ((rc = ws_get(ctx, WS_SPLIT_B, per_b * (passes == 3 ? 2 : 1) + (ext ? per_ext : 0), (void **)&split_b))) return rc;
     const long long rows_a4 = (rows_a + 3) & ~3ll;  // column norms start 16 B aligned (vector loads in the epilogue)
     if ((rc = ws_get(ctx, WS_NORMS, sizeof(float) * (size_t)(rows_a4 + rows_b), (void **)&norms))) return rc;
     float *a_hi = split_a, *a_lo = passes == 3 ? split_a + (size_t)rows_a * TC_D : nullptr;
     float *b_hi = split_b, *b_lo = passes == 3 ? split_b + (size_t)rows_b * TC_D : nullptr;
+    float *b_ext = ext ? split_b + (size_t)rows_b * TC_D : nullptr;
     float *row_norm = norms, *col_norm = norms + rows_a4;
 
     VO_PROF(ctx, st, VO_STAGE_PREP);
-    prep_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, a_hi, a_lo, l2 ? row_norm : nullptr);
+    prep_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, a_hi, a_lo, l2 ? row_norm : nullptr, nullptr);
     VO_LAUNCH_CHECK(ctx);
-    prep_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b_hi, b_lo, l2 ? col_norm : nullptr);
+    prep_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b_hi, b_lo, l2 ? col_norm : nullptr, b_ext);
     VO_LAUNCH_CHECK(ctx);
 
     CUtensorMap mbh, mbl;
     if ((rc = make_map(ctx, &mbh, b_hi, rows_b))) return rc;
-    if ((rc = make_map(ctx, &mbl, passes == 3 ? b_lo : b_hi, rows_b))) return rc;
+    if (ext) rc = make_map(ctx, &mbl, b_ext, rows_b, TC_KB);
+    else rc = make_map(ctx, &mbl, passes == 3 ? b_lo : b_hi, rows_b);
+    if (rc) return rc;
 
     const int row_blocks = ceil_div(n_stride, TC_BM);
     const int grid_x = ceil_div(row_blocks, TC_CLUSTER) * TC_CLUSTER;  // clusters pair adjacent row blocks

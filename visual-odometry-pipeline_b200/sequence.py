@@ -113,7 +113,7 @@ class HostPairRunner:
     vo_pipeline on the compute stream -> D2H of poses / status.  This is the call a user with frames in host
     memory makes; bench.py times it as `e2e`."""
 
-    def __init__(self, host_batch, cfg, chunk, device="cuda", depth_mode="sampled"):
+    def __init__(self, host_batch, cfg, chunk, device="cuda", depth_mode="dense"):
         """depth_mode "dense": the whole depth map of every reference frame crosses PCIe (1.87 MB at 1241x376);
         "sampled": the maps stay in pinned host memory and vo_sample_depth reads depth[int(y), int(x)] of the
         reference keypoints through the mapped pointer on the copy stream (one 32 B sector per keypoint)."""

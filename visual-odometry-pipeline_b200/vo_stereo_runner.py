@@ -1,13 +1,12 @@
 """Offline RGB-D driver — interface of the reference's vo_stereo_runner.py: `vo_offline_data(cam_intr, img_path,
 output_filename)` (:27-60) walks sorted `*.png` / `*_depth.npy` pairs, feeds VisualOdometry.process_frame and saves
 the (N,4,4) float64 global poses with np.save."""
-import glob
 import time
 
-import cv2
 import numpy as np
 
 from VisualOdometry_Stereo import VisualOdometry
+from vo_b200.frame_io import FramePrefetcher
 
 midpoints = [(100, 100)]
 numpyseeds = [8214]
@@ -17,18 +16,12 @@ for _seed in numpyseeds:           # kept for parity of the global numpy stream 
 
 def vo_offline_data(cam_intr, img_path, output_filename):
     vo = VisualOdometry(cam_intr, seq=0)
-    images = sorted(glob.glob(img_path + "/*.png"))
-    depths = sorted(glob.glob(img_path + "/*_depth.npy"))
     poses = []
     t_start = time.time()
-    for index, (image_file, depth_file) in enumerate(zip(images, depths)):
+    # same files, same order, same BGR->RGB conversion as the reference loop (:38-50); decoding runs ahead in threads
+    for index, frame, depth in FramePrefetcher(img_path):
         if index == 1:
             t_start = time.time()
-        frame = cv2.imread(image_file)
-        if frame is None:
-            raise FileNotFoundError(image_file)
-        depth = np.load(depth_file)
-        frame = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
         pose = vo.process_frame(frame, depth, midpoints[0], index)
         print("Time taken:" + str(time.time() - t_start))
         print("frame_pose.t.T" + str(pose.t.T))
