@@ -111,13 +111,20 @@ def run_resident(batch, cfg, pair0=0, chunk=None, out=None):
 class HostPairRunner:
     """End-to-end path for HOST inputs: pinned host buffers -> H2D on a copy stream, double-buffered against
     vo_pipeline on the compute stream -> D2H of poses / status.  This is the call a user with frames in host
-    memory makes; bench.py times it as `e2e`."""
+    memory makes; bench.py times it as `e2e`.
 
-    def __init__(self, host_batch, cfg, chunk, device="cuda", depth_mode="dense"):
-        """depth_mode "dense": the whole depth map of every reference frame crosses PCIe (1.87 MB at 1241x376);
-        "sampled": the maps stay in pinned host memory and vo_sample_depth reads depth[int(y), int(x)] of the
-        reference keypoints through the mapped pointer on the copy stream (one 32 B sector per keypoint)."""
-        if depth_mode not in ("dense", "sampled"):
+    Depth maps are 82 % of the bytes of an ORB pair (1.87 MB of 2.27 MB at 1241x376) although only the pixels under the
+    reference keypoints are read, and the bulk copy alone saturates PCIe.  depth_mode selects how they travel:
+      "dense"    whole maps by DMA (copy engine);
+      "sampled"  maps stay in pinned host memory; vo_sample_depth reads depth[int(y), int(x)] of every reference
+                 keypoint through the mapped pointer (one 32 B sector per keypoint, ~125 M reads/s measured);
+      "hybrid"   both at once: the first (1 - sampled_frac) of each chunk's maps go by DMA on the copy stream while the
+                 SMs pull the samples of the rest zero-copy on a third stream — the two paths are limited by different
+                 things (link bandwidth vs outstanding small reads), so together they move a chunk faster than either.
+    In the last two modes vo_pipeline consumes the compact depth_kp array (sampled on the device for DMA'd maps)."""
+
+    def __init__(self, host_batch, cfg, chunk, device="cuda", depth_mode="dense", sampled_frac=0.2):
+        if depth_mode not in ("dense", "sampled", "hybrid"):
             raise ValueError(depth_mode)
         self.depth_mode = depth_mode
         self.cfg, self.chunk, self.device = cfg, chunk, torch.device(device)
@@ -125,23 +132,35 @@ class HostPairRunner:
         keys = ("ref_desc", "cur_desc", "ref_kp", "cur_kp", "depth")
         self.host = {k: torch.from_numpy(np.ascontiguousarray(host_batch[k])).pin_memory() for k in keys}
         self.B = self.host["ref_desc"].shape[0]
-        staged = [k for k in keys if not (k == "depth" and depth_mode == "sampled")]
-        self.stage = [{k: torch.empty((chunk,) + tuple(self.host[k].shape[1:]), dtype=self.host[k].dtype, device=self.device)
-                       for k in staged} for _ in range(2)]
+        # pairs [0, n_dma) of a chunk send their map by DMA, pairs [n_dma, chunk) are sampled from host memory
+        frac = {"dense": 0.0, "sampled": 1.0, "hybrid": float(sampled_frac)}[depth_mode]
+        self.n_dma = chunk - int(round(chunk * frac))
         self.hw = tuple(self.host["depth"].shape[1:])
-        if depth_mode == "sampled":
-            for st in self.stage:
-                st["depth_kp"] = torch.empty((chunk, self.host["ref_kp"].shape[1]), dtype=torch.float32, device=self.device)
+        N = self.host["ref_kp"].shape[1]
+        self.stage = []
+        for _ in range(2):
+            st = {k: torch.empty((chunk,) + tuple(self.host[k].shape[1:]), dtype=self.host[k].dtype, device=self.device)
+                  for k in keys if k != "depth"}
+            if self.n_dma:
+                st["depth"] = torch.empty((self.n_dma,) + self.hw, dtype=torch.float32, device=self.device)
+            if depth_mode != "dense":
+                st["depth_kp"] = torch.empty((chunk, N), dtype=torch.float32, device=self.device)
+            self.stage.append(st)
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.sample_stream = torch.cuda.Stream(device=self.device)
         self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.kp_ready = [torch.cuda.Event() for _ in range(2)]
+        self.sampled = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
         self.out = ops.PipelineBuffers(self.B, self.device)
         self.host_T = torch.empty((self.B, 4, 4), dtype=torch.float64).pin_memory()
         self.host_status = torch.empty((self.B,), dtype=torch.int32).pin_memory()
         self.host_inl = torch.empty((self.B,), dtype=torch.int32).pin_memory()
-        self.h2d_bytes = sum(v.numel() * v.element_size() for k, v in self.host.items() if k in staged)
-        if depth_mode == "sampled":   # one 32-byte sector per reference keypoint crosses the bus
-            self.h2d_bytes += int(self.host["ref_kp"].shape[0]) * int(self.host["ref_kp"].shape[1]) * 32
+        per_pair = {k: v[0].numel() * v.element_size() for k, v in self.host.items()}
+        n_chunks = (self.B + chunk - 1) // chunk
+        dma_pairs = sum(min(self.n_dma, min(self.B, (c + 1) * chunk) - c * chunk) for c in range(n_chunks))
+        self.h2d_bytes = self.B * sum(b for k, b in per_pair.items() if k != "depth") + dma_pairs * per_pair["depth"] \
+            + (self.B - dma_pairs) * N * 32          # one 32-byte sector per zero-copy sample
         self.d2h_bytes = self.host_T.numel() * 8 + self.host_status.numel() * 4 + self.host_inl.numel() * 4
 
     def run(self, pair0=0):
@@ -150,30 +169,38 @@ class HostPairRunner:
         n_chunks = (self.B + self.chunk - 1) // self.chunk
         for c in range(n_chunks):
             lo, hi = c * self.chunk, min(self.B, (c + 1) * self.chunk)
-            buf = c % 2
+            n, buf = hi - lo, c % 2
+            st = self.stage[buf]
+            n_dma = min(self.n_dma, n)
             with torch.cuda.stream(self.copy_stream):
                 if c >= 2:
                     self.copy_stream.wait_event(self.consumed[buf])
-                for k, v in self.host.items():
-                    if k in self.stage[buf]:
-                        self.stage[buf][k][: hi - lo].copy_(v[lo:hi], non_blocking=True)
-                if self.depth_mode == "sampled":
-                    ops.sample_depth(self.stage[buf]["ref_kp"][: hi - lo], self.host["depth"][lo:hi],
-                                     out=self.stage[buf]["depth_kp"][: hi - lo])
+                st["ref_kp"][:n].copy_(self.host["ref_kp"][lo:hi], non_blocking=True)
+                self.kp_ready[buf].record(self.copy_stream)
+                for k in ("cur_kp", "ref_desc", "cur_desc"):   # one copy stream: a second one for the descriptors measured slower
+                    st[k][:n].copy_(self.host[k][lo:hi], non_blocking=True)
+                if n_dma:
+                    st["depth"][:n_dma].copy_(self.host["depth"][lo:lo + n_dma], non_blocking=True)
+                    if self.depth_mode != "dense":   # maps that came by DMA are sampled from HBM
+                        ops.sample_depth(st["ref_kp"][:n_dma], st["depth"][:n_dma], out=st["depth_kp"][:n_dma])
                 self.copied[buf].record(self.copy_stream)
+            if n > n_dma:
+                with torch.cuda.stream(self.sample_stream):   # zero-copy samples, concurrent with the DMA above
+                    self.sample_stream.wait_event(self.kp_ready[buf])
+                    ops.sample_depth(st["ref_kp"][n_dma:n], self.host["depth"][lo + n_dma:hi], out=st["depth_kp"][n_dma:n])
+                    self.sampled[buf].record(self.sample_stream)
+                compute.wait_event(self.sampled[buf])
             compute.wait_event(self.copied[buf])
-            s = self.stage[buf]
             view = ops.PipelineBuffers.__new__(ops.PipelineBuffers)
             view.T_rel, view.rt = self.out.T_rel[lo:hi], self.out.rt[lo:hi]
             view.n_matches, view.n_corr = self.out.n_matches[lo:hi], self.out.n_corr[lo:hi]
             view.n_inl, view.status = self.out.n_inl[lo:hi], self.out.status[lo:hi]
-            if self.depth_mode == "sampled":
-                ops.pipeline(s["ref_desc"][: hi - lo], s["cur_desc"][: hi - lo], s["ref_kp"][: hi - lo], s["cur_kp"][: hi - lo],
-                             None, self.K, pair0=pair0 + lo, out=view, depth_kp=s["depth_kp"][: hi - lo], hw=self.hw,
-                             **self.cfg.kw)
+            if self.depth_mode == "dense":
+                ops.pipeline(st["ref_desc"][:n], st["cur_desc"][:n], st["ref_kp"][:n], st["cur_kp"][:n], st["depth"][:n],
+                             self.K, pair0=pair0 + lo, out=view, **self.cfg.kw)
             else:
-                ops.pipeline(s["ref_desc"][: hi - lo], s["cur_desc"][: hi - lo], s["ref_kp"][: hi - lo], s["cur_kp"][: hi - lo],
-                             s["depth"][: hi - lo], self.K, pair0=pair0 + lo, out=view, **self.cfg.kw)
+                ops.pipeline(st["ref_desc"][:n], st["cur_desc"][:n], st["ref_kp"][:n], st["cur_kp"][:n], None, self.K,
+                             pair0=pair0 + lo, out=view, depth_kp=st["depth_kp"][:n], hw=self.hw, **self.cfg.kw)
             self.consumed[buf].record(compute)
         self.host_T.copy_(self.out.T_rel, non_blocking=True)
         self.host_status.copy_(self.out.status, non_blocking=True)
