@@ -205,6 +205,7 @@ def run_ours(args, wl):
     from vo_b200 import ops, sequence
 
     rank, local_rank, world = env_rank()
+    numa_cores = sequence.bind_to_gpu_numa(local_rank) if world > 1 else None   # pinned buffers on the GPU's NUMA node
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -414,7 +415,8 @@ def run_ours(args, wl):
         "config": {"workload": f"{args.workload}: {wl['desc']}", "pairs_per_gpu_per_step": P, "unique_pairs": unique,
                    "chunk": chunk, "l2": "inputs larger than L2 (every pair has its own HBM copy: "
                    f"{batch.nbytes() / 1e6:.0f} MB per GPU per step)", "parallelism": f"pairs sharded over {world} GPU(s), "
-                   "1 NCCL all-gather of 4x4 poses per step" if world > 1 else "single GPU"},
+                   "1 NCCL all-gather of 4x4 poses per step" if world > 1 else "single GPU",
+                   "host_numa_binding": (f"rank 0 bound to {len(numa_cores)} GPU-local cores" if numa_cores else "none")},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": runner.h2d_bytes,
                 "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
                 "depth": args.e2e_depth},

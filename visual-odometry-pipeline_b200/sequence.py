@@ -11,6 +11,30 @@ import torch
 from . import ops
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPU cores NVML reports as local to the GPU, BEFORE host buffers are allocated, so that
+    pinned staging memory lands on the GPU's NUMA node (first touch).  With one process per GPU on an 8-GPU box the
+    host-to-device legs otherwise all pull from whichever node the ranks happened to start on.  Returns the core
+    list, or None when NVML / affinity is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
 def shard_range(n_pairs, rank, world):
     """Contiguous block [lo, hi) of the pair list owned by `rank`."""
     base, rem = divmod(int(n_pairs), int(world))
