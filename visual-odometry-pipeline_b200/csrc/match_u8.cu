@@ -41,8 +41,19 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
     return d;
 }
 
+// Multipliers the compiler cannot see through: `x * opaque(4) + y` stays an IMAD (FMA pipe) instead of being strength-
+// reduced to LEA / IADD3 on the logic pipe, which is the pipe this kernel is bound by.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+struct U8Mul {
+    uint32_t m1, m2, m4, mrow, mcol;
+};
+
 template <int NORM>
-__device__ __forceinline__ uint32_t dist256(const uint32_t (&a)[8], const uint4 b0, const uint4 b1) {
+__device__ __forceinline__ uint32_t dist256(const uint32_t (&a)[8], const uint4 b0, const uint4 b1, const U8Mul &mu) {
     const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     if (NORM == VO_NORM_HAMMING) {
         uint32_t x[8];
@@ -53,7 +64,9 @@ __device__ __forceinline__ uint32_t dist256(const uint32_t (&a)[8], const uint4 
         const uint32_t sc = xor3(sa, sb, x[6]), cc = maj3(sa, sb, x[6]);
         const uint32_t t = xor3(ca, cb, cc), f = maj3(ca, cb, cc);
         // ones: sc, x7; twos: t; fours: f
-        return (__popc(sc) + __popc(x[7])) + (2u * __popc(t) + 4u * __popc(f));
+        const uint32_t t1 = (uint32_t)__popc(t) * mu.m2 + (uint32_t)__popc(sc);
+        const uint32_t t2 = (uint32_t)__popc(f) * mu.m4 + (uint32_t)__popc(x[7]);
+        return t1 * mu.m1 + t2;
     } else {
         uint32_t d = 0;
 #pragma unroll
@@ -103,6 +116,7 @@ match_u8_kernel(const uint8_t *__restrict__ ref, const uint8_t *__restrict__ cur
     }
 
     const uint4 *cur4 = reinterpret_cast<const uint4 *>(cur + (size_t)b * m_stride * 32);
+    const U8Mul mu = {opaque_u32(1u), opaque_u32(2u), opaque_u32(4u), opaque_u32(1u << U8_ROW_BITS), opaque_u32(1u << U8_COL_BITS)};
     if (row_base < N) {
         for (int c0 = c_begin; c0 < c_end; c0 += U8_CHUNK) {
             const int cnt = min(U8_CHUNK, c_end - c0);
@@ -110,14 +124,37 @@ match_u8_kernel(const uint8_t *__restrict__ ref, const uint8_t *__restrict__ cur
             for (int t = tid; t < cnt * 2; t += U8_THREADS) sdesc[t] = cur4[(size_t)c0 * 2 + t];
             __syncthreads();
 
+            int j = 0;
+            if (PACKED && !SECOND) {
+                // two columns per iteration: the row minimum of both keys and the running one is a single 3-input
+                // VIMNMX3, the column minimum over the thread's four rows is VIMNMX3 + VIMNMX, and lane 0 stores both
+                // warp minima with one 64-bit STS
+                for (; j + 1 < cnt; j += 2) {
+                    const uint4 b00 = sdesc[2 * j], b01 = sdesc[2 * j + 1], b10 = sdesc[2 * j + 2], b11 = sdesc[2 * j + 3];
+                    const uint32_t col = (uint32_t)(c0 + j);
+                    uint32_t ck0[U8_ROWS_PT], ck1[U8_ROWS_PT];
+#pragma unroll
+                    for (int r = 0; r < U8_ROWS_PT; ++r) {
+                        const uint32_t d0 = dist256<NORM>(a[r], b00, b01, mu), d1 = dist256<NORM>(a[r], b10, b11, mu);
+                        s1[r] = min(min(d0 * mu.mcol + col, d1 * mu.mcol + (col + 1u)), s1[r]);
+                        ck0[r] = d0 * mu.mrow + rowid[r];
+                        ck1[r] = d1 * mu.mrow + rowid[r];
+                    }
+                    static_assert(U8_ROWS_PT == 4, "column reduction below is written for 4 rows per thread");
+                    const uint32_t m0 = min(min(min(ck0[0], ck0[1]), ck0[2]), ck0[3]);
+                    const uint32_t m1 = min(min(min(ck1[0], ck1[1]), ck1[2]), ck1[3]);
+                    const uint32_t w0 = __reduce_min_sync(0xffffffffu, m0), w1 = __reduce_min_sync(0xffffffffu, m1);
+                    if (lane == 0) *reinterpret_cast<uint2 *>(&swcol[warp][j]) = make_uint2(w0, w1);
+                }
+            }
 #pragma unroll 2
-            for (int j = 0; j < cnt; ++j) {
+            for (; j < cnt; ++j) {
                 const uint4 b0 = sdesc[2 * j], b1 = sdesc[2 * j + 1];
                 const uint32_t col = (uint32_t)(c0 + j);
                 uint32_t ckey = 0xffffffffu;
 #pragma unroll
                 for (int r = 0; r < U8_ROWS_PT; ++r) {
-                    const uint32_t d = dist256<NORM>(a[r], b0, b1);
+                    const uint32_t d = dist256<NORM>(a[r], b0, b1, mu);
                     if (PACKED) {
                         const uint32_t k = (d << U8_COL_BITS) + col;
                         if (SECOND) s2[r] = min(s2[r], max(s1[r], k));
