@@ -283,6 +283,16 @@ VO_API int vo_seq_push(vo_seq *seq, const void *desc, const float *kp, int n_kp,
 VO_API int vo_seq_frames(const vo_seq *seq);
 VO_API int vo_seq_read(vo_seq *seq, int first, int count, double *poses_h, int32_t *info_h, void *stream);
 
+/*
+ * "Same" 2-D convolution on the tensor cores (3xTF32 implicit GEMM; TMA zero fill is the padding): the layer type of
+ * the R2D2 network (feature_extractors/r2d2/nets/patchnet.py:56-66, torch.nn.Conv2d with padding = (k-1)*dil/2).
+ *   x float [H][W][C_in] (NHWC), w float [C_out][k][k][C_in], out float [H][W][C_out]
+ *   out = relu?( conv(x, w) * scale[c] + shift[c] )   — bias and inference batch-norm folded into scale / shift
+ *   C_in a multiple of 32, C_out in {32, 64, 128}.
+ */
+VO_API int vo_conv2d(vo_ctx *ctx, const float *x, int H, int W, int cin, const float *w, int cout, int k, int dil,
+              const float *scale, const float *shift, int relu, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,6 +173,20 @@ def sample_depth(kp, depth, n_kp=None, out=None):
     return out
 
 
+def conv2d(x, w, scale, shift, k, dil=1, relu=False):
+    """vo_conv2d: x [H,W,Cin] NHWC, w [Cout,k,k,Cin], scale/shift [Cout] (all CUDA float32) -> [H,W,Cout]."""
+    for t, name in ((x, "x"), (w, "w"), (scale, "scale"), (shift, "shift")):
+        _chk(t, torch.float32, name)
+    H, W, cin = x.shape
+    cout = w.shape[0]
+    out = torch.empty((H, W, cout), dtype=torch.float32, device=x.device)
+    ctx = context(x.device)
+    with torch.cuda.device(x.device):
+        check(ctx.lib.vo_conv2d(ctx.handle, _ptr(x), H, W, cin, _ptr(w), cout, int(k), int(dil), _ptr(scale), _ptr(shift),
+                                int(bool(relu)), _ptr(out), _stream()), "vo_conv2d")
+    return out
+
+
 class Correspondences:
     def __init__(self, xyz, ref_uv, cur_uv, src, count, status):
         self.xyz, self.ref_uv, self.cur_uv, self.src, self.count, self.status = xyz, ref_uv, cur_uv, src, count, status
