@@ -293,6 +293,42 @@ VO_API int vo_seq_read(vo_seq *seq, int first, int count, double *poses_h, int32
 VO_API int vo_conv2d(vo_ctx *ctx, const float *x, int H, int W, int cin, const float *w, int cout, int k, int dil,
               const float *scale, const float *shift, int relu, float *out, void *stream);
 
+/*
+ * R2D2 front-end: `extract_features_and_desc` of R2D2.py:202-232 for one image at scale 1 (the
+ * reference's extract_multiscale leaves its loop after the first scale, R2D2.py:133-135): network forward
+ * (nets/patchnet.py:141-186: a stack of "same" convolutions with inference batch-norm / ReLU, an optional 2x2 max-pool
+ * and a final bilinear x2 up-sampling), reliability / repeatability heads on x^2 (:181-186, :16-27), 3x3 non-maximum
+ * suppression with both thresholds (R2D2.py:82-101), score = reliability * repeatability > score_thr (:186-188),
+ * L2-normalised descriptors of the surviving pixels.
+ *   layers[0] must have C_in = 3 (runs on the CUDA cores, with the ImageNet mean / std normalisation of
+ *   tools/dataloader.py:norm_RGB folded in); every other layer runs as vo_conv2d.  All weight pointers are HOST
+ *   pointers and are copied at creation.  w: [C_out][k][k][C_in].
+ *   vo_r2d2_extract: rgb uint8 [H][W][3] (device or pinned host).  Outputs (device): xys float [max_kp][3]
+ *   (x, y, 32), desc float [max_kp][128], scores float [max_kp], count int32[1] (total found; at most max_kp are
+ *   written, in row-major pixel order like torch.nonzero), rel_map / rep_map float [Ho][Wo] (optional).
+ */
+typedef struct vo_r2d2_layer {
+    int cin, cout, k, dil;
+    int bn, relu, pool_after;         /* pool_after: 2 = MaxPool2d(2) follows, 0 = none */
+    const float *w, *bias, *bn_mean, *bn_var;
+} vo_r2d2_layer;
+typedef struct vo_r2d2_config {
+    int H, W;
+    int n_layers;
+    const vo_r2d2_layer *layers;
+    int upsample;                     /* 1 or 2 (Fast_Quad_L2Net ends with Upsample(scale_factor=2, bilinear)) */
+    const float *clf_w, *clf_b;       /* reliability head  [2][C], [2] */
+    const float *sal_w, *sal_b;       /* repeatability head [C], [1]   */
+    float bn_eps;
+    int max_kp;
+} vo_r2d2_config;
+typedef struct vo_r2d2 vo_r2d2;
+VO_API int vo_r2d2_create(vo_ctx *ctx, const vo_r2d2_config *cfg, vo_r2d2 **out);
+VO_API void vo_r2d2_destroy(vo_r2d2 *net);
+VO_API int vo_r2d2_out_shape(const vo_r2d2 *net, int *Ho, int *Wo);
+VO_API int vo_r2d2_extract(vo_r2d2 *net, const uint8_t *rgb, float rel_thr, float rep_thr, float score_thr, float *xys,
+                    float *desc, float *scores, int32_t *count, float *rel_map, float *rep_map, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ Sources of each fixture (file:line under /root/reference):
   pnp.npz             cv2.solveP3P, cv2.projectPoints, cv2.solvePnP(ITERATIVE), cv2.solvePnPRansac
                       (VisualOdometry_Stereo.py:129 call signature)
   kitti03_eval.npz    plot_utils/kittievalodom.py:513-570 eval() on plot_utils/data (known-answer tuple)
+  r2d2_net.npz        the reference's R2D2 network + NMS on a synthetic image, with the shipped faster2d2 weights
   kitti03_segments.npz  the evaluator's per-segment table and reductions on the same data (:181-233, :247-270, :361-469)
 """
 import ast
@@ -233,6 +234,57 @@ def gen_kitti_eval():
          dist=np.asarray(ev.trajectory_distances(pg), np.float64))
 
 
+def gen_r2d2_net():
+    """The reference's R2D2 network (nets/patchnet.py) with its shipped faster2d2_WASF_N16 weights (the model R2D2.py:191
+    selects), run on CPU in fp32 on a small synthetic image; NonMaxSuppression and the scale-1 body of extract_multiscale
+    are taken from R2D2.py by name (the module itself asserts a CUDA device at import, :195)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    r2 = os.path.join(REF, "feature_extractors", "r2d2")
+    sys.path.insert(0, r2)
+    import nets.patchnet as patchnet
+    sys.path.remove(r2)
+    ck = torch.load(os.path.join(r2, "models", "faster2d2_WASF_N16.pt"), map_location="cpu", weights_only=False)
+    net = eval(ck["net"], vars(patchnet))
+    sd = {k.replace("module.", ""): v for k, v in ck["state_dict"].items()}
+    net.load_state_dict(sd)
+    net.eval()
+    tree = ast.parse(open(os.path.join(REF, "R2D2.py")).read())
+    ns = dict(torch=torch, nn=nn, F=F, np=np)
+    for node in tree.body:
+        if isinstance(node, (ast.ClassDef, ast.FunctionDef)) and node.name in ("NonMaxSuppression", "extract_multiscale"):
+            exec(compile(ast.Module([node], []), "R2D2.py", "exec"), ns)
+    rng = np.random.default_rng(8214)
+    H, W = 97, 163                                   # odd sizes: MaxPool2d(2) floors, the up-sampled maps are 96 x 162
+    img = np.full((H, W, 3), 110, np.uint8)
+    for _ in range(70):
+        x0, y0 = int(rng.integers(0, W)), int(rng.integers(0, H))
+        w, h = int(rng.integers(4, 40)), int(rng.integers(4, 30))
+        col = tuple(int(c) for c in rng.integers(0, 256, 3))
+        if rng.random() < 0.5:
+            cv2.rectangle(img, (x0, y0), (x0 + w, y0 + h), col, -1)
+        else:
+            cv2.circle(img, (x0, y0), w // 2 + 2, col, -1)
+    img = cv2.GaussianBlur(img, (3, 3), 0.8)
+    img = np.clip(img.astype(np.int32) + rng.integers(-6, 7, img.shape), 0, 255).astype(np.uint8)
+    # tools/dataloader.py norm_RGB: ToTensor + Normalize(ImageNet mean / std)
+    t = torch.from_numpy(img).permute(2, 0, 1).float().div(255)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+    x = ((t - mean) / std)[None]
+    with torch.no_grad():
+        res = net(imgs=[x])
+        rel, rep, desc = res["reliability"][0], res["repeatability"][0], res["descriptors"][0]
+        det = ns["NonMaxSuppression"](rel_thr=0.7, rep_thr=0.7)
+        xys, D, scores = ns["extract_multiscale"](net, x, det, min_size=0, max_size=9999, trt=False)
+    idxs = np.argwhere(scores.numpy() > 0.85)        # extract_keypoints, R2D2.py:186-188
+    arrs = {"w__" + k: v.numpy() for k, v in sd.items() if v.ndim > 0}
+    save("r2d2_net.npz", net=np.array(ck["net"]), image=img, rel=rel[0, 0].numpy(), rep=rep[0, 0].numpy(),
+         xys_all=xys.numpy(), scores_all=scores.numpy(), desc_all=D.numpy(), keep=idxs.reshape(-1),
+         desc_map_sample=desc[0, :, ::7, ::11].numpy(), **arrs)
+    print("r2d2:", ck["net"], "maps", tuple(rel.shape), "keypoints", len(scores), "score > 0.85:", len(idxs))
+
+
 if __name__ == "__main__":
     orb_mod, sift_mod = import_reference_extractors()
     gen_match_u8(orb_mod)
@@ -241,3 +293,4 @@ if __name__ == "__main__":
     gen_backproject()
     gen_pnp()
     gen_kitti_eval()
+    gen_r2d2_net()

@@ -1,0 +1,96 @@
+"""R2D2 front-end (vo_r2d2_*) against the reference's own network, NMS and score filter run on CPU
+in fp32 with the shipped faster2d2_WASF_N16 weights (tests/golden/r2d2_net.npz, made by make_golden.py: gen_r2d2_net).
+Floating point: maps within 2e-4, descriptors within 2e-4; the keypoint set is identical except for pixels the
+reference itself decides within that tolerance of a threshold or of a 3x3 tie."""
+import numpy as np
+import pytest
+
+
+def _weights(g):
+    return str(g["net"]).split("(")[0], {k[3:]: g[k] for k in g.files if k.startswith("w__")}
+
+
+def test_architecture_table_matches_the_checkpoint(golden):
+    import vo_b200  # noqa: F401
+    from vo_b200 import r2d2_frontend as rf
+    g = golden("r2d2_net.npz")
+    name, sd = _weights(g)
+    assert name == "Fast_Quad_L2Net_ConfCFS"
+    layers = rf.layer_table(name, sd)
+    assert [(L["cin"], L["cout"], L["k"], L["dil"], L["bn"], L["relu"], L["pool_after"]) for L in layers] == [
+        (3, 32, 3, 1, 1, 1, 0), (32, 32, 3, 1, 1, 1, 0), (32, 64, 3, 1, 1, 1, 2), (64, 64, 3, 1, 1, 1, 0), (64, 128, 3, 1, 1, 1, 0),
+        (128, 128, 3, 2, 1, 1, 0), (128, 128, 2, 2, 1, 0, 0), (128, 128, 2, 4, 1, 0, 0), (128, 128, 2, 8, 0, 0, 0)]
+    assert layers[0]["w"].shape == (32, 3, 3, 3) and layers[6]["w"].shape == (128, 2, 2, 128)
+    # layout: [C_out][ky][kx][C_in] is the transpose of torch's [C_out][C_in][ky][kx]
+    assert np.array_equal(layers[5]["w"][7, 2, 0, 33], sd["ops.16.weight"][7, 33, 2, 0])
+    with pytest.raises(ValueError):
+        rf.layer_table("L2_Net", sd)
+    with pytest.raises(ValueError):
+        rf.layer_table("Quad_L2Net_ConfCFS", {k: v for k, v in sd.items() if not k.startswith("ops.23")})
+
+
+@pytest.mark.gpu
+def test_maps_keypoints_descriptors_vs_reference_network(golden):
+    import torch
+    import vo_b200  # noqa: F401
+    from vo_b200 import r2d2_frontend as rf
+    g = golden("r2d2_net.npz")
+    name, sd = _weights(g)
+    img = g["image"]
+    net = rf.R2D2Net(name, sd, img.shape[0], img.shape[1], max_kp=4096)
+    assert (net.Ho, net.Wo) == g["rel"].shape == (96, 162)
+    xys, desc, scores, rel, rep = net.extract(img, 0.7, 0.7, 0.85, want_maps=True)
+    rel, rep = rel.cpu().numpy(), rep.cpu().numpy()
+    assert np.abs(rel - g["rel"]).max() < 2e-4 and np.abs(rep - g["rep"]).max() < 2e-4
+    keep = g["keep"]
+    want_xy = g["xys_all"][keep][:, :2].astype(np.int64)
+    want = {(int(x), int(y)): i for i, (x, y) in zip(keep, want_xy)}
+    got_xy = xys.cpu().numpy()
+    assert np.all(got_xy[:, 2] == 32.0)
+    got = {(int(x), int(y)): i for i, (x, y) in enumerate(got_xy[:, :2])}
+    # row-major order, like torch.nonzero
+    lin = got_xy[:, 1].astype(np.int64) * net.Wo + got_xy[:, 0].astype(np.int64)
+    assert np.all(np.diff(lin) > 0)
+    tol = 3e-4
+    for (x, y) in set(got) ^ set(want):                    # a differing pixel must sit on a decision boundary
+        c, q = float(g["rel"][y, x]), float(g["rep"][y, x])
+        nb = g["rep"][max(0, y - 1):y + 2, max(0, x - 1):x + 2]
+        second = np.sort(nb.reshape(-1))[-2] if nb.size > 1 else -1
+        near = abs(c - 0.7) < tol or abs(q - 0.7) < tol or abs(c * q - 0.85) < tol or abs(q - nb.max()) < tol and abs(q - second) < tol
+        assert near, (x, y, c, q)
+    common = sorted(set(got) & set(want))
+    assert len(common) >= len(want) - 2 and len(common) > 50
+    gi = np.array([got[k] for k in common]); wi = np.array([want[k] for k in common])
+    d = desc.cpu().numpy()
+    assert np.abs(d[gi] - g["desc_all"][wi]).max() < 2e-4
+    assert np.abs(np.linalg.norm(d, axis=1) - 1.0).max() < 1e-5
+    assert np.abs(scores.cpu().numpy()[gi] - g["scores_all"][wi]).max() < 3e-4
+    # lower thresholds: more keypoints, still the reference's rule (checked against its maps)
+    xys2, _, sc2 = net.extract(img, 0.5, 0.5, 0.3)
+    assert len(xys2) > len(xys)
+    # pinned host input gives the same result as a device tensor
+    a = net.extract(torch.from_numpy(img).pin_memory(), 0.7, 0.7, 0.85)[0].clone()
+    b = net.extract(torch.from_numpy(img).cuda(), 0.7, 0.7, 0.85)[0].clone()
+    assert torch.equal(a, b) and torch.equal(a, xys)
+
+
+@pytest.mark.gpu
+def test_kitti_sized_image_runs_and_is_deterministic(golden):
+    import torch
+    import vo_b200  # noqa: F401
+    from vo_b200 import r2d2_frontend as rf
+    g = golden("r2d2_net.npz")
+    name, sd = _weights(g)
+    H, W = 376, 1241
+    rng = np.random.default_rng(1)
+    img = np.kron(rng.integers(0, 256, (H // 8, W // 8 + 1, 3)), np.ones((8, 8, 1)))[:H, :W].astype(np.uint8)
+    net = rf.R2D2Net(name, sd, H, W)
+    assert (net.Ho, net.Wo) == (376, 1240)
+    xys, desc, scores = net.extract(img, 0.7, 0.7, 0.85)
+    n = len(xys)
+    first = (xys.clone(), desc.clone())
+    xys_b, desc_b, _ = net.extract(img, 0.7, 0.7, 0.85)
+    assert len(xys_b) == n and torch.equal(first[0], xys_b) and torch.equal(first[1], desc_b)
+    assert n > 100 and float(scores.min()) > 0.85
+    assert float((desc.norm(dim=1) - 1).abs().max()) < 1e-5
+    assert float(xys[:, 0].max()) < 1240 and float(xys[:, 1].max()) < 376

@@ -72,6 +72,17 @@ class SeqConfig(ctypes.Structure):
     ]
 
 
+class R2d2Layer(ctypes.Structure):
+    _fields_ = [("cin", c_int), ("cout", c_int), ("k", c_int), ("dil", c_int), ("bn", c_int), ("relu", c_int),
+                ("pool_after", c_int), ("w", c_void_p), ("bias", c_void_p), ("bn_mean", c_void_p), ("bn_var", c_void_p)]
+
+
+class R2d2Config(ctypes.Structure):
+    _fields_ = [("H", c_int), ("W", c_int), ("n_layers", c_int), ("layers", ctypes.POINTER(R2d2Layer)), ("upsample", c_int),
+                ("clf_w", c_void_p), ("clf_b", c_void_p), ("sal_w", c_void_p), ("sal_b", c_void_p), ("bn_eps", c_float),
+                ("max_kp", c_int)]
+
+
 PROTOTYPES = {
     "vo_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     "vo_destroy": (None, [c_void_p]),
@@ -101,6 +112,11 @@ PROTOTYPES = {
     "vo_seq_read": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vo_conv2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                           c_void_p, c_void_p]),
+    "vo_r2d2_create": (c_int, [c_void_p, ctypes.POINTER(R2d2Config), ctypes.POINTER(c_void_p)]),
+    "vo_r2d2_destroy": (None, [c_void_p]),
+    "vo_r2d2_out_shape": (c_int, [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "vo_r2d2_extract": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
     "vo_profile_enable": (c_int, [c_void_p, c_int]),
     "vo_profile_collect": (c_int, [c_void_p, c_void_p, c_void_p]),
 }
