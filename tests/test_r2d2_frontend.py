@@ -94,3 +94,42 @@ def test_kitti_sized_image_runs_and_is_deterministic(golden):
     assert n > 100 and float(scores.min()) > 0.85
     assert float((desc.norm(dim=1) - 1).abs().max()) < 1e-5
     assert float(xys[:, 0].max()) < 1240 and float(xys[:, 1].max()) < 376
+
+
+@pytest.mark.gpu
+def test_dropin_module_extracts_and_matches(golden, tmp_path):
+    """The reference's module-level interface: R2D2.extract_features_and_desc(image BGR) -> (kps (N,3) numpy, desc (N,128)
+    CUDA tensor), fed into R2D2.get_matches — with a checkpoint FILE in the reference's format (R2D2.py:68-79)."""
+    import importlib
+    import os
+    import sys
+    import torch
+    g = golden("r2d2_net.npz")
+    name, sd = _weights(g)
+    ckpt = tmp_path / "model.pt"
+    state = {"module." + k: torch.from_numpy(v) for k, v in sd.items()}
+    state["module.ops.1.num_batches_tracked"] = torch.tensor(0)
+    torch.save({"net": name + "()", "state_dict": state}, str(ckpt))
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "visual-odometry-pipeline_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    sys.modules.pop("R2D2", None)
+    r2 = importlib.import_module("R2D2")
+    r2.args["model"] = str(ckpt)
+    img_rgb = g["image"]
+    bgr = np.ascontiguousarray(img_rgb[:, :, ::-1])
+    kps, desc = r2.extract_features_and_desc(bgr)
+    keep = g["keep"]
+    assert kps.dtype == np.float32 and kps.shape[1] == 3 and isinstance(desc, torch.Tensor) and desc.is_cuda
+    assert abs(len(kps) - len(keep)) <= 2 and desc.shape == (len(kps), 128)
+    # a shifted copy of the image: the plug-in's own matcher pairs most keypoints with their shifted selves
+    shifted = np.roll(bgr, 4, axis=1)
+    kps2, desc2 = r2.extract_features_and_desc(shifted)
+    m = r2.get_matches(kps, desc, kps2, desc2, bgr.shape)
+    assert m.dtype == np.int64 and m.shape[1] == 2 and len(m) > 0.5 * len(kps)
+    dx = kps2[m[:, 1], 0] - kps[m[:, 0], 0]
+    assert np.mean(np.abs(dx - 4) < 1.5) > 0.8
+    r2.args["model"] = "/nonexistent/model.pt"
+    r2._weights = None; r2._nets.clear()
+    with pytest.raises(RuntimeError):
+        r2.extract_features_and_desc(bgr)

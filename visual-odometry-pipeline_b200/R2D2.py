@@ -1,4 +1,4 @@
-"""R2D2 plug-in — the matcher half of the reference's R2D2.py on the tensor cores.
+"""R2D2 plug-in — the reference's R2D2.py (matchers and feature extraction) on the tensor cores.
 
 Interface kept: `mnn_matcher` (:29-37), `similarity_matcher` (:40-51), `ratio_mutual_nn_matcher` (:53-66),
 `get_matches(ref_kp, ref_desc, cur_kp, cur_desc, imgshape)` (:234-236) and `extract_features_and_desc(image)`
@@ -8,9 +8,8 @@ The reference materialises `sim = d1 @ d2.t()` (N x M fp32 in HBM) and runs topk
 tcgen05 kernel (3xTF32, accumulator in TMEM) produces the row top-2 and the column arg-max directly and a small
 finalize kernel applies `ratio <= 0.90 and mutual` (or the similarity threshold) — see csrc/match_f32_tc.cu.
 
-The R2D2 network itself is a front-end outside the accelerated path and is not redistributed
-(CC BY-NC-SA): `extract_features_and_desc` loads it from a naver/r2d2 checkout at feature_extractors/r2d2 if the
-user has placed one there, and raises otherwise.
+`extract_features_and_desc` runs the R2D2 network on the tensor cores too (csrc/conv_tc.cu, csrc/r2d2_net.cu); the
+weights are read from the user's naver/r2d2 checkpoint file (CC BY-NC-SA, not redistributed).
 """
 import os
 import sys
@@ -58,48 +57,35 @@ def get_matches(ref_kp, ref_desc, cur_kp, cur_desc, imgshape):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# Front-end (not accelerated here): thin loader around a user-supplied naver/r2d2 checkout.
-args = {"model": "feature_extractors/r2d2/models/faster2d2_WASF_N16.pt", "reliability_thr": 0.7,
-        "repeatability_thr": 0.7, "score_thr": 0.85}
-_net = None
+# Front-end: the network, the heads, NMS and the score filter run in libvo_b200.so (vo_r2d2_*, csrc/r2d2_net.cu +
+# csrc/conv_tc.cu).  Only the checkpoint FILE is the user's: the weights are not redistributed (CC BY-NC-SA); point
+# args['model'] at a naver/r2d2 checkpoint (the reference's default path is kept).
+args = {"model": "feature_extractors/r2d2/models/faster2d2_WASF_N16.pt", "scale_f": 2 ** 0.25, "min_size": 256,
+        "max_size": 1380, "min_scale": 0, "max_scale": 1, "reliability_thr": 0.7, "repeatability_thr": 0.7,
+        "score_thr": 0.85, "gpu": [0]}
+_nets = {}          # (H, W) -> R2D2Net
+_weights = None
 
 
-def _load_frontend():
-    global _net
-    if _net is not None:
-        return _net
-    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "feature_extractors", "r2d2")
-    if not os.path.isdir(root) or not os.path.exists(args["model"]):
-        raise RuntimeError(
-            "R2D2 feature extraction needs a naver/r2d2 checkout at feature_extractors/r2d2 (with "
-            "models/faster2d2_WASF_N16.pt); it is a third-party front-end outside this package's scope. "
-            "The matchers in this module work on any L2-normalised 128-d descriptors.")
-    sys.path.insert(1, root)
-    from nets.patchnet import Fast_Quad_L2Net_ConfCFS  # noqa: F401  (names resolved by eval below)
-    import nets.patchnet as patchnet
-    ckpt = torch.load(args["model"], map_location="cpu")
-    net = eval("patchnet." + ckpt["net"])
-    net.load_state_dict({k.replace("module.", ""): v for k, v in ckpt["state_dict"].items()})
-    _net = net.eval().cuda()
-    return _net
+def _frontend(H, W):
+    global _weights
+    from vo_b200 import r2d2_frontend
+    if _weights is None:
+        if not os.path.exists(args["model"]):
+            raise RuntimeError(f"R2D2 checkpoint {args['model']!r} not found: set R2D2.args['model'] to a naver/r2d2 model file "
+                               "(e.g. faster2d2_WASF_N16.pt).  The matchers in this module work on any L2-normalised "
+                               "128-d descriptors.")
+        _weights = r2d2_frontend.load_checkpoint(args["model"])
+    if (H, W) not in _nets:
+        _nets[(H, W)] = r2d2_frontend.R2D2Net(_weights[0], _weights[1], H, W)
+    return _nets[(H, W)]
 
 
 def extract_features_and_desc(image, trt=False):
-    """image: HxWx3 uint8 -> (keypoints (N,3) [x, y, scale] numpy, descriptors (N,128) CUDA tensor)."""
-    import cv2
-    net = _load_frontend()
-    rgb = cv2.cvtColor(image, cv2.COLOR_BGR2RGB).astype(np.float32) / 255.0
-    mean, std = np.array([0.485, 0.456, 0.406], np.float32), np.array([0.229, 0.224, 0.225], np.float32)
-    x = torch.from_numpy(((rgb - mean) / std).transpose(2, 0, 1))[None].cuda()
-    with torch.no_grad():
-        out = net(imgs=[x])
-    desc, rel, rep = out["descriptors"][0], out["reliability"][0], out["repeatability"][0]
-    peak = rep == torch.nn.functional.max_pool2d(rep, 3, 1, 1)
-    keep = peak & (rep >= args["repeatability_thr"]) & (rel >= args["reliability_thr"])
-    ys, xs = keep[0, 0].nonzero(as_tuple=True)
-    score = rel[0, 0, ys, xs] * rep[0, 0, ys, xs]
-    sel = score > args["score_thr"]
-    ys, xs = ys[sel], xs[sel]
-    d = desc[0, :, ys, xs].t().contiguous()
-    kp = torch.stack([xs.float(), ys.float(), torch.full_like(xs, 32.0, dtype=torch.float32)], 1)
-    return kp.cpu().numpy(), d
+    """image: HxWx3 uint8 BGR (OpenCV) -> (keypoints (N,3) [x, y, scale] numpy float32, descriptors (N,128) CUDA
+    tensor), as the reference returns them (R2D2.py:202-232).  Extraction happens at scale 1 only, like the
+    reference (its multi-scale loop leaves after the first iteration, :133-135)."""
+    rgb = np.ascontiguousarray(image[:, :, ::-1])                      # cv2.cvtColor(image, COLOR_BGR2RGB)
+    net = _frontend(rgb.shape[0], rgb.shape[1])
+    xys, desc, _ = net.extract(rgb, args["reliability_thr"], args["repeatability_thr"], args["score_thr"])
+    return xys.cpu().numpy(), desc.clone()
