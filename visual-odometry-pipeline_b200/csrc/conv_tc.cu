@@ -3,8 +3,8 @@
 // Quad_L2Net / Fast_Quad_L2Net keeps the resolution; strides become dilations).
 //
 // Layout: activations NHWC fp32, already split into tf32 hi / lo parts by the producing layer; weights
-// [C_out][tap][C_in] (K-major), split once on the host.  One CTA computes 128 consecutive pixels of one image row for
-// all C_out channels:
+// [C_out][tap][C_in] (K-major), split once on the host.  A tile is 128 consecutive pixels of one image row for all
+// C_out channels; persistent CTAs (one per SM) walk the tile list:
 //   * per (tap, 32-channel block) the producer thread issues four TMA boxes into a 3-stage ring: the activation box
 //     {32 c, 128 w, 1 h} at the tap's shifted coordinates (hi and lo) — TMA's out-of-bounds zero fill IS the
 //     convolution's zero padding, there is no im2col buffer and no border code — and the weight box {32 k, C_out};
@@ -43,6 +43,10 @@ struct ConvGeom {
     int relu;
 };
 
+// Persistent: one CTA per SM walks the tile list (tile = 128 consecutive pixels of one image row).  The producer runs
+// ahead across tile boundaries, the MMA thread alternates between two accumulators in tensor memory, and the epilogue
+// warps drain one accumulator while the next tile's MMAs fill the other — per-tile set-up (barriers, TMEM allocation)
+// and the TMEM -> registers -> global epilogue are off the tensor pipe's critical path.
 template <int COUT>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -54,25 +58,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h0 = blockIdx.x / g.tiles_x;
-    const int w0 = (blockIdx.x % g.tiles_x) * CV_PIX;
     const int cblocks = g.cin / CV_KB;
     const int n_items = g.taps_x * g.taps_y * cblocks;
+    const int n_tiles = g.H * g.tiles_x;
 
     const uint32_t s_bar = base + S::OFF_BAR;
     auto bar_full = [&](int s) { return s_bar + 8u * s; };
     auto bar_empty = [&](int s) { return s_bar + 8u * (CV_STAGES + s); };
-    const uint32_t bar_done = s_bar + 8u * (2 * CV_STAGES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::OFF_BAR + 8 * (2 * CV_STAGES + 1));
+    auto bar_tfull = [&](int a) { return s_bar + 8u * (2 * CV_STAGES + a); };
+    auto bar_tempty = [&](int a) { return s_bar + 8u * (2 * CV_STAGES + 2 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::OFF_BAR + 8 * (2 * CV_STAGES + 4));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < CV_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        mbar_init(bar_done, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)COUT)
+                     "r"((uint32_t)(2 * COUT))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -85,92 +89,111 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // ===================== TMA producer =====================
         if (lane == 0) {
             int it = 0;
-            for (int ty = 0; ty < g.taps_y; ++ty)
-                for (int tx = 0; tx < g.taps_x; ++tx) {
-                    const int hh = h0 - g.pad + ty * g.dil, ww = w0 - g.pad + tx * g.dil;  // may be out of bounds: zero fill
-                    const int krow = (ty * g.taps_x + tx) * g.cin;
-                    for (int cb = 0; cb < cblocks; ++cb, ++it) {
-                        const int stage = it % CV_STAGES;
-                        const uint32_t phase = (uint32_t)(it / CV_STAGES) & 1u;
-                        mbar_wait(bar_empty(stage), phase ^ 1u);
-                        mbar_expect_tx(bar_full(stage), S::STAGE_BYTES);
-                        const uint32_t dst = base + stage * S::STAGE_BYTES;
-                        tma_load_3d(dst, &map_a_hi, cb * CV_KB, ww, hh, bar_full(stage));
-                        tma_load_3d(dst + CV_A_BYTES, &map_a_lo, cb * CV_KB, ww, hh, bar_full(stage));
-                        tma_load_2d(dst + 2 * CV_A_BYTES, &map_b_hi, krow + cb * CV_KB, 0, bar_full(stage));
-                        tma_load_2d(dst + 2 * CV_A_BYTES + S::B_BYTES, &map_b_lo, krow + cb * CV_KB, 0, bar_full(stage));
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int h0 = t / g.tiles_x, w0 = (t % g.tiles_x) * CV_PIX;
+                for (int ty = 0; ty < g.taps_y; ++ty)
+                    for (int tx = 0; tx < g.taps_x; ++tx) {
+                        const int hh = h0 - g.pad + ty * g.dil, ww = w0 - g.pad + tx * g.dil;  // may be out of bounds: zero fill
+                        const int krow = (ty * g.taps_x + tx) * g.cin;
+                        for (int cb = 0; cb < cblocks; ++cb, ++it) {
+                            const int stage = it % CV_STAGES;
+                            const uint32_t phase = (uint32_t)(it / CV_STAGES) & 1u;
+                            mbar_wait(bar_empty(stage), phase ^ 1u);
+                            mbar_expect_tx(bar_full(stage), S::STAGE_BYTES);
+                            const uint32_t dst = base + stage * S::STAGE_BYTES;
+                            tma_load_3d(dst, &map_a_hi, cb * CV_KB, ww, hh, bar_full(stage));
+                            tma_load_3d(dst + CV_A_BYTES, &map_a_lo, cb * CV_KB, ww, hh, bar_full(stage));
+                            tma_load_2d(dst + 2 * CV_A_BYTES, &map_b_hi, krow + cb * CV_KB, 0, bar_full(stage));
+                            tma_load_2d(dst + 2 * CV_A_BYTES + S::B_BYTES, &map_b_lo, krow + cb * CV_KB, 0, bar_full(stage));
+                        }
                     }
-                }
+            }
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
         constexpr uint32_t IDESC = cv_idesc(COUT);
         uint32_t stage = 0, phase = 0;
-        for (int it = 0; it < n_items; ++it) {
-            mbar_wait(bar_full(stage), phase);
+        int lt = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+            const int buf = lt & 1;
+            mbar_wait(bar_tempty(buf), (((uint32_t)(lt >> 1)) & 1u) ^ 1u);  // epilogue has drained this accumulator
             tc_fence_after();
-            if (elect_one()) {
-                const uint32_t sa = base + stage * S::STAGE_BYTES;
-                const uint32_t a_hi = ((sa & 0x3ffffu) >> 4) | (1u << 16);
-                const uint32_t a_lo = (((sa + CV_A_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
-                const uint32_t b_hi = (((sa + 2 * CV_A_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
-                const uint32_t b_lo = (((sa + 2 * CV_A_BYTES + S::B_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * COUT);
+            for (int it = 0; it < n_items; ++it) {
+                mbar_wait(bar_full(stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = base + stage * S::STAGE_BYTES;
+                    const uint32_t a_hi = ((sa & 0x3ffffu) >> 4) | (1u << 16);
+                    const uint32_t a_lo = (((sa + CV_A_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
+                    const uint32_t b_hi = (((sa + 2 * CV_A_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
+                    const uint32_t b_lo = (((sa + 2 * CV_A_BYTES + S::B_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
 #pragma unroll
-                for (int k8 = 0; k8 < CV_KB / 8; ++k8) {
-                    const uint64_t hi = (uint64_t)TC_SDESC_HI << 32;
-                    const uint64_t dah = hi | (uint64_t)(a_hi + k8 * 2), dal = hi | (uint64_t)(a_lo + k8 * 2);
-                    const uint64_t dbh = hi | (uint64_t)(b_hi + k8 * 2), dbl = hi | (uint64_t)(b_lo + k8 * 2);
-                    tc_mma_tf32_ss(tmem_base, dal, dbh, IDESC, (it | k8) ? 1u : 0u);  // small terms first
-                    tc_mma_tf32_ss(tmem_base, dah, dbl, IDESC, 1u);
-                    tc_mma_tf32_ss(tmem_base, dah, dbh, IDESC, 1u);
+                    for (int k8 = 0; k8 < CV_KB / 8; ++k8) {
+                        const uint64_t hi = (uint64_t)TC_SDESC_HI << 32;
+                        const uint64_t dah = hi | (uint64_t)(a_hi + k8 * 2), dal = hi | (uint64_t)(a_lo + k8 * 2);
+                        const uint64_t dbh = hi | (uint64_t)(b_hi + k8 * 2), dbl = hi | (uint64_t)(b_lo + k8 * 2);
+                        tc_mma_tf32_ss(d_tmem, dal, dbh, IDESC, (it | k8) ? 1u : 0u);  // small terms first
+                        tc_mma_tf32_ss(d_tmem, dah, dbl, IDESC, 1u);
+                        tc_mma_tf32_ss(d_tmem, dah, dbh, IDESC, 1u);
+                    }
+                    tc_commit(bar_empty(stage));
+                    if (it == n_items - 1) tc_commit(bar_tfull(buf));
                 }
-                tc_commit(bar_empty(stage));
-                if (it == n_items - 1) tc_commit(bar_done);
+                __syncwarp();
+                if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
             }
-            __syncwarp();
-            if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
         }
     } else {
         // ===================== epilogue: warp w owns TMEM lanes (= pixels) 32 w .. 32 w + 31 =====================
-        mbar_wait(bar_done, 0);
-        tc_fence_after();
-        const int w = w0 + warp * 32 + lane;
-        const bool ok = w < g.W;
-        const size_t pix = ((size_t)h0 * g.W + (ok ? w : 0)) * COUT;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        int lt = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+            const int buf = lt & 1;
+            const int h0 = t / g.tiles_x, w0 = (t % g.tiles_x) * CV_PIX;
+            mbar_wait(bar_tfull(buf), ((uint32_t)(lt >> 1)) & 1u);
+            tc_fence_after();
+            const int w = w0 + warp * 32 + lane;
+            const bool ok = w < g.W;
+            const size_t pix = ((size_t)h0 * g.W + (ok ? w : 0)) * COUT;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * COUT);
 #pragma unroll 1
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
-            float v[32];
-            tc_ld32(taddr + c0, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float y = __fmaf_rn(v[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
-                v[j] = g.relu ? fmaxf(y, 0.0f) : y;
-            }
-            if (ok) {
-                if (out_full) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4 *>(out_full + pix + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+                float v[32];
+                tc_ld32(taddr + c0, v);
+                if (c0 + 32 == COUT) {  // last read of this accumulator: hand it back before the stores
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(bar_tempty(buf));
                 }
-                if (out_hi) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 hv = make_float4(to_tf32(v[j]), to_tf32(v[j + 1]), to_tf32(v[j + 2]), to_tf32(v[j + 3]));
-                        *reinterpret_cast<float4 *>(out_hi + pix + c0 + j) = hv;
-                        *reinterpret_cast<float4 *>(out_lo + pix + c0 + j) =
-                            make_float4(to_tf32(v[j] - hv.x), to_tf32(v[j + 1] - hv.y), to_tf32(v[j + 2] - hv.z),
-                                        to_tf32(v[j + 3] - hv.w));
+                for (int j = 0; j < 32; ++j) {
+                    float y = __fmaf_rn(v[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+                    v[j] = g.relu ? fmaxf(y, 0.0f) : y;
+                }
+                if (ok) {
+                    if (out_full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(out_full + pix + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    if (out_hi) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 hv = make_float4(to_tf32(v[j]), to_tf32(v[j + 1]), to_tf32(v[j + 2]), to_tf32(v[j + 3]));
+                            *reinterpret_cast<float4 *>(out_hi + pix + c0 + j) = hv;
+                            *reinterpret_cast<float4 *>(out_lo + pix + c0 + j) =
+                                make_float4(to_tf32(v[j] - hv.x), to_tf32(v[j + 1] - hv.y), to_tf32(v[j + 2] - hv.z),
+                                            to_tf32(v[j + 3] - hv.w));
+                        }
                     }
                 }
             }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)COUT) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * COUT)) : "memory");
     }
 }
 
@@ -239,7 +262,8 @@ int conv_tc_launch(vo_ctx *ctx, const void *map_a_hi, const void *map_a_lo, cons
     VO_REQUIRE(cout == 32 || cout == 64 || cout == 128, "conv: C_out must be 32, 64 or 128 (got %d)", cout);
     VO_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "conv: out_hi and out_lo go together");
     ConvGeom g{H, W, cin, k, k, dil, pad, ceil_div(W, CV_PIX), relu};
-    const int grid = H * g.tiles_x;
+    const int n_tiles = H * g.tiles_x;
+    const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;  // persistent: one CTA per SM
 #define CV_LAUNCH(CO)                                                                                                  \
     do {                                                                                                               \
         auto kern = conv_tc_kernel<CO>;                                                                                \

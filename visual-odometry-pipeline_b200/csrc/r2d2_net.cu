@@ -164,40 +164,61 @@ __device__ __forceinline__ float4 bilin_sample4(const float *__restrict__ feat, 
                        mix(v00.w, v01.w, v10.w, v11.w));
 }
 
-// ---------------------------------------------------------------- heads: one warp per output pixel, 4 channels per lane
-// reliability = softmax(clf(x^2))[1], repeatability = softplus(sal(x^2)) / (1 + softplus) (patchnet.py:16-22, :181-186)
+// ---------------------------------------------------------------- heads
+// reliability = softmax(clf(x^2))[1], repeatability = softplus(sal(x^2)) / (1 + softplus) (patchnet.py:16-22, :181-186).
+// One warp per block of output pixels that interpolate the SAME four feature vectors: with x2 up-sampling the output
+// pixels 2k-1 and 2k both read half-resolution columns (k-1, k), so a 2 x 2 output block shares its 2 x 2 neighbours
+// and every feature vector is loaded once per block instead of once per pixel.  4 channels per lane (C = 128 k).
+__device__ __forceinline__ void head_finish(float s0, float s1, float s2, const float *__restrict__ hw, int C, float *rel, float *rep,
+                                            size_t p) {
+    const float u0 = s0 + hw[3 * C], u1 = s1 + hw[3 * C + 1], us = s2 + hw[3 * C + 2];
+    const float m = fmaxf(u0, u1);
+    const float e0 = expf(u0 - m), e1 = expf(u1 - m);
+    rel[p] = e1 / (e0 + e1);
+    const float sp = us > 20.0f ? us : log1pf(expf(us));  // torch softplus, threshold 20
+    rep[p] = sp / (1.0f + sp);
+}
+
 __global__ void __launch_bounds__(256)
 head_maps_kernel(const float *__restrict__ feat, int Hf, int Wf, int C, int up, int Ho, int Wo, const float *__restrict__ hw,
                  float *__restrict__ rel, float *__restrict__ rep) {
-    const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long blk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (p >= (long long)Ho * Wo) return;
-    const int yo = (int)(p / Wo), xo = (int)(p % Wo);
-    const Bilin b = bilin_setup(yo, xo, Hf, Wf, up);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    const int bw = up == 2 ? Wf + 1 : Wo, bh = up == 2 ? Hf + 1 : Ho;  // blocks per row / column
+    if (blk >= (long long)bw * bh) return;
+    const int by = (int)(blk / bw), bx = (int)(blk % bw);
+    // output pixels of the block: rows {2by-1, 2by}, columns {2bx-1, 2bx} (those inside the map); up == 1: one pixel
+    const int y_lo = up == 2 ? max(2 * by - 1, 0) : by, y_hi = up == 2 ? min(2 * by, Ho - 1) : by;
+    const int x_lo = up == 2 ? max(2 * bx - 1, 0) : bx, x_hi = up == 2 ? min(2 * bx, Wo - 1) : bx;
+    const Bilin b0 = bilin_setup(y_lo, x_lo, Hf, Wf, up);  // indices shared by the whole block
     for (int c = lane * 4; c < C; c += 128) {
-        const float4 v = bilin_sample4(feat, Wf, C, b, c);
-        const float4 q = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+        auto at = [&](int yy, int xx) { return __ldg(reinterpret_cast<const float4 *>(feat + ((size_t)yy * Wf + xx) * C + c)); };
+        const float4 v00 = at(b0.y0, b0.x0), v01 = at(b0.y0, b0.x1), v10 = at(b0.y1, b0.x0), v11 = at(b0.y1, b0.x1);
         const float4 a0 = __ldg(reinterpret_cast<const float4 *>(hw + c));
         const float4 a1 = __ldg(reinterpret_cast<const float4 *>(hw + C + c));
         const float4 a2 = __ldg(reinterpret_cast<const float4 *>(hw + 2 * C + c));
-        s0 += q.x * a0.x + q.y * a0.y + q.z * a0.z + q.w * a0.w;
-        s1 += q.x * a1.x + q.y * a1.y + q.z * a1.z + q.w * a1.w;
-        s2 += q.x * a2.x + q.y * a2.y + q.z * a2.z + q.w * a2.w;
-    }
+        for (int yo = y_lo; yo <= y_hi; ++yo)
+            for (int xo = x_lo; xo <= x_hi; ++xo) {
+                const Bilin b = bilin_setup(yo, xo, Hf, Wf, up);
+                auto mix = [&](float p00, float p01, float p10, float p11) {
+                    return b.h0 * (b.w0 * p00 + b.w1 * p01) + b.h1 * (b.w0 * p10 + b.w1 * p11);
+                };
+                const float4 v = make_float4(mix(v00.x, v01.x, v10.x, v11.x), mix(v00.y, v01.y, v10.y, v11.y),
+                                             mix(v00.z, v01.z, v10.z, v11.z), mix(v00.w, v01.w, v10.w, v11.w));
+                const float4 q = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+                float s0 = q.x * a0.x + q.y * a0.y + q.z * a0.z + q.w * a0.w;
+                float s1 = q.x * a1.x + q.y * a1.y + q.z * a1.z + q.w * a1.w;
+                float s2 = q.x * a2.x + q.y * a2.y + q.z * a2.z + q.w * a2.w;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) {
-        const float u0 = s0 + hw[3 * C], u1 = s1 + hw[3 * C + 1], us = s2 + hw[3 * C + 2];
-        const float m = fmaxf(u0, u1);
-        const float e0 = expf(u0 - m), e1 = expf(u1 - m);
-        rel[p] = e1 / (e0 + e1);
-        const float sp = us > 20.0f ? us : log1pf(expf(us));  // torch softplus, threshold 20
-        rep[p] = sp / (1.0f + sp);
+                for (int o = 16; o > 0; o >>= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                // C == 128: one pass per pixel, lane 0 finishes.  (C > 128 would need the partial sums carried across
+                // the channel loop; vo_r2d2_create restricts the head to C == 128.)
+                if (lane == 0) head_finish(s0, s1, s2, hw, C, rel, rep, (size_t)yo * Wo + xo);
+            }
     }
 }
 
@@ -261,11 +282,11 @@ row_scan_kernel(const int32_t *__restrict__ row_count, int Ho, int32_t *__restri
     if (threadIdx.x == 0) { row_base[Ho] = carry; *total = carry; }
 }
 
-// one warp per row: ballot-ordered write of (x, y, 32), score; then descriptors by the same warp
+// one warp per row: ballot-ordered write of (x, y, 32) and the score
 __global__ void __launch_bounds__(32)
 nms_write_kernel(const float *__restrict__ rel, const float *__restrict__ rep, int Ho, int Wo, float rel_thr, float rep_thr,
-                 float score_thr, const int32_t *__restrict__ row_base, int max_kp, const float *__restrict__ feat, int Hf, int Wf,
-                 int C, int up, float *__restrict__ xys, float *__restrict__ scores, float *__restrict__ desc) {
+                 float score_thr, const int32_t *__restrict__ row_base, int max_kp, float *__restrict__ xys,
+                 float *__restrict__ scores) {
     const int y = blockIdx.x, lane = threadIdx.x;
     int base = row_base[y];
     if (row_base[y + 1] == base) return;
@@ -282,31 +303,24 @@ nms_write_kernel(const float *__restrict__ rel, const float *__restrict__ rep, i
                 scores[idx] = rel[(size_t)y * Wo + x] * rep[(size_t)y * Wo + x];
             }
         }
-        // descriptors: the whole warp works on one keypoint at a time (4 channels per lane, C = 128)
-        unsigned rest = bal;
-        while (rest) {
-            const int l = __ffs(rest) - 1;
-            rest &= rest - 1;
-            const int idx = base + __popc(bal & ((1u << l) - 1u));
-            if (idx >= max_kp) break;
-            const Bilin b = bilin_setup(y, x0 + l, Hf, Wf, up);
-            float ss = 0.f;
-            float4 v[4];
-            int nv = 0;
-            for (int c = lane * 4; c < C; c += 128, ++nv) {
-                v[nv] = bilin_sample4(feat, Wf, C, b, c);
-                ss += v[nv].x * v[nv].x + v[nv].y * v[nv].y + v[nv].z * v[nv].z + v[nv].w * v[nv].w;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(p=2, eps=1e-12)
-            nv = 0;
-            for (int c = lane * 4; c < C; c += 128, ++nv)
-                *reinterpret_cast<float4 *>(desc + (size_t)idx * C + c) =
-                    make_float4(v[nv].x * inv, v[nv].y * inv, v[nv].z * inv, v[nv].w * inv);
-        }
         base += __popc(bal);
     }
+}
+
+// one warp per keypoint: interpolate the feature vector at its pixel, L2-normalise (F.normalize, eps 1e-12)
+__global__ void __launch_bounds__(256)
+desc_gather_kernel(const float *__restrict__ xys, const int32_t *__restrict__ total, int max_kp, const float *__restrict__ feat,
+                   int Hf, int Wf, int C, int up, float *__restrict__ desc) {
+    const int idx = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (idx >= min(*total, max_kp)) return;
+    const int x = (int)xys[(size_t)idx * 3 + 0], y = (int)xys[(size_t)idx * 3 + 1];
+    const Bilin b = bilin_setup(y, x, Hf, Wf, up);
+    const float4 v = bilin_sample4(feat, Wf, C, b, lane * 4);
+    float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    *reinterpret_cast<float4 *>(desc + (size_t)idx * C + lane * 4) = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
 }
 
 void *dev_alloc(vo_r2d2 *n, size_t bytes) {
@@ -396,7 +410,7 @@ extern "C" int vo_r2d2_create(vo_ctx *ctx, const vo_r2d2_config *cfg, vo_r2d2 **
     }
     n->Hf = H; n->Wf = W; n->C = cfg->layers[cfg->n_layers - 1].cout;
     n->Ho = H * cfg->upsample; n->Wo = W * cfg->upsample;
-    if (n->C % 128 != 0) { set_error("vo_r2d2_create: descriptor length must be a multiple of 128 (got %d)", n->C); return fail(VO_ERR_ARG); }
+    if (n->C != 128) { set_error("vo_r2d2_create: the descriptor length must be 128 (got %d)", n->C); return fail(VO_ERR_ARG); }
     const int C = n->C;
     std::vector<float> hw(3 * C + 4, 0.f);
     for (int c = 0; c < C; ++c) { hw[c] = cfg->clf_w[c]; hw[C + c] = cfg->clf_w[C + c]; hw[2 * C + c] = cfg->sal_w[c]; }
@@ -448,7 +462,7 @@ extern "C" int vo_r2d2_extract(vo_r2d2 *net, const uint8_t *rgb, float rel_thr, 
     }
     const float *feat = net->st.back().out_full;
     float *rel = rel_map ? rel_map : net->rel, *rep = rep_map ? rep_map : net->rep;
-    const long long warps = (long long)net->Ho * net->Wo;
+    const long long warps = net->upsample == 2 ? (long long)(net->Hf + 1) * (net->Wf + 1) : (long long)net->Ho * net->Wo;
     head_maps_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(feat, net->Hf, net->Wf, net->C, net->upsample, net->Ho, net->Wo,
                                                                             net->head_w, rel, rep);
     VO_LAUNCH_CHECK(ctx);
@@ -456,8 +470,12 @@ extern "C" int vo_r2d2_extract(vo_r2d2 *net, const uint8_t *rgb, float rel_thr, 
     VO_LAUNCH_CHECK(ctx);
     row_scan_kernel<<<1, 1024, 0, st>>>(net->row_count, net->Ho, net->row_base, count);
     VO_LAUNCH_CHECK(ctx);
-    nms_write_kernel<<<net->Ho, 32, 0, st>>>(rel, rep, net->Ho, net->Wo, rel_thr, rep_thr, score_thr, net->row_base, net->max_kp, feat,
-                                             net->Hf, net->Wf, net->C, net->upsample, xys, scores, desc);
+    nms_write_kernel<<<net->Ho, 32, 0, st>>>(rel, rep, net->Ho, net->Wo, rel_thr, rep_thr, score_thr, net->row_base, net->max_kp, xys,
+                                             scores);
+    VO_LAUNCH_CHECK(ctx);
+    // the keypoint count lives on the device: launch for the capacity, surplus warps exit on the count
+    desc_gather_kernel<<<(unsigned)(((long long)net->max_kp * 32 + 255) / 256), 256, 0, st>>>(xys, count, net->max_kp, feat, net->Hf,
+                                                                                               net->Wf, net->C, net->upsample, desc);
     VO_LAUNCH_CHECK(ctx);
     return VO_OK;
 }
