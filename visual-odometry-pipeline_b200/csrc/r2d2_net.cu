@@ -65,17 +65,22 @@ __global__ void __launch_bounds__(128)
 first_conv_kernel(const uint8_t *__restrict__ rgb, int H, int W, int k, int dil, int pad, const float *__restrict__ w,
                   const float *__restrict__ scale, const float *__restrict__ shift, int relu, float *__restrict__ out_hi,
                   float *__restrict__ out_lo) {
-    extern __shared__ float sw[];  // [k*k*3][COUT] (transposed for broadcast-free reads)
+    extern __shared__ float sw[];  // [k*k*3][COUT] (transposed for broadcast-free reads) | lut[3][256]
     const int taps = k * k * 3;
+    float *lut = sw + taps * COUT;  // (v / 255 - mean) / std for every byte value: the two IEEE divisions are done once
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
     for (int i = threadIdx.x; i < taps * COUT; i += blockDim.x) {
         const int t = i / COUT, co = i % COUT;
         sw[i] = w[(size_t)co * taps + t];
+    }
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const int ch = i >> 8;
+        lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), mean[ch]), stdv[ch]);
     }
     __syncthreads();
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long long)H * W) return;
     const int y = (int)(p / W), x = (int)(p % W);
-    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
     float acc[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
@@ -87,7 +92,7 @@ first_conv_kernel(const uint8_t *__restrict__ rgb, int H, int W, int k, int dil,
             const uint8_t *px = rgb + ((size_t)yy * W + xx) * 3;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const float v = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[ch], 255.0f), mean[ch]), stdv[ch]);
+                const float v = lut[ch * 256 + px[ch]];
                 const float *wr = sw + ((ty * k + tx) * 3 + ch) * COUT;
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) acc[c] = __fmaf_rn(v, wr[c], acc[c]);
@@ -282,20 +287,29 @@ row_scan_kernel(const int32_t *__restrict__ row_count, int Ho, int32_t *__restri
     if (threadIdx.x == 0) { row_base[Ho] = carry; *total = carry; }
 }
 
-// one warp per row: ballot-ordered write of (x, y, 32) and the score
-__global__ void __launch_bounds__(32)
+// one CTA per row: ordered write of (x, y, 32) and the score (ballot within a warp, warp counts scanned per chunk)
+constexpr int NW_THREADS = 256;
+__global__ void __launch_bounds__(NW_THREADS)
 nms_write_kernel(const float *__restrict__ rel, const float *__restrict__ rep, int Ho, int Wo, float rel_thr, float rep_thr,
                  float score_thr, const int32_t *__restrict__ row_base, int max_kp, float *__restrict__ xys,
                  float *__restrict__ scores) {
-    const int y = blockIdx.x, lane = threadIdx.x;
+    const int y = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int wcnt[NW_THREADS / 32];
     int base = row_base[y];
     if (row_base[y + 1] == base) return;
-    for (int x0 = 0; x0 < Wo; x0 += 32) {
-        const int x = x0 + lane;
+    for (int x0 = 0; x0 < Wo; x0 += NW_THREADS) {
+        const int x = x0 + threadIdx.x;
         const bool kp = x < Wo && is_keypoint(rel, rep, Ho, Wo, y, x, rel_thr, rep_thr, score_thr);
         const unsigned bal = __ballot_sync(0xffffffffu, kp);
+        if (lane == 0) wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int prefix = base, total = 0;
+        for (int w = 0; w < NW_THREADS / 32; ++w) {
+            if (w < warp) prefix += wcnt[w];
+            total += wcnt[w];
+        }
         if (kp) {
-            const int idx = base + __popc(bal & ((1u << lane) - 1u));
+            const int idx = prefix + __popc(bal & ((1u << lane) - 1u));
             if (idx < max_kp) {
                 xys[(size_t)idx * 3 + 0] = (float)x;   // X = x * W / nw with nw == W at scale 1 (R2D2.py:150)
                 xys[(size_t)idx * 3 + 1] = (float)y;
@@ -303,7 +317,8 @@ nms_write_kernel(const float *__restrict__ rel, const float *__restrict__ rep, i
                 scores[idx] = rel[(size_t)y * Wo + x] * rep[(size_t)y * Wo + x];
             }
         }
-        base += __popc(bal);
+        base += total;
+        __syncthreads();
     }
 }
 
@@ -441,7 +456,7 @@ extern "C" int vo_r2d2_extract(vo_r2d2 *net, const uint8_t *rgb, float rel_thr, 
         vo_r2d2_stage &s = net->st[li];
         if (li == 0) {
             const long long px = (long long)s.H * s.W;
-            const size_t smem = (size_t)s.k * s.k * 3 * s.cout * sizeof(float);
+            const size_t smem = ((size_t)s.k * s.k * 3 * s.cout + 768) * sizeof(float);
             if (s.cout == 32)
                 first_conv_kernel<32><<<(unsigned)((px + 127) / 128), 128, smem, st>>>(net->rgb, s.H, s.W, s.k, s.dil, s.pad, s.w_hi, s.scale,
                                                                                         s.shift, s.relu, s.out_hi, s.out_lo);
@@ -470,7 +485,7 @@ extern "C" int vo_r2d2_extract(vo_r2d2 *net, const uint8_t *rgb, float rel_thr, 
     VO_LAUNCH_CHECK(ctx);
     row_scan_kernel<<<1, 1024, 0, st>>>(net->row_count, net->Ho, net->row_base, count);
     VO_LAUNCH_CHECK(ctx);
-    nms_write_kernel<<<net->Ho, 32, 0, st>>>(rel, rep, net->Ho, net->Wo, rel_thr, rep_thr, score_thr, net->row_base, net->max_kp, xys,
+    nms_write_kernel<<<net->Ho, NW_THREADS, 0, st>>>(rel, rep, net->Ho, net->Wo, rel_thr, rep_thr, score_thr, net->row_base, net->max_kp, xys,
                                              scores);
     VO_LAUNCH_CHECK(ctx);
     // the keypoint count lives on the device: launch for the capacity, surplus warps exit on the count
