@@ -133,3 +133,43 @@ def test_dropin_module_extracts_and_matches(golden, tmp_path):
     r2._weights = None; r2._nets.clear()
     with pytest.raises(RuntimeError):
         r2.extract_features_and_desc(bgr)
+
+
+@pytest.mark.gpu
+def test_yaml_run_with_r2d2_recovers_camera_motion(golden, tmp_path):
+    """feature_extractor: r2d2 through the drop-in VisualOdometry.process_frame — images in, poses out, every stage on
+    the GPU (network, matcher, back-projection, PnP).  Scene: a textured fronto-parallel plane 5 m away, camera moving
+    sideways, so consecutive frames are shifted copies and the true trajectory is known in closed form."""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from test_gpu_dropin import _load_dropin
+    from vo_b200 import synthetic
+    g = golden("r2d2_net.npz")
+    name, sd = _weights(g)
+    ckpt = tmp_path / "model.pt"
+    torch.save({"net": name + "()", "state_dict": {"module." + k: torch.from_numpy(v) for k, v in sd.items()}}, str(ckpt))
+    cwd = os.getcwd()
+    try:
+        sys.modules.pop("R2D2", None)
+        vos = _load_dropin(tmp_path, "r2d2")
+        sys.modules["R2D2"].args["model"] = str(ckpt)
+        W, H = synthetic.KITTI_WH
+        rng = np.random.default_rng(3)
+        big = np.kron(rng.integers(0, 256, (H // 6 + 1, (W + 200) // 6 + 1, 3)), np.ones((6, 6, 1))).astype(np.uint8)
+        Z, shift = 5.0, 14                                       # pixels per frame -> metres: shift * Z / fx
+        step = shift * Z / synthetic.KITTI_K[0, 0]
+        depth = np.full((H, W), Z, np.float32)
+        vo = vos.VisualOdometry(synthetic.KITTI_K, seq=0)
+        poses = []
+        for i in range(5):
+            frame = np.ascontiguousarray(big[:H, i * shift:i * shift + W])    # camera moved +x: the scene slides left
+            poses.append(vo.process_frame(frame, depth, (100, 100), i).pose.copy())
+        poses = np.stack(poses)
+        assert vo.bad_pnp == 0
+        for i in range(5):
+            assert np.allclose(poses[i][:3, :3], np.eye(3), atol=2e-3), i
+            assert np.allclose(poses[i][:3, 3], [i * step, 0.0, 0.0], atol=0.01), (i, poses[i][:3, 3])
+    finally:
+        os.chdir(cwd)
