@@ -173,3 +173,78 @@ def test_yaml_run_with_r2d2_recovers_camera_motion(golden, tmp_path):
             assert np.allclose(poses[i][:3, 3], [i * step, 0.0, 0.0], atol=0.01), (i, poses[i][:3, 3])
     finally:
         os.chdir(cwd)
+
+
+def _torch_net(name, sd, dev):
+    """The architecture of nets/patchnet.py rebuilt from plain torch modules (fp32 reference for a floating-point kernel)."""
+    import torch
+    import torch.nn as nn
+    from vo_b200 import r2d2_frontend as rf
+    mods = []
+    for L in rf.layer_table(name, sd):
+        conv = nn.Conv2d(L["cin"], L["cout"], L["k"], padding=((L["k"] - 1) * L["dil"]) // 2, dilation=L["dil"])
+        conv.weight.data = torch.from_numpy(L["w"].transpose(0, 3, 1, 2).copy())
+        conv.bias.data = torch.from_numpy(L["bias"].copy())
+        mods.append(conv)
+        if L["bn"]:
+            bn = nn.BatchNorm2d(L["cout"], affine=False)
+            bn.running_mean.data = torch.from_numpy(L["bn_mean"].copy())
+            bn.running_var.data = torch.from_numpy(L["bn_var"].copy())
+            mods.append(bn)
+        if L["relu"]:
+            mods.append(nn.ReLU())
+        if L["pool_after"]:
+            mods.append(nn.MaxPool2d(2))
+    if rf.ARCH[name]["upsample"] == 2:
+        mods.append(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False))
+    return nn.Sequential(*mods).eval().double().to(dev)
+
+
+@pytest.mark.gpu
+def test_full_resolution_architecture_vs_torch_fp64():
+    """Quad_L2Net_ConfCFS (the non-'faster' models: no pooling, no up-sampling, 2x2 taps up to dilation 16) with random
+    weights against the same stack in torch fp64: covers the upsample == 1 head path and the widest dilations."""
+    import torch
+    import torch.nn.functional as F
+    import vo_b200  # noqa: F401
+    from vo_b200 import r2d2_frontend as rf
+    rng = np.random.default_rng(5)
+    name = "Quad_L2Net_ConfCFS"
+    chans = [3, 32, 32, 64, 64, 128, 128, 128, 128, 128]
+    sd, idx = {}, 0
+    for li, (k, dil, bn, relu, pool) in enumerate(rf.ARCH[name]["layers"]):
+        cin, cout = chans[li], chans[li + 1]
+        sd[f"ops.{idx}.weight"] = (rng.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k)).astype(np.float32)
+        sd[f"ops.{idx}.bias"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+        if bn:
+            sd[f"ops.{idx + 1}.running_mean"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+            sd[f"ops.{idx + 1}.running_var"] = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+        idx += 1 + bn + relu
+    sd["clf.weight"] = (rng.standard_normal((2, 128, 1, 1)) * 0.3).astype(np.float32)
+    sd["clf.bias"] = rng.standard_normal(2).astype(np.float32) * 0.1
+    sd["sal.weight"] = (rng.standard_normal((1, 128, 1, 1)) * 0.3).astype(np.float32)
+    sd["sal.bias"] = rng.standard_normal(1).astype(np.float32) * 0.1
+    H, W = 70, 150
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    net = rf.R2D2Net(name, sd, H, W, max_kp=H * W)
+    assert (net.Ho, net.Wo) == (H, W)
+    xys, desc, scores, rel, rep = net.extract(img, 0.0, 0.0, -1.0, want_maps=True)     # thresholds off: every local maximum
+    dev = torch.device("cuda")
+    body = _torch_net(name, sd, dev)
+    mean = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1)
+    x = ((torch.from_numpy(img).to(dev).permute(2, 0, 1)[None].float() / 255 - mean) / std).double()
+    with torch.no_grad():
+        f = body(x)
+        u = F.conv2d(f ** 2, torch.from_numpy(sd["clf.weight"]).double().to(dev), torch.from_numpy(sd["clf.bias"]).double().to(dev))
+        rel_t = F.softmax(u, dim=1)[0, 1]
+        s = F.softplus(F.conv2d(f ** 2, torch.from_numpy(sd["sal.weight"]).double().to(dev), torch.from_numpy(sd["sal.bias"]).double().to(dev)))
+        rep_t = (s / (1 + s))[0, 0]
+        d_t = F.normalize(f, p=2, dim=1)[0]
+    assert float((rel.double() - rel_t).abs().max()) < 2e-4 and float((rep.double() - rep_t).abs().max()) < 2e-4
+    xi, yi = xys[:, 0].long(), xys[:, 1].long()
+    assert len(xys) > 200
+    assert float((desc.double() - d_t[:, yi, xi].t()).abs().max()) < 2e-4
+    # every reported keypoint is a 3x3 local maximum of the repeatability map the library itself produced
+    mx = F.max_pool2d(rep[None, None], 3, 1, 1)[0, 0]
+    assert bool((rep[yi, xi] == mx[yi, xi]).all()) and int((rep == mx).sum()) == len(xys)

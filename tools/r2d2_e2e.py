@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Images -> poses on one GPU with every stage in libvo_b200.so: R2D2 front-end (tcgen05 convolutions, heads, NMS),
+device-resident keyframe loop (tcgen05 3xTF32 matcher, back-projection, PnP-RANSAC, policy kernels).  Scene: a textured
+fronto-parallel plane, camera moving sideways (frames are shifted copies), so the true trajectory is known.  Features
+never leave the device: the front-end's output buffers are pushed into the loop's frame slot by a device-to-device copy.
+Prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import vo_b200  # noqa: F401
+    from vo_b200 import ops, r2d2_frontend as rf, synthetic
+    from vo_b200.device_loop import DeviceLoop
+    g = np.load(os.path.join(ROOT, "tests", "golden", "r2d2_net.npz"))
+    name, sd = str(g["net"]).split("(")[0], {k[3:]: g[k] for k in g.files if k.startswith("w__")}
+    W, H = synthetic.KITTI_WH
+    n_frames = int(os.environ.get("E2E_FRAMES", 40))
+    shift, Z = 14, 5.0
+    step = shift * Z / synthetic.KITTI_K[0, 0]
+    rng = np.random.default_rng(3)
+    big = np.kron(rng.integers(0, 256, (H // 6 + 1, (W + shift * n_frames) // 6 + 2, 3)), np.ones((6, 6, 1))).astype(np.uint8)
+    frames = [torch.from_numpy(np.ascontiguousarray(big[:H, i * shift:i * shift + W])).pin_memory() for i in range(n_frames)]
+    depth = torch.full((H, W), Z, dtype=torch.float32).pin_memory()
+    cap = 8192
+    net = rf.R2D2Net(name, sd, H, W, max_kp=cap)
+
+    def run():
+        loop = DeviceLoop(synthetic.KITTI_K, (W, H), cap, kind="r2d2", kp_stride=3, norm_or_metric=ops.VO_METRIC_COSINE,
+                          mode=ops.VO_MODE_RATIO_MUTUAL, match_param=0.90, precision=ops.VO_PREC_TF32X3, n_hyp=512,
+                          max_frames=n_frames)
+        counts = []
+        for i, f in enumerate(frames):
+            xys, desc, _ = net.extract(f)            # one .item() per frame: the keypoint count sizes the push
+            counts.append(len(xys))
+            loop.push(xys, desc, depth, i)
+        poses, info = loop.poses()
+        return poses, info, counts
+
+    run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    poses, info, counts = run()
+    dt = time.perf_counter() - t0
+    want = np.array([[i * step, 0.0, 0.0] for i in range(n_frames)])
+    err = np.linalg.norm(poses[:, :3, 3] - want, axis=1)
+    print(json.dumps({"frames": n_frames, "frame": f"{W}x{H}", "images_to_poses_fps": n_frames / dt, "ms_per_frame": dt / n_frames * 1e3,
+                      "keypoints_per_frame": float(np.mean(counts)), "bad_pnp": int((info[1:, 0] != 0).sum()),
+                      "keyframes": int(info[:, 5].sum()), "max_position_error_m": float(err.max()),
+                      "h2d_bytes_per_frame": int(H * W * 3 + H * W * 4)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
