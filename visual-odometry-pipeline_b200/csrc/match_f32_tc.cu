@@ -407,26 +407,30 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                 if (full_tile && !partial_rows) { TC_EPI_LOOP(false, false) } else { TC_EPI_LOOP(true, true) }
 #undef TC_EPI_LOOP
             } else {
-                uint32_t cur[16], nxt[16];
-                tc_ld16_issue(taddr + 64 * h, cur);
-                tc_ld_wait16(cur);
+                // no column side: 16-column reads, two register buffers used alternately (unrolled by two, so no moves)
+                uint32_t bufa[16], bufb[16];
+                tc_ld16_issue(taddr + 64 * h, bufa);
+                tc_ld_wait16(bufa);
+#define TC_FOLD16(BUF, J0, MASKC, MASKR)                                                                                   \
+    _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                                                        \
+        float v[8];                                                                                                        \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[8 * u + i]);                              \
+        epi_group8<METRIC, MASKC, MASKR, COLS, EXT>(v, col0 + (J0) + 8 * u, M, row_ok, na, cn, cn_vec, lane,               \
+                                                    my_cv + (J0) + 8 * u, my_cb + (J0) + 8 * u, s1, s2, i1, i2);           \
+    }
 #define TC_EPI_LOOP(MASKC, MASKR)                                                                                          \
-    _Pragma("unroll 1") for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 16) {                                                \
-        const bool more = j0 + 16 < 64 * h + 64;                                                                           \
-        if (more) tc_ld16_issue(taddr + j0 + 16, nxt);                                                                     \
-        _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                                                    \
-            float v[8];                                                                                                    \
-            _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(cur[8 * u + i]);                          \
-            epi_group8<METRIC, MASKC, MASKR, COLS, EXT>(v, col0 + j0 + 8 * u, M, row_ok, na, cn, cn_vec, lane,             \
-                                                        my_cv + j0 + 8 * u, my_cb + j0 + 8 * u, s1, s2, i1, i2);           \
-        }                                                                                                                  \
-        if (more) {                                                                                                        \
-            tc_ld_wait16(nxt);                                                                                             \
-            _Pragma("unroll") for (int i = 0; i < 16; ++i) cur[i] = nxt[i];                                                \
-        }                                                                                                                  \
+    _Pragma("unroll 1") for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 32) {                                                \
+        tc_ld16_issue(taddr + j0 + 16, bufb);                                                                              \
+        TC_FOLD16(bufa, j0, MASKC, MASKR)                                                                                  \
+        tc_ld_wait16(bufb);                                                                                                \
+        const bool more = j0 + 32 < 64 * h + 64;                                                                           \
+        if (more) tc_ld16_issue(taddr + j0 + 32, bufa);                                                                    \
+        TC_FOLD16(bufb, j0 + 16, MASKC, MASKR)                                                                             \
+        if (more) tc_ld_wait16(bufa);                                                                                      \
     }
                 if (full_tile && !partial_rows) { TC_EPI_LOOP(false, false) } else { TC_EPI_LOOP(true, true) }
 #undef TC_EPI_LOOP
+#undef TC_FOLD16
             }
             tc_fence_before();  // this warp's share of the accumulator has been read: hand it back
             if (lane == 0) mbar_arrive(bar_tempty(g));
