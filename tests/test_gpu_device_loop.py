@@ -33,6 +33,7 @@ def _run_dropin(tmp_path, kind, frames, extra=""):
     ("orb", "", 1, 0, 0),                                        # reference ORB semantics: byte-L2 + ratio
     ("orb", "\norb_matcher: hamming_mutual\n", 0, 1, 0),         # north-star semantics
     ("sift", "", 0, 0, 1),
+    ("r2d2", "", 1, 2, 0),                                       # cosine ratio+mutual 0.90, 3xTF32, (x, y, scale) keypoints
 ])
 def test_device_loop_equals_host_policy(tmp_path, kind, extra, norm, mode, prec):
     import vo_b200  # noqa: F401
@@ -41,9 +42,13 @@ def test_device_loop_equals_host_policy(tmp_path, kind, extra, norm, mode, prec)
     cwd = os.getcwd()
     try:
         frames, gt = synthetic_sequence.make_sequence(n_frames=20, n_kp=1500, kind=kind, seed=91)
+        if kind == "r2d2":      # the reference's R2D2 keypoints are (x, y, scale) float32 rows (R2D2.py:160-166)
+            for f in frames:
+                f["kp"] = np.concatenate([f["kp"], np.full((len(f["kp"]), 1), 32.0)], 1).astype(np.float32)
         want, keys, vo = _run_dropin(tmp_path, kind, frames, extra)
         loop = DeviceLoop(synthetic.KITTI_K, synthetic.KITTI_WH, 1500, kind=kind, norm_or_metric=norm, mode=mode,
-                          match_param=0.85, precision=prec, n_hyp=vo.n_hyp, seed=vo.seed)
+                          match_param=0.90 if kind == "r2d2" else 0.85, precision=prec, n_hyp=vo.n_hyp, seed=vo.seed,
+                          kp_stride=3 if kind == "r2d2" else 2)
         for i, f in enumerate(frames):
             loop.push(f["kp"], f["desc"], f["depth"], i)        # enqueue only
         got, info = loop.poses()                                 # the one synchronisation
