@@ -30,29 +30,35 @@ namespace vo {
 namespace {
 
 constexpr int TC_BM = 128;      // rows of A per CTA (= TMEM lanes)
-constexpr int TC_BN = 128;      // columns per B tile (= accumulator columns)
+constexpr int TC_BN = 128;      // columns per B tile (= accumulator columns), 3xTF32; single pass uses TcCfg<1>::BN
 constexpr int TC_D = 128;       // descriptor length
 constexpr int TC_KB = 32;       // k elements per swizzle-128B row (32 fp32 = 128 B)
 constexpr int TC_NKB = TC_D / TC_KB;
-constexpr int TC_STAGES = 13;
-constexpr int TC_BLOCK_BYTES = TC_BN * 128;  // one [128 rows x 32 k] fp32 box = 16 KB
+// Per-mode tile geometry.  3xTF32: 128-column tiles, 13-stage ring of 16 KB boxes, TMEM = acc0 0 | acc1 128 | A_hi 256 |
+// A_lo 384.  Single pass has no A_lo, so the accumulators can be wider: 160-column tiles (27 % fewer tcgen05.mma per
+// FLOP — the single-pass kernel is bound by the MMA-issuing thread, not by the pipe), 10-stage ring of 20 KB boxes,
+// TMEM = acc0 0 | acc1 160 | ones block of the norm extension 320 | A_hi 384.
+template <int PASSES>
+struct TcCfg {
+    static constexpr int BN = (PASSES == 1) ? 160 : 128;
+    static constexpr int STAGES = (PASSES == 1) ? 10 : 13;
+    static constexpr int BLOCK_BYTES = BN * 128;                  // one [BN rows x 32 k] fp32 box
+    static constexpr int TMEM_A = (PASSES == 1) ? 384 : 256;      // first column of A_hi (A_lo follows in 3xTF32)
+    static constexpr int TMEM_EXT = 320;                          // single pass only
+    static constexpr int OFF_SCOL = STAGES * BLOCK_BYTES;         // [2 groups][2 bufs][4 quarters][BN] x (float, u32)
+    static constexpr int OFF_BAR = OFF_SCOL + 2 * 2 * 4 * BN * 8;
+    static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;       // barriers + alignment slack
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+};
 constexpr int TC_THREADS = 576;              // warps 0..15 epilogue, warp 16 TMA, warp 17 MMA
 constexpr int TC_WARP_TMA = 16, TC_WARP_MMA = 17;
 constexpr int TC_TMEM_COLS = 512;            // 2 accumulators x 128 | A_hi 128 | A_lo 128
-constexpr int TC_TMEM_A = 256;               // first column of A_hi (A_lo follows)
 constexpr int TC_CLUSTER = 2;
-
-// shared memory map (offsets from the 1024-aligned base)
-constexpr int TC_OFF_B = 0;
-constexpr int TC_OFF_SCOL = TC_OFF_B + TC_STAGES * TC_BLOCK_BYTES;  // [2 groups][4 quarters][128] x (float, u32)
-constexpr int TC_OFF_BAR = TC_OFF_SCOL + 2 * 2 * 4 * TC_BN * 8;  // scol is double-buffered per group
-constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 512 + 1024;              // barriers + alignment slack
 
 using namespace tc;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
-// A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29) — TcCfg<>::IDESC
 
 // ---------------------------------------------------------------- pre-pass: tf32 split + squared norms
 
@@ -182,7 +188,11 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     const int N = n_ref ? min(n_ref[b], n_stride) : n_stride;
     const int M = n_cur ? min(n_cur[b], m_stride) : m_stride;
     const int row0 = blockIdx.x * TC_BM;
-    const int tiles_total = (M + TC_BN - 1) / TC_BN;
+    using Cfg = TcCfg<PASSES>;
+    constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES, BLOCK_BYTES = Cfg::BLOCK_BYTES, HALF = BN / 2;
+    constexpr int TMEM_A = Cfg::TMEM_A, TMEM_EXT = Cfg::TMEM_EXT;
+    constexpr uint32_t IDESC = Cfg::IDESC;
+    const int tiles_total = (M + BN - 1) / BN;
     const int tiles_per_split = (tiles_total + n_split - 1) / n_split;
     const int t_begin = min(tiles_total, split * tiles_per_split);
     const int t_end = min(tiles_total, t_begin + tiles_per_split);
@@ -199,20 +209,20 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     // single-pass L2: one extra box per tile carries -|b|^2 (three tf32 pieces), multiplied by a column block of ones in A
     constexpr bool EXT = (PASSES == 1) && (METRIC == VO_METRIC_L2);
     constexpr int ITEMS = (PASSES == 3) ? 2 * TC_NKB : (EXT ? TC_NKB + 1 : TC_NKB);  // B boxes streamed per tile
-    const uint32_t s_b = base + TC_OFF_B;
-    float *scol_v = reinterpret_cast<float *>(smem + TC_OFF_SCOL);                       // [2 groups][2 bufs][4][128]
-    uint32_t *scol_b = reinterpret_cast<uint32_t *>(smem + TC_OFF_SCOL + 2 * 2 * 4 * TC_BN * 4);
-    const uint32_t s_bar = base + TC_OFF_BAR;
+    const uint32_t s_b = base;
+    float *scol_v = reinterpret_cast<float *>(smem + Cfg::OFF_SCOL);                      // [2 groups][2 bufs][4][BN]
+    uint32_t *scol_b = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_SCOL + 2 * 2 * 4 * BN * 4);
+    const uint32_t s_bar = base + Cfg::OFF_BAR;
     // barrier slots (8 B each): full[S] empty[S] a_full tmem_full[2] tmem_empty[2]; then the TMEM base word
     auto bar_full = [&](int s) { return s_bar + 8u * s; };
-    auto bar_empty = [&](int s) { return s_bar + 8u * (TC_STAGES + s); };
-    const uint32_t bar_a = s_bar + 8u * (2 * TC_STAGES);
-    auto bar_tfull = [&](int g) { return s_bar + 8u * (2 * TC_STAGES + 1 + g); };
-    auto bar_tempty = [&](int g) { return s_bar + 8u * (2 * TC_STAGES + 3 + g); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TC_OFF_BAR + 8 * (2 * TC_STAGES + 5));
+    auto bar_empty = [&](int s) { return s_bar + 8u * (STAGES + s); };
+    const uint32_t bar_a = s_bar + 8u * (2 * STAGES);
+    auto bar_tfull = [&](int g) { return s_bar + 8u * (2 * STAGES + 1 + g); };
+    auto bar_tempty = [&](int g) { return s_bar + 8u * (2 * STAGES + 3 + g); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_BAR + 8 * (2 * STAGES + 5));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full(s), 1);            // this CTA's producer arms it; TMA bytes complete it
             mbar_init(bar_empty(s), TC_CLUSTER);  // one commit from each CTA of the cluster
         }
@@ -239,17 +249,17 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         if (lane == 0) {
             int it = 0;
             for (int lt = 0; lt < n_tiles; ++lt) {
-                const int brow = b * m_stride + tile_of(lt) * TC_BN;
+                const int brow = b * m_stride + tile_of(lt) * BN;
                 for (int item = 0; item < ITEMS; ++item, ++it) {
-                    const int stage = it % TC_STAGES;
-                    const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
+                    const int stage = it % STAGES;
+                    const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
                     { TC_DBG_BEGIN(); mbar_wait(bar_empty(stage), phase ^ 1u); TC_DBG_END(0); }  // both CTAs consumed the slot
-                    mbar_expect_tx(bar_full(stage), TC_BLOCK_BYTES);  // bytes arrive by multicast, whoever issues
+                    mbar_expect_tx(bar_full(stage), BLOCK_BYTES);  // bytes arrive by multicast, whoever issues
                     if ((uint32_t)(it & 1) == crank) {
                         const bool is_ext = EXT && item == TC_NKB;  // map_b_lo is the extension map in that mode
                         const int kb = is_ext ? 0 : ((PASSES == 3) ? (item >> 1) : item);
                         const bool is_lo = is_ext || ((PASSES == 3) && (item & 1));
-                        tma_load_2d_mc(s_b + stage * TC_BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * TC_KB, brow,
+                        tma_load_2d_mc(s_b + stage * BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * TC_KB, brow,
                                        bar_full(stage), (uint16_t)((1u << TC_CLUSTER) - 1u));
                     }
                 }
@@ -272,7 +282,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                   mbar_wait(bar_tempty(buf), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
                   if (dbg_on) mma_wait_tempty += clock64() - _t0; }
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * TC_BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
 #pragma unroll
                 for (int item = 0; item < ITEMS; ++item) {
                     { const long long _t0 = dbg_on ? clock64() : 0;
@@ -282,22 +292,22 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                     if (elect_one()) {
                         const int kb = (PASSES == 3) ? (item >> 1) : item;       // compile-time after unrolling
                         const bool is_lo = (PASSES == 3) && (item & 1);
-                        const uint32_t b_lo32 = (((s_b + stage * TC_BLOCK_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
-                        const uint32_t a_hi_t = tmem_base + (uint32_t)(TC_TMEM_A + kb * TC_KB);
+                        const uint32_t b_lo32 = (((s_b + stage * BLOCK_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
+                        const uint32_t a_hi_t = tmem_base + (uint32_t)(TMEM_A + kb * TC_KB);
                         if (EXT && item == TC_NKB) {  // ones[128 x 8] * (-|b|^2 pieces)[8 x 128]
                             const uint64_t bdesc = ((uint64_t)TC_SDESC_HI << 32) | (uint64_t)b_lo32;
-                            tc_mma_tf32_ts(d_tmem, tmem_base + (uint32_t)(TC_TMEM_A + TC_D), bdesc, TC_IDESC, 1u);
+                            tc_mma_tf32_ts(d_tmem, tmem_base + (uint32_t)TMEM_EXT, bdesc, IDESC, 1u);
                         } else
 #pragma unroll
                         for (int k8 = 0; k8 < TC_KB / 8; ++k8) {
                             const uint64_t bdesc = ((uint64_t)TC_SDESC_HI << 32) | (uint64_t)(b_lo32 + k8 * 2);
                             const uint32_t ahi = a_hi_t + k8 * 8;
                             if (is_lo) {  // a_hi * b_lo
-                                tc_mma_tf32_ts(d_tmem, ahi, bdesc, TC_IDESC, 1u);
+                                tc_mma_tf32_ts(d_tmem, ahi, bdesc, IDESC, 1u);
                             } else {
                                 if (PASSES == 3)  // a_lo * b_hi first (small term), then a_hi * b_hi
-                                    tc_mma_tf32_ts(d_tmem, ahi + TC_D, bdesc, TC_IDESC, (item | k8) ? 1u : 0u);
-                                tc_mma_tf32_ts(d_tmem, ahi, bdesc, TC_IDESC, (PASSES == 3 || (item | k8)) ? 1u : 0u);
+                                    tc_mma_tf32_ts(d_tmem, ahi + TC_D, bdesc, IDESC, (item | k8) ? 1u : 0u);
+                                tc_mma_tf32_ts(d_tmem, ahi, bdesc, IDESC, (PASSES == 3 || (item | k8)) ? 1u : 0u);
                             }
                         }
                         // slot reusable (in BOTH CTAs' rings) once these MMAs retire
@@ -305,7 +315,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                         if (item == ITEMS - 1) tc_commit(bar_tfull(buf));  // accumulator complete
                     }
                     __syncwarp();
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
             if (dbg_on && lane == 0) { dbg[1] = mma_wait_full; dbg[2] = mma_wait_tempty; dbg[3] = clock64() - t_kernel0; dbg[11] = n_tiles; }
@@ -334,7 +344,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                     const float sc2 = EXT ? 2.0f : 1.0f;  // exact
                     v[4 * k] = sc2 * x.x; v[4 * k + 1] = sc2 * x.y; v[4 * k + 2] = sc2 * x.z; v[4 * k + 3] = sc2 * x.w;
                 }
-                tc_st32(lane_base + (uint32_t)(TC_TMEM_A + g * TC_D + c * 32), v);
+                tc_st32(lane_base + (uint32_t)(TMEM_A + g * TC_D + c * 32), v);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
@@ -343,7 +353,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
 
         if (EXT && n_tiles > 0 && g == 1 && h == 0) {  // the ones block of A (TMEM columns of the unused lo half)
             const float ones[8] = {1.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            tc_st8(lane_base + (uint32_t)(TC_TMEM_A + TC_D), ones);
+            tc_st8(lane_base + (uint32_t)TMEM_EXT, ones);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar_a);
@@ -351,24 +361,24 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
 
         float s1 = -INFINITY, s2 = -INFINITY;  // running top-2 of -|a-b|^2 or a.b over this warp's columns
         int32_t i1 = -1, i2 = -1;
-        float *grp_cv = scol_v + g * 2 * 4 * TC_BN;
-        uint32_t *grp_cb = scol_b + g * 2 * 4 * TC_BN;
+        float *grp_cv = scol_v + g * 2 * 4 * BN;
+        uint32_t *grp_cb = scol_b + g * 2 * 4 * BN;
         const float *cn = (METRIC == VO_METRIC_L2) ? col_norm + (size_t)b * m_stride : nullptr;
         const float na = (METRIC == VO_METRIC_L2 && row_ok) ? row_norm[(size_t)b * n_stride + row] : 0.0f;
         const bool cn_vec = (METRIC == VO_METRIC_L2) && ((reinterpret_cast<uintptr_t>(cn) & 15u) == 0);
 
         for (int lt = g; lt < n_tiles; lt += 2) {
-            const int col0 = tile_of(lt) * TC_BN;
+            const int col0 = tile_of(lt) * BN;
             const uint32_t use = (uint32_t)(lt >> 1);
-            const bool full_tile = col0 + TC_BN <= M;
-            float *tile_cv = grp_cv + (use & 1u) * 4 * TC_BN;   // this tile's column scratch (alternates per use)
-            uint32_t *tile_cb = grp_cb + (use & 1u) * 4 * TC_BN;
-            float *my_cv = tile_cv + q * TC_BN;
-            uint32_t *my_cb = tile_cb + q * TC_BN;
+            const bool full_tile = col0 + BN <= M;
+            float *tile_cv = grp_cv + (use & 1u) * 4 * BN;   // this tile's column scratch (alternates per use)
+            uint32_t *tile_cb = grp_cb + (use & 1u) * 4 * BN;
+            float *my_cv = tile_cv + q * BN;
+            uint32_t *my_cb = tile_cb + q * BN;
             { TC_DBG_BEGIN(); mbar_wait(bar_tfull(g), use & 1u); TC_DBG_END(0); }
             tc_fence_after();
             const long long _tc0 = dbg_on ? clock64() : 0;
-            const uint32_t taddr = lane_base + (uint32_t)(g * TC_BN);
+            const uint32_t taddr = lane_base + (uint32_t)(g * BN);
             // Three epilogue schedules.  3xTF32 is bound by the tensor pipe: plain load -> wait -> fold.  Single pass is
             // bound by the epilogue, whose cost per 8 columns was the TMEM read latency, so the read of the next
             // columns is kept in flight while the current ones are folded (two register buffers swapped by moves: the
@@ -376,7 +386,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             // column arg-max there are registers to spare and the reads are 16 columns wide.
             if (PASSES == 3) {
 #define TC_EPI_LOOP(MASKC, MASKR)                                                                                          \
-    _Pragma("unroll 1") for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 8) {                                                 \
+    _Pragma("unroll 1") for (int j0 = HALF * h; j0 < HALF * h + HALF; j0 += 8) {                                                 \
         uint32_t cur[8];                                                                                                   \
         tc_ld8_issue(taddr + j0, cur);                                                                                     \
         tc_ld_wait8(cur);                                                                                                  \
@@ -389,11 +399,11 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
 #undef TC_EPI_LOOP
             } else if (COLS) {
                 uint32_t cur[8], nxt[8];
-                tc_ld8_issue(taddr + 64 * h, cur);
+                tc_ld8_issue(taddr + HALF * h, cur);
                 tc_ld_wait8(cur);
 #define TC_EPI_LOOP(MASKC, MASKR)                                                                                          \
-    _Pragma("unroll 1") for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 8) {                                                 \
-        const bool more = j0 + 8 < 64 * h + 64;                                                                            \
+    _Pragma("unroll 1") for (int j0 = HALF * h; j0 < HALF * h + HALF; j0 += 8) {                                                 \
+        const bool more = j0 + 8 < HALF * h + HALF;                                                                            \
         if (more) tc_ld8_issue(taddr + j0 + 8, nxt);                                                                       \
         float v[8];                                                                                                        \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(cur[i]);                                      \
@@ -409,7 +419,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             } else {
                 // no column side: 16-column reads, two register buffers used alternately (unrolled by two, so no moves)
                 uint32_t bufa[16], bufb[16];
-                tc_ld16_issue(taddr + 64 * h, bufa);
+                tc_ld16_issue(taddr + HALF * h, bufa);
                 tc_ld_wait16(bufa);
 #define TC_FOLD16(BUF, J0, MASKC, MASKR)                                                                                   \
     _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                                                        \
@@ -419,14 +429,17 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                                                     my_cv + (J0) + 8 * u, my_cb + (J0) + 8 * u, s1, s2, i1, i2);           \
     }
 #define TC_EPI_LOOP(MASKC, MASKR)                                                                                          \
-    _Pragma("unroll 1") for (int j0 = 64 * h; j0 < 64 * h + 64; j0 += 32) {                                                \
-        tc_ld16_issue(taddr + j0 + 16, bufb);                                                                              \
+    _Pragma("unroll 1") for (int j0 = HALF * h; j0 < HALF * h + HALF; j0 += 32) {                                          \
+        const bool has_b = j0 + 16 < HALF * h + HALF;   /* HALF is a multiple of 16, not necessarily of 32 */               \
+        if (has_b) tc_ld16_issue(taddr + j0 + 16, bufb);                                                                   \
         TC_FOLD16(bufa, j0, MASKC, MASKR)                                                                                  \
-        tc_ld_wait16(bufb);                                                                                                \
-        const bool more = j0 + 32 < 64 * h + 64;                                                                           \
-        if (more) tc_ld16_issue(taddr + j0 + 32, bufa);                                                                    \
-        TC_FOLD16(bufb, j0 + 16, MASKC, MASKR)                                                                             \
-        if (more) tc_ld_wait16(bufa);                                                                                      \
+        if (has_b) {                                                                                                       \
+            tc_ld_wait16(bufb);                                                                                            \
+            const bool more = j0 + 32 < HALF * h + HALF;                                                                   \
+            if (more) tc_ld16_issue(taddr + j0 + 32, bufa);                                                                \
+            TC_FOLD16(bufb, j0 + 16, MASKC, MASKR)                                                                         \
+            if (more) tc_ld_wait16(bufa);                                                                                  \
+        }                                                                                                                  \
     }
                 if (full_tile && !partial_rows) { TC_EPI_LOOP(false, false) } else { TC_EPI_LOOP(true, true) }
 #undef TC_EPI_LOOP
@@ -437,18 +450,18 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             if (dbg_on) dbg_acc[1] += clock64() - _tc0;
             const long long _tm0 = dbg_on ? clock64() : 0;
             if (COLS) group_bar(1 + g);
-            if (COLS && h == 0) {  // 128 threads: one column each, merge the 4 lane quarters (ascending rows)
-                const int j = q * 32 + lane;
+            if (COLS && (h * 4 + q) * 32 < BN) {  // one column per thread, merge the 4 lane quarters (ascending rows)
+                const int j = (h * 4 + q) * 32 + lane;
                 const int col = col0 + j;
                 float best = -INFINITY;
                 int brow = -1;
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
-                    const float val = tile_cv[qq * TC_BN + j];
-                    const uint32_t bal = tile_cb[qq * TC_BN + j];
+                    const float val = tile_cv[qq * BN + j];
+                    const uint32_t bal = tile_cb[qq * BN + j];
                     if (bal != 0u && val > best) { best = val; brow = qq * 32 + __ffs(bal) - 1; }
                 }
-                if (col < M && brow >= 0 && row0 + brow < N) {
+                if (j < BN && col < M && brow >= 0 && row0 + brow < N) {
                     const unsigned long long key =
                         ((unsigned long long)float_to_ordered(-best) << 32) | (unsigned long long)(uint32_t)(row0 + brow);
                     unsigned long long *dst = colkey + (size_t)b * m_stride + col;
@@ -486,11 +499,11 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(vo_ctx *ctx, CUtensorMap *map, const float *ptr, long long rows, int row_floats = TC_D) {
+int make_map(vo_ctx *ctx, CUtensorMap *map, const float *ptr, long long rows, int box_rows, int row_floats = TC_D) {
     PFN_encodeTiled fn = (PFN_encodeTiled)ctx->encode_tiled;
     cuuint64_t dims[2] = {(cuuint64_t)row_floats, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)row_floats * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_BN};
+    cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -514,8 +527,8 @@ int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &
         VO_CUDA(cudaMemsetAsync(dbg_dev, 0, 16 * sizeof(long long), st));
         dbg = dbg_dev;
     }
-    VO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(bh, bl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm,
+    VO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<PASSES>::SMEM_BYTES));
+    kern<<<grid, TC_THREADS, TcCfg<PASSES>::SMEM_BYTES, st>>>(bh, bl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm,
                                                   n_split, part, colkey, dbg);
     VO_LAUNCH_CHECK(ctx);
     if (dbg) {
@@ -571,14 +584,15 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     VO_LAUNCH_CHECK(ctx);
 
     CUtensorMap mbh, mbl;
-    if ((rc = make_map(ctx, &mbh, b_hi, rows_b))) return rc;
-    if (ext) rc = make_map(ctx, &mbl, b_ext, rows_b, TC_KB);
-    else rc = make_map(ctx, &mbl, passes == 3 ? b_lo : b_hi, rows_b);
+    const int bn = passes == 3 ? TcCfg<3>::BN : TcCfg<1>::BN;
+    if ((rc = make_map(ctx, &mbh, b_hi, rows_b, bn))) return rc;
+    if (ext) rc = make_map(ctx, &mbl, b_ext, rows_b, bn, TC_KB);
+    else rc = make_map(ctx, &mbl, passes == 3 ? b_lo : b_hi, rows_b, bn);
     if (rc) return rc;
 
     const int row_blocks = ceil_div(n_stride, TC_BM);
     const int grid_x = ceil_div(row_blocks, TC_CLUSTER) * TC_CLUSTER;  // clusters pair adjacent row blocks
-    const int n_split = pick_split(ctx, B, grid_x, ceil_div(m_stride, TC_BN), 4);
+    const int n_split = pick_split(ctx, B, grid_x, ceil_div(m_stride, bn), 4);
     vo_row_partial *part;
     if ((rc = ws_get(ctx, WS_ROWPART, sizeof(vo_row_partial) * (size_t)B * n_split * 4 * n_stride, (void **)&part))) return rc;
     dim3 grid(grid_x, n_split, B);
