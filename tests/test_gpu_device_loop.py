@@ -86,3 +86,22 @@ def test_device_loop_failures_and_bad_pnp_counter():
     from vo_b200 import _lib
     with pytest.raises(_lib.VoError):
         loop.push(np.zeros((900, 2)), np.zeros((900, 32), np.uint8), frames[0]["depth"], 99)
+
+
+def test_device_loop_empty_frames_and_history_limit():
+    import vo_b200  # noqa: F401
+    from vo_b200 import _lib, synthetic, synthetic_sequence
+    from vo_b200.device_loop import DeviceLoop
+    frames, _ = synthetic_sequence.make_sequence(n_frames=4, n_kp=300, kind="orb", seed=2)
+    loop = DeviceLoop(synthetic.KITTI_K, synthetic.KITTI_WH, 300, kind="orb", norm_or_metric=0, mode=1, n_hyp=128, max_frames=4)
+    loop.push(frames[0]["kp"], frames[0]["desc"], frames[0]["depth"], 0)
+    loop.push(np.zeros((0, 2)), np.zeros((0, 32), np.uint8), frames[1]["depth"], 1)      # a frame without keypoints
+    loop.push(frames[2]["kp"], frames[2]["desc"], frames[2]["depth"], 2)
+    loop.push(frames[3]["kp"], frames[3]["desc"], frames[3]["depth"], 3)
+    poses, info = loop.poses()
+    assert info[1, 0] != 0 and np.array_equal(poses[1], poses[0])       # bad PnP: pose of the keyframe (:290)
+    assert info[2, 0] == 0 and info[2, 4] == 0                          # still matched against keyframe 0
+    with pytest.raises(_lib.VoError):
+        loop.push(frames[0]["kp"], frames[0]["desc"], frames[0]["depth"], 4)               # history full
+    p2, i2 = loop.poses(first=2, count=2)
+    assert np.array_equal(p2, poses[2:]) and np.array_equal(i2, info[2:])

@@ -248,3 +248,33 @@ def test_full_resolution_architecture_vs_torch_fp64():
     # every reported keypoint is a 3x3 local maximum of the repeatability map the library itself produced
     mx = F.max_pool2d(rep[None, None], 3, 1, 1)[0, 0]
     assert bool((rep[yi, xi] == mx[yi, xi]).all()) and int((rep == mx).sum()) == len(xys)
+
+
+@pytest.mark.gpu
+def test_capacity_overflow_and_bad_configs(golden):
+    """More keypoints than max_kp: the first max_kp in row-major order are kept and the total is still reported; broken
+    configurations fail loudly at creation."""
+    import torch
+    import vo_b200  # noqa: F401
+    from vo_b200 import _lib, r2d2_frontend as rf
+    g = golden("r2d2_net.npz")
+    name, sd = _weights(g)
+    img = g["image"]
+    big = rf.R2D2Net(name, sd, img.shape[0], img.shape[1], max_kp=4096)
+    xa, da, _ = big.extract(img, 0.3, 0.3, 0.1)
+    xa, da = xa.clone(), da.clone()
+    assert len(xa) > 60
+    small = rf.R2D2Net(name, sd, img.shape[0], img.shape[1], max_kp=50)
+    xb, db, _ = small.extract(img, 0.3, 0.3, 0.1)
+    assert len(xb) == 50 and int(small.count.item()) == len(xa)
+    assert torch.equal(xb, xa[:50]) and torch.equal(db, da[:50])
+    with pytest.raises(ValueError):
+        small.extract(img[:-1])                                   # wrong shape
+    bad = dict(sd)
+    bad["ops.3.weight"] = sd["ops.3.weight"][:, :16]              # C_in no longer matches the previous C_out
+    with pytest.raises(_lib.VoError):
+        rf.R2D2Net(name, bad, 64, 64)
+    # a 1-row image and an image narrower than one 128-pixel tile still run
+    tiny = rf.R2D2Net(name, sd, 2, 40, max_kp=64)
+    x, d, s = tiny.extract(np.zeros((2, 40, 3), np.uint8), 0.0, 0.0, -1.0)
+    assert tiny.Ho == 2 and tiny.Wo == 40 and d.shape[1] == 128
