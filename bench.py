@@ -372,7 +372,9 @@ def run_ours(args, wl):
                         "hbm_gbs": (corr_per_launch * 20.0 + pairs_per_launch * Hh * 52.0) / t / 1e9,
                         "l2_to_sm_gbs": sc_bytes / t / 1e9,
                         "note": "HBM figure is structurally << peak: every correspondence is re-read from L2 by H/32 CTAs "
-                                "and tested against all H hypotheses (SURVEY D5: FP32-pipe bound)"})
+                                "and tested against all H hypotheses (SURVEY D5: FP32-pipe bound).  evals = hypotheses x points "
+                                "BEFORE the exact pruning (hypotheses that can no longer reach the running best count stop "
+                                "being scored), so achieved is an effective rate"})
     if "gather" in stage_ms:
         t = stage_ms["gather"] / 1e3
         gb = match_per_launch * 53.0

@@ -164,6 +164,15 @@ def test_c4_ransac_16k_hypotheses_bit_exact(orc):
     assert np.array_equal(res.mask[0, :n].cpu().numpy(), mask)                       # inlier SET bit-exact
     ang, dt = synthetic.pose_errors(res.T_rel[0].cpu().numpy(), p["T_rel"])
     assert ang < 1e-3 and dt < 1e-2
+    # the production path (no per-hypothesis counts requested) prunes hypotheses that can no longer win: same winner,
+    # same count, same inlier set, same pose — also with several pairs in flight
+    B = 3
+    rep = lambda t: t.repeat(B, *([1] * (t.dim() - 1))).contiguous()
+    res2 = ops.pnp_ransac(rep(_gpu(xyz)[None]), rep(_gpu(cuv)[None]), torch.full((B,), n, dtype=torch.int32, device="cuda"),
+                          p["K"], rep(_gpu(hyp)[None]))
+    for b in range(B):
+        assert int(res2.best_h[b].item()) == best and int(res2.n_inl[b].item()) == int(res.n_inl[0].item())
+        assert torch.equal(res2.mask[b], res.mask[0]) and torch.equal(res2.T_rel[b], res.T_rel[0])
 
 
 # ------------------------------------------------------------------------------------------------ c5: ZED frame

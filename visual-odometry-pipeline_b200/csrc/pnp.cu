@@ -70,19 +70,26 @@ p3p_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const in
 // correspondences the CTA staged in shared memory, so every staged point (one LDS.128 + one LDS.32) feeds
 // SC_HPW independent inlier tests: 17 fp32 instructions each, no division, no branch (pnp_math.cuh).
 constexpr int SC_WARPS = 8;
-constexpr int SC_TILE = 2048;  // correspondences staged per pass: 2048 x 20 B = 40 KB
+constexpr int SC_TILE = 1024;  // correspondences staged per pass (20 KB); also the granularity of the pruning test
 
+// Exact pruning: `lower[b]` is a running lower bound of the winning inlier count of pair b (every warp publishes its
+// partial counts after each staged tile — a final count can only be larger).  A hypothesis whose count so far plus ALL
+// remaining points is still below that bound can neither win nor tie, so the warp stops scoring it; the winner, its
+// count and the tie rule (lowest index) are unchanged.  The host scores the first 32 hypotheses in a launch of their own
+// so that the bulk starts with a bound that is already close to the final one (with ~60 % inliers a fifth of the random
+// minimal samples is all-inlier).  Disabled when the caller wants every hypothesis' count.
 template <int SC_HPW, int MIN_CTAS>  // hypotheses per warp, resident CTAs per SM the register budget must allow
 __global__ void __launch_bounds__(SC_WARPS * 32, MIN_CTAS)
 score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ n_pts, int cap,
-             const float *__restrict__ poses, int H, IntrF k, float thr, unsigned long long *__restrict__ bestkey,
-             int32_t *__restrict__ hyp_counts) {
+             const float *__restrict__ poses, int H, int h_begin, int h_end, IntrF k, float thr,
+             unsigned long long *__restrict__ bestkey, unsigned int *__restrict__ lower, int32_t *__restrict__ hyp_counts) {
     __shared__ float4 sP[SC_TILE];  // X, Y, Z, u - cx
     __shared__ float sV[SC_TILE];   // v - cy
     const int b = blockIdx.y;
     const int n = min(n_pts[b], cap);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h0 = (blockIdx.x * SC_WARPS + warp) * SC_HPW;
+    const int h0 = h_begin + (blockIdx.x * SC_WARPS + warp) * SC_HPW;  // this launch scores hypotheses [h_begin, h_end)
+    const bool prune = hyp_counts == nullptr;
     ScoreModel m[SC_HPW];
 #pragma unroll
     for (int q = 0; q < SC_HPW; ++q) {
@@ -98,6 +105,10 @@ score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
     int count[SC_HPW];
 #pragma unroll
     for (int q = 0; q < SC_HPW; ++q) count[q] = 0;
+    unsigned alive = 0;  // warp-uniform mask of hypotheses still scored
+#pragma unroll
+    for (int q = 0; q < SC_HPW; ++q) alive |= (h0 + q < h_end) ? (1u << q) : 0u;
+    constexpr unsigned ALL = (1u << SC_HPW) - 1u;
     const float *pxyz = xyz + (size_t)b * cap * 3;
     const float *puv = uv + (size_t)b * cap * 2;
     for (int p0 = 0; p0 < n; p0 += SC_TILE) {
@@ -110,7 +121,7 @@ score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
             sV[i] = VO_FSUBF(q2.y, k.cy);
         }
         __syncthreads();
-        if (h0 < H) {
+        if (alive == ALL) {  // common case: no per-hypothesis branches in the loop
 #pragma unroll 2
             for (int i = lane; i < cnt; i += 32) {
                 const float4 P = sP[i];
@@ -118,12 +129,34 @@ score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
 #pragma unroll
                 for (int q = 0; q < SC_HPW; ++q) count[q] += is_inlier(m[q], thr, P.x, P.y, P.z, P.w, vc) ? 1 : 0;
             }
+        } else if (alive) {
+            for (int i = lane; i < cnt; i += 32) {
+                const float4 P = sP[i];
+                const float vc = sV[i];
+#pragma unroll
+                for (int q = 0; q < SC_HPW; ++q)
+                    if (alive & (1u << q)) count[q] += is_inlier(m[q], thr, P.x, P.y, P.z, P.w, vc) ? 1 : 0;
+            }
+        }
+        if (prune && alive && p0 + SC_TILE < n) {  // between tiles: publish partial counts, drop the hopeless
+            const int remaining = n - (p0 + cnt);
+            int tot[SC_HPW], wbest = 0;
+#pragma unroll
+            for (int q = 0; q < SC_HPW; ++q) {
+                tot[q] = (alive & (1u << q)) ? __reduce_add_sync(0xffffffffu, count[q]) : 0;
+                wbest = max(wbest, tot[q]);
+            }
+            if (lane == 0 && wbest > 0) atomicMax(&lower[b], (unsigned int)wbest);
+            const unsigned int lb = *reinterpret_cast<volatile unsigned int *>(&lower[b]);
+#pragma unroll
+            for (int q = 0; q < SC_HPW; ++q)
+                if ((alive & (1u << q)) && (unsigned int)(tot[q] + remaining) < lb) alive &= ~(1u << q);
         }
     }
 #pragma unroll
     for (int q = 0; q < SC_HPW; ++q) {
         const int h = h0 + q;
-        if (h < H) {
+        if (alive & (1u << q)) {
             const int c = __reduce_add_sync(0xffffffffu, count[q]);
             if (lane == 0) {
                 if (hyp_counts) hyp_counts[(size_t)b * H + h] = c;
@@ -131,6 +164,7 @@ score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
                 const unsigned long long key =
                     ((unsigned long long)(uint32_t)c << 32) | (unsigned long long)(0xffffffffu - (uint32_t)h);
                 atomicMax(&bestkey[b], key);
+                if (prune) atomicMax(&lower[b], (unsigned int)c);
             }
         }
     }
@@ -435,8 +469,9 @@ int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_
     unsigned long long *bestkey;
     int rc;
     if ((rc = ws_get(ctx, WS_POSES, sizeof(float) * 12 * (size_t)B * H, (void **)&poses))) return rc;
-    if ((rc = ws_get(ctx, WS_BESTKEY, sizeof(unsigned long long) * (size_t)B, (void **)&bestkey))) return rc;
-    VO_CUDA(cudaMemsetAsync(bestkey, 0, sizeof(unsigned long long) * (size_t)B, st));
+    if ((rc = ws_get(ctx, WS_BESTKEY, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)B, (void **)&bestkey))) return rc;
+    unsigned int *lower = reinterpret_cast<unsigned int *>(bestkey + B);  // running lower bound of the best count (pruning)
+    VO_CUDA(cudaMemsetAsync(bestkey, 0, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)B, st));
 
     IntrD kd{K_h[0], K_h[4], K_h[2], K_h[5]};
     IntrF kf{(float)K_h[0], (float)K_h[4], (float)K_h[2], (float)K_h[5]};
@@ -447,8 +482,15 @@ int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_
     VO_PROF(ctx, st, VO_STAGE_SCORE);
     // 4 hypotheses per warp, 3 CTAs per SM: 2 / 8 per warp and 2 / 4 CTAs per SM all measure within 5 % (the kernel sits
     // at 0.73 issued instructions per cycle and scheduler whatever the occupancy: profiles/README.md)
-    score_kernel<4, 3><<<dim3(ceil_div(H, SC_WARPS * 4), B), SC_WARPS * 32, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, thr_px,
-                                                                                      bestkey, hyp_counts);
+    constexpr int SC_PER_CTA = SC_WARPS * 4;
+    const int h_first = (hyp_counts || H <= 2 * SC_PER_CTA) ? 0 : SC_PER_CTA;  // scouts: one CTA per pair, scored to the end
+    if (h_first) {
+        score_kernel<4, 3><<<dim3(1, B), SC_WARPS * 32, 0, st>>>(xyz, uv, n_pts, cap, poses, H, 0, h_first, kf, thr_px, bestkey, lower,
+                                                                  hyp_counts);
+        VO_LAUNCH_CHECK(ctx);
+    }
+    score_kernel<4, 3><<<dim3(ceil_div(H - h_first, SC_PER_CTA), B), SC_WARPS * 32, 0, st>>>(xyz, uv, n_pts, cap, poses, H, h_first, H,
+                                                                                              kf, thr_px, bestkey, lower, hyp_counts);
     VO_LAUNCH_CHECK(ctx);
     VO_PROF(ctx, st, VO_STAGE_REFIT);
     refit_kernel<<<B, RF_THREADS, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, kd, thr_px, min_inliers, refine_iters,
