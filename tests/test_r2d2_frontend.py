@@ -278,3 +278,65 @@ def test_capacity_overflow_and_bad_configs(golden):
     tiny = rf.R2D2Net(name, sd, 2, 40, max_kp=64)
     x, d, s = tiny.extract(np.zeros((2, 40, 3), np.uint8), 0.0, 0.0, -1.0)
     assert tiny.Ho == 2 and tiny.Wo == 40 and d.shape[1] == 128
+
+
+@pytest.mark.gpu
+def test_reference_yaml_offline_run(golden, tmp_path):
+    """`python3 vo_runner.py` with the REFERENCE's own vo_params.yaml keys (feature_extractor: r2d2, visualize_results:
+    True, ...): png + *_depth.npy files on disk -> vo_runner.read_yaml_file() -> <output>.npy of (N,4,4) float64 poses,
+    which then goes through prepare_data and the evaluator like the reference's plot_utils workflow."""
+    import importlib
+    import os
+    import sys
+    import cv2
+    import torch
+    from vo_b200 import synthetic
+    g = golden("r2d2_net.npz")
+    name, sd = _weights(g)
+    ckpt = tmp_path / "model.pt"
+    torch.save({"net": name + "()", "state_dict": {"module." + k: torch.from_numpy(v) for k, v in sd.items()}}, str(ckpt))
+    W, H = synthetic.KITTI_WH
+    rng = np.random.default_rng(9)
+    big = np.kron(rng.integers(0, 256, (H // 6 + 1, (W + 100) // 6 + 1, 3)), np.ones((6, 6, 1))).astype(np.uint8)
+    data = tmp_path / "frames"
+    data.mkdir()
+    Z, shift, n = 6.0, 12, 4
+    for i in range(n):
+        cv2.imwrite(str(data / f"{i:06d}.png"), np.ascontiguousarray(big[:H, i * shift:i * shift + W]))
+        np.save(str(data / f"{i:06d}_depth.npy"), np.full((H, W), Z, np.float32))
+    (tmp_path / "config").mkdir()
+    (tmp_path / "config" / "vo_params.yaml").write_text(
+        'vo_method: "rgbd"\nfeature_extractor: "r2d2"\n'
+        f'image_path: "{data}"\n'
+        "camera_intrinsic_matrix:\n" + "".join(f"  - {v}\n" for v in synthetic.KITTI_K.reshape(-1)) +
+        f"output_filename: {tmp_path}/global_poses\nvisualize_results: True\n"
+        'gt_txt_file_path : "../plot_utils/data/03.txt"\nposes_file_path : "../plot_utils/data/global_poses.npy"\n')
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "visual-odometry-pipeline_b200")
+    cwd = os.getcwd()
+    try:
+        os.chdir(tmp_path)
+        if pkg not in sys.path:
+            sys.path.insert(0, pkg)
+        for m in ("VisualOdometry_Stereo", "vo_stereo_runner", "vo_runner", "R2D2"):
+            sys.modules.pop(m, None)
+        runner = importlib.import_module("vo_runner")
+        sys.modules["R2D2"].args["model"] = str(ckpt)
+        runner.read_yaml_file()
+        poses = np.load(str(tmp_path / "global_poses.npy"))
+        assert poses.shape == (n, 4, 4) and poses.dtype == np.float64
+        step = shift * Z / synthetic.KITTI_K[0, 0]
+        for i in range(n):
+            assert np.allclose(poses[i][:3, 3], [i * step, 0, 0], atol=0.01), (i, poses[i][:3, 3])
+        # the reference's evaluation workflow on the produced file (plot_utils/prepare_data.py + kittievalodom.py)
+        from vo_b200.plot_utils import prepare_data as pd
+        from vo_b200.plot_utils.kittievalodom import KittiEvalOdom
+        pd.prepare_data(str(tmp_path / "global_poses.npy"))
+        ev = KittiEvalOdom()
+        pred = ev.load_poses_from_txt(str(tmp_path / "global_poses.npy.txt"))
+        gt = {i: np.eye(4) for i in range(n)}
+        for i in range(n):
+            gt[i][0, 3] = i * step
+        ate, rpe, rot, dist = ev.eval_poses(gt, pred, alignment="6dof")
+        assert dist == pytest.approx((n - 1) * step) and rpe < 0.05
+    finally:
+        os.chdir(cwd)
