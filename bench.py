@@ -365,16 +365,29 @@ def run_ours(args, wl):
         t = stage_ms["score"] / 1e3
         evals = corr_per_launch * Hh                                             # (hypothesis, point) inlier tests
         sc_bytes = corr_per_launch * 20.0 * (Hh / 32.0) + pairs_per_launch * Hh * 52.0   # L2->SM staging per CTA + poses
-        kernels.append({"kernel": "score_kernel (one warp per 4 hypotheses, points in shared memory)", "bound": "fp32",
-                        "achieved": evals * 27.0 / t / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                        "frac": evals * 27.0 / t / 1e12 / fp32_peak, "avg_launch_ms": stage_ms["score"],
-                        "evals_per_s": evals / t, "flop_per_eval": 27, "instr_per_eval": 17,
-                        "hbm_gbs": (corr_per_launch * 20.0 + pairs_per_launch * Hh * 52.0) / t / 1e9,
-                        "l2_to_sm_gbs": sc_bytes / t / 1e9,
-                        "note": "HBM figure is structurally << peak: every correspondence is re-read from L2 by H/32 CTAs "
-                                "and tested against all H hypotheses (SURVEY D5: FP32-pipe bound).  evals = hypotheses x points "
-                                "BEFORE the exact pruning (hypotheses that can no longer reach the running best count stop "
-                                "being scored), so achieved is an effective rate"})
+        entry = {"kernel": "score_kernel (packed FFMA2 inlier tests, 4 hypotheses per warp x 2 points per lane, TMA-staged tiles)",
+                 "bound": "fp32", "achieved": evals * 27.0 / t / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                 "frac": evals * 27.0 / t / 1e12 / fp32_peak, "avg_launch_ms": stage_ms["score"],
+                 "evals_per_s": evals / t, "flop_per_eval": 27, "fp32_lane_ops_per_eval": 15,
+                 "hbm_gbs": (corr_per_launch * 40.0 + pairs_per_launch * Hh * 52.0) / t / 1e9,
+                 "l2_to_sm_gbs": sc_bytes / t / 1e9,
+                 "note": "HBM figure is structurally << peak: every correspondence is re-read from L2 by H/32 CTAs "
+                         "and tested against all H hypotheses (SURVEY D5: FP32-pipe bound).  evals = hypotheses x points "
+                         "BEFORE the exact pruning (hypotheses that can no longer reach the running best count stop "
+                         "being scored), so achieved is an EFFECTIVE rate and may exceed the pipe peak; raw_unpruned is "
+                         "the same kernel with pruning off (every test executed)"}
+        try:  # raw rate of the same kernel, pruning off, same shape (outside the timed region)
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+            import score_bench
+            n_med = int(max(np.median(n_corr), 8))
+            rb = score_bench.measure(int(min(max(pairs_per_launch, 1), 64)), Hh, n_med, reps=3, dev=dev)
+            raw = rb["unpruned"]["tests_per_s"]
+            entry["raw_unpruned"] = {"evals_per_s": raw, "achieved": raw * 27.0 / 1e12, "frac": raw * 27.0 / 1e12 / fp32_peak,
+                                     "fp32_lane_frac": raw * 15.0 / (148 * 128 * sm_mhz * 1e6),
+                                     "pairs": rb["pairs"], "points": n_med, "score_ms": rb["unpruned"]["score_ms"]}
+        except Exception as e:  # the probe is informative only
+            entry["raw_unpruned"] = {"error": repr(e)}
+        kernels.append(entry)
     if "gather" in stage_ms:
         t = stage_ms["gather"] / 1e3
         gb = match_per_launch * 53.0

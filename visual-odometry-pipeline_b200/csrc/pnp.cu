@@ -11,6 +11,7 @@
 // Compile this file with -fmad=false (see pnp_math.cuh).
 #include "common.cuh"
 #include "pnp_math.cuh"
+#include "tc_ptx.cuh"
 
 namespace vo {
 namespace {
@@ -66,31 +67,138 @@ p3p_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const in
 }
 
 // ---------------------------------------------------------------- scoring
-// One warp owns SC_HPW hypotheses at a time (their scaled poses live in registers); its lanes stride over the
-// correspondences the CTA staged in shared memory, so every staged point (one LDS.128 + one LDS.32) feeds
-// SC_HPW independent inlier tests: 17 fp32 instructions each, no division, no branch (pnp_math.cuh).
+// One warp owns SC_HPW hypotheses (their scaled poses live in registers, each value duplicated into both halves of a
+// 64-bit register pair); its lanes stride over PAIRS of correspondences.  The 15 fp32 operations of the inlier test
+// (pnp_math.cuh, is_inlier) run as packed FFMA2 / FMUL2 (`fma.rn.f32x2`, sm_100): two points per instruction, every
+// half rounded exactly like the scalar operation, so counts are bit-identical to the scalar rule the refit kernel and
+// the oracle use.  FFMA2 needs half the issue slots of two FFMAs, which is what bounded the scalar kernel (0.76
+// instructions per clock and scheduler at 55 % FMA-pipe utilisation): measured with tools/probe/ffma2_probe.cu,
+// 8 FFMA2 + 2 LOP3 per round keep 118 of 128 FMA lanes per clock and SM busy, 8 FFMA + 2 LOP3 only 94.
+//
+// Correspondences reach shared memory by TMA: `score_prep_kernel` lays every 1024-point tile out once per pair as one
+// contiguous 20 KB block in the packed order the lanes read ({X0 X1 Y0 Y1}, {Z0 Z1 u0-cx u1-cx}, {v0-cy v1-cy}; points
+// past the end are NaN = never an inlier), and each scoring CTA pulls tiles through a two-slot `cp.async.bulk` /
+// mbarrier ring, so the copy of tile t+1 overlaps the tests of tile t and no thread spends instructions on staging.
 constexpr int SC_WARPS = 8;
-constexpr int SC_TILE = 1024;  // correspondences staged per pass (20 KB); also the granularity of the pruning test
+constexpr int SC_TILE = 1024;                     // correspondences per staged tile; also the granularity of the pruning test
+constexpr int SC_TILE_FLOATS = SC_TILE * 5;       // 20 KB
+constexpr int SC_TILE_BYTES = SC_TILE_FLOATS * 4;
+
+typedef unsigned long long f32x2;  // two fp32 in one 64-bit register pair
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// is_inlier (pnp_math.cuh) for two points at once.  M = the ScoreModel with rows 0 and 1 negated (exact), every entry
+// in both halves, so a = z*(u-cx) + (-x) is a single FFMA2.  Adds the number of inliers among the two points (0..2) to `count`.
+__device__ __forceinline__ void inliers2(int &count, const f32x2 (&M)[12], f32x2 THR, f32x2 X, f32x2 Y, f32x2 Z, f32x2 U, f32x2 V) {
+    const f32x2 nx = fma2(M[0], X, fma2(M[1], Y, fma2(M[2], Z, M[9])));
+    const f32x2 ny = fma2(M[3], X, fma2(M[4], Y, fma2(M[5], Z, M[10])));
+    const f32x2 z = fma2(M[6], X, fma2(M[7], Y, fma2(M[8], Z, M[11])));
+    const f32x2 a = fma2(z, U, nx);
+    const f32x2 b = fma2(z, V, ny);
+    const f32x2 w = mul2(THR, z);
+    const f32x2 l = fma2(a, a, mul2(b, b));
+    const f32x2 r = mul2(w, w);
+    float l0, l1, r0, r1;
+    unpk2(l, l0, l1);
+    unpk2(r, r0, r1);
+    // ordered compare (NaN -> not an inlier) + predicated increment: two instructions per point
+    asm("{\n\t.reg .pred p0, p1;\n\t"
+        "setp.le.f32 p0, %1, %2;\n\t"
+        "setp.le.f32 p1, %3, %4;\n\t"
+        "@p0 add.s32 %0, %0, 1;\n\t"
+        "@p1 add.s32 %0, %0, 1;\n\t}"
+        : "+r"(count)
+        : "f"(l0), "f"(r0), "f"(l1), "f"(r1));
+}
+
+// grid (tiles, B): tile t of pair b -> staged + (b * tiles + t) * SC_TILE_FLOATS
+__global__ void __launch_bounds__(256)
+score_prep_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ n_pts, int cap,
+                  IntrF k, float *__restrict__ staged) {
+    const int b = blockIdx.y, t = blockIdx.x;
+    const int n = min(n_pts[b], cap);
+    const int p0 = t * SC_TILE;
+    if (p0 >= n) return;  // never read
+    const float *pxyz = xyz + (size_t)b * cap * 3;
+    const float *puv = uv + (size_t)b * cap * 2;
+    float *dst = staged + ((size_t)b * gridDim.x + t) * SC_TILE_FLOATS;
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int j = threadIdx.x; j < SC_TILE / 2; j += 256) {
+        float v[2][5];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = p0 + 2 * j + e;
+            if (i < n) {
+                const float2 q2 = *reinterpret_cast<const float2 *>(puv + (size_t)i * 2);
+                v[e][0] = pxyz[(size_t)i * 3]; v[e][1] = pxyz[(size_t)i * 3 + 1]; v[e][2] = pxyz[(size_t)i * 3 + 2];
+                v[e][3] = VO_FSUBF(q2.x, k.cx); v[e][4] = VO_FSUBF(q2.y, k.cy);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) v[e][c] = qnan;
+            }
+        }
+        reinterpret_cast<float4 *>(dst)[j] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
+        reinterpret_cast<float4 *>(dst + 2 * SC_TILE)[j] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
+        reinterpret_cast<float2 *>(dst + 4 * SC_TILE)[j] = make_float2(v[0][4], v[1][4]);
+    }
+}
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    tc::mbar_expect_tx(bar, bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 // Exact pruning: `lower[b]` is a running lower bound of the winning inlier count of pair b (every warp publishes its
 // partial counts after each staged tile — a final count can only be larger).  A hypothesis whose count so far plus ALL
 // remaining points is still below that bound can neither win nor tie, so the warp stops scoring it; the winner, its
-// count and the tie rule (lowest index) are unchanged.  The host scores the first 32 hypotheses in a launch of their own
-// so that the bulk starts with a bound that is already close to the final one (with ~60 % inliers a fifth of the random
-// minimal samples is all-inlier).  Disabled when the caller wants every hypothesis' count.
+// count and the tie rule (lowest index) are unchanged.  A CTA whose hypotheses are all out stops fetching tiles.  The
+// host scores the first 32 hypotheses in a launch of their own so that the bulk starts with a bound that is already
+// close to the final one (with ~60 % inliers a fifth of the random minimal samples is all-inlier).  Disabled when the
+// caller wants every hypothesis' count.
 template <int SC_HPW, int MIN_CTAS>  // hypotheses per warp, resident CTAs per SM the register budget must allow
 __global__ void __launch_bounds__(SC_WARPS * 32, MIN_CTAS)
-score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ n_pts, int cap,
+score_kernel(const float *__restrict__ staged, int tiles, const int32_t *__restrict__ n_pts, int cap,
              const float *__restrict__ poses, int H, int h_begin, int h_end, IntrF k, float thr,
              unsigned long long *__restrict__ bestkey, unsigned int *__restrict__ lower, int32_t *__restrict__ hyp_counts) {
-    __shared__ float4 sP[SC_TILE];  // X, Y, Z, u - cx
-    __shared__ float sV[SC_TILE];   // v - cy
+    __shared__ __align__(128) float sbuf[2][SC_TILE_FLOATS];
+    __shared__ __align__(8) unsigned long long sbar[2];
     const int b = blockIdx.y;
     const int n = min(n_pts[b], cap);
+    const int T = (n + SC_TILE - 1) / SC_TILE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h0 = h_begin + (blockIdx.x * SC_WARPS + warp) * SC_HPW;  // this launch scores hypotheses [h_begin, h_end)
     const bool prune = hyp_counts == nullptr;
-    ScoreModel m[SC_HPW];
+    const float *tiles_b = staged + (size_t)b * tiles * SC_TILE_FLOATS;
+    const uint32_t bar0 = tc::smem_u32(&sbar[0]), buf0 = tc::smem_u32(&sbuf[0][0]);
+    if (threadIdx.x == 0) {
+        tc::mbar_init(bar0, 1);
+        tc::mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2 && s < T; ++s)
+            bulk_load(buf0 + s * SC_TILE_BYTES, tiles_b + (size_t)s * SC_TILE_FLOATS, SC_TILE_BYTES, bar0 + 8 * s);
+    }
+    // scaled poses, duplicated into both halves; rows 0 and 1 negated (exact), so that a = z*(u-cx) + (-x) is one FFMA2
+    f32x2 M[SC_HPW][12];
 #pragma unroll
     for (int q = 0; q < SC_HPW; ++q) {
         PoseF p;
@@ -100,8 +208,15 @@ score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
         for (int j = 0; j < 9; ++j) p.r[j] = __ldg(src + j);
 #pragma unroll
         for (int j = 0; j < 3; ++j) p.t[j] = __ldg(src + 9 + j);
-        m[q] = score_model(p, k);
+        const ScoreModel m = score_model(p, k);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const bool neg = (j < 6) || j == 9 || j == 10;
+            const float v = neg ? -m.m[j] : m.m[j];
+            M[q][j] = pk2(v, v);
+        }
     }
+    const f32x2 THR = pk2(thr, thr);
     int count[SC_HPW];
 #pragma unroll
     for (int q = 0; q < SC_HPW; ++q) count[q] = 0;
@@ -109,36 +224,38 @@ score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
 #pragma unroll
     for (int q = 0; q < SC_HPW; ++q) alive |= (h0 + q < h_end) ? (1u << q) : 0u;
     constexpr unsigned ALL = (1u << SC_HPW) - 1u;
-    const float *pxyz = xyz + (size_t)b * cap * 3;
-    const float *puv = uv + (size_t)b * cap * 2;
-    for (int p0 = 0; p0 < n; p0 += SC_TILE) {
+
+    for (int t = 0; t < T; ++t) {
+        const int s = t & 1;
+        const int p0 = t * SC_TILE;
         const int cnt = min(SC_TILE, n - p0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < cnt; i += SC_WARPS * 32) {
-            const float *q3 = pxyz + (size_t)(p0 + i) * 3;
-            const float2 q2 = *reinterpret_cast<const float2 *>(puv + (size_t)(p0 + i) * 2);
-            sP[i] = make_float4(q3[0], q3[1], q3[2], VO_FSUBF(q2.x, k.cx));
-            sV[i] = VO_FSUBF(q2.y, k.cy);
-        }
-        __syncthreads();
+        const int np = (cnt + 1) >> 1;
+        // the bound is read before the tile is scored, so its L2 latency hides behind the tests; a stale (smaller)
+        // value only prunes later, never wrongly
+        unsigned int lb = 0;
+        if (prune && t + 1 < T) lb = *reinterpret_cast<volatile unsigned int *>(&lower[b]);
+        tc::mbar_wait(bar0 + 8 * s, (uint32_t)(t >> 1) & 1u);
+        const ulonglong2 *sA = reinterpret_cast<const ulonglong2 *>(&sbuf[s][0]);             // {X0 X1}, {Y0 Y1}
+        const ulonglong2 *sB = reinterpret_cast<const ulonglong2 *>(&sbuf[s][2 * SC_TILE]);  // {Z0 Z1}, {uc0 uc1}
+        const f32x2 *sC = reinterpret_cast<const f32x2 *>(&sbuf[s][4 * SC_TILE]);            // {vc0 vc1}
         if (alive == ALL) {  // common case: no per-hypothesis branches in the loop
 #pragma unroll 2
-            for (int i = lane; i < cnt; i += 32) {
-                const float4 P = sP[i];
-                const float vc = sV[i];
+            for (int j = lane; j < np; j += 32) {
+                const ulonglong2 A = sA[j], Bv = sB[j];
+                const f32x2 V = sC[j];
 #pragma unroll
-                for (int q = 0; q < SC_HPW; ++q) count[q] += is_inlier(m[q], thr, P.x, P.y, P.z, P.w, vc) ? 1 : 0;
+                for (int q = 0; q < SC_HPW; ++q) inliers2(count[q], M[q], THR, A.x, A.y, Bv.x, Bv.y, V);
             }
         } else if (alive) {
-            for (int i = lane; i < cnt; i += 32) {
-                const float4 P = sP[i];
-                const float vc = sV[i];
+            for (int j = lane; j < np; j += 32) {
+                const ulonglong2 A = sA[j], Bv = sB[j];
+                const f32x2 V = sC[j];
 #pragma unroll
                 for (int q = 0; q < SC_HPW; ++q)
-                    if (alive & (1u << q)) count[q] += is_inlier(m[q], thr, P.x, P.y, P.z, P.w, vc) ? 1 : 0;
+                    if (alive & (1u << q)) inliers2(count[q], M[q], THR, A.x, A.y, Bv.x, Bv.y, V);
             }
         }
-        if (prune && alive && p0 + SC_TILE < n) {  // between tiles: publish partial counts, drop the hopeless
+        if (prune && alive && t + 1 < T) {  // between tiles: publish partial counts, drop the hopeless
             const int remaining = n - (p0 + cnt);
             int tot[SC_HPW], wbest = 0;
 #pragma unroll
@@ -146,11 +263,21 @@ score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
                 tot[q] = (alive & (1u << q)) ? __reduce_add_sync(0xffffffffu, count[q]) : 0;
                 wbest = max(wbest, tot[q]);
             }
-            if (lane == 0 && wbest > 0) atomicMax(&lower[b], (unsigned int)wbest);
-            const unsigned int lb = *reinterpret_cast<volatile unsigned int *>(&lower[b]);
+            if (lane == 0 && wbest > (int)lb) atomicMax(&lower[b], (unsigned int)wbest);
+            lb = max(lb, (unsigned int)wbest);
 #pragma unroll
             for (int q = 0; q < SC_HPW; ++q)
                 if ((alive & (1u << q)) && (unsigned int)(tot[q] + remaining) < lb) alive &= ~(1u << q);
+        }
+        if (t + 1 < T) {
+            // every warp is done with slot s; if no hypothesis of the CTA is left, drain the copy in flight and stop
+            const int any = __syncthreads_or(alive != 0u);
+            if (!any) {
+                if (threadIdx.x == 0) tc::mbar_wait(bar0 + 8 * (s ^ 1), (uint32_t)((t + 1) >> 1) & 1u);
+                break;
+            }
+            if (threadIdx.x == 0 && t + 2 < T)
+                bulk_load(buf0 + s * SC_TILE_BYTES, tiles_b + (size_t)(t + 2) * SC_TILE_FLOATS, SC_TILE_BYTES, bar0 + 8 * s);
         }
     }
 #pragma unroll
@@ -468,7 +595,10 @@ int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_
     float *poses;
     unsigned long long *bestkey;
     int rc;
-    if ((rc = ws_get(ctx, WS_POSES, sizeof(float) * 12 * (size_t)B * H, (void **)&poses))) return rc;
+    const int tiles = ceil_div(cap, SC_TILE);
+    const size_t pose_floats = ((size_t)12 * B * H + 31) & ~(size_t)31;  // staged tiles start 128 B aligned
+    if ((rc = ws_get(ctx, WS_POSES, sizeof(float) * (pose_floats + (size_t)B * tiles * SC_TILE_FLOATS), (void **)&poses))) return rc;
+    float *staged = poses + pose_floats;
     if ((rc = ws_get(ctx, WS_BESTKEY, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)B, (void **)&bestkey))) return rc;
     unsigned int *lower = reinterpret_cast<unsigned int *>(bestkey + B);  // running lower bound of the best count (pruning)
     VO_CUDA(cudaMemsetAsync(bestkey, 0, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)B, st));
@@ -480,18 +610,21 @@ int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_
     p3p_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(xyz, uv, n_pts, B, cap, hyp, H, kd, poses);
     VO_LAUNCH_CHECK(ctx);
     VO_PROF(ctx, st, VO_STAGE_SCORE);
-    // 4 hypotheses per warp, 3 CTAs per SM: 2 / 8 per warp and 2 / 4 CTAs per SM all measure within 5 % (the kernel sits
-    // at 0.73 issued instructions per cycle and scheduler whatever the occupancy: profiles/README.md)
-    constexpr int SC_PER_CTA = SC_WARPS * 4;
-    const int h_first = (hyp_counts || H <= 2 * SC_PER_CTA) ? 0 : SC_PER_CTA;  // scouts: one CTA per pair, scored to the end
-    if (h_first) {
-        score_kernel<4, 3><<<dim3(1, B), SC_WARPS * 32, 0, st>>>(xyz, uv, n_pts, cap, poses, H, 0, h_first, kf, thr_px, bestkey, lower,
-                                                                  hyp_counts);
+    if (tiles > 0) {
+        score_prep_kernel<<<dim3(tiles, B), 256, 0, st>>>(xyz, uv, n_pts, cap, kf, staged);
         VO_LAUNCH_CHECK(ctx);
     }
-    score_kernel<4, 3><<<dim3(ceil_div(H - h_first, SC_PER_CTA), B), SC_WARPS * 32, 0, st>>>(xyz, uv, n_pts, cap, poses, H, h_first, H,
-                                                                                              kf, thr_px, bestkey, lower, hyp_counts);
-    VO_LAUNCH_CHECK(ctx);
+    constexpr int SCOUTS = 32;
+    const int h_first = (hyp_counts || H <= 2 * SCOUTS) ? 0 : SCOUTS;  // scouts: the first hypotheses of every pair, scored first
+    // 4 hypotheses per warp, 3 CTAs per SM.  Measured (B200, 32 pairs x 16 384 hypotheses x 13.7 k points, tools/score_bench.py):
+    // 2 / 4 / 8 hypotheses per warp at 2-3 CTAs per SM: 2.73 / 2.52 / 2.70 ms pruned, 4.26 / 4.07 / 4.02 ms unpruned.
+    constexpr int HPW = 4, CTAS = 3;
+    for (int part = h_first ? 0 : 1; part < 2; ++part) {
+        const int hb = part ? h_first : 0, he = part ? H : h_first;
+        score_kernel<HPW, CTAS><<<dim3(ceil_div(he - hb, SC_WARPS * HPW), B), SC_WARPS * 32, 0, st>>>(
+            staged, tiles, n_pts, cap, poses, H, hb, he, kf, thr_px, bestkey, lower, hyp_counts);
+        VO_LAUNCH_CHECK(ctx);
+    }
     VO_PROF(ctx, st, VO_STAGE_REFIT);
     refit_kernel<<<B, RF_THREADS, 0, st>>>(xyz, uv, n_pts, cap, poses, H, kf, kd, thr_px, min_inliers, refine_iters,
                                            bestkey, rt, rvec_tvec, T_rel, n_inl, best_h, inlier_mask, status,
