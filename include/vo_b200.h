@@ -65,6 +65,9 @@ extern "C" {
 #define VO_PREC_TF32X3 0    /* tcgen05 kind::tf32, hi/lo split, 3 MMAs per k-step (fp32-grade)   */
 #define VO_PREC_TF32X1 1    /* tcgen05 kind::tf32, 1 MMA per k-step (exact for integer-valued SIFT) */
 #define VO_PREC_FP32_SIMT 2 /* CUDA-core FP32, direct (a-b)^2 / dot form (validation kernel)      */
+#define VO_PREC_F16X1 3     /* tcgen05 kind::f16, operands rounded to fp16 (11 significant bits, as tf32): exact for
+                               integer-valued descriptors |x| <= 2048 (SIFT: 0..255) at twice the tf32 rate; rules
+                               that need the column arg-max run the TF32X1 kernel (identical results there)      */
 
 typedef struct vo_ctx vo_ctx;
 

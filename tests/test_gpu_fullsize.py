@@ -88,6 +88,24 @@ def test_c4_sift_20k_subsets_bit_exact_and_permutation(orc, prec):
     assert np.array_equal(rm.col_idx[0].cpu().numpy(), gc)
 
 
+def test_c4_sift_20k_f16_pass_equals_tf32_pass_and_oracle_subset(orc):
+    """The fp16 single pass (VO_PREC_F16X1, what the SIFT plug-in and bench c1 / c4 run) at 20k x 20k: its row top-2
+    equals the tf32 pass on every row and the oracle on a random subset of rows, bit for bit."""
+    from vo_b200 import ops
+    N = 20000
+    ref, cur = _descs("sift", N, 46)
+    rng = np.random.default_rng(6)
+    h = ops.match_f32(_gpu(ref), _gpu(cur), ops.VO_METRIC_L2, ops.VO_MODE_RATIO, 0.85, precision=ops.VO_PREC_F16X1, want_knn="rows")
+    t = ops.match_f32(_gpu(ref), _gpu(cur), ops.VO_METRIC_L2, ops.VO_MODE_RATIO, 0.85, precision=ops.VO_PREC_TF32X1, want_knn="rows")
+    assert np.array_equal(h.knn_idx[0].cpu().numpy(), t.knn_idx[0].cpu().numpy())
+    assert np.array_equal(h.knn_val[0].cpu().numpy(), t.knn_val[0].cpu().numpy())
+    assert np.array_equal(h.numpy(), t.numpy()) and len(h.numpy()) > 8000
+    rows = np.sort(rng.choice(N, 384, replace=False))
+    ridx, rval, _ = orc.knn_f32(np.ascontiguousarray(ref[rows]), cur, orc.METRIC_L2)
+    assert np.array_equal(h.knn_idx[0].cpu().numpy()[rows], ridx)
+    assert np.array_equal(h.knn_val[0].cpu().numpy()[rows], rval)
+
+
 def test_c4_self_match_identity():
     from vo_b200 import ops
     ref, _ = _descs("sift", 20000, 45)

@@ -118,3 +118,56 @@ def test_ragged_batch(orc):
         for b in range(B):
             want, _ = orc.match_f32(ref[b, :n_ref[b]], cur[b, :n_cur[b]], orc.METRIC_L2, orc.MODE_RATIO, 0.85)
             assert np.array_equal(r.numpy(b), want.reshape(-1, 2)), (prec, b)
+
+
+# ------------------------------------------------------------------------------------------------ fp16 single pass
+def test_golden_sift_f16_pass_bit_exact(golden):
+    """VO_PREC_F16X1 (tcgen05 kind::f16, all-warp epilogue): the row top-2 (index and distance) and the accepted pairs
+    of the reference's SIFT get_matches, bit for bit.  want_knn="rows" keeps the column side off, so the fp16 kernel
+    itself runs (with a column arg-min requested the library takes the tf32 single pass)."""
+    from vo_b200 import ops
+    g = golden("match_f32_sift.npz")
+    r = ops.match_f32(_gpu(g["ref"]), _gpu(g["cur"]), ops.VO_METRIC_L2, ops.VO_MODE_RATIO, 0.85,
+                      precision=ops.VO_PREC_F16X1, want_knn="rows")
+    assert r.col_idx is None
+    assert np.array_equal(r.knn_idx[0].cpu().numpy(), g["knn_idx"])
+    assert np.array_equal(r.knn_val[0].cpu().numpy(), g["knn_dist"])
+    assert np.array_equal(r.numpy(), g["ref_sift_pairs"])
+
+
+@pytest.mark.parametrize("n,m", [(2000, 2000), (777, 1500), (129, 64), (1, 300), (300, 1), (5000, 4099), (193, 385)])
+def test_sift_f16_pass_vs_oracle_sizes(orc, n, m):
+    from vo_b200 import ops, synthetic
+    p = synthetic.make_pair(n * 3 + m, n_kp=max(n, 8), n_cur=max(m, 8), kind="sift")
+    ref, cur = p["ref_desc"][:n], p["cur_desc"][:m]
+    r = ops.match_f32(_gpu(ref), _gpu(cur), ops.VO_METRIC_L2, ops.VO_MODE_RATIO, 0.85, precision=ops.VO_PREC_F16X1,
+                      want_knn="rows")
+    ridx, rval, cidx = orc.knn_f32(ref, cur, orc.METRIC_L2)
+    assert np.array_equal(r.knn_idx[0].cpu().numpy(), ridx)
+    assert np.array_equal(r.knn_val[0].cpu().numpy(), rval)
+    want, _ = orc.accept(ridx, rval, cidx, orc.MODE_RATIO, 0.85, orc.METRIC_L2)
+    assert np.array_equal(r.numpy(), want)
+
+
+def test_f16_pass_batched_ragged_and_mutual_fallback(orc):
+    """B = 3 pairs with ragged counts through the fp16 pass; a mutual rule under VO_PREC_F16X1 (needs the column
+    arg-min) must give exactly what the tf32 pass gives."""
+    import torch
+    from vo_b200 import ops, synthetic
+    B, N = 3, 700
+    batch = synthetic.make_batch(40, B, n_kp=N, kind="sift")
+    n_ref = torch.tensor([700, 333, 1], dtype=torch.int32).cuda()
+    n_cur = torch.tensor([512, 700, 64], dtype=torch.int32).cuda()
+    ref, cur = _gpu(batch["ref_desc"]), _gpu(batch["cur_desc"])
+    r = ops.match_f32(ref, cur, ops.VO_METRIC_L2, ops.VO_MODE_RATIO, 0.85, precision=ops.VO_PREC_F16X1, n_ref=n_ref,
+                      n_cur=n_cur, want_knn="rows")
+    for b in range(B):
+        nr, nc = int(n_ref[b]), int(n_cur[b])
+        ridx, rval, cidx = orc.knn_f32(batch["ref_desc"][b][:nr], batch["cur_desc"][b][:nc], orc.METRIC_L2)
+        assert np.array_equal(r.knn_idx[b, :nr].cpu().numpy(), ridx)
+        assert np.array_equal(r.knn_val[b, :nr].cpu().numpy(), rval)
+        want, _ = orc.accept(ridx, rval, cidx, orc.MODE_RATIO, 0.85, orc.METRIC_L2)
+        assert np.array_equal(r.numpy(b), want)
+    a = ops.match_f32(ref, cur, ops.VO_METRIC_L2, ops.VO_MODE_MUTUAL, 0.0, precision=ops.VO_PREC_F16X1, want_knn=True)
+    t = ops.match_f32(ref, cur, ops.VO_METRIC_L2, ops.VO_MODE_MUTUAL, 0.0, precision=ops.VO_PREC_TF32X1, want_knn=True)
+    assert torch.equal(a.pairs[0, :int(a.count[0])], t.pairs[0, :int(t.count[0])]) and torch.equal(a.col_idx, t.col_idx)

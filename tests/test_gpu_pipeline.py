@@ -15,6 +15,7 @@ def _gpu(a):
     ("orb", 1, 0, 0.85, 0),         # reference ORB semantics: L2 bytes + ratio
     ("sift", 0, 0, 0.85, 2),        # c1: SIFT L2 + ratio, SIMT
     ("sift", 0, 0, 0.85, 1),        # c1 on the tensor-core path
+    ("sift", 0, 0, 0.85, 3),        # c1 on the fp16 tensor-core pass (what bench c1 / c4 run)
 ])
 def test_pipeline_vs_oracle(orc, kind, norm_or_metric, mode, param, prec):
     from vo_b200 import ops, synthetic

@@ -24,6 +24,7 @@
 // epilogue (the row norm matters for the column arg-min, the column norm for the row arg-min).
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace vo {
@@ -38,17 +39,25 @@ constexpr int TC_NKB = TC_D / TC_KB;
 // A_lo 384.  Single pass has no A_lo, so the accumulators can be wider: 160-column tiles (27 % fewer tcgen05.mma per
 // FLOP — the single-pass kernel is bound by the MMA-issuing thread, not by the pipe), 10-stage ring of 20 KB boxes,
 // TMEM = acc0 0 | acc1 160 | ones block of the norm extension 320 | A_hi 384.
+// PASSES == 16 selects the fp16 single pass (VO_PREC_F16X1): operands rounded to fp16 (11 significant bits like tf32,
+// so integer-valued SIFT descriptors stay exact), tcgen05.mma.kind::f16 with K = 16 per instruction at twice the tf32
+// rate.  192-column tiles, 9-stage ring of 24 KB boxes ([192 rows x 64 k] fp16), A as 64 packed columns:
+// TMEM = acc0 0 | acc1 192 | ones block 384 | A 416.
 template <int PASSES>
 struct TcCfg {
-    static constexpr int BN = (PASSES == 1) ? 160 : 128;
-    static constexpr int STAGES = (PASSES == 1) ? 10 : 13;
-    static constexpr int BLOCK_BYTES = BN * 128;                  // one [BN rows x 32 k] fp32 box
-    static constexpr int TMEM_A = (PASSES == 1) ? 384 : 256;      // first column of A_hi (A_lo follows in 3xTF32)
-    static constexpr int TMEM_EXT = 320;                          // single pass only
+    static constexpr bool F16 = PASSES == 16;
+    static constexpr bool SINGLE = PASSES != 3;
+    static constexpr int BN = F16 ? 192 : (SINGLE ? 160 : 128);
+    static constexpr int STAGES = F16 ? 9 : (SINGLE ? 10 : 13);
+    static constexpr int BLOCK_BYTES = BN * 128;                  // one [BN rows x 128 B] box: 32 fp32 or 64 fp16 along k
+    static constexpr int TMEM_A = F16 ? 416 : (SINGLE ? 384 : 256);  // first column of A_hi (A_lo follows in 3xTF32)
+    static constexpr int TMEM_EXT = F16 ? 384 : 320;              // single pass only
     static constexpr int OFF_SCOL = STAGES * BLOCK_BYTES;         // [2 groups][2 bufs][4 quarters][BN] x (float, u32)
-    static constexpr int OFF_BAR = OFF_SCOL + 2 * 2 * 4 * BN * 8;
+    static constexpr int OFF_BAR = OFF_SCOL + (F16 ? 0 : 2 * 2 * 4 * BN * 8);  // the fp16 pass has no column side
     static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;       // barriers + alignment slack
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    // kind::f16: D = f32 [4,6) = 1, A = B = fp16 (format 0)
+    static constexpr uint32_t IDESC16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 };
 constexpr int TC_THREADS = 576;              // warps 0..15 epilogue, warp 16 TMA, warp 17 MMA
 constexpr int TC_WARP_TMA = 16, TC_WARP_MMA = 17;
@@ -95,18 +104,48 @@ prep_kernel(const float *__restrict__ x, long long rows, float *__restrict__ hi,
     }
 }
 
+// fp16 single pass: x -> fp16 (round to nearest even), norms and extension rows as above (from the fp32 values)
+__global__ void __launch_bounds__(256)
+prep16_kernel(const float *__restrict__ x, long long rows, __half *__restrict__ h16, float *__restrict__ norm2,
+              float *__restrict__ ext) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float4 v = reinterpret_cast<const float4 *>(x)[row * 32 + lane];
+    const __half2 p0 = __floats2half2_rn(v.x, v.y), p1 = __floats2half2_rn(v.z, v.w);
+    uint2 w;
+    w.x = *reinterpret_cast<const uint32_t *>(&p0);
+    w.y = *reinterpret_cast<const uint32_t *>(&p1);
+    reinterpret_cast<uint2 *>(h16)[row * 32 + lane] = w;
+    if (norm2) {
+        float s = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fadd_rn(__fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+        if (lane == 0) norm2[row] = s;
+        if (ext) {
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane == 0) {
+                const float n1 = to_tf32(s), n2 = to_tf32(__fsub_rn(s, n1));
+                const float n3 = to_tf32(__fsub_rn(__fsub_rn(s, n1), n2));
+                e = make_float4(-n1, -n2, -n3, 0.f);
+            }
+            if (lane < 8) reinterpret_cast<float4 *>(ext)[row * 8 + lane] = e;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- epilogue helpers
-// Fold one (score, column) into the row's running top-2 (larger is better), branch-free.  Ties go to the lower
-// column index explicitly (an unset slot is (-inf, -1): neither a -inf score nor an index comparison can take it).
+// Fold one (score, column) into the row's running top-2 (larger is better), branch-free: 2 FSETP + 3 FMNMX + 3 SEL.
+// Ties go to the lower column index without an index comparison, because every thread meets its columns in
+// ascending order (tiles ascending, columns ascending inside a tile): a later column only ever replaces an entry
+// it strictly beats.  An unset slot is (-inf, -1): a -inf (masked) or NaN score never enters.
 __device__ __forceinline__ void row_insert(float s, int col, float &s1, float &s2, int32_t &i1, int32_t &i2) {
-    const bool gt1 = (s > s1) | ((s == s1) & (col < i1));
-    const bool gt2 = (s > s2) | ((s == s2) & (col < i2));
-    const float ns2 = gt1 ? s1 : (gt2 ? s : s2);
-    const int32_t ni2 = gt1 ? i1 : (gt2 ? col : i2);
-    s1 = gt1 ? s : s1;
+    const bool gt1 = s > s1;
+    const bool gt2 = s > s2;
+    i2 = gt1 ? i1 : (gt2 ? col : i2);
     i1 = gt1 ? col : i1;
-    s2 = ns2;
-    i2 = ni2;
+    s2 = gt2 ? fminf(s1, s) : s2;  // (not fmaxf(s2, fminf(s1, s)): a NaN score must leave the slots untouched)
+    s1 = gt1 ? s : s1;
 }
 
 // ---------------------------------------------------------------- epilogue: 8 accumulator columns
@@ -162,7 +201,7 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
 #pragma unroll
     for (int j0 = 0; j0 < 8; j0 += 4) {
         const float m4 = fmaxf(fmaxf(sc[j0], sc[j0 + 1]), fmaxf(sc[j0 + 2], sc[j0 + 3]));
-        if ((!ROW_MASK || row_ok) && m4 >= s2) {
+        if ((!ROW_MASK || row_ok) && m4 > s2) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) row_insert(sc[j0 + j], cbase + j0 + j, s1, s2, i1, i2);
         }
@@ -207,8 +246,10 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     long long dbg_acc[4] = {0, 0, 0, 0};
 
     // single-pass L2: one extra box per tile carries -|b|^2 (three tf32 pieces), multiplied by a column block of ones in A
-    constexpr bool EXT = (PASSES == 1) && (METRIC == VO_METRIC_L2);
-    constexpr int ITEMS = (PASSES == 3) ? 2 * TC_NKB : (EXT ? TC_NKB + 1 : TC_NKB);  // B boxes streamed per tile
+    constexpr bool F16 = Cfg::F16;
+    constexpr bool EXT = (PASSES != 3) && (METRIC == VO_METRIC_L2);
+    constexpr int NKB = F16 ? TC_D / 64 : TC_NKB;                                // k boxes per tile (128 B of k each)
+    constexpr int ITEMS = (PASSES == 3) ? 2 * NKB : (EXT ? NKB + 1 : NKB);       // B boxes streamed per tile
     const uint32_t s_b = base;
     float *scol_v = reinterpret_cast<float *>(smem + Cfg::OFF_SCOL);                      // [2 groups][2 bufs][4][BN]
     uint32_t *scol_b = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_SCOL + 2 * 2 * 4 * BN * 4);
@@ -227,7 +268,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             mbar_init(bar_empty(s), TC_CLUSTER);  // one commit from each CTA of the cluster
         }
         mbar_init(bar_a, PASSES == 3 ? 16 : (EXT ? 12 : 8));
-        for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull(g), 1); mbar_init(bar_tempty(g), 8); }
+        for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull(g), 1); mbar_init(bar_tempty(g), F16 ? 16 : 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_WARP_MMA) {  // TMEM allocation is warp-collective; this warp also frees it
@@ -256,10 +297,10 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                     { TC_DBG_BEGIN(); mbar_wait(bar_empty(stage), phase ^ 1u); TC_DBG_END(0); }  // both CTAs consumed the slot
                     mbar_expect_tx(bar_full(stage), BLOCK_BYTES);  // bytes arrive by multicast, whoever issues
                     if ((uint32_t)(it & 1) == crank) {
-                        const bool is_ext = EXT && item == TC_NKB;  // map_b_lo is the extension map in that mode
+                        const bool is_ext = EXT && item == NKB;  // map_b_lo is the extension map in that mode
                         const int kb = is_ext ? 0 : ((PASSES == 3) ? (item >> 1) : item);
                         const bool is_lo = is_ext || ((PASSES == 3) && (item & 1));
-                        tma_load_2d_mc(s_b + stage * BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * TC_KB, brow,
+                        tma_load_2d_mc(s_b + stage * BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * (F16 ? 64 : TC_KB), brow,
                                        bar_full(stage), (uint16_t)((1u << TC_CLUSTER) - 1u));
                     }
                 }
@@ -294,7 +335,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                         const bool is_lo = (PASSES == 3) && (item & 1);
                         const uint32_t b_lo32 = (((s_b + stage * BLOCK_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
                         const uint32_t a_hi_t = tmem_base + (uint32_t)(TMEM_A + kb * TC_KB);
-                        if (EXT && item == TC_NKB) {  // ones[128 x 8] * (-|b|^2 pieces)[8 x 128]
+                        if (EXT && item == NKB) {  // ones[128 x 8] * (-|b|^2 pieces)[8 x BN], always kind::tf32
                             const uint64_t bdesc = ((uint64_t)TC_SDESC_HI << 32) | (uint64_t)b_lo32;
                             tc_mma_tf32_ts(d_tmem, tmem_base + (uint32_t)TMEM_EXT, bdesc, IDESC, 1u);
                         } else
@@ -302,7 +343,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                         for (int k8 = 0; k8 < TC_KB / 8; ++k8) {
                             const uint64_t bdesc = ((uint64_t)TC_SDESC_HI << 32) | (uint64_t)(b_lo32 + k8 * 2);
                             const uint32_t ahi = a_hi_t + k8 * 8;
-                            if (is_lo) {  // a_hi * b_lo
+                            if (F16) {  // 16 k per instruction: the same 32 B of B and 8 TMEM columns of A per step
+                                tc_mma_f16_ts(d_tmem, ahi, bdesc, Cfg::IDESC16, (item | k8) ? 1u : 0u);
+                            } else if (is_lo) {  // a_hi * b_lo
                                 tc_mma_tf32_ts(d_tmem, ahi, bdesc, IDESC, 1u);
                             } else {
                                 if (PASSES == 3)  // a_lo * b_hi first (small term), then a_hi * b_hi
@@ -321,6 +364,98 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             if (dbg_on && lane == 0) { dbg[1] = mma_wait_full; dbg[2] = mma_wait_tempty; dbg[3] = clock64() - t_kernel0; dbg[11] = n_tiles; }
         }
     } else {
+        if constexpr (Cfg::F16) {
+        // ===================== fp16 pass epilogue: all 16 warps on every tile =====================
+        // warp -> TMEM lane quarter q (hardware rule), column quarter cq of the tile (48 columns).  A thread pulls its
+        // 48 accumulator columns into registers with three tcgen05.ld, hands the accumulator back to the MMA thread
+        // at once, and only then folds them into its row's top-2: the accumulator is blocked for one TMEM read, not
+        // for the fold (with two 8-warp groups the fold time of a tile sat on the critical path of its buffer).
+        constexpr int QW = BN / 4;
+        static_assert(QW == 48, "three 16-column reads per thread");
+        const int cq = warp >> 2;
+        const int q = warp & 3;
+        const int row = row0 + q * 32 + lane;
+        const bool row_ok = row < N;
+        const bool partial_rows = row0 + TC_BM > N;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (n_tiles > 0 && cq < 2) {  // A -> tensor memory, once: 64 k (one 32-column chunk of packed halves) per warp
+            const __half *src = reinterpret_cast<const __half *>(a_hi) + ((size_t)b * n_stride + min(row, n_stride - 1)) * TC_D + cq * 64;
+            const bool have = row < n_stride;
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint4 x = have ? __ldg(reinterpret_cast<const uint4 *>(src) + k) : make_uint4(0, 0, 0, 0);
+                uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (EXT) {  // A scaled by 2 (exact): the accumulator holds 2 a.b - |b|^2
+                        const __half2 d = __hmul2(*reinterpret_cast<const __half2 *>(&w[i]), __floats2half2_rn(2.0f, 2.0f));
+                        w[i] = *reinterpret_cast<const uint32_t *>(&d);
+                    }
+                    v[4 * k + i] = __uint_as_float(w[i]);
+                }
+            }
+            tc_st32(lane_base + (uint32_t)(TMEM_A + cq * 32), v);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar_a);
+        }
+        if (EXT && n_tiles > 0 && cq == 2) {  // the ones block of A
+            const float ones[8] = {1.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            tc_st8(lane_base + (uint32_t)TMEM_EXT, ones);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar_a);
+        }
+        float s1 = -INFINITY, s2 = -INFINITY;
+        int32_t i1 = -1, i2 = -1;
+        const float na = (METRIC == VO_METRIC_L2 && row_ok) ? row_norm[(size_t)b * n_stride + row] : 0.0f;
+        for (int lt = 0; lt < n_tiles; ++lt) {
+            const int buf = lt & 1;
+            const uint32_t use = (uint32_t)(lt >> 1);
+            const int col0 = tile_of(lt) * BN + cq * QW;
+            const bool full_tile = tile_of(lt) * BN + BN <= M;
+            { TC_DBG_BEGIN(); mbar_wait(bar_tfull(buf), use & 1u); TC_DBG_END(0); }
+            tc_fence_after();
+            const long long _tc0 = dbg_on ? clock64() : 0;
+            const uint32_t taddr = lane_base + (uint32_t)(buf * BN + cq * QW);
+            uint32_t ra[16], rb[16], rc[16];
+            tc_ld16_issue(taddr, ra);
+            tc_ld16_issue(taddr + 16, rb);
+            tc_ld16_issue(taddr + 32, rc);
+            tc_ld_wait16(ra);
+            tc_ld_wait16(rb);
+            tc_ld_wait16(rc);
+            tc_fence_before();  // the tile slice is in registers: hand the accumulator back before folding
+            if (lane == 0) mbar_arrive(bar_tempty(buf));
+            if (dbg_on) dbg_acc[1] += clock64() - _tc0;
+            const long long _tm0 = dbg_on ? clock64() : 0;
+#define TC_FOLD16(BUF, J0, MASKC, MASKR)                                                                                   \
+    _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                                                        \
+        float v[8];                                                                                                        \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[8 * u + i]);                              \
+        epi_group8<METRIC, MASKC, MASKR, false, EXT>(v, col0 + (J0) + 8 * u, M, row_ok, na, nullptr, false, lane, nullptr, \
+                                                     nullptr, s1, s2, i1, i2);                                             \
+    }
+            if (full_tile && !partial_rows) {
+                TC_FOLD16(ra, 0, false, false) TC_FOLD16(rb, 16, false, false) TC_FOLD16(rc, 32, false, false)
+            } else {
+                TC_FOLD16(ra, 0, true, true) TC_FOLD16(rb, 16, true, true) TC_FOLD16(rc, 32, true, true)
+            }
+#undef TC_FOLD16
+            if (dbg_on) dbg_acc[2] += clock64() - _tm0;
+        }
+        if (dbg_on && q == 0 && lane == 0 && cq < 2) { dbg[5 + cq] = dbg_acc[0]; dbg[7 + cq] = dbg_acc[1]; dbg[9 + cq] = dbg_acc[2]; }
+        if (METRIC == VO_METRIC_L2) {  // the deferred row norm (-inf stays -inf)
+            s1 = __fsub_rn(s1, na); s2 = __fsub_rn(s2, na);
+        }
+        if (row < n_stride) {  // four column quarters: four partials per (row, split), merged by finalize
+            vo_row_partial p;
+            p.s1 = float_to_ordered(-s1); p.s2 = float_to_ordered(-s2);
+            p.i1 = i1; p.i2 = i2;
+            part[((size_t)b * (n_split * 4) + split * 4 + cq) * n_stride + row] = p;
+        }
+        } else {
         // ===================== epilogue: 2 groups (one per accumulator) x 8 warps =====================
         // warp -> lane quarter q (hardware rule: warp w may touch TMEM lanes 32*(w%4)..), column half h, group g
         const int g = warp >> 3;
@@ -483,6 +618,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             p.i1 = i1; p.i2 = i2;
             part[((size_t)b * (n_split * 4) + split * 4 + g * 2 + h) * n_stride + row] = p;
         }
+        }  // !F16
     }
 
     if (dbg_on && threadIdx.x == 0) dbg[0] = clock64() - t_kernel0;
@@ -499,13 +635,16 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(vo_ctx *ctx, CUtensorMap *map, const float *ptr, long long rows, int box_rows, int row_floats = TC_D) {
+// [rows][row_elems] fp32 (or fp16 when `half`), box = 128 B of k x box_rows rows, SWIZZLE_128B
+int make_map(vo_ctx *ctx, CUtensorMap *map, const void *ptr, long long rows, int box_rows, int row_elems = TC_D,
+             bool half = false) {
     PFN_encodeTiled fn = (PFN_encodeTiled)ctx->encode_tiled;
-    cuuint64_t dims[2] = {(cuuint64_t)row_floats, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)row_floats * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)box_rows};
+    const size_t esz = half ? 2 : 4;
+    cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_elems * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
+    CUresult r = fn(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -560,32 +699,42 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
         ctx->encode_tiled = fn;
         ctx->tc_ready = 1;
     }
+    if (passes == 16 && need_cols) passes = 1;  // the fp16 pass has no column arg-max: same results from the tf32 pass
     const long long rows_a = (long long)B * n_stride, rows_b = (long long)B * m_stride;
     const bool l2 = metric == VO_METRIC_L2;
     // workspace: A_hi | A_lo  and  B_hi | B_lo  and  row norms | column norms
     float *split_a, *split_b, *norms;
     int rc;
-    const size_t per_a = (size_t)rows_a * TC_D * sizeof(float), per_b = (size_t)rows_b * TC_D * sizeof(float);
+    const bool f16 = passes == 16;
+    const size_t esz = f16 ? sizeof(__half) : sizeof(float);
+    const size_t per_a = (size_t)rows_a * TC_D * esz, per_b = (size_t)rows_b * TC_D * esz;
     if ((rc = ws_get(ctx, WS_SPLIT_A, per_a * (passes == 3 ? 2 : 1), (void **)&split_a))) return rc;
-    const bool ext = passes == 1 && l2;  // B extension rows [rows_b][32] live behind B_hi
+    const bool ext = passes != 3 && l2;  // B extension rows [rows_b][32] live behind B_hi
     const size_t per_ext = (size_t)rows_b * TC_KB * sizeof(float);
     if ((rc = ws_get(ctx, WS_SPLIT_B, per_b * (passes == 3 ? 2 : 1) + (ext ? per_ext : 0), (void **)&split_b))) return rc;
     const long long rows_a4 = (rows_a + 3) & ~3ll;  // column norms start 16 B aligned (vector loads in the epilogue)
     if ((rc = ws_get(ctx, WS_NORMS, sizeof(float) * (size_t)(rows_a4 + rows_b), (void **)&norms))) return rc;
     float *a_hi = split_a, *a_lo = passes == 3 ? split_a + (size_t)rows_a * TC_D : nullptr;
     float *b_hi = split_b, *b_lo = passes == 3 ? split_b + (size_t)rows_b * TC_D : nullptr;
-    float *b_ext = ext ? split_b + (size_t)rows_b * TC_D : nullptr;
+    float *b_ext = ext ? reinterpret_cast<float *>(reinterpret_cast<char *>(split_b) + per_b) : nullptr;
     float *row_norm = norms, *col_norm = norms + rows_a4;
 
     VO_PROF(ctx, st, VO_STAGE_PREP);
-    prep_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, a_hi, a_lo, l2 ? row_norm : nullptr, nullptr);
-    VO_LAUNCH_CHECK(ctx);
-    prep_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b_hi, b_lo, l2 ? col_norm : nullptr, b_ext);
-    VO_LAUNCH_CHECK(ctx);
+    if (f16) {
+        prep16_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, reinterpret_cast<__half *>(a_hi), l2 ? row_norm : nullptr, nullptr);
+        VO_LAUNCH_CHECK(ctx);
+        prep16_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, reinterpret_cast<__half *>(b_hi), l2 ? col_norm : nullptr, b_ext);
+        VO_LAUNCH_CHECK(ctx);
+    } else {
+        prep_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, a_hi, a_lo, l2 ? row_norm : nullptr, nullptr);
+        VO_LAUNCH_CHECK(ctx);
+        prep_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b_hi, b_lo, l2 ? col_norm : nullptr, b_ext);
+        VO_LAUNCH_CHECK(ctx);
+    }
 
     CUtensorMap mbh, mbl;
-    const int bn = passes == 3 ? TcCfg<3>::BN : TcCfg<1>::BN;
-    if ((rc = make_map(ctx, &mbh, b_hi, rows_b, bn))) return rc;
+    const int bn = passes == 3 ? TcCfg<3>::BN : (f16 ? TcCfg<16>::BN : TcCfg<1>::BN);
+    if ((rc = make_map(ctx, &mbh, b_hi, rows_b, bn, TC_D, f16))) return rc;
     if (ext) rc = make_map(ctx, &mbl, b_ext, rows_b, bn, TC_KB);
     else rc = make_map(ctx, &mbl, passes == 3 ? b_lo : b_hi, rows_b, bn);
     if (rc) return rc;
@@ -600,6 +749,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
 #define TC_ARGS ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st
 #define TC_PICK(P, MET) (need_cols ? launch_tc<P, MET, true>(TC_ARGS) : launch_tc<P, MET, false>(TC_ARGS))
     if (passes == 3) rc = l2 ? TC_PICK(3, VO_METRIC_L2) : TC_PICK(3, VO_METRIC_COSINE);
+    else if (f16) rc = l2 ? launch_tc<16, VO_METRIC_L2, false>(TC_ARGS) : launch_tc<16, VO_METRIC_COSINE, false>(TC_ARGS);
     else rc = l2 ? TC_PICK(1, VO_METRIC_L2) : TC_PICK(1, VO_METRIC_COSINE);
 #undef TC_PICK
 #undef TC_ARGS

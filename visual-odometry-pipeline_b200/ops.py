@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import (KnnOut, PipelineArgs, VO_METRIC_COSINE, VO_METRIC_L2, VO_MODE_MUTUAL, VO_MODE_NN, VO_MODE_RATIO,
                    VO_MODE_RATIO_MUTUAL, VO_MODE_THRESH, VO_MODE_THRESH_MUTUAL, VO_NORM_HAMMING, VO_NORM_L2_U8,
-                   VO_PREC_FP32_SIMT, VO_PREC_TF32X1, VO_PREC_TF32X3, check)
+                   VO_PREC_F16X1, VO_PREC_FP32_SIMT, VO_PREC_TF32X1, VO_PREC_TF32X3, check)
 
 _contexts = {}
 
@@ -95,8 +95,9 @@ def _match_common(ref, cur, n_ref, n_cur, want_knn, want_dist):
     if want_knn:
         kidx = torch.empty((B, max(N, 1), 2), dtype=torch.int32, device=dev)
         kval = torch.empty((B, max(N, 1), 2), dtype=torch.float32, device=dev)
-        cidx = torch.empty((B, max(M, 1)), dtype=torch.int32, device=dev)
-        knn = KnnOut(kidx.data_ptr(), kval.data_ptr(), cidx.data_ptr())
+        if want_knn != "rows":  # "rows": the row top-2 only (no column arg-min: the matcher may skip its column side)
+            cidx = torch.empty((B, max(M, 1)), dtype=torch.int32, device=dev)
+        knn = KnnOut(kidx.data_ptr(), kval.data_ptr(), cidx.data_ptr() if cidx is not None else None)
     if n_ref is not None:
         _chk(n_ref, torch.int32, "n_ref")
     if n_cur is not None:
