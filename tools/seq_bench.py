@@ -23,7 +23,7 @@ def main():
     from test_gpu_dropin import _load_dropin
     import pathlib
     n_frames = int(os.environ.get("SEQ_FRAMES", 60))
-    for kind, n_kp, norm, mode, prec, extra in (("orb", 5000, 0, 1, 0, "\norb_matcher: hamming_mutual\n"), ("sift", 2000, 0, 0, 1, "")):
+    for kind, n_kp, norm, mode, prec, extra in (("orb", 5000, 0, 1, 0, "\norb_matcher: hamming_mutual\n"), ("sift", 2000, 0, 0, 3, "")):
         frames, gt = synthetic_sequence.make_sequence(n_frames=n_frames, n_kp=n_kp, kind=kind, seed=3)
         cwd = os.getcwd()
         tmp = pathlib.Path(tempfile.mkdtemp())
