@@ -117,14 +117,14 @@ def test_c4_self_match_identity():
 
 
 # ------------------------------------------------------------------------------------------------ c3 / c5: R2D2
-@pytest.mark.parametrize("n", [10000, 50000])
-def test_c3_c5_r2d2_subsets_near_tie_aware(orc, n):
+@pytest.mark.parametrize("n,prec", [(10000, 0), (50000, 0), (10000, 4), (50000, 4)])
+def test_c3_c5_r2d2_subsets_near_tie_aware(orc, n, prec):
     from vo_b200 import ops
     ref, cur = _descs("r2d2", n, 46 + n)
     rng = np.random.default_rng(7)
     perm = rng.permutation(n)
     cur = np.ascontiguousarray(cur[perm])
-    r = ops.match_f32(_gpu(ref), _gpu(cur), ops.VO_METRIC_COSINE, ops.VO_MODE_RATIO_MUTUAL, 0.90, precision=0,
+    r = ops.match_f32(_gpu(ref), _gpu(cur), ops.VO_METRIC_COSINE, ops.VO_MODE_RATIO_MUTUAL, 0.90, precision=prec,
                       want_knn=True)
     gi, gv, gc = r.knn_idx[0].cpu().numpy(), r.knn_val[0].cpu().numpy(), r.col_idx[0].cpu().numpy()
     k = 256 if n > 20000 else 512

@@ -39,7 +39,7 @@ def test_golden_sift_knn_bit_exact(golden, prec):
     assert np.array_equal(r.numpy(), g["ref_sift_pairs"])
 
 
-@pytest.mark.parametrize("prec", [2, 0])
+@pytest.mark.parametrize("prec", [2, 0, 4])
 def test_golden_r2d2_matchers(golden, orc, prec):
     from vo_b200 import ops
     g = golden("match_f32_r2d2.npz")
@@ -79,7 +79,7 @@ def test_sift_vs_oracle_sizes(orc, prec, n, m):
     assert np.array_equal(r.numpy(), want)
 
 
-@pytest.mark.parametrize("prec", [2, 0])
+@pytest.mark.parametrize("prec", [2, 0, 4])
 def test_r2d2_vs_oracle_with_recorded_near_ties(orc, prec):
     from vo_b200 import ops, synthetic
     p = synthetic.make_pair(5, n_kp=3000, n_cur=2800, kind="r2d2")

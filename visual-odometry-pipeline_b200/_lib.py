@@ -19,7 +19,7 @@ VO_NORM_HAMMING, VO_NORM_L2_U8 = 0, 1
 VO_METRIC_L2, VO_METRIC_COSINE = 0, 1
 (VO_MODE_RATIO, VO_MODE_MUTUAL, VO_MODE_RATIO_MUTUAL, VO_MODE_THRESH_MUTUAL, VO_MODE_THRESH,
  VO_MODE_NN) = range(6)
-VO_PREC_TF32X3, VO_PREC_TF32X1, VO_PREC_FP32_SIMT, VO_PREC_F16X1 = 0, 1, 2, 3
+VO_PREC_TF32X3, VO_PREC_TF32X1, VO_PREC_FP32_SIMT, VO_PREC_F16X1, VO_PREC_F16X3 = 0, 1, 2, 3, 4
 
 c_void_p, c_int, c_float, c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
 c_u64, c_i64 = ctypes.c_uint64, ctypes.c_int64

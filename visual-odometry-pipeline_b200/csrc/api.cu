@@ -149,7 +149,7 @@ extern "C" int vo_match_f32(vo_ctx *ctx, const float *ref, const float *cur, int
     VO_REQUIRE(mode >= VO_MODE_RATIO && mode <= VO_MODE_NN, "vo_match_f32: bad mode %d", mode);
     VO_REQUIRE(!((mode == VO_MODE_THRESH || mode == VO_MODE_THRESH_MUTUAL) && metric != VO_METRIC_COSINE),
                "vo_match_f32: similarity-threshold modes need VO_METRIC_COSINE");
-    VO_REQUIRE(precision >= VO_PREC_TF32X3 && precision <= VO_PREC_F16X1, "vo_match_f32: bad precision %d", precision);
+    VO_REQUIRE(precision >= VO_PREC_TF32X3 && precision <= VO_PREC_F16X3, "vo_match_f32: bad precision %d", precision);
     VO_REQUIRE(B >= 0 && n_stride >= 0 && m_stride >= 0 && dim > 0, "vo_match_f32: bad size");
     VO_REQUIRE(out_pairs && out_count, "vo_match_f32: null output");
     VO_REQUIRE(((uintptr_t)ref % 16) == 0 && ((uintptr_t)cur % 16) == 0, "vo_match_f32: descriptors must be 16B aligned");
@@ -179,7 +179,7 @@ extern "C" int vo_match_f32(vo_ctx *ctx, const float *ref, const float *cur, int
         const int need_cols = mode == VO_MODE_MUTUAL || mode == VO_MODE_RATIO_MUTUAL || mode == VO_MODE_THRESH_MUTUAL ||
                               (knn && knn->col_idx);
         if ((rc = match_f32_tc(ctx, ref, cur, B, n_stride, m_stride, n_ref, n_cur, metric,
-                               precision == VO_PREC_TF32X3 ? 3 : (precision == VO_PREC_F16X1 ? 16 : 1), need_cols, &part, &n_split, colkey, &row_norm, st)))
+                               precision == VO_PREC_TF32X3 ? 3 : (precision == VO_PREC_F16X1 ? 16 : (precision == VO_PREC_F16X3 ? 48 : 1)), need_cols, &part, &n_split, colkey, &row_norm, st)))
             return rc;
     }
     return match_finalize(ctx, part, n_split, colkey, B, n_stride, m_stride, n_ref, n_cur,

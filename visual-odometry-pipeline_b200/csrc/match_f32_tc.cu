@@ -43,10 +43,17 @@ constexpr int TC_NKB = TC_D / TC_KB;
 // so integer-valued SIFT descriptors stay exact), tcgen05.mma.kind::f16 with K = 16 per instruction at twice the tf32
 // rate.  192-column tiles, 9-stage ring of 24 KB boxes ([192 rows x 64 k] fp16), A as 64 packed columns:
 // TMEM = acc0 0 | acc1 192 | ones block 384 | A 416.
+// PASSES == 48 is the split form of the same idea (VO_PREC_F16X3): x * 2^8 = hi + lo with hi, lo in fp16 carries the same
+// 22 operand bits as the tf32 hi/lo split (the scaling keeps the lo parts of unit-norm descriptors out of the fp16
+// subnormals; 2^-16 is taken off the accumulator in the epilogue, exactly), three kind::f16 MMAs per 16 k instead of
+// three kind::tf32 MMAs per 8 k.  Tile geometry, ring and epilogue are those of 3xTF32.
 template <int PASSES>
 struct TcCfg {
-    static constexpr bool F16 = PASSES == 16;
-    static constexpr bool SINGLE = PASSES != 3;
+    static constexpr bool F16 = PASSES == 16;                     // fp16 single pass (own epilogue)
+    static constexpr bool H16 = PASSES == 16 || PASSES == 48;     // fp16 operands
+    static constexpr bool THREE = PASSES == 3 || PASSES == 48;    // hi/lo split, three MMAs per k-step
+    static constexpr bool SINGLE = !THREE;
+    static constexpr int ALO = H16 ? 64 : TC_D;                   // TMEM columns from A_hi to A_lo
     static constexpr int BN = F16 ? 192 : (SINGLE ? 160 : 128);
     static constexpr int STAGES = F16 ? 9 : (SINGLE ? 10 : 13);
     static constexpr int BLOCK_BYTES = BN * 128;                  // one [BN rows x 128 B] box: 32 fp32 or 64 fp16 along k
@@ -58,6 +65,7 @@ struct TcCfg {
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     // kind::f16: D = f32 [4,6) = 1, A = B = fp16 (format 0)
     static constexpr uint32_t IDESC16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    static constexpr float ACC_SCALE = PASSES == 48 ? 1.0f / 65536.0f : 1.0f;  // accumulator -> a.b
 };
 constexpr int TC_THREADS = 576;              // warps 0..15 epilogue, warp 16 TMA, warp 17 MMA
 constexpr int TC_WARP_TMA = 16, TC_WARP_MMA = 17;
@@ -134,6 +142,36 @@ prep16_kernel(const float *__restrict__ x, long long rows, __half *__restrict__ 
     }
 }
 
+// split fp16 (VO_PREC_F16X3): x * 2^8 = hi + lo, both fp16; squared norms of the unscaled rows
+__global__ void __launch_bounds__(256)
+prep16x3_kernel(const float *__restrict__ x, long long rows, __half *__restrict__ hi16, __half *__restrict__ lo16,
+                float *__restrict__ norm2) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float4 v = reinterpret_cast<const float4 *>(x)[row * 32 + lane];
+    const float e[4] = {v.x * 256.0f, v.y * 256.0f, v.z * 256.0f, v.w * 256.0f};  // exact scaling
+    __half h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = __float2half_rn(e[i]);
+        l[i] = __float2half_rn(e[i] - __half2float(h[i]));  // the residual is exact in fp32
+    }
+    uint2 wh, wl;
+    wh.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    wh.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    wl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+    wl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    reinterpret_cast<uint2 *>(hi16)[row * 32 + lane] = wh;
+    reinterpret_cast<uint2 *>(lo16)[row * 32 + lane] = wl;
+    if (norm2) {
+        float s = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fadd_rn(__fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+        if (lane == 0) norm2[row] = s;
+    }
+}
+
 // ---------------------------------------------------------------- epilogue helpers
 // Fold one (score, column) into the row's running top-2 (larger is better), branch-free: 2 FSETP + 3 FMNMX + 3 SEL.
 // Ties go to the lower column index without an index comparison, because every thread meets its columns in
@@ -153,7 +191,7 @@ __device__ __forceinline__ void row_insert(float s, int col, float &s1, float &s
 // maximum and the ballot of the lanes that attain it (both warp-uniform; lane 0 stores them as two vectors).
 // ROW_MASK is set only for the last, partial row block: elsewhere every lane holds a valid row.
 // Kept small on purpose (a rolled loop calls it 8 times per tile and warp): 16 warps share the instruction cache.
-template <int METRIC, bool MASK_COLS, bool ROW_MASK, bool COLS, bool EXT>
+template <int METRIC, bool MASK_COLS, bool ROW_MASK, bool COLS, bool EXT, bool SCALED = false>
 __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M, bool row_ok, float na,
                                            const float *__restrict__ cn, bool cn_vec, int lane, float *cv_out,
                                            uint32_t *cb_out, float &s1, float &s2, int32_t &i1, int32_t &i2) {
@@ -178,8 +216,10 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
             // with a column arg-min the row norm orders rows inside a column; without one it is a per-row
             // constant that the caller subtracts once, after the scan (same two roundings either way)
             // EXT: the accumulator already holds 2 a.b - |b|^2 (A scaled by 2, norm folded in as one more K-step)
-            if (!EXT) s = __fmaf_rn(2.0f, s, -nb[j]);
+            if (!EXT) s = __fmaf_rn(SCALED ? 2.0f / 65536.0f : 2.0f, s, -nb[j]);  // SCALED: accumulator = 2^16 a.b
             if (COLS) s = __fsub_rn(s, na);
+        } else if (SCALED) {
+            s = __fmul_rn(s, 1.0f / 65536.0f);  // exact
         }
         if (MASK_COLS) s = (col < M) ? s : -INFINITY;
         sc[j] = s;
@@ -196,8 +236,10 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
         *reinterpret_cast<uint4 *>(cb_out + 4) = make_uint4(bal[4], bal[5], bal[6], bal[7]);
     }
     // Row top-2: a 4-wide max filter, then a branch-free insert of the 4 candidates.  The branch is taken by the
-    // whole warp if any lane needs it, so the filter is kept narrow (expected entries ~ 64/k per
-    // 4 columns once a row has seen k columns).
+    // whole warp if any lane needs it, so the filter is kept narrow (expected entries ~ 256/k per 4 columns and warp
+    // once a row has seen k columns).  Measured alternative: descending to the halves / single columns that really
+    // enter (one insert instead of four per hit) costs a third FMNMX per group and nested divergent branches — the
+    // single-pass kernels lost 5-8 % (20k x 20k fp16 pass 910 -> 862 TF), so the four straight inserts stay.
 #pragma unroll
     for (int j0 = 0; j0 < 8; j0 += 4) {
         const float m4 = fmaxf(fmaxf(sc[j0], sc[j0 + 1]), fmaxf(sc[j0 + 2], sc[j0 + 3]));
@@ -247,9 +289,10 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
 
     // single-pass L2: one extra box per tile carries -|b|^2 (three tf32 pieces), multiplied by a column block of ones in A
     constexpr bool F16 = Cfg::F16;
-    constexpr bool EXT = (PASSES != 3) && (METRIC == VO_METRIC_L2);
-    constexpr int NKB = F16 ? TC_D / 64 : TC_NKB;                                // k boxes per tile (128 B of k each)
-    constexpr int ITEMS = (PASSES == 3) ? 2 * NKB : (EXT ? NKB + 1 : NKB);       // B boxes streamed per tile
+    constexpr bool H16 = Cfg::H16, THREE = Cfg::THREE, SCALED = PASSES == 48;
+    constexpr bool EXT = !THREE && (METRIC == VO_METRIC_L2);
+    constexpr int NKB = H16 ? TC_D / 64 : TC_NKB;                                // k boxes per tile (128 B of k each)
+    constexpr int ITEMS = THREE ? 2 * NKB : (EXT ? NKB + 1 : NKB);               // B boxes streamed per tile
     const uint32_t s_b = base;
     float *scol_v = reinterpret_cast<float *>(smem + Cfg::OFF_SCOL);                      // [2 groups][2 bufs][4][BN]
     uint32_t *scol_b = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_SCOL + 2 * 2 * 4 * BN * 4);
@@ -267,8 +310,8 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             mbar_init(bar_full(s), 1);            // this CTA's producer arms it; TMA bytes complete it
             mbar_init(bar_empty(s), TC_CLUSTER);  // one commit from each CTA of the cluster
         }
-        mbar_init(bar_a, PASSES == 3 ? 16 : (EXT ? 12 : 8));
-        for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull(g), 1); mbar_init(bar_tempty(g), F16 ? 16 : 8); }
+        mbar_init(bar_a, THREE ? 16 : (EXT ? 12 : 8));
+        for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull(g), 1); mbar_init(bar_tempty(g), H16 ? 16 : 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_WARP_MMA) {  // TMEM allocation is warp-collective; this warp also frees it
@@ -298,9 +341,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                     mbar_expect_tx(bar_full(stage), BLOCK_BYTES);  // bytes arrive by multicast, whoever issues
                     if ((uint32_t)(it & 1) == crank) {
                         const bool is_ext = EXT && item == NKB;  // map_b_lo is the extension map in that mode
-                        const int kb = is_ext ? 0 : ((PASSES == 3) ? (item >> 1) : item);
-                        const bool is_lo = is_ext || ((PASSES == 3) && (item & 1));
-                        tma_load_2d_mc(s_b + stage * BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * (F16 ? 64 : TC_KB), brow,
+                        const int kb = is_ext ? 0 : (THREE ? (item >> 1) : item);
+                        const bool is_lo = is_ext || (THREE && (item & 1));
+                        tma_load_2d_mc(s_b + stage * BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * (H16 ? 64 : TC_KB), brow,
                                        bar_full(stage), (uint16_t)((1u << TC_CLUSTER) - 1u));
                     }
                 }
@@ -331,8 +374,8 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                       if (dbg_on) mma_wait_full += clock64() - _t0; }
                     tc_fence_after();
                     if (elect_one()) {
-                        const int kb = (PASSES == 3) ? (item >> 1) : item;       // compile-time after unrolling
-                        const bool is_lo = (PASSES == 3) && (item & 1);
+                        const int kb = THREE ? (item >> 1) : item;       // compile-time after unrolling
+                        const bool is_lo = THREE && (item & 1);
                         const uint32_t b_lo32 = (((s_b + stage * BLOCK_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
                         const uint32_t a_hi_t = tmem_base + (uint32_t)(TMEM_A + kb * TC_KB);
                         if (EXT && item == NKB) {  // ones[128 x 8] * (-|b|^2 pieces)[8 x BN], always kind::tf32
@@ -345,12 +388,19 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                             const uint32_t ahi = a_hi_t + k8 * 8;
                             if (F16) {  // 16 k per instruction: the same 32 B of B and 8 TMEM columns of A per step
                                 tc_mma_f16_ts(d_tmem, ahi, bdesc, Cfg::IDESC16, (item | k8) ? 1u : 0u);
+                            } else if (H16) {  // split fp16: a_hi * b_lo on the lo boxes; a_lo * b_hi, a_hi * b_hi on the hi boxes
+                                if (is_lo) {
+                                    tc_mma_f16_ts(d_tmem, ahi, bdesc, Cfg::IDESC16, 1u);
+                                } else {
+                                    tc_mma_f16_ts(d_tmem, ahi + Cfg::ALO, bdesc, Cfg::IDESC16, (item | k8) ? 1u : 0u);
+                                    tc_mma_f16_ts(d_tmem, ahi, bdesc, Cfg::IDESC16, 1u);
+                                }
                             } else if (is_lo) {  // a_hi * b_lo
                                 tc_mma_tf32_ts(d_tmem, ahi, bdesc, IDESC, 1u);
                             } else {
-                                if (PASSES == 3)  // a_lo * b_hi first (small term), then a_hi * b_hi
+                                if (THREE)  // a_lo * b_hi first (small term), then a_hi * b_hi
                                     tc_mma_tf32_ts(d_tmem, ahi + TC_D, bdesc, IDESC, (item | k8) ? 1u : 0u);
-                                tc_mma_tf32_ts(d_tmem, ahi, bdesc, IDESC, (PASSES == 3 || (item | k8)) ? 1u : 0u);
+                                tc_mma_tf32_ts(d_tmem, ahi, bdesc, IDESC, (THREE || (item | k8)) ? 1u : 0u);
                             }
                         }
                         // slot reusable (in BOTH CTAs' rings) once these MMAs retire
@@ -455,6 +505,112 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             p.i1 = i1; p.i2 = i2;
             part[((size_t)b * (n_split * 4) + split * 4 + cq) * n_stride + row] = p;
         }
+        } else if constexpr (PASSES == 48) {
+        // ===================== split-fp16 epilogue: all 16 warps on every tile, with the column side =====================
+        // Same idea as the fp16 single pass: lane quarter q x column quarter cq (32 columns per thread), the tile slice
+        // goes to registers, the accumulator is released, then the fold.  Column arg-max: per warp and column
+        // redux.max + ballot into shared memory (lane 0), a 128-thread named barrier per column quarter, and the q == 0
+        // warp of the quarter merges its 32 columns (one per lane) over the four lane quarters -> one atomicMin each.
+        constexpr int QW = BN / 4;
+        static_assert(QW == 32, "two 16-column reads per thread, one merged column per lane");
+        const int cq = warp >> 2;
+        const int q = warp & 3;
+        const int row = row0 + q * 32 + lane;
+        const bool row_ok = row < N;
+        const bool partial_rows = row0 + TC_BM > N;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (n_tiles > 0) {  // A -> tensor memory: column quarters 0,1 store the hi part (k 0..63, 64..127), 2,3 the lo part
+            const __half *src = reinterpret_cast<const __half *>(cq < 2 ? a_hi : a_lo) +
+                                ((size_t)b * n_stride + min(row, n_stride - 1)) * TC_D + (cq & 1) * 64;
+            const bool have = row < n_stride;
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint4 x = have ? __ldg(reinterpret_cast<const uint4 *>(src) + k) : make_uint4(0, 0, 0, 0);
+                v[4 * k] = __uint_as_float(x.x); v[4 * k + 1] = __uint_as_float(x.y);
+                v[4 * k + 2] = __uint_as_float(x.z); v[4 * k + 3] = __uint_as_float(x.w);
+            }
+            tc_st32(lane_base + (uint32_t)(TMEM_A + cq * 32), v);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar_a);
+        }
+        float s1 = -INFINITY, s2 = -INFINITY;
+        int32_t i1 = -1, i2 = -1;
+        const float *cn = (METRIC == VO_METRIC_L2) ? col_norm + (size_t)b * m_stride : nullptr;
+        const float na = (METRIC == VO_METRIC_L2 && row_ok) ? row_norm[(size_t)b * n_stride + row] : 0.0f;
+        const bool cn_vec = (METRIC == VO_METRIC_L2) && ((reinterpret_cast<uintptr_t>(cn) & 15u) == 0);
+        for (int lt = 0; lt < n_tiles; ++lt) {
+            const int buf = lt & 1;
+            const uint32_t use = (uint32_t)(lt >> 1);
+            const int tcol0 = tile_of(lt) * BN;
+            const int col0 = tcol0 + cq * QW;
+            const bool full_tile = tcol0 + BN <= M;
+            float *tile_cv = scol_v + buf * 4 * BN;      // [4 lane quarters][BN], alternating per tile
+            uint32_t *tile_cb = scol_b + buf * 4 * BN;
+            float *my_cv = tile_cv + q * BN + cq * QW;
+            uint32_t *my_cb = tile_cb + q * BN + cq * QW;
+            { TC_DBG_BEGIN(); mbar_wait(bar_tfull(buf), use & 1u); TC_DBG_END(0); }
+            tc_fence_after();
+            const long long _tc0 = dbg_on ? clock64() : 0;
+            const uint32_t taddr = lane_base + (uint32_t)(buf * BN + cq * QW);
+            uint32_t ra[16], rb[16];
+            tc_ld16_issue(taddr, ra);
+            tc_ld16_issue(taddr + 16, rb);
+            tc_ld_wait16(ra);
+            tc_ld_wait16(rb);
+            tc_fence_before();  // the tile slice is in registers: hand the accumulator back before folding
+            if (lane == 0) mbar_arrive(bar_tempty(buf));
+            if (dbg_on) dbg_acc[1] += clock64() - _tc0;
+            const long long _tm0 = dbg_on ? clock64() : 0;
+#define TC_FOLD16(BUF, J0, MASKC, MASKR)                                                                                   \
+    _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                                                        \
+        float v[8];                                                                                                        \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[8 * u + i]);                              \
+        epi_group8<METRIC, MASKC, MASKR, COLS, false, true>(v, col0 + (J0) + 8 * u, M, row_ok, na, cn, cn_vec, lane,       \
+                                                            my_cv + (J0) + 8 * u, my_cb + (J0) + 8 * u, s1, s2, i1, i2);   \
+    }
+            if (full_tile && !partial_rows) {
+                TC_FOLD16(ra, 0, false, false) TC_FOLD16(rb, 16, false, false)
+            } else {
+                TC_FOLD16(ra, 0, true, true) TC_FOLD16(rb, 16, true, true)
+            }
+#undef TC_FOLD16
+            if (COLS) {
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + cq) : "memory");  // the four lane quarters of this column quarter
+                if (q == 0) {  // one column per lane
+                    const int j = cq * QW + lane;
+                    const int col = tcol0 + j;
+                    float best = -INFINITY;
+                    int brow = -1;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const float val = tile_cv[qq * BN + j];
+                        const uint32_t bal = tile_cb[qq * BN + j];
+                        if (bal != 0u && val > best) { best = val; brow = qq * 32 + __ffs(bal) - 1; }
+                    }
+                    if (col < M && brow >= 0 && row0 + brow < N) {
+                        const unsigned long long key =
+                            ((unsigned long long)float_to_ordered(-best) << 32) | (unsigned long long)(uint32_t)(row0 + brow);
+                        unsigned long long *dst = colkey + (size_t)b * m_stride + col;
+                        if (key < *reinterpret_cast<volatile unsigned long long *>(dst)) atomicMin(dst, key);
+                    }
+                }
+                // no second barrier: tile lt+1 writes the other scratch buffer, and tile lt+2 cannot be written before
+                // the merging warp has arrived at the barrier of tile lt+1, i.e. after it has read this one
+            }
+            if (dbg_on) dbg_acc[2] += clock64() - _tm0;
+        }
+        if (dbg_on && q == 0 && lane == 0 && cq < 2) { dbg[5 + cq] = dbg_acc[0]; dbg[7 + cq] = dbg_acc[1]; dbg[9 + cq] = dbg_acc[2]; }
+        if (METRIC == VO_METRIC_L2 && !COLS) {  // the deferred row norm (-inf stays -inf)
+            s1 = __fsub_rn(s1, na); s2 = __fsub_rn(s2, na);
+        }
+        if (row < n_stride) {  // four column quarters: four partials per (row, split), merged by finalize
+            vo_row_partial p;
+            p.s1 = float_to_ordered(-s1); p.s2 = float_to_ordered(-s2);
+            p.i1 = i1; p.i2 = i2;
+            part[((size_t)b * (n_split * 4) + split * 4 + cq) * n_stride + row] = p;
+        }
         } else {
         // ===================== epilogue: 2 groups (one per accumulator) x 8 warps =====================
         // warp -> lane quarter q (hardware rule: warp w may touch TMEM lanes 32*(w%4)..), column half h, group g
@@ -467,7 +623,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 
         // ---- A -> tensor memory, once: group 0 stores the tf32 hi part, group 1 the lo part; each warp 2 k-chunks
-        if (n_tiles > 0 && (g == 0 || PASSES == 3)) {
+        if (n_tiles > 0 && (g == 0 || THREE)) {
             const float *src = (g == 0 ? a_hi : a_lo) + ((size_t)b * n_stride + min(row, n_stride - 1)) * TC_D;
             const bool have = row < n_stride;
 #pragma unroll 1
@@ -519,7 +675,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             // columns is kept in flight while the current ones are folded (two register buffers swapped by moves: the
             // loops stay rolled with one or two epi_group8 bodies, 16 warps share the instruction cache); without the
             // column arg-max there are registers to spare and the reads are 16 columns wide.
-            if (PASSES == 3) {
+            if (THREE) {
 #define TC_EPI_LOOP(MASKC, MASKR)                                                                                          \
     _Pragma("unroll 1") for (int j0 = HALF * h; j0 < HALF * h + HALF; j0 += 8) {                                                 \
         uint32_t cur[8];                                                                                                   \
@@ -527,7 +683,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         tc_ld_wait8(cur);                                                                                                  \
         float v[8];                                                                                                        \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(cur[i]);                                      \
-        epi_group8<METRIC, MASKC, MASKR, COLS, EXT>(v, col0 + j0, M, row_ok, na, cn, cn_vec, lane, my_cv + j0, my_cb + j0, \
+        epi_group8<METRIC, MASKC, MASKR, COLS, EXT, SCALED>(v, col0 + j0, M, row_ok, na, cn, cn_vec, lane, my_cv + j0, my_cb + j0, \
                                                     s1, s2, i1, i2);                                                       \
     }
                 if (full_tile && !partial_rows) { TC_EPI_LOOP(false, false) } else { TC_EPI_LOOP(true, true) }
@@ -705,22 +861,27 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     // workspace: A_hi | A_lo  and  B_hi | B_lo  and  row norms | column norms
     float *split_a, *split_b, *norms;
     int rc;
-    const bool f16 = passes == 16;
-    const size_t esz = f16 ? sizeof(__half) : sizeof(float);
+    const bool f16 = passes == 16, h16 = passes == 16 || passes == 48, three = passes == 3 || passes == 48;
+    const size_t esz = h16 ? sizeof(__half) : sizeof(float);
     const size_t per_a = (size_t)rows_a * TC_D * esz, per_b = (size_t)rows_b * TC_D * esz;
-    if ((rc = ws_get(ctx, WS_SPLIT_A, per_a * (passes == 3 ? 2 : 1), (void **)&split_a))) return rc;
-    const bool ext = passes != 3 && l2;  // B extension rows [rows_b][32] live behind B_hi
+    if ((rc = ws_get(ctx, WS_SPLIT_A, per_a * (three ? 2 : 1), (void **)&split_a))) return rc;
+    const bool ext = !three && l2;  // B extension rows [rows_b][32] live behind B_hi
     const size_t per_ext = (size_t)rows_b * TC_KB * sizeof(float);
-    if ((rc = ws_get(ctx, WS_SPLIT_B, per_b * (passes == 3 ? 2 : 1) + (ext ? per_ext : 0), (void **)&split_b))) return rc;
+    if ((rc = ws_get(ctx, WS_SPLIT_B, per_b * (three ? 2 : 1) + (ext ? per_ext : 0), (void **)&split_b))) return rc;
     const long long rows_a4 = (rows_a + 3) & ~3ll;  // column norms start 16 B aligned (vector loads in the epilogue)
     if ((rc = ws_get(ctx, WS_NORMS, sizeof(float) * (size_t)(rows_a4 + rows_b), (void **)&norms))) return rc;
-    float *a_hi = split_a, *a_lo = passes == 3 ? split_a + (size_t)rows_a * TC_D : nullptr;
-    float *b_hi = split_b, *b_lo = passes == 3 ? split_b + (size_t)rows_b * TC_D : nullptr;
+    float *a_hi = split_a, *a_lo = three ? reinterpret_cast<float *>(reinterpret_cast<char *>(split_a) + per_a) : nullptr;
+    float *b_hi = split_b, *b_lo = three ? reinterpret_cast<float *>(reinterpret_cast<char *>(split_b) + per_b) : nullptr;
     float *b_ext = ext ? reinterpret_cast<float *>(reinterpret_cast<char *>(split_b) + per_b) : nullptr;
     float *row_norm = norms, *col_norm = norms + rows_a4;
 
     VO_PROF(ctx, st, VO_STAGE_PREP);
-    if (f16) {
+    if (passes == 48) {
+        prep16x3_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, reinterpret_cast<__half *>(a_hi), reinterpret_cast<__half *>(a_lo), l2 ? row_norm : nullptr);
+        VO_LAUNCH_CHECK(ctx);
+        prep16x3_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, reinterpret_cast<__half *>(b_hi), reinterpret_cast<__half *>(b_lo), l2 ? col_norm : nullptr);
+        VO_LAUNCH_CHECK(ctx);
+    } else if (f16) {
         prep16_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, reinterpret_cast<__half *>(a_hi), l2 ? row_norm : nullptr, nullptr);
         VO_LAUNCH_CHECK(ctx);
         prep16_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, reinterpret_cast<__half *>(b_hi), l2 ? col_norm : nullptr, b_ext);
@@ -733,10 +894,10 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     }
 
     CUtensorMap mbh, mbl;
-    const int bn = passes == 3 ? TcCfg<3>::BN : (f16 ? TcCfg<16>::BN : TcCfg<1>::BN);
-    if ((rc = make_map(ctx, &mbh, b_hi, rows_b, bn, TC_D, f16))) return rc;
+    const int bn = three ? TcCfg<3>::BN : (f16 ? TcCfg<16>::BN : TcCfg<1>::BN);
+    if ((rc = make_map(ctx, &mbh, b_hi, rows_b, bn, TC_D, h16))) return rc;
     if (ext) rc = make_map(ctx, &mbl, b_ext, rows_b, bn, TC_KB);
-    else rc = make_map(ctx, &mbl, passes == 3 ? b_lo : b_hi, rows_b, bn);
+    else rc = make_map(ctx, &mbl, three ? b_lo : b_hi, rows_b, bn, TC_D, h16);
     if (rc) return rc;
 
     const int row_blocks = ceil_div(n_stride, TC_BM);
@@ -749,6 +910,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
 #define TC_ARGS ctx, grid, mbh, mbl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st
 #define TC_PICK(P, MET) (need_cols ? launch_tc<P, MET, true>(TC_ARGS) : launch_tc<P, MET, false>(TC_ARGS))
     if (passes == 3) rc = l2 ? TC_PICK(3, VO_METRIC_L2) : TC_PICK(3, VO_METRIC_COSINE);
+    else if (passes == 48) rc = l2 ? TC_PICK(48, VO_METRIC_L2) : TC_PICK(48, VO_METRIC_COSINE);
     else if (f16) rc = l2 ? launch_tc<16, VO_METRIC_L2, false>(TC_ARGS) : launch_tc<16, VO_METRIC_COSINE, false>(TC_ARGS);
     else rc = l2 ? TC_PICK(1, VO_METRIC_L2) : TC_PICK(1, VO_METRIC_COSINE);
 #undef TC_PICK
