@@ -333,20 +333,24 @@ def run_ours(args, wl):
                                 "popc_pipe_frac": dists * 4.0 / match_s / (16.0 * 148 * sm_mhz * 1e6),
                                 "peak_source": "64 ALU lanes/clk/SM x 148 SM x sampled SM clock / 17 ALU instructions per distance"}
     else:
-        passes = 3 if mc["precision"] == ops.VO_PREC_TF32X3 else 1
+        passes = 3 if mc["precision"] in (ops.VO_PREC_TF32X3, ops.VO_PREC_F16X3) else 1
         flops = pairs_per_launch * 2.0 * N * M * 128 * (passes if mc["precision"] != ops.VO_PREC_FP32_SIMT else 1)
         tf32_half_bf16 = bf16_peak / 2.0
-        if mc["precision"] == ops.VO_PREC_F16X1:
-            # fp16 operands (exact on integer-valued SIFT descriptors), kind::f16 MMAs + one kind::tf32 K-step per tile for
-            # the column norm: the ceiling is the dense 16-bit tensor peak MEASURED_PEAKS.json holds
-            roof = {"kernel": "match_f32_tc_kernel<fp16 single pass> (tcgen05 kind::f16 fused GEMM + row top-2)",
+        if mc["precision"] in (ops.VO_PREC_F16X1, ops.VO_PREC_F16X3):
+            # fp16 operands: single pass (exact on integer-valued SIFT descriptors; + one kind::tf32 K-step per tile for the
+            # column norm) or the hi/lo split x*2^8 = hi + lo (22 operand bits, as 3xTF32).  The ceiling is the dense
+            # 16-bit tensor peak MEASURED_PEAKS.json holds
+            single = mc["precision"] == ops.VO_PREC_F16X1
+            roof = {"kernel": "match_f32_tc_kernel<fp16 single pass> (tcgen05 kind::f16 fused GEMM + row top-2)" if single else
+                              "match_f32_tc_kernel<split fp16, 3 MMAs per 16 k> (tcgen05 kind::f16 fused GEMM + row top-2 / column arg-max)",
                     "bound": "tensor", "achieved": flops / match_s / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
-                    "traffic": ncu_traffic("match_f32_tc_kernel_f16", pairs_per_launch),
+                    "traffic": ncu_traffic("match_f32_tc_kernel_f16" if single else "match_f32_tc_kernel_f16x3", pairs_per_launch),
                     "peak_source": f"dense bf16 cuBLAS burst peak of MEASURED_PEAKS.json ({peak_kind}); fp16 and bf16 share the rate",
                     "frac_of_tf32_proxy": flops / match_s / 1e12 / tf32_half_bf16,
-                    "issued_passes": 1, "algorithmic_flops": flops,
-                    "note": "the epilogue (row top-2 on the ALU pipe: FMNMX / FSETP / SEL, 64 lanes/clk/SM), not the tensor "
-                            "pipe, bounds this pass: ncu sm__pipe_tensor_cycles_active 54 %, ALU pipe 65 % (profiles/)"}
+                    "issued_passes": passes, "algorithmic_flops": flops / passes,
+                    "note": "achieved counts ISSUED tensor FLOPs.  The epilogue (row top-2 / column arg-max on the ALU pipe: FMNMX / "
+                            "FSETP / SEL / VOTE, 64 lanes/clk/SM), not the tensor pipe, bounds the fp16 passes: ncu "
+                            "sm__pipe_tensor_cycles_active 50-54 %, ALU pipe 61-65 % (profiles/r01i_ncu_raw_match_f16*.csv)"}
         else:
             tf32_cublas = measure_tf32_peak(dev)
             roof = {"kernel": "match_f32_tc_kernel (tcgen05 kind::tf32 fused GEMM + row top-2 / column arg-max)",

@@ -29,7 +29,11 @@ def _prep(d):
 
 def _run(d1, d2, mode, param):
     a, b = _prep(d1), _prep(d2)
-    prec = ops.VO_PREC_TF32X3 if a.shape[-1] == 128 else ops.VO_PREC_FP32_SIMT
+    # 3xTF32 by default (the north-star GEMM); VO_MATCH_PRECISION=f16x3 selects the split-fp16 pass: the same 22 operand
+    # bits at twice the MMA rate, valid for |x| < 255 (R2D2 descriptors are unit-norm)
+    prec = ops.VO_PREC_F16X3 if os.environ.get("VO_MATCH_PRECISION", "tf32x3").lower() == "f16x3" else ops.VO_PREC_TF32X3
+    if a.shape[-1] != 128:
+        prec = ops.VO_PREC_FP32_SIMT
     return ops.match_f32(a, b, ops.VO_METRIC_COSINE, mode, param, precision=prec, want_dist=True)
 
 
