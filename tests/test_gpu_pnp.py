@@ -127,3 +127,50 @@ def test_points_beyond_one_staging_tile(orc):
     o = orc.pnp_ransac(xyz, cuv, p["K"], hyp[0].cpu().numpy())
     assert np.array_equal(res.hyp_counts[0].cpu().numpy(), o["counts"])
     assert np.array_equal(res.mask[0, :len(xyz)].cpu().numpy(), o["mask"])
+
+
+def _scene(rng, n, K, outliers=0.3):
+    """n correspondences of one rigid motion (0.3 px noise) with a fraction of wrong image points."""
+    u, v, z = rng.uniform(0, 1241, n), rng.uniform(0, 376, n), rng.uniform(4, 45, n)
+    P = np.stack([(u - K[0, 2]) / K[0, 0] * z, (v - K[1, 2]) / K[1, 1] * z, z], 1)
+    w = np.array([0.004, -0.006, 0.003])
+    th = np.linalg.norm(w)
+    k = w / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    Q = P @ R.T + np.array([0.02, -0.01, -0.6])
+    q = np.stack([K[0, 0] * Q[:, 0] / Q[:, 2] + K[0, 2], K[1, 1] * Q[:, 1] / Q[:, 2] + K[1, 2]], 1) + rng.normal(0, 0.3, (n, 2))
+    bad = rng.random(n) < outliers
+    q[bad] = np.stack([rng.uniform(0, 1241, bad.sum()), rng.uniform(0, 376, bad.sum())], 1)
+    return P.astype(np.float32), q.astype(np.float32)
+
+
+def test_score_tiles_ragged_counts_and_pruning_is_exact(orc):
+    """The FFMA2 score kernel reads 1024-point tiles in pairs of points: counts around the tile and pair boundaries
+    (0, 3, 4, odd, 1023 / 1024 / 1025, 2049, 3071) in ONE ragged batch with a capacity that is no multiple of the tile.
+    Per-hypothesis counts equal the oracle's, and the pruned run (no counts requested: hypotheses that cannot reach the
+    running best stop early, scouts launch) returns the same winner, inlier count, mask and pose as the unpruned one."""
+    import torch
+    from vo_b200 import ops, synthetic
+    K = synthetic.KITTI_K
+    rng = np.random.default_rng(11)
+    ns = [0, 3, 4, 5, 37, 1023, 1024, 1025, 2049, 3071]
+    cap, H = 3100, 160
+    X = np.zeros((len(ns), cap, 3), np.float32)
+    U = np.zeros((len(ns), cap, 2), np.float32)
+    for b, n in enumerate(ns):
+        X[b, :n], U[b, :n] = _scene(rng, n, K)
+        X[b, n:], U[b, n:] = 7.0, 100.0          # garbage past the count must never be read as a point
+    n_pts = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    hyp = ops.hypotheses(n_pts, H, 8214, 0)
+    full = ops.pnp_ransac(_gpu(X), _gpu(U), n_pts, K, hyp, 1.5, 20, 10, want_counts=True)
+    fast = ops.pnp_ransac(_gpu(X), _gpu(U), n_pts, K, hyp, 1.5, 20, 10, want_counts=False)
+    for b, n in enumerate(ns):
+        if n >= 4:
+            o = orc.pnp_ransac(X[b, :n], U[b, :n], K, hyp[b].cpu().numpy())
+            assert np.array_equal(full.hyp_counts[b].cpu().numpy(), o["counts"]), n
+            assert np.array_equal(full.mask[b, :n].cpu().numpy(), o["mask"]), n
+        else:
+            assert int(full.status[b].item()) == ops._lib.VO_ST_TOO_FEW_POINTS
+    for name in ("n_inl", "best_h", "status", "mask", "T_rel", "rt"):
+        assert torch.equal(getattr(full, name), getattr(fast, name)), name
