@@ -60,8 +60,13 @@ struct TcCfg {
     static constexpr int TMEM_A = F16 ? 416 : (SINGLE ? 384 : 256);  // first column of A_hi (A_lo follows in 3xTF32)
     static constexpr int TMEM_EXT = F16 ? 384 : 320;              // single pass only
     static constexpr int OFF_SCOL = STAGES * BLOCK_BYTES;         // [2 groups][2 bufs][4 quarters][BN] x (float, u32)
-    static constexpr int OFF_BAR = OFF_SCOL + (F16 ? 0 : 2 * 2 * 4 * BN * 8);  // the fp16 pass has no column side
+    // column scratch, (float, u32) per entry: [2 groups][2 bufs][4 quarters][BN]; the all-warp epilogue of the split fp16
+    // pass needs [2 bufs][4][BN]; the fp16 single pass has no column side
+    static constexpr int SCOL_N = F16 ? 0 : (PASSES == 48 ? 2 * 4 * BN : 2 * 2 * 4 * BN);
+    static constexpr int OFF_ROW2 = OFF_SCOL + SCOL_N * 8;
+    static constexpr int OFF_BAR = OFF_ROW2 + (H16 ? 4 * TC_BM * 4 : 0);        // [4 column quarters][128 rows] shared second-bests
     static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;       // barriers + alignment slack
+    static_assert(SMEM_BYTES <= 232448, "dynamic shared memory of one CTA (227 KB)");
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     // kind::f16: D = f32 [4,6) = 1, A = B = fp16 (format 0)
     static constexpr uint32_t IDESC16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -186,6 +191,20 @@ __device__ __forceinline__ void row_insert(float s, int col, float &s1, float &s
     s1 = gt1 ? s : s1;
 }
 
+// Filter threshold of a row.  The four threads that share a row (one per column quarter) publish their running
+// second-best after every tile; `tau` = the best of the other three is a lower bound of the row's final second-best,
+// so a column scoring below it can never reach the row's top-2, whichever thread owns it (two columns scoring >= tau
+// exist).  A column scoring exactly tau must still enter (it may win a tie on the column index), hence the largest
+// float below tau.  Sharing makes a thread filter as if it had seen four times as many columns: the warp-wide slow
+// path (expected ~ 256/k per 4 columns after k columns) is hit ~ 60 % less often.  Stale reads are harmless (the
+// published values only grow) and no barrier is involved.
+__device__ __forceinline__ float row_threshold(float s2_own, float tau) {
+    uint32_t tb = __float_as_uint(tau);
+    tb = (tau > 0.f) ? tb - 1u : ((tau < 0.f) ? tb + 1u : 0x80000001u);
+    const float below = (tau == -INFINITY) ? tau : __uint_as_float(tb);
+    return fmaxf(s2_own, below);
+}
+
 // ---------------------------------------------------------------- epilogue: 8 accumulator columns
 // v[] = 8 accumulator columns of this thread's row.  Updates the row top-2 and leaves, per column, the warp's
 // maximum and the ballot of the lanes that attain it (both warp-uniform; lane 0 stores them as two vectors).
@@ -194,7 +213,7 @@ __device__ __forceinline__ void row_insert(float s, int col, float &s1, float &s
 template <int METRIC, bool MASK_COLS, bool ROW_MASK, bool COLS, bool EXT, bool SCALED = false>
 __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M, bool row_ok, float na,
                                            const float *__restrict__ cn, bool cn_vec, int lane, float *cv_out,
-                                           uint32_t *cb_out, float &s1, float &s2, int32_t &i1, int32_t &i2) {
+                                           uint32_t *cb_out, float &s1, float &s2, int32_t &i1, int32_t &i2, float &thr) {
     float sc[8], wm[8], nb[8];
     uint32_t bal[8];
     if (METRIC == VO_METRIC_L2 && !EXT) {
@@ -243,9 +262,10 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
 #pragma unroll
     for (int j0 = 0; j0 < 8; j0 += 4) {
         const float m4 = fmaxf(fmaxf(sc[j0], sc[j0 + 1]), fmaxf(sc[j0 + 2], sc[j0 + 3]));
-        if ((!ROW_MASK || row_ok) && m4 > s2) {
+        if ((!ROW_MASK || row_ok) && m4 > thr) {  // thr >= s2: see row_threshold()
 #pragma unroll
             for (int j = 0; j < 4; ++j) row_insert(sc[j0 + j], cbase + j0 + j, s1, s2, i1, i2);
+            thr = fmaxf(thr, s2);
         }
     }
 }
@@ -295,7 +315,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     constexpr int ITEMS = THREE ? 2 * NKB : (EXT ? NKB + 1 : NKB);               // B boxes streamed per tile
     const uint32_t s_b = base;
     float *scol_v = reinterpret_cast<float *>(smem + Cfg::OFF_SCOL);                      // [2 groups][2 bufs][4][BN]
-    uint32_t *scol_b = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_SCOL + 2 * 2 * 4 * BN * 4);
+    uint32_t *scol_b = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_SCOL + Cfg::SCOL_N * 4);
     const uint32_t s_bar = base + Cfg::OFF_BAR;
     // barrier slots (8 B each): full[S] empty[S] a_full tmem_full[2] tmem_empty[2]; then the TMEM base word
     auto bar_full = [&](int s) { return s_bar + 8u * s; };
@@ -304,6 +324,8 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     auto bar_tfull = [&](int g) { return s_bar + 8u * (2 * STAGES + 1 + g); };
     auto bar_tempty = [&](int g) { return s_bar + 8u * (2 * STAGES + 3 + g); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Cfg::OFF_BAR + 8 * (2 * STAGES + 5));
+    volatile float *srow2 = reinterpret_cast<volatile float *>(smem + Cfg::OFF_ROW2);  // fp16 passes: row_threshold()
+    if (Cfg::H16 && threadIdx.x < 4 * TC_BM) srow2[threadIdx.x] = -INFINITY;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -457,8 +479,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar_a);
         }
-        float s1 = -INFINITY, s2 = -INFINITY;
+        float s1 = -INFINITY, s2 = -INFINITY, thr = -INFINITY;
         int32_t i1 = -1, i2 = -1;
+        const int rr = q * 32 + lane;  // row inside the CTA: index into the shared second-bests
         const float na = (METRIC == VO_METRIC_L2 && row_ok) ? row_norm[(size_t)b * n_stride + row] : 0.0f;
         for (int lt = 0; lt < n_tiles; ++lt) {
             const int buf = lt & 1;
@@ -473,6 +496,11 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             tc_ld16_issue(taddr, ra);
             tc_ld16_issue(taddr + 16, rb);
             tc_ld16_issue(taddr + 32, rc);
+            {  // the other three column quarters' second-bests of this row (read while the TMEM loads fly)
+                const float tau = fmaxf(fmaxf(srow2[((cq + 1) & 3) * TC_BM + rr], srow2[((cq + 2) & 3) * TC_BM + rr]),
+                                        srow2[((cq + 3) & 3) * TC_BM + rr]);
+                thr = fmaxf(thr, row_threshold(s2, tau));
+            }
             tc_ld_wait16(ra);
             tc_ld_wait16(rb);
             tc_ld_wait16(rc);
@@ -485,7 +513,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         float v[8];                                                                                                        \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[8 * u + i]);                              \
         epi_group8<METRIC, MASKC, MASKR, false, EXT>(v, col0 + (J0) + 8 * u, M, row_ok, na, nullptr, false, lane, nullptr, \
-                                                     nullptr, s1, s2, i1, i2);                                             \
+                                                     nullptr, s1, s2, i1, i2, thr);                                             \
     }
             if (full_tile && !partial_rows) {
                 TC_FOLD16(ra, 0, false, false) TC_FOLD16(rb, 16, false, false) TC_FOLD16(rc, 32, false, false)
@@ -493,6 +521,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                 TC_FOLD16(ra, 0, true, true) TC_FOLD16(rb, 16, true, true) TC_FOLD16(rc, 32, true, true)
             }
 #undef TC_FOLD16
+            srow2[cq * TC_BM + rr] = s2;
             if (dbg_on) dbg_acc[2] += clock64() - _tm0;
         }
         if (dbg_on && q == 0 && lane == 0 && cq < 2) { dbg[5 + cq] = dbg_acc[0]; dbg[7 + cq] = dbg_acc[1]; dbg[9 + cq] = dbg_acc[2]; }
@@ -535,8 +564,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar_a);
         }
-        float s1 = -INFINITY, s2 = -INFINITY;
+        float s1 = -INFINITY, s2 = -INFINITY, thr = -INFINITY;
         int32_t i1 = -1, i2 = -1;
+        const int rr = q * 32 + lane;  // row inside the CTA: index into the shared second-bests
         const float *cn = (METRIC == VO_METRIC_L2) ? col_norm + (size_t)b * m_stride : nullptr;
         const float na = (METRIC == VO_METRIC_L2 && row_ok) ? row_norm[(size_t)b * n_stride + row] : 0.0f;
         const bool cn_vec = (METRIC == VO_METRIC_L2) && ((reinterpret_cast<uintptr_t>(cn) & 15u) == 0);
@@ -557,6 +587,11 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             uint32_t ra[16], rb[16];
             tc_ld16_issue(taddr, ra);
             tc_ld16_issue(taddr + 16, rb);
+            {  // the other three column quarters' second-bests of this row (read while the TMEM loads fly)
+                const float tau = fmaxf(fmaxf(srow2[((cq + 1) & 3) * TC_BM + rr], srow2[((cq + 2) & 3) * TC_BM + rr]),
+                                        srow2[((cq + 3) & 3) * TC_BM + rr]);
+                thr = fmaxf(thr, row_threshold(s2, tau));
+            }
             tc_ld_wait16(ra);
             tc_ld_wait16(rb);
             tc_fence_before();  // the tile slice is in registers: hand the accumulator back before folding
@@ -568,7 +603,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         float v[8];                                                                                                        \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[8 * u + i]);                              \
         epi_group8<METRIC, MASKC, MASKR, COLS, false, true>(v, col0 + (J0) + 8 * u, M, row_ok, na, cn, cn_vec, lane,       \
-                                                            my_cv + (J0) + 8 * u, my_cb + (J0) + 8 * u, s1, s2, i1, i2);   \
+                                                            my_cv + (J0) + 8 * u, my_cb + (J0) + 8 * u, s1, s2, i1, i2, thr);   \
     }
             if (full_tile && !partial_rows) {
                 TC_FOLD16(ra, 0, false, false) TC_FOLD16(rb, 16, false, false)
@@ -576,6 +611,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                 TC_FOLD16(ra, 0, true, true) TC_FOLD16(rb, 16, true, true)
             }
 #undef TC_FOLD16
+            srow2[cq * TC_BM + rr] = s2;
             if (COLS) {
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + cq) : "memory");  // the four lane quarters of this column quarter
                 if (q == 0) {  // one column per lane
@@ -651,6 +687,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         }
 
         float s1 = -INFINITY, s2 = -INFINITY;  // running top-2 of -|a-b|^2 or a.b over this warp's columns
+        float thr = -INFINITY;                 // filter threshold (= s2 here: no sharing between the two groups)
         int32_t i1 = -1, i2 = -1;
         float *grp_cv = scol_v + g * 2 * 4 * BN;
         uint32_t *grp_cb = scol_b + g * 2 * 4 * BN;
@@ -684,7 +721,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         float v[8];                                                                                                        \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(cur[i]);                                      \
         epi_group8<METRIC, MASKC, MASKR, COLS, EXT, SCALED>(v, col0 + j0, M, row_ok, na, cn, cn_vec, lane, my_cv + j0, my_cb + j0, \
-                                                    s1, s2, i1, i2);                                                       \
+                                                    s1, s2, i1, i2, thr);                                                       \
     }
                 if (full_tile && !partial_rows) { TC_EPI_LOOP(false, false) } else { TC_EPI_LOOP(true, true) }
 #undef TC_EPI_LOOP
@@ -699,7 +736,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         float v[8];                                                                                                        \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(cur[i]);                                      \
         epi_group8<METRIC, MASKC, MASKR, COLS, EXT>(v, col0 + j0, M, row_ok, na, cn, cn_vec, lane, my_cv + j0, my_cb + j0, \
-                                                    s1, s2, i1, i2);                                                       \
+                                                    s1, s2, i1, i2, thr);                                                       \
         if (more) {                                                                                                        \
             tc_ld_wait8(nxt);                                                                                              \
             _Pragma("unroll") for (int i = 0; i < 8; ++i) cur[i] = nxt[i];                                                 \
@@ -717,7 +754,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         float v[8];                                                                                                        \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[8 * u + i]);                              \
         epi_group8<METRIC, MASKC, MASKR, COLS, EXT>(v, col0 + (J0) + 8 * u, M, row_ok, na, cn, cn_vec, lane,               \
-                                                    my_cv + (J0) + 8 * u, my_cb + (J0) + 8 * u, s1, s2, i1, i2);           \
+                                                    my_cv + (J0) + 8 * u, my_cb + (J0) + 8 * u, s1, s2, i1, i2, thr);           \
     }
 #define TC_EPI_LOOP(MASKC, MASKR)                                                                                          \
     _Pragma("unroll 1") for (int j0 = HALF * h; j0 < HALF * h + HALF; j0 += 32) {                                          \
