@@ -83,3 +83,14 @@ def test_all_gather_and_chain_world_size_2_gloo(tmp_path):
     T = _random_poses(12, seed=5)
     ok = np.ones(12, bool); ok[[2, 7]] = False
     assert np.allclose(a, seq.chain_poses(T, ok), atol=1e-12)
+
+
+def test_chunk_schedule_covers_all_pairs_and_tapers_the_tail():
+    from vo_b200.sequence import chunk_schedule
+    for B, chunk in [(1000, 125), (250, 125), (100, 125), (8, 4), (1, 1), (32, 16), (1000, 1000), (7, 3), (5, 2), (40, 5)]:
+        sch = chunk_schedule(B, chunk)
+        assert sch[0][0] == 0 and sch[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(sch, sch[1:]))                      # contiguous, in order
+        assert all(0 < hi - lo <= chunk for lo, hi in sch)                          # fits the staging buffers
+    sizes = [hi - lo for lo, hi in chunk_schedule(1000, 125)]
+    assert sizes[-2:] == [62, 31] and max(sizes[:-2]) - min(sizes[:-2]) <= 1       # short drain, equal body
