@@ -149,13 +149,14 @@ def test_score_tiles_ragged_counts_and_pruning_is_exact(orc):
     """The FFMA2 score kernel reads 1024-point tiles in pairs of points: counts around the tile and pair boundaries
     (0, 3, 4, odd, 1023 / 1024 / 1025, 2049, 3071) in ONE ragged batch with a capacity that is no multiple of the tile.
     Per-hypothesis counts equal the oracle's, and the pruned run (no counts requested: hypotheses that cannot reach the
-    running best stop early, scouts launch) returns the same winner, inlier count, mask and pose as the unpruned one."""
+    running best stop early; hypotheses scored in the order of their tile-0 counts) returns the same winner, inlier
+    count, mask and pose as the unpruned one.  A second, 4-tile capacity covers the unsorted pruned path."""
     import torch
     from vo_b200 import ops, synthetic
     K = synthetic.KITTI_K
     rng = np.random.default_rng(11)
-    ns = [0, 3, 4, 5, 37, 1023, 1024, 1025, 2049, 3071]
-    cap, H = 3100, 160
+    ns = [0, 3, 4, 5, 37, 1023, 1024, 1025, 2049, 3071, 6145]
+    cap, H = 6200, 160      # 7 tiles: the pruned run takes the sorted path (tile-0 pass, hypothesis sort, carried counts)
     X = np.zeros((len(ns), cap, 3), np.float32)
     U = np.zeros((len(ns), cap, 2), np.float32)
     for b, n in enumerate(ns):
@@ -174,3 +175,12 @@ def test_score_tiles_ragged_counts_and_pruning_is_exact(orc):
             assert int(full.status[b].item()) == ops._lib.VO_ST_TOO_FEW_POINTS
     for name in ("n_inl", "best_h", "status", "mask", "T_rel", "rt"):
         assert torch.equal(getattr(full, name), getattr(fast, name)), name
+    keep = [i for i, n in enumerate(ns) if n <= 3100]
+    Xs, Us = np.ascontiguousarray(X[keep, :3100]), np.ascontiguousarray(U[keep, :3100])
+    n_s = n_pts[keep].contiguous()
+    hyp_s = hyp[keep].contiguous()
+    full_s = ops.pnp_ransac(_gpu(Xs), _gpu(Us), n_s, K, hyp_s, 1.5, 20, 10, want_counts=True)
+    fast_s = ops.pnp_ransac(_gpu(Xs), _gpu(Us), n_s, K, hyp_s, 1.5, 20, 10, want_counts=False)
+    for name in ("n_inl", "best_h", "status", "mask", "T_rel", "rt"):
+        assert torch.equal(getattr(full_s, name), getattr(fast_s, name)), name
+        assert torch.equal(getattr(full_s, name), getattr(full, name)[keep][..., :3100] if name == "mask" else getattr(full, name)[keep]), name

@@ -172,18 +172,38 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
 // host scores the first 32 hypotheses in a launch of their own so that the bulk starts with a bound that is already
 // close to the final one (with ~60 % inliers a fifth of the random minimal samples is all-inlier).  Disabled when the
 // caller wants every hypothesis' count.
-template <int SC_HPW, int MIN_CTAS>  // hypotheses per warp, resident CTAs per SM the register budget must allow
+//
+// Order of the hypotheses.  With pruning, a CTA lives as long as its longest-lived hypothesis, and a fifth of random
+// minimal samples is good: in index order practically every CTA keeps a few hypotheses to the very end while most of
+// its warps idle at the tile barrier (ncu: barrier = top stall, FMA pipe 56 %).  So the pipeline first scores ALL
+// hypotheses on tile 0 only (`t_limit` = 1, counts to `hyp_counts`, no key), sorts them by that count
+// (`hyp_sort_kernel`), and scores the rest in sorted order (`perm`, counts carried over through `init`, tiles from
+// `t_begin` = 1): CTAs are homogeneous — the good ones run dense to the end, the others leave together and free their
+// SM slots.  The scouts are the 32 best-looking hypotheses, so the bound is near-final from the start.  The
+// processing order changes nothing in the result: keys carry the original hypothesis index.
+struct ScoreOrder {
+    const int32_t *perm;   // [B][H] slot -> hypothesis, or null (identity)
+    const int32_t *init;   // [B][H] counts of the tiles before t_begin, by hypothesis, or null
+    int t_begin, t_limit;  // tiles [t_begin, min(T, t_limit)) are scored
+    int write_key;         // 0: partial pass, counts only
+};
+
+// ORDERED = false compiles the order away (identity, all tiles, keys written): the unpruned / short-run kernel.
+template <int SC_HPW, int MIN_CTAS, bool ORDERED>  // hypotheses per warp, resident CTAs per SM the register budget must allow
 __global__ void __launch_bounds__(SC_WARPS * 32, MIN_CTAS)
 score_kernel(const float *__restrict__ staged, int tiles, const int32_t *__restrict__ n_pts, int cap,
              const float *__restrict__ poses, int H, int h_begin, int h_end, IntrF k, float thr,
-             unsigned long long *__restrict__ bestkey, unsigned int *__restrict__ lower, int32_t *__restrict__ hyp_counts) {
+             unsigned long long *__restrict__ bestkey, unsigned int *__restrict__ lower, int32_t *__restrict__ hyp_counts,
+             ScoreOrder ord_in) {
+    const ScoreOrder ord = ORDERED ? ord_in : ScoreOrder{nullptr, nullptr, 0, 0x7fffffff, 1};
     __shared__ __align__(128) float sbuf[2][SC_TILE_FLOATS];
     __shared__ __align__(8) unsigned long long sbar[2];
     const int b = blockIdx.y;
     const int n = min(n_pts[b], cap);
-    const int T = (n + SC_TILE - 1) / SC_TILE;
+    const int T = min((n + SC_TILE - 1) / SC_TILE, ord.t_limit);
+    const int t0 = min(ord.t_begin, T);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h0 = h_begin + (blockIdx.x * SC_WARPS + warp) * SC_HPW;  // this launch scores hypotheses [h_begin, h_end)
+    const int h0 = h_begin + (blockIdx.x * SC_WARPS + warp) * SC_HPW;  // this launch scores SLOTS [h_begin, h_end)
     const bool prune = hyp_counts == nullptr;
     const float *tiles_b = staged + (size_t)b * tiles * SC_TILE_FLOATS;
     const uint32_t bar0 = tc::smem_u32(&sbar[0]), buf0 = tc::smem_u32(&sbuf[0][0]);
@@ -194,15 +214,18 @@ score_kernel(const float *__restrict__ staged, int tiles, const int32_t *__restr
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2 && s < T; ++s)
-            bulk_load(buf0 + s * SC_TILE_BYTES, tiles_b + (size_t)s * SC_TILE_FLOATS, SC_TILE_BYTES, bar0 + 8 * s);
+        for (int s = 0; s < 2 && t0 + s < T; ++s)
+            bulk_load(buf0 + s * SC_TILE_BYTES, tiles_b + (size_t)(t0 + s) * SC_TILE_FLOATS, SC_TILE_BYTES, bar0 + 8 * s);
     }
     // scaled poses, duplicated into both halves; rows 0 and 1 negated (exact), so that a = z*(u-cx) + (-x) is one FFMA2
     f32x2 M[SC_HPW][12];
+    int count[SC_HPW];
 #pragma unroll
     for (int q = 0; q < SC_HPW; ++q) {
         PoseF p;
-        const int h = min(h0 + q, H - 1);
+        const int slot = min(h0 + q, H - 1);
+        const int h = ord.perm ? ord.perm[(size_t)b * H + slot] : slot;
+        count[q] = (ord.init && lane == 0) ? ord.init[(size_t)b * H + h] : 0;
         const float *src = poses + ((size_t)b * H + h) * 12;
 #pragma unroll
         for (int j = 0; j < 9; ++j) p.r[j] = __ldg(src + j);
@@ -217,16 +240,13 @@ score_kernel(const float *__restrict__ staged, int tiles, const int32_t *__restr
         }
     }
     const f32x2 THR = pk2(thr, thr);
-    int count[SC_HPW];
-#pragma unroll
-    for (int q = 0; q < SC_HPW; ++q) count[q] = 0;
     unsigned alive = 0;  // warp-uniform mask of hypotheses still scored
 #pragma unroll
     for (int q = 0; q < SC_HPW; ++q) alive |= (h0 + q < h_end) ? (1u << q) : 0u;
     constexpr unsigned ALL = (1u << SC_HPW) - 1u;
 
-    for (int t = 0; t < T; ++t) {
-        const int s = t & 1;
+    for (int t = t0; t < T; ++t) {
+        const int s = (t - t0) & 1;
         const int p0 = t * SC_TILE;
         const int cnt = min(SC_TILE, n - p0);
         const int np = (cnt + 1) >> 1;
@@ -234,7 +254,7 @@ score_kernel(const float *__restrict__ staged, int tiles, const int32_t *__restr
         // value only prunes later, never wrongly
         unsigned int lb = 0;
         if (prune && t + 1 < T) lb = *reinterpret_cast<volatile unsigned int *>(&lower[b]);
-        tc::mbar_wait(bar0 + 8 * s, (uint32_t)(t >> 1) & 1u);
+        tc::mbar_wait(bar0 + 8 * s, (uint32_t)((t - t0) >> 1) & 1u);
         const ulonglong2 *sA = reinterpret_cast<const ulonglong2 *>(&sbuf[s][0]);             // {X0 X1}, {Y0 Y1}
         const ulonglong2 *sB = reinterpret_cast<const ulonglong2 *>(&sbuf[s][2 * SC_TILE]);  // {Z0 Z1}, {uc0 uc1}
         const f32x2 *sC = reinterpret_cast<const f32x2 *>(&sbuf[s][4 * SC_TILE]);            // {vc0 vc1}
@@ -273,7 +293,7 @@ score_kernel(const float *__restrict__ staged, int tiles, const int32_t *__restr
             // every warp is done with slot s; if no hypothesis of the CTA is left, drain the copy in flight and stop
             const int any = __syncthreads_or(alive != 0u);
             if (!any) {
-                if (threadIdx.x == 0) tc::mbar_wait(bar0 + 8 * (s ^ 1), (uint32_t)((t + 1) >> 1) & 1u);
+                if (threadIdx.x == 0) tc::mbar_wait(bar0 + 8 * (s ^ 1), (uint32_t)((t + 1 - t0) >> 1) & 1u);
                 break;
             }
             if (threadIdx.x == 0 && t + 2 < T)
@@ -282,19 +302,60 @@ score_kernel(const float *__restrict__ staged, int tiles, const int32_t *__restr
     }
 #pragma unroll
     for (int q = 0; q < SC_HPW; ++q) {
-        const int h = h0 + q;
         if (alive & (1u << q)) {
             const int c = __reduce_add_sync(0xffffffffu, count[q]);
             if (lane == 0) {
+                const int h = ord.perm ? ord.perm[(size_t)b * H + h0 + q] : h0 + q;
                 if (hyp_counts) hyp_counts[(size_t)b * H + h] = c;
-                // larger count wins; ties -> lowest hypothesis index
-                const unsigned long long key =
-                    ((unsigned long long)(uint32_t)c << 32) | (unsigned long long)(0xffffffffu - (uint32_t)h);
-                atomicMax(&bestkey[b], key);
-                if (prune) atomicMax(&lower[b], (unsigned int)c);
+                if (ord.write_key) {  // larger count wins; ties -> lowest hypothesis index
+                    const unsigned long long key =
+                        ((unsigned long long)(uint32_t)c << 32) | (unsigned long long)(0xffffffffu - (uint32_t)h);
+                    atomicMax(&bestkey[b], key);
+                }
+                if (prune || !ord.write_key) atomicMax(&lower[b], (unsigned int)c);  // a partial count is a lower bound too
             }
         }
     }
+}
+
+// Orders the hypotheses of every pair by their tile-0 inlier count, descending (counting sort over 0..SC_TILE; the order
+// inside a bin is whatever the atomics give — it only affects scheduling).  One CTA per pair.
+__global__ void __launch_bounds__(1024)
+hyp_sort_kernel(const int32_t *__restrict__ c0, int H, int32_t *__restrict__ perm) {
+    __shared__ int hist[SC_TILE + 1];   // hist[c] = hypotheses with count c, then the first slot of bin c
+    __shared__ int wsum[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t *c = c0 + (size_t)b * H;
+    for (int i = tid; i <= SC_TILE; i += 1024) hist[i] = 0;
+    __syncthreads();
+    for (int h = tid; h < H; h += 1024) atomicAdd(&hist[min(max(c[h], 0), SC_TILE)], 1);
+    __syncthreads();
+    // exclusive scan in descending count order: thread tid owns bin SC_TILE - tid (bin 0 comes last)
+    const int mine = hist[SC_TILE - tid];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        wsum[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    const int excl = wsum[warp] + incl - mine;
+    __syncthreads();
+    hist[SC_TILE - tid] = excl;
+    if (tid == 1023) hist[0] = excl + mine;  // bin 0 starts after bins SC_TILE..1
+    __syncthreads();
+    for (int h = tid; h < H; h += 1024) perm[(size_t)b * H + atomicAdd(&hist[min(max(c[h], 0), SC_TILE)], 1)] = h;
 }
 
 // ---------------------------------------------------------------- winner mask + refit + outputs
@@ -597,8 +658,16 @@ int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_
     int rc;
     const int tiles = ceil_div(cap, SC_TILE);
     const size_t pose_floats = ((size_t)12 * B * H + 31) & ~(size_t)31;  // staged tiles start 128 B aligned
-    if ((rc = ws_get(ctx, WS_POSES, sizeof(float) * (pose_floats + (size_t)B * tiles * SC_TILE_FLOATS), (void **)&poses))) return rc;
+    const size_t staged_floats = (size_t)B * tiles * SC_TILE_FLOATS;
+    // sorted scoring (pruned runs with more than one tile and enough hypotheses): tile-0 counts + permutation, [B][H] each
+    constexpr int SCOUTS = 32;
+    // (worth its two extra launches from ~6 tiles on: c2-sized runs, 4 tiles x 1024 hypotheses, measured 0.41 -> 0.42 ms)
+    const bool sorted = !hyp_counts && tiles >= 6 && H > 2 * SCOUTS;
+    if ((rc = ws_get(ctx, WS_POSES, sizeof(float) * (pose_floats + staged_floats) + (sorted ? sizeof(int32_t) * 2 * (size_t)B * H : 0),
+                     (void **)&poses)))
+        return rc;
     float *staged = poses + pose_floats;
+    int32_t *c0 = reinterpret_cast<int32_t *>(staged + staged_floats), *perm = c0 + (size_t)B * H;
     if ((rc = ws_get(ctx, WS_BESTKEY, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)B, (void **)&bestkey))) return rc;
     unsigned int *lower = reinterpret_cast<unsigned int *>(bestkey + B);  // running lower bound of the best count (pruning)
     VO_CUDA(cudaMemsetAsync(bestkey, 0, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)B, st));
@@ -614,15 +683,36 @@ int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_
         score_prep_kernel<<<dim3(tiles, B), 256, 0, st>>>(xyz, uv, n_pts, cap, kf, staged);
         VO_LAUNCH_CHECK(ctx);
     }
-    constexpr int SCOUTS = 32;
-    const int h_first = (hyp_counts || H <= 2 * SCOUTS) ? 0 : SCOUTS;  // scouts: the first hypotheses of every pair, scored first
     // 4 hypotheses per warp, 3 CTAs per SM.  Measured (B200, 32 pairs x 16 384 hypotheses x 13.7 k points, tools/score_bench.py):
     // 2 / 4 / 8 hypotheses per warp at 2-3 CTAs per SM: 2.73 / 2.52 / 2.70 ms pruned, 4.26 / 4.07 / 4.02 ms unpruned.
-    constexpr int HPW = 4, CTAS = 3;
-    for (int part = h_first ? 0 : 1; part < 2; ++part) {
-        const int hb = part ? h_first : 0, he = part ? H : h_first;
-        score_kernel<HPW, CTAS><<<dim3(ceil_div(he - hb, SC_WARPS * HPW), B), SC_WARPS * 32, 0, st>>>(
-            staged, tiles, n_pts, cap, poses, H, hb, he, kf, thr_px, bestkey, lower, hyp_counts);
+    constexpr int HPW = 4, CTAS = 3, PER_CTA = SC_WARPS * HPW;
+    const int no_limit = 0x7fffffff;
+    auto launch = [&](int hb, int he, int32_t *counts, const ScoreOrder &ord) {
+        if (ord.perm || ord.t_limit != no_limit)
+            score_kernel<HPW, CTAS, true><<<dim3(ceil_div(he - hb, PER_CTA), B), SC_WARPS * 32, 0, st>>>(
+                staged, tiles, n_pts, cap, poses, H, hb, he, kf, thr_px, bestkey, lower, counts, ord);
+        else
+            score_kernel<HPW, CTAS, false><<<dim3(ceil_div(he - hb, PER_CTA), B), SC_WARPS * 32, 0, st>>>(
+                staged, tiles, n_pts, cap, poses, H, hb, he, kf, thr_px, bestkey, lower, counts, ord);
+    };
+    if (sorted) {
+        launch(0, H, c0, ScoreOrder{nullptr, nullptr, 0, 1, 0});  // every hypothesis on tile 0
+        VO_LAUNCH_CHECK(ctx);
+        hyp_sort_kernel<<<B, 1024, 0, st>>>(c0, H, perm);
+        VO_LAUNCH_CHECK(ctx);
+        const ScoreOrder rest{perm, c0, 1, no_limit, 1};
+        launch(0, SCOUTS, nullptr, rest);                         // scouts: the 32 best-looking hypotheses, scored to the end
+        VO_LAUNCH_CHECK(ctx);
+        launch(SCOUTS, H, nullptr, rest);
+        VO_LAUNCH_CHECK(ctx);
+    } else {
+        const ScoreOrder all{nullptr, nullptr, 0, no_limit, 1};
+        const int h_first = (hyp_counts || H <= 2 * SCOUTS) ? 0 : SCOUTS;  // scouts: the first hypotheses of every pair
+        if (h_first) {
+            launch(0, h_first, hyp_counts, all);
+            VO_LAUNCH_CHECK(ctx);
+        }
+        launch(h_first, H, hyp_counts, all);
         VO_LAUNCH_CHECK(ctx);
     }
     VO_PROF(ctx, st, VO_STAGE_REFIT);
