@@ -134,7 +134,7 @@ extern "C" void vo_destroy(vo_ctx *ctx) {
         for (cudaEvent_t e : p->pool) cudaEventDestroy(e);
         delete p;
     }
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < vo::WS_SLOTS; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     free(ctx);
 }

@@ -85,8 +85,8 @@ struct vo_ctx {
     int sm_count;
     long long launches;
     // growable workspace regions (device)
-    void *ws[8];
-    size_t ws_bytes[8];
+    void *ws[9];
+    size_t ws_bytes[9];
     int tc_ready;  // tcgen05 path initialised (driver entry point resolved)
     void *encode_tiled;  // PFN_cuTensorMapEncodeTiled
     void *prof;          // vo::Profiler* when profiling was ever enabled
@@ -94,7 +94,7 @@ struct vo_ctx {
 };
 
 namespace vo {
-enum WsSlot { WS_ROWPART = 0, WS_COLKEY = 1, WS_POSES = 2, WS_BESTKEY = 3, WS_SPLIT_A = 4, WS_SPLIT_B = 5, WS_PIPE = 6, WS_NORMS = 7 };
+enum WsSlot { WS_ROWPART = 0, WS_COLKEY = 1, WS_POSES = 2, WS_BESTKEY = 3, WS_SPLIT_A = 4, WS_SPLIT_B = 5, WS_PIPE = 6, WS_NORMS = 7, WS_FIN = 8, WS_SLOTS = 9 };
 // Returns a device buffer of at least `bytes` for `slot`, reallocating (stream-ordered
 // free of the old block) only when it must grow.
 int ws_get(vo_ctx *ctx, int slot, size_t bytes, void **out);

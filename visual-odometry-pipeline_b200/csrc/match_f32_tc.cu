@@ -303,6 +303,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     // optional cycle accounting of CTA (0,0,0) for bring-up / tuning (dbg == nullptr in production)
     const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     const long long t_kernel0 = dbg_on ? clock64() : 0;
+    // VO_TC_TRACE: every CTA leaves (clock64 at entry, clock64 at exit, SM id) behind: idle time between CTAs of one SM
+    const bool trace_on = dbg != nullptr && dbg[15] == 1;
+    const long long t_trace0 = (trace_on && threadIdx.x == 0) ? clock64() : 0;
 #define TC_DBG_BEGIN() const long long _t0 = dbg_on ? clock64() : 0
 #define TC_DBG_END(slot) do { if (dbg_on) dbg_acc[slot] += clock64() - _t0; } while (0)
     long long dbg_acc[4] = {0, 0, 0, 0};
@@ -822,6 +825,12 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
     }
+    if (trace_on && threadIdx.x == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *t = dbg + 16 + 3 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+        t[0] = t_trace0; t[1] = clock64(); t[2] = smid;
+    }
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -853,17 +862,52 @@ int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &
               const float *col_norm, int n_split, vo_row_partial *part, unsigned long long *colkey, cudaStream_t st) {
     auto kern = match_f32_tc_kernel<PASSES, METRIC, COLS>;
     long long *dbg = nullptr;
-    if (getenv("VO_TC_DEBUG")) {  // bring-up only: cycle accounting of CTA (0,0,0), printed after a sync
+    const size_t n_ctas = (size_t)grid.x * grid.y * grid.z;
+    const bool trace = getenv("VO_TC_TRACE") != nullptr;
+    if (getenv("VO_TC_DEBUG") || trace) {  // bring-up only: cycle accounting of CTA (0,0,0), printed after a sync
         static long long *dbg_dev = nullptr;
-        if (!dbg_dev) VO_CUDA(cudaMalloc(&dbg_dev, 16 * sizeof(long long)));
+        static size_t dbg_cap = 0;
+        const size_t need = 16 + (trace ? 3 * n_ctas : 0);
+        if (dbg_cap < need) {
+            if (dbg_dev) VO_CUDA(cudaFree(dbg_dev));
+            VO_CUDA(cudaMalloc(&dbg_dev, need * sizeof(long long)));
+            dbg_cap = need;
+        }
         VO_CUDA(cudaMemsetAsync(dbg_dev, 0, 16 * sizeof(long long), st));
+        if (trace) {
+            const long long one = 1;
+            VO_CUDA(cudaMemcpyAsync(dbg_dev + 15, &one, sizeof(one), cudaMemcpyHostToDevice, st));
+        }
         dbg = dbg_dev;
     }
     VO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<PASSES>::SMEM_BYTES));
     kern<<<grid, TC_THREADS, TcCfg<PASSES>::SMEM_BYTES, st>>>(bh, bl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm,
                                                   n_split, part, colkey, dbg);
     VO_LAUNCH_CHECK(ctx);
-    if (dbg) {
+    if (dbg && trace) {  // per SM: busy cycles of its CTAs and the idle cycles between one CTA's exit and the next one's entry
+        VO_CUDA(cudaStreamSynchronize(st));
+        long long *h = (long long *)malloc(3 * n_ctas * sizeof(long long));
+        VO_CUDA(cudaMemcpy(h, dbg + 16, 3 * n_ctas * sizeof(long long), cudaMemcpyDeviceToHost));
+        double busy = 0, gap = 0;
+        long long n_gap = 0, max_gap = 0;
+        for (int sm = 0; sm < 256; ++sm) {
+            long long last_end = -1;
+            for (;;) {  // next CTA of this SM in start order (selection scan: a few thousand CTAs)
+                long long best = -1;
+                size_t bi = 0;
+                for (size_t i = 0; i < n_ctas; ++i)
+                    if (h[3 * i + 2] == sm && h[3 * i] > last_end - (last_end < 0 ? 0 : 0) && (best < 0 || h[3 * i] < best) &&
+                        (last_end < 0 || h[3 * i] >= last_end)) { best = h[3 * i]; bi = i; }
+                if (best < 0) break;
+                if (last_end >= 0) { gap += (double)(best - last_end); ++n_gap; if (best - last_end > max_gap) max_gap = best - last_end; }
+                busy += (double)(h[3 * bi + 1] - h[3 * bi]);
+                last_end = h[3 * bi + 1];
+            }
+        }
+        fprintf(stderr, "[vo tc trace] passes=%d ctas=%zu mean_cta_cycles=%.0f mean_gap_cycles=%.0f max_gap=%lld gaps=%lld\n", PASSES,
+                n_ctas, busy / (double)n_ctas, n_gap ? gap / (double)n_gap : 0.0, max_gap, n_gap);
+        free(h);
+    } else if (dbg) {
         long long h[16];
         VO_CUDA(cudaStreamSynchronize(st));
         VO_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
