@@ -210,10 +210,15 @@ __device__ __forceinline__ float row_threshold(float s2_own, float tau) {
 // maximum and the ballot of the lanes that attain it (both warp-uniform; lane 0 stores them as two vectors).
 // ROW_MASK is set only for the last, partial row block: elsewhere every lane holds a valid row.
 // Kept small on purpose (a rolled loop calls it 8 times per tile and warp): 16 warps share the instruction cache.
-template <int METRIC, bool MASK_COLS, bool ROW_MASK, bool COLS, bool EXT, bool SCALED = false>
+// COLFILT (all-warp epilogue of the split fp16 pass): the column side runs only for 4-column groups in which some row of
+// the warp reaches `colthr`, a lower bound of what the warp's columns already hold in colkey (their best over the row
+// blocks seen so far, weakest column; >= keeps exact ties, which a lower row index may still win).  Slots of skipped
+// columns keep the zero ballot the caller wrote.  Needs row blocks of a pair that run at different times (pair_group).
+template <int METRIC, bool MASK_COLS, bool ROW_MASK, bool COLS, bool EXT, bool SCALED = false, bool COLFILT = false>
 __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M, bool row_ok, float na,
                                            const float *__restrict__ cn, bool cn_vec, int lane, float *cv_out,
-                                           uint32_t *cb_out, float &s1, float &s2, int32_t &i1, int32_t &i2, float &thr) {
+                                           uint32_t *cb_out, float &s1, float &s2, int32_t &i1, int32_t &i2, float &thr,
+                                           float colthr = 0.f, bool *col_any = nullptr) {
     float sc[8], wm[8], nb[8];
     uint32_t bal[8];
     if (METRIC == VO_METRIC_L2 && !EXT) {
@@ -242,13 +247,33 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
         }
         if (MASK_COLS) s = (col < M) ? s : -INFINITY;
         sc[j] = s;
-        if (COLS) {
+        if (COLS && !COLFILT) {
             const float sr = ROW_MASK ? (row_ok ? s : -INFINITY) : s;
             wm[j] = warp_max_f32(sr);
             bal[j] = __ballot_sync(0xffffffffu, sr == wm[j]);
         }
     }
-    if (COLS && lane == 0) {
+    if (COLS && COLFILT) {
+#pragma unroll
+        for (int j0 = 0; j0 < 8; j0 += 4) {
+            const float m4 = fmaxf(fmaxf(sc[j0], sc[j0 + 1]), fmaxf(sc[j0 + 2], sc[j0 + 3]));
+            const bool reach = (!ROW_MASK || row_ok) && m4 >= colthr;
+            if (__any_sync(0xffffffffu, reach)) {  // warp-uniform: the collectives below need every lane
+#pragma unroll
+                for (int j = j0; j < j0 + 4; ++j) {
+                    const float sr = ROW_MASK ? (row_ok ? sc[j] : -INFINITY) : sc[j];
+                    wm[j] = warp_max_f32(sr);
+                    bal[j] = __ballot_sync(0xffffffffu, sr == wm[j]);
+                }
+                if (lane == 0) {
+                    *reinterpret_cast<float4 *>(cv_out + j0) = make_float4(wm[j0], wm[j0 + 1], wm[j0 + 2], wm[j0 + 3]);
+                    *reinterpret_cast<uint4 *>(cb_out + j0) = make_uint4(bal[j0], bal[j0 + 1], bal[j0 + 2], bal[j0 + 3]);
+                }
+                *col_any = true;
+            }
+        }
+    }
+    if (COLS && !COLFILT && lane == 0) {
         *reinterpret_cast<float4 *>(cv_out) = make_float4(wm[0], wm[1], wm[2], wm[3]);
         *reinterpret_cast<float4 *>(cv_out + 4) = make_float4(wm[4], wm[5], wm[6], wm[7]);
         *reinterpret_cast<uint4 *>(cb_out) = make_uint4(bal[0], bal[1], bal[2], bal[3]);
@@ -280,15 +305,29 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                     const int32_t *__restrict__ n_ref, const int32_t *__restrict__ n_cur,
                     const float *__restrict__ row_norm, const float *__restrict__ col_norm, int n_split,
                     vo_row_partial *__restrict__ part, unsigned long long *__restrict__ colkey,
-                    long long *__restrict__ dbg) {
+                    long long *__restrict__ dbg, int pair_group) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - smem_u32(smem_raw));
 
-    const int b = blockIdx.z, split = blockIdx.y;
+    // Launch order -> work.  Hardware hands out CTAs in x, y, z order, so with the plain mapping the row blocks of one pair
+    // run together and march through the column tiles in lockstep.  The column filter of the split fp16 epilogue wants the
+    // opposite (row blocks of a pair at different times, so that later ones see the earlier ones' column bests): inside a
+    // set of `pair_group` consecutive pairs the clusters are dealt round-robin over the pairs.  The set is sized by the
+    // host to keep its current-frame descriptors in L2.  A bijection; both CTAs of a cluster stay on one pair.
+    int b = blockIdx.z, rblock = blockIdx.x;
+    if (pair_group > 1) {
+        const int clusters_x = gridDim.x / TC_CLUSTER;
+        const int set0 = (blockIdx.z / pair_group) * pair_group;
+        const int gs = min(pair_group, (int)gridDim.z - set0);
+        const int l = (blockIdx.z - set0) * clusters_x + (int)(blockIdx.x / TC_CLUSTER);
+        b = set0 + l % gs;
+        rblock = (l / gs) * TC_CLUSTER + (int)(blockIdx.x % TC_CLUSTER);
+    }
+    const int split = blockIdx.y;
     const int N = n_ref ? min(n_ref[b], n_stride) : n_stride;
     const int M = n_cur ? min(n_cur[b], m_stride) : m_stride;
-    const int row0 = blockIdx.x * TC_BM;
+    const int row0 = rblock * TC_BM;
     using Cfg = TcCfg<PASSES>;
     constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES, BLOCK_BYTES = Cfg::BLOCK_BYTES, HALF = BN / 2;
     constexpr int TMEM_A = Cfg::TMEM_A, TMEM_EXT = Cfg::TMEM_EXT;
@@ -301,7 +340,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_rank();
     // optional cycle accounting of CTA (0,0,0) for bring-up / tuning (dbg == nullptr in production)
-    const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    const bool dbg_on = dbg != nullptr && rblock == 0 && blockIdx.y == 0 && b == 0;
     const long long t_kernel0 = dbg_on ? clock64() : 0;
     // VO_TC_TRACE: every CTA leaves (clock64 at entry, clock64 at exit, SM id) behind: idle time between CTAs of one SM
     const bool trace_on = dbg != nullptr && dbg[15] == 1;
@@ -595,6 +634,19 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                                         srow2[((cq + 3) & 3) * TC_BM + rr]);
                 thr = fmaxf(thr, row_threshold(s2, tau));
             }
+            float colthr = -INFINITY;  // weakest current best among this warp's 32 columns (colkey: -score ordered << 32 | row)
+            bool col_any = false;
+            if (COLS) {
+                const int c = col0 + lane;
+                float cur_best = INFINITY;  // columns past M never lower the bound
+                if (c < M) {
+                    const unsigned long long key = *reinterpret_cast<const volatile unsigned long long *>(colkey + (size_t)b * m_stride + c);
+                    cur_best = (key == ~0ull) ? -INFINITY : -ordered_to_float((uint32_t)(key >> 32));
+                }
+                colthr = -warp_max_f32(-cur_best);
+                my_cb[lane] = 0u;  // empty ballot = "this warp has no candidate for the column"
+                __syncwarp();
+            }
             tc_ld_wait16(ra);
             tc_ld_wait16(rb);
             tc_fence_before();  // the tile slice is in registers: hand the accumulator back before folding
@@ -605,8 +657,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                                                        \
         float v[8];                                                                                                        \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[8 * u + i]);                              \
-        epi_group8<METRIC, MASKC, MASKR, COLS, false, true>(v, col0 + (J0) + 8 * u, M, row_ok, na, cn, cn_vec, lane,       \
-                                                            my_cv + (J0) + 8 * u, my_cb + (J0) + 8 * u, s1, s2, i1, i2, thr);   \
+        epi_group8<METRIC, MASKC, MASKR, COLS, false, true, true>(v, col0 + (J0) + 8 * u, M, row_ok, na, cn, cn_vec, lane, \
+                                                                  my_cv + (J0) + 8 * u, my_cb + (J0) + 8 * u, s1, s2, i1,  \
+                                                                  i2, thr, colthr, &col_any);                              \
     }
             if (full_tile && !partial_rows) {
                 TC_FOLD16(ra, 0, false, false) TC_FOLD16(rb, 16, false, false)
@@ -616,8 +669,14 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
 #undef TC_FOLD16
             srow2[cq * TC_BM + rr] = s2;
             if (COLS) {
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + cq) : "memory");  // the four lane quarters of this column quarter
-                if (q == 0) {  // one column per lane
+                // the four lane quarters of this column quarter meet; the barrier also tells whether any of them left a
+                // candidate (usually none: then there is nothing to merge)
+                uint32_t merge;
+                asm volatile("{\n\t.reg .pred p, r;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred r, %2, 128, p;\n\tselp.u32 %0, 1, 0, r;\n\t}"
+                             : "=r"(merge)
+                             : "r"((uint32_t)col_any), "r"(1 + cq)
+                             : "memory");
+                if (q == 0 && merge) {  // one column per lane
                     const int j = cq * QW + lane;
                     const int col = tcol0 + j;
                     float best = -INFINITY;
@@ -881,8 +940,12 @@ int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &
         dbg = dbg_dev;
     }
     VO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<PASSES>::SMEM_BYTES));
+    // split fp16 with the column side: interleave as many pairs as keep their current-frame descriptors (hi + lo fp16) in L2
+    int pair_group = 1;
+    if (PASSES == 48 && COLS && !getenv("VO_TC_NO_INTERLEAVE"))
+        pair_group = (int)max(1ll, min(8ll, (64ll << 20) / ((long long)m_stride * TC_D * 4)));
     kern<<<grid, TC_THREADS, TcCfg<PASSES>::SMEM_BYTES, st>>>(bh, bl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm,
-                                                  n_split, part, colkey, dbg);
+                                                  n_split, part, colkey, dbg, pair_group);
     VO_LAUNCH_CHECK(ctx);
     if (dbg && trace) {  // per SM: busy cycles of its CTAs and the idle cycles between one CTA's exit and the next one's entry
         VO_CUDA(cudaStreamSynchronize(st));
