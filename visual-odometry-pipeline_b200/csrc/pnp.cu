@@ -35,7 +35,8 @@ __global__ void hypotheses_kernel(const int32_t *__restrict__ n_pts, int B, int 
 // ---------------------------------------------------------------- minimal solves
 // One thread per (pair, hypothesis).  Writes the fp32 pose the scorer uses; an inadmissible
 // hypothesis gets a NaN pose, which can never count an inlier.
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 p3p_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ n_pts, int B,
            int cap, const int32_t *__restrict__ hyp, int H, IntrD k, float *__restrict__ poses) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -676,7 +677,9 @@ int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_
     IntrF kf{(float)K_h[0], (float)K_h[4], (float)K_h[2], (float)K_h[5]};
     const long long total = (long long)B * H;
     VO_PROF(ctx, st, VO_STAGE_P3P);
-    p3p_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(xyz, uv, n_pts, B, cap, hyp, H, kd, poses);
+    // occupancy over registers: the f64 solve is a long dependent chain, so 8 blocks per SM (64 registers, spills to L1)
+    // beat 3 blocks at 136 registers: 0.270 -> 0.204 ms per 524 k hypotheses (3 / 4 / 5 / 6 / 8: 0.270 / 0.232 / 0.219 / 0.214 / 0.204)
+    p3p_kernel<8><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(xyz, uv, n_pts, B, cap, hyp, H, kd, poses);
     VO_LAUNCH_CHECK(ctx);
     VO_PROF(ctx, st, VO_STAGE_SCORE);
     if (tiles > 0) {
