@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # GPU-box visit: full parity suite, all five workloads, front-end benches, ncu launch list + full captures of the
 # dominant kernels.  Usage (under gpurun): bash tools/gpu_round.sh [tag]
-tag="${1:-r01j}"
+tag="${1:-r01k}"
 out=gpurun_out
 mkdir -p "$out"
 timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > "$out/pytest_gpu_${tag}.log" 2>&1; echo "pytest rc=$?" >> "$out/pytest_gpu_${tag}.log"

@@ -17,8 +17,8 @@ namespace vo {
 namespace {
 
 constexpr int FIN_THREADS = 512;
-constexpr int FIN_ROUNDS = 4;                          // rows per thread
-constexpr int FIN_CHUNK = FIN_THREADS * FIN_ROUNDS;    // rows per CTA
+constexpr int FIN_ROUNDS = 4;                          // rows per thread, at most
+constexpr int FIN_CHUNK = FIN_THREADS * FIN_ROUNDS;    // rows per CTA, at most (the host picks 512 .. 2048: chunk_rows)
 
 __device__ __forceinline__ void top2_insert(uint32_t s, int32_t i, uint32_t &s1, int32_t &i1, uint32_t &s2,
                                             int32_t &i2) {
@@ -50,9 +50,10 @@ finalize_kernel(const vo_row_partial *__restrict__ part, int n_split, const unsi
                 int n_stride, int m_stride, const int32_t *__restrict__ n_ref, const int32_t *__restrict__ n_cur,
                 int kind, int mode, double param, const float *__restrict__ row_norm, int32_t *__restrict__ out_pairs,
                 float *__restrict__ out_dist, int32_t *__restrict__ chunk_count, int32_t *__restrict__ knn_row_idx,
-                float *__restrict__ knn_row_val, int32_t *__restrict__ knn_col_idx, uint8_t *__restrict__ near_tie) {
+                float *__restrict__ knn_row_val, int32_t *__restrict__ knn_col_idx, uint8_t *__restrict__ near_tie,
+                int chunk_rows) {
     const int b = blockIdx.y, chunk = blockIdx.x;
-    const int chunk0 = chunk * FIN_CHUNK;
+    const int chunk0 = chunk * chunk_rows;
     const int N = n_ref ? min(n_ref[b], n_stride) : n_stride;
     const int M = n_cur ? min(n_cur[b], m_stride) : m_stride;
     const unsigned long long *ck = colkey + (size_t)b * m_stride;
@@ -69,7 +70,7 @@ finalize_kernel(const vo_row_partial *__restrict__ part, int n_split, const unsi
     }
     __syncthreads();
 
-    for (int r0 = chunk0; r0 < min(n_stride, chunk0 + FIN_CHUNK); r0 += FIN_THREADS) {
+    for (int r0 = chunk0; r0 < min(n_stride, chunk0 + chunk_rows); r0 += FIN_THREADS) {
         const int row = r0 + threadIdx.x;
         bool keep = false;
         int32_t i1 = -1, i2 = -1;
@@ -147,15 +148,15 @@ finalize_kernel(const vo_row_partial *__restrict__ part, int n_split, const unsi
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
-finalize_pack_kernel(const int32_t *__restrict__ chunk_count, int n_chunks, int n_stride, int32_t *__restrict__ out_pairs,
-                     float *__restrict__ out_dist, int32_t *__restrict__ out_count) {
+finalize_pack_kernel(const int32_t *__restrict__ chunk_count, int n_chunks, int chunk_rows, int n_stride,
+                     int32_t *__restrict__ out_pairs, float *__restrict__ out_dist, int32_t *__restrict__ out_count) {
     const int b = blockIdx.x;
     int2 *pairs = reinterpret_cast<int2 *>(out_pairs) + (size_t)b * n_stride;
     float *dist = out_dist ? out_dist + (size_t)b * n_stride : nullptr;
     int off = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int cnt = chunk_count[b * n_chunks + c];
-        const int src = c * FIN_CHUNK;
+        const int src = c * chunk_rows;
         if (off != src && cnt > 0) {
             int2 p[FIN_ROUNDS];
             float d[FIN_ROUNDS];
@@ -183,7 +184,10 @@ int match_finalize(vo_ctx *ctx, const vo_row_partial *part, int n_split, const u
                    int n_stride, int m_stride, const int32_t *n_ref, const int32_t *n_cur, int score_kind, int mode,
                    double param, const float *row_norm, int32_t *out_pairs, float *out_dist, int32_t *out_count,
                    const vo_knn_out *knn, uint8_t *near_tie, cudaStream_t st) {
-    const int n_chunks = max(1, ceil_div(n_stride, FIN_CHUNK));
+    // 2048-row chunks when there are pairs enough to fill the GPU, 512-row chunks for the single-pair calls of the keyframe
+    // loop (one CTA per 512 rows: the merge of the per-split partials is a latency chain per row)
+    const int chunk_rows = ((long long)B * ceil_div(n_stride, FIN_CHUNK) >= ctx->sm_count) ? FIN_CHUNK : FIN_THREADS;
+    const int n_chunks = max(1, ceil_div(n_stride, chunk_rows));
     int32_t *chunk_count = out_count;  // a single chunk per pair is already the final layout: no pack launch
     int rc;
     if (n_chunks > 1 && (rc = ws_get(ctx, WS_FIN, sizeof(int32_t) * (size_t)B * n_chunks, (void **)&chunk_count))) return rc;
@@ -191,10 +195,10 @@ int match_finalize(vo_ctx *ctx, const vo_row_partial *part, int n_split, const u
     finalize_kernel<<<dim3(n_chunks, B), FIN_THREADS, 0, st>>>(part, n_split, colkey, n_stride, m_stride, n_ref, n_cur, score_kind,
                                                                mode, param, row_norm, out_pairs, out_dist, chunk_count,
                                                                knn ? knn->row_idx : nullptr, knn ? knn->row_val : nullptr,
-                                                               knn ? knn->col_idx : nullptr, near_tie);
+                                                               knn ? knn->col_idx : nullptr, near_tie, chunk_rows);
     VO_LAUNCH_CHECK(ctx);
     if (n_chunks > 1) {
-        finalize_pack_kernel<<<B, FIN_THREADS, 0, st>>>(chunk_count, n_chunks, n_stride, out_pairs, out_dist, out_count);
+        finalize_pack_kernel<<<B, FIN_THREADS, 0, st>>>(chunk_count, n_chunks, chunk_rows, n_stride, out_pairs, out_dist, out_count);
         VO_LAUNCH_CHECK(ctx);
     }
     VO_PROF(ctx, st, -1);
