@@ -959,8 +959,10 @@ int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &
                 long long best = -1;
                 size_t bi = 0;
                 for (size_t i = 0; i < n_ctas; ++i)
-                    if (h[3 * i + 2] == sm && h[3 * i] > last_end - (last_end < 0 ? 0 : 0) && (best < 0 || h[3 * i] < best) &&
-                        (last_end < 0 || h[3 * i] >= last_end)) { best = h[3 * i]; bi = i; }
+                    if (h[3 * i + 2] == sm && (last_end < 0 || h[3 * i] >= last_end) && (best < 0 || h[3 * i] < best)) {
+                        best = h[3 * i];
+                        bi = i;
+                    }
                 if (best < 0) break;
                 if (last_end >= 0) { gap += (double)(best - last_end); ++n_gap; if (best - last_end > max_gap) max_gap = best - last_end; }
                 busy += (double)(h[3 * bi + 1] - h[3 * bi]);
