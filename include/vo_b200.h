@@ -66,7 +66,8 @@ extern "C" {
 #define VO_PREC_TF32X1 1    /* tcgen05 kind::tf32, 1 MMA per k-step (exact for integer-valued SIFT) */
 #define VO_PREC_FP32_SIMT 2 /* CUDA-core FP32, direct (a-b)^2 / dot form (validation kernel)      */
 #define VO_PREC_F16X1 3     /* tcgen05 kind::f16, operands rounded to fp16 (11 significant bits, as tf32): exact for
-                               integer-valued descriptors |x| <= 2048 (SIFT: 0..255) at twice the tf32 rate; rules
+                               integer-valued 128-d descriptors with |x| <= 255 (SIFT; every partial sum < 2^24) at twice
+                               the tf32 rate; rules
                                that need the column arg-max run the TF32X1 kernel (identical results there)      */
 #define VO_PREC_F16X3 4     /* tcgen05 kind::f16, x * 2^8 = hi + lo in fp16: the 22 operand bits of TF32X3 at twice the
                                MMA rate; for |x| < 255 (unit-norm R2D2 descriptors, SIFT)                         */

@@ -30,9 +30,9 @@ def mutual_u8(ref_desc, cur_desc, norm=ops.VO_NORM_HAMMING):
 def knn_ratio_f32(ref_desc, cur_desc, ratio=0.85, tag="sift"):
     a, b = _dev(ref_desc, torch.float32), _dev(cur_desc, torch.float32)
     if tag not in _int_valued:
-        # OpenCV SIFT descriptors are integer-valued in [0,255]: one fp16 pass (11 significant bits) is then exact.
-        # Checked once.
-        _int_valued[tag] = bool(((a == a.round()) & (a.abs() <= 2047)).all().item())
+        # OpenCV SIFT descriptors are integer-valued in [0,255]: one fp16 pass (11 significant bits) is then exact, and
+        # so is the fp32 accumulation (128 x 255 x 510 < 2^24).  Checked once per run, on both frames.
+        _int_valued[tag] = all(bool(((t == t.round()) & (t.abs() <= 255)).all().item()) for t in (a, b))
     prec = ops.VO_PREC_F16X1 if _int_valued[tag] else ops.VO_PREC_TF32X3
     if a.shape[-1] != 128:
         prec = ops.VO_PREC_FP32_SIMT
