@@ -29,6 +29,10 @@ WORKLOADS = {
                desc="SIFT 2k kp, L2 kNN-2 + ratio 0.85, PnP-RANSAC 512 hyp, KITTI 1241x376"),
     "c2": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="hamming_mutual",
                desc="ORB 5k kp, 256-bit Hamming mutual-NN, PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
+    # c2 with the reference's OWN ORB rule (feature_extractors/ORB.py: cv2.BFMatcher() = NORM_L2 over byte values, ratio 0.85;
+    # SURVEY D2) instead of the north-star's Hamming / mutual rule: an exact fp16 tensor-core pass
+    "c2r": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="knn_ratio", orb_l2=True,
+                desc="ORB 5k kp, reference rule: byte-wise L2 kNN-2 + ratio 0.85, PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
     "c3": dict(kind="r2d2", n_kp=10000, n_hyp=4096, pairs=64, chunk=64, shape="kitti", cpu_matcher="r2d2",
                desc="R2D2 10k kp, cosine GEMM-argmin ratio+mutual, PnP-RANSAC 4096 hyp, KITTI 1241x376"),
     # the two multi-GPU configurations of BASELINE.json (per-GPU block of the sharded sequence; weak scaling)
@@ -43,7 +47,9 @@ def env_rank():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def matcher_cfg(kind, ops):
+def matcher_cfg(kind, ops, orb_l2=False):
+    if kind == "orb" and orb_l2:
+        return dict(norm_or_metric=ops.VO_NORM_L2_U8, mode=ops.VO_MODE_RATIO, match_param=0.85, precision=0)
     if kind == "orb":
         return dict(norm_or_metric=ops.VO_NORM_HAMMING, mode=ops.VO_MODE_MUTUAL, match_param=0.0, precision=0)
     if kind == "sift":
@@ -171,7 +177,7 @@ def run_reference(args, wl):
     rank, _, world = env_rank()
     if rank != 0:
         return
-    sample = args.cpu_pairs or {"c1": 24, "c2": 16, "c3": 4, "c4": 2, "c5": 1}[args.workload]
+    sample = args.cpu_pairs or {"c1": 24, "c2": 16, "c2r": 16, "c3": 4, "c4": 2, "c5": 1}[args.workload]
     vals, secs = [], []
     for s in range(args.warmup + args.steps):
         v, dt, threads, ok = time_cpu_pairs(wl, sample, first_index=s * (sample + 1))
@@ -193,7 +199,9 @@ def run_reference(args, wl):
 
 
 def dtype_of(wl):
-    return {"orb": "u8 (XOR+POPC) / f32+f64 PnP", "sift": "tf32 (1x, exact on integer SIFT) / f32+f64 PnP",
+    if wl.get("orb_l2"):
+        return "u8 -> fp16 (1x, exact on byte values) / f32+f64 PnP"
+    return {"orb": "u8 (XOR+POPC) / f32+f64 PnP", "sift": "fp16 (1x, exact on integer SIFT) / f32+f64 PnP",
             "r2d2": "tf32x3 / f32+f64 PnP"}[wl["kind"]]
 
 
@@ -217,7 +225,7 @@ def run_ours(args, wl):
     host = make_host_batch(wl, unique, first_index=rank * P)
     batch_full = sequence.PairBatch.from_numpy(host, dev, repeat=reps)
     batch = batch_full.slice(0, P)                     # distinct memory per pair: inputs >> L2
-    mc = matcher_cfg(wl["kind"], ops)
+    mc = matcher_cfg(wl["kind"], ops, wl.get("orb_l2", False))
     if args.precision is not None:
         mc["precision"] = args.precision
     cfg = sequence.PipelineConfig(n_hyp=wl["n_hyp"], **mc)
@@ -315,7 +323,17 @@ def run_ours(args, wl):
     launches_match = stages["match"][1]
     pairs_per_launch = P * args.steps / max(launches_match, 1)
     match_s = stage_ms.get("match", float("nan")) / 1e3
-    if wl["kind"] == "orb":
+    if wl.get("orb_l2"):
+        # bytes widened to fp16 and zero-padded to 128 dimensions: the pass SIFT runs (kind::f16, exact integers)
+        flops = pairs_per_launch * 2.0 * N * M * 128
+        roof = {"kernel": "match_f32_tc_kernel<fp16 single pass> on byte descriptors (tcgen05 kind::f16 fused GEMM + row top-2)",
+                "bound": "tensor", "achieved": flops / match_s / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+                "traffic": None, "peak_source": f"dense bf16 cuBLAS burst peak of MEASURED_PEAKS.json ({peak_kind})",
+                "issued_passes": 1, "algorithmic_flops": flops / 4.0,
+                "distances_per_s": pairs_per_launch * float(N) * M / match_s,
+                "note": "issued FLOPs (128 padded dimensions; 32 carry data).  The pass is bound by its row top-2 epilogue "
+                        "(ALU pipe), not by the GEMM, which is why the padding is free: see the c4 line and DESIGN 3.2"}
+    elif wl["kind"] == "orb":
         alg_bytes = pairs_per_launch * (32.0 * (N + M) + 16.0 * N + 8.0 * M)      # descriptors + row partials + column keys
         roof = {"kernel": "match_u8_kernel (XOR+POPC Hamming, fused row/column arg-min)", "bound": "hbm",
                 "achieved": alg_bytes / match_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -434,7 +452,7 @@ def run_ours(args, wl):
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
-        sample = args.cpu_pairs or {"c1": 48, "c2": 24, "c3": 6, "c4": 2, "c5": 1}[args.workload]
+        sample = args.cpu_pairs or {"c1": 48, "c2": 24, "c2r": 24, "c3": 6, "c4": 2, "c5": 1}[args.workload]
         v, dt, threads, okc = time_cpu_pairs(wl, sample, first_index=0)
         cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
                "sample": f"first {sample} pairs of the same synthetic workload, {dt:.1f} s, reference CPU path "

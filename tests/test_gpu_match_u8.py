@@ -94,3 +94,56 @@ def test_self_match_is_identity_at_full_size():
     pairs = r.numpy()
     assert np.array_equal(pairs[:, 0], np.arange(5000)) and np.array_equal(pairs[:, 1], np.arange(5000))
     assert float(r.dist[0].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ byte-L2 on the tensor cores
+def test_golden_reference_orb_l2_bytes_tensor_core_pass(golden):
+    """The reference's ORB rule (BFMatcher NORM_L2 over byte values + ratio 0.85) without a column arg-min request runs as
+    the exact fp16 tensor-core pass: row top-2 (index, distance) equal to cv2's and accepted pairs equal to the reference's
+    own get_matches, bit for bit; and equal to the CUDA-core kernel (VO_U8_L2_SIMT=1) on the same input."""
+    import os
+    from vo_b200 import ops
+    g = golden("match_u8.npz")
+    r = ops.match_u8(_gpu(g["ref"]), _gpu(g["cur"]), ops.VO_NORM_L2_U8, ops.VO_MODE_RATIO, 0.85, want_knn="rows")
+    assert r.col_idx is None
+    assert np.array_equal(r.knn_idx[0].cpu().numpy(), g["l2_idx"])
+    assert np.array_equal(r.knn_val[0].cpu().numpy(), g["l2_dist"])
+    assert np.array_equal(_pairs(r), g["ref_orb_pairs"].reshape(-1, 2))
+    os.environ["VO_U8_L2_SIMT"] = "1"
+    try:
+        s = ops.match_u8(_gpu(g["ref"]), _gpu(g["cur"]), ops.VO_NORM_L2_U8, ops.VO_MODE_RATIO, 0.85, want_knn="rows")
+    finally:
+        del os.environ["VO_U8_L2_SIMT"]
+    assert np.array_equal(r.knn_idx[0].cpu().numpy(), s.knn_idx[0].cpu().numpy())
+    assert np.array_equal(r.knn_val[0].cpu().numpy(), s.knn_val[0].cpu().numpy())
+    k = int(r.count[0])
+    assert k == int(s.count[0]) and np.array_equal(r.dist[0, :k].cpu().numpy(), s.dist[0, :k].cpu().numpy())
+
+
+@pytest.mark.parametrize("n,m", [(5000, 5000), (1237, 3001), (513, 255), (1, 700), (700, 1), (193, 385)])
+def test_l2_bytes_tensor_core_pass_vs_oracle_sizes(orc, n, m):
+    from vo_b200 import ops, synthetic
+    p = synthetic.make_pair(n + m, n_kp=max(n, 8), n_cur=max(m, 8), kind="orb")
+    ref, cur = p["ref_desc"][:n], p["cur_desc"][:m]
+    ridx, rval, cidx = orc.knn_u8(ref, cur, ops.VO_NORM_L2_U8)
+    for mode, param in ((ops.VO_MODE_RATIO, 0.85), (ops.VO_MODE_NN, 0.0)):
+        r = ops.match_u8(_gpu(ref), _gpu(cur), ops.VO_NORM_L2_U8, mode, param, want_knn="rows")
+        assert np.array_equal(r.knn_idx[0].cpu().numpy(), ridx)
+        assert np.array_equal(r.knn_val[0].cpu().numpy(), rval)
+        want, wd = orc.accept(ridx, rval, cidx, mode, param)
+        assert np.array_equal(_pairs(r), want)
+        assert np.array_equal(r.dist[0, :len(want)].cpu().numpy(), wd)
+
+
+def test_l2_bytes_tensor_core_pass_ragged_batch(orc):
+    from vo_b200 import ops, synthetic
+    B, N, M = 4, 640, 600
+    ps = [synthetic.make_pair(60 + b, n_kp=N, n_cur=M, kind="orb") for b in range(B)]
+    ref = np.stack([p["ref_desc"] for p in ps])
+    cur = np.stack([p["cur_desc"] for p in ps])
+    n_ref = np.array([640, 1, 333, 512], np.int32)
+    n_cur = np.array([600, 600, 17, 2], np.int32)
+    r = ops.match_u8(_gpu(ref), _gpu(cur), ops.VO_NORM_L2_U8, ops.VO_MODE_RATIO, 0.85, n_ref=_gpu(n_ref), n_cur=_gpu(n_cur))
+    for b in range(B):
+        want, _ = orc.match_u8(ref[b, :n_ref[b]], cur[b, :n_cur[b]], orc.NORM_L2_U8, orc.MODE_RATIO, 0.85)
+        assert np.array_equal(_pairs(r, b), want), b

@@ -119,7 +119,7 @@ int match_f32_simt(vo_ctx *ctx, const float *ref, const float *cur, int B, int n
 int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_stride, int m_stride,
                  const int32_t *n_ref, const int32_t *n_cur, int metric, int passes, int need_cols,
                  vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey, const float **row_norm_out,
-                 cudaStream_t st);
+                 cudaStream_t st, int src_u8 = 0);
 int pick_split(vo_ctx *ctx, int B, int row_blocks, int col_tiles, int min_tiles_per_split);
 int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_t *n_pts, int B, int cap,
                     const double *K_h, const int32_t *hyp, int H, float thr_px, int min_inliers, int refine_iters,

@@ -147,6 +147,38 @@ prep16_kernel(const float *__restrict__ x, long long rows, __half *__restrict__ 
     }
 }
 
+// byte descriptors (32 per row, the reference's ORB semantics: BFMatcher NORM_L2 over byte values) as 128-d fp16 rows,
+// zero beyond the 32nd element: every value, product and partial sum is an exact integer, as for SIFT
+__global__ void __launch_bounds__(256)
+prep16_u8_kernel(const uint8_t *__restrict__ x, long long rows, __half *__restrict__ h16, float *__restrict__ norm2,
+                 float *__restrict__ ext) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    uint2 w = make_uint2(0u, 0u);
+    float s = 0.f;
+    if (lane < 8) {
+        const uchar4 v = reinterpret_cast<const uchar4 *>(x)[row * 8 + lane];
+        const __half2 p0 = __floats2half2_rn((float)v.x, (float)v.y), p1 = __floats2half2_rn((float)v.z, (float)v.w);
+        w.x = *reinterpret_cast<const uint32_t *>(&p0);
+        w.y = *reinterpret_cast<const uint32_t *>(&p1);
+        s = (float)((int)v.x * v.x + (int)v.y * v.y + (int)v.z * v.z + (int)v.w * v.w);
+    }
+    reinterpret_cast<uint2 *>(h16)[row * 32 + lane] = w;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));  // integers < 2^21: exact
+    if (lane == 0) norm2[row] = s;
+    if (ext) {
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane == 0) {
+            const float n1 = to_tf32(s), n2 = to_tf32(__fsub_rn(s, n1));
+            const float n3 = to_tf32(__fsub_rn(__fsub_rn(s, n1), n2));
+            e = make_float4(-n1, -n2, -n3, 0.f);
+        }
+        if (lane < 8) reinterpret_cast<float4 *>(ext)[row * 8 + lane] = e;
+    }
+}
+
 // split fp16 (VO_PREC_F16X3): x * 2^8 = hi + lo, both fp16; squared norms of the unscaled rows
 __global__ void __launch_bounds__(256)
 prep16x3_kernel(const float *__restrict__ x, long long rows, __half *__restrict__ hi16, __half *__restrict__ lo16,
@@ -989,7 +1021,12 @@ int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &
 int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_stride, int m_stride,
                  const int32_t *n_ref, const int32_t *n_cur, int metric, int passes, int need_cols,
                  vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey, const float **row_norm_out,
-                 cudaStream_t st) {
+                 cudaStream_t st, int src_u8) {
+    // src_u8: ref / cur are 32-byte descriptors (uint8 [rows][32]); only the fp16 single pass without column side takes them
+    if (src_u8 && (passes != 16 || need_cols || metric != VO_METRIC_L2)) {
+        set_error("match_f32_tc: byte descriptors run the fp16 single pass (L2, no column arg-min) only");
+        return VO_ERR_ARG;
+    }
     if (!ctx->tc_ready) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -1026,6 +1063,11 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
         prep16x3_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, reinterpret_cast<__half *>(a_hi), reinterpret_cast<__half *>(a_lo), l2 ? row_norm : nullptr);
         VO_LAUNCH_CHECK(ctx);
         prep16x3_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, reinterpret_cast<__half *>(b_hi), reinterpret_cast<__half *>(b_lo), l2 ? col_norm : nullptr);
+        VO_LAUNCH_CHECK(ctx);
+    } else if (f16 && src_u8) {
+        prep16_u8_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(ref), rows_a, reinterpret_cast<__half *>(a_hi), row_norm, nullptr);
+        VO_LAUNCH_CHECK(ctx);
+        prep16_u8_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(cur), rows_b, reinterpret_cast<__half *>(b_hi), col_norm, b_ext);
         VO_LAUNCH_CHECK(ctx);
     } else if (f16) {
         prep16_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, reinterpret_cast<__half *>(a_hi), l2 ? row_norm : nullptr, nullptr);

@@ -17,6 +17,7 @@
 // words of weight 1, one of weight 2 and one of weight 4, which leaves 4 POPC per distance and
 // moves the bound to the logic pipe (16 LOP3 per distance at 64 lanes/clk/SM).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace vo {
 namespace {
@@ -247,6 +248,24 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
     }
     VO_REQUIRE(norm != VO_NORM_HAMMING || m_stride < (1 << U8_COL_BITS),
                "vo_match_u8: Hamming matcher supports at most %d descriptors per frame", (1 << U8_COL_BITS) - 1);
+    // The reference's ORB semantics (BFMatcher NORM_L2 over byte values) is a float-style L2 match of
+    // integer-valued vectors: without a column arg-min (ratio / plain-NN rules) it runs as the exact fp16 tensor-core
+    // pass SIFT uses, bytes widened to fp16 and zero-padded to 128 dimensions (3x the CUDA-core kernel: the pass is bound
+    // by its row top-2 epilogue, not by the padded GEMM).  Same scores (exact integers), same tie rule, same finalize.
+    const bool need_cols = mode == VO_MODE_MUTUAL || (knn && knn->col_idx);
+    if (norm == VO_NORM_L2_U8 && !need_cols && !getenv("VO_U8_L2_SIMT")) {
+        int rc;
+        unsigned long long *colkey_tc;
+        if ((rc = ws_get(ctx, WS_COLKEY, sizeof(unsigned long long) * (size_t)B * m_stride, (void **)&colkey_tc))) return rc;
+        vo_row_partial *part_tc;
+        const float *row_norm_tc = nullptr;
+        int n_split_tc;
+        if ((rc = match_f32_tc(ctx, reinterpret_cast<const float *>(ref), reinterpret_cast<const float *>(cur), B, n_stride,
+                               m_stride, n_ref, n_cur, VO_METRIC_L2, 16, 0, &part_tc, &n_split_tc, colkey_tc, &row_norm_tc, st, 1)))
+            return rc;
+        return match_finalize(ctx, part_tc, n_split_tc, colkey_tc, B, n_stride, m_stride, n_ref, n_cur, SCORE_L2SQ_F32, mode,
+                              ratio, row_norm_tc, out_pairs, out_dist, out_count, knn, nullptr, st);
+    }
     const int row_blocks = ceil_div(n_stride, U8_ROWS_CTA);
     // Column splits: every CTA costs the same, so pick the smallest split count whose CTA total fills the
     // resident slots (3 CTAs per SM) to >= 94 % in its last wave, with >= 256 columns per split.
