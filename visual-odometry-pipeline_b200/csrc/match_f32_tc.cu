@@ -22,6 +22,14 @@
 //
 // L2 mode uses the GEMM form -|a_i - b_j|^2 = (2 a_i.b_j - |b_j|^2) - |a_i|^2, evaluated per element in the
 // epilogue (the row norm matters for the column arg-min, the column norm for the row arg-min).
+//
+// Operand arithmetic (template parameter PASSES):
+//    3  3xTF32      hi/lo tf32 split, three kind::tf32 MMAs per 8 k            R2D2 default (fp32-grade)
+//    1  1xTF32      single tf32 pass, column norm as an extra K-step           integer-valued data, rules with a column side
+//   16  1xFP16      single fp16 pass (kind::f16, K = 16), 192-column tiles     integer-valued data: SIFT, ORB bytes (exact)
+//   48  3xFP16      x * 2^8 = hi + lo in fp16, three kind::f16 MMAs per 16 k   the 22 operand bits of 3xTF32 at twice the rate
+// The two fp16 modes use the all-warp epilogue (16 warps on every tile, accumulator released right after the TMEM read,
+// the four threads of a row share their filter threshold); tools/probe/mma_issue_probe.cu has the pipe rates.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda_fp16.h>
