@@ -155,35 +155,38 @@ prep16_kernel(const float *__restrict__ x, long long rows, __half *__restrict__ 
     }
 }
 
-// byte descriptors (32 per row, the reference's ORB semantics: BFMatcher NORM_L2 over byte values) as 128-d fp16 rows,
-// zero beyond the 32nd element: every value, product and partial sum is an exact integer, as for SIFT
+// byte descriptors (32 per row, the reference's ORB semantics: BFMatcher NORM_L2 over byte values) as fp16 rows of 32
+// values; the matcher treats them as 128-d rows that are zero beyond the 32nd element (TMA out-of-bounds fill for B,
+// a bounds test in the A load): every value, product and partial sum is an exact integer, as for SIFT
 __global__ void __launch_bounds__(256)
 prep16_u8_kernel(const uint8_t *__restrict__ x, long long rows, __half *__restrict__ h16, float *__restrict__ norm2,
                  float *__restrict__ ext) {
-    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const int lane = threadIdx.x & 31;
-    uint2 w = make_uint2(0u, 0u);
+    // eight lanes per row (4 bytes each), four rows per warp, 32 rows per block
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 5) * 4 + (lane >> 3);
+    const bool ok = row < rows;
     float s = 0.f;
-    if (lane < 8) {
-        const uchar4 v = reinterpret_cast<const uchar4 *>(x)[row * 8 + lane];
+    if (ok) {  // compact fp16 rows of 32 values: TMA zero-fills the other 96 dimensions of every box (out of bounds)
+        const uchar4 v = reinterpret_cast<const uchar4 *>(x)[row * 8 + sub];
         const __half2 p0 = __floats2half2_rn((float)v.x, (float)v.y), p1 = __floats2half2_rn((float)v.z, (float)v.w);
+        uint2 w;
         w.x = *reinterpret_cast<const uint32_t *>(&p0);
         w.y = *reinterpret_cast<const uint32_t *>(&p1);
         s = (float)((int)v.x * v.x + (int)v.y * v.y + (int)v.z * v.z + (int)v.w * v.w);
+        reinterpret_cast<uint2 *>(h16)[row * 8 + sub] = w;
     }
-    reinterpret_cast<uint2 *>(h16)[row * 32 + lane] = w;
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));  // integers < 2^21: exact
-    if (lane == 0) norm2[row] = s;
+    if (!ok) return;
+    if (sub == 0) norm2[row] = s;
     if (ext) {
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane == 0) {
+        if (sub == 0) {
             const float n1 = to_tf32(s), n2 = to_tf32(__fsub_rn(s, n1));
             const float n3 = to_tf32(__fsub_rn(__fsub_rn(s, n1), n2));
             e = make_float4(-n1, -n2, -n3, 0.f);
         }
-        if (lane < 8) reinterpret_cast<float4 *>(ext)[row * 8 + lane] = e;
+        reinterpret_cast<float4 *>(ext)[row * 8 + sub] = e;
     }
 }
 
@@ -345,7 +348,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                     const int32_t *__restrict__ n_ref, const int32_t *__restrict__ n_cur,
                     const float *__restrict__ row_norm, const float *__restrict__ col_norm, int n_split,
                     vo_row_partial *__restrict__ part, unsigned long long *__restrict__ colkey,
-                    long long *__restrict__ dbg, int pair_group) {
+                    long long *__restrict__ dbg, int pair_group, int row_elems) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - smem_u32(smem_raw));
@@ -533,12 +536,13 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         const bool partial_rows = row0 + TC_BM > N;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         if (n_tiles > 0 && cq < 2) {  // A -> tensor memory, once: 64 k (one 32-column chunk of packed halves) per warp
-            const __half *src = reinterpret_cast<const __half *>(a_hi) + ((size_t)b * n_stride + min(row, n_stride - 1)) * TC_D + cq * 64;
+            // row_elems < 128: compact rows (byte descriptors: 32 values), the missing dimensions are zero
+            const __half *src = reinterpret_cast<const __half *>(a_hi) + ((size_t)b * n_stride + min(row, n_stride - 1)) * row_elems + cq * 64;
             const bool have = row < n_stride;
             float v[32];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                uint4 x = have ? __ldg(reinterpret_cast<const uint4 *>(src) + k) : make_uint4(0, 0, 0, 0);
+                uint4 x = (have && cq * 64 + k * 8 < row_elems) ? __ldg(reinterpret_cast<const uint4 *>(src) + k) : make_uint4(0, 0, 0, 0);
                 uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -958,7 +962,8 @@ int make_map(vo_ctx *ctx, CUtensorMap *map, const void *ptr, long long rows, int
 template <int PASSES, int METRIC, bool COLS>
 int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &bl, const float *a_hi, const float *a_lo,
               int n_stride, int m_stride, const int32_t *n_ref, const int32_t *n_cur, const float *row_norm,
-              const float *col_norm, int n_split, vo_row_partial *part, unsigned long long *colkey, cudaStream_t st) {
+              const float *col_norm, int n_split, vo_row_partial *part, unsigned long long *colkey, cudaStream_t st,
+              int row_elems = TC_D) {
     auto kern = match_f32_tc_kernel<PASSES, METRIC, COLS>;
     long long *dbg = nullptr;
     const size_t n_ctas = (size_t)grid.x * grid.y * grid.z;
@@ -985,7 +990,7 @@ int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &
     if (PASSES == 48 && COLS && !getenv("VO_TC_NO_INTERLEAVE"))
         pair_group = (int)max(1ll, min(8ll, (64ll << 20) / ((long long)m_stride * TC_D * 4)));
     kern<<<grid, TC_THREADS, TcCfg<PASSES>::SMEM_BYTES, st>>>(bh, bl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm,
-                                                  n_split, part, colkey, dbg, pair_group);
+                                                  n_split, part, colkey, dbg, pair_group, row_elems);
     VO_LAUNCH_CHECK(ctx);
     if (dbg && trace) {  // per SM: busy cycles of its CTAs and the idle cycles between one CTA's exit and the next one's entry
         VO_CUDA(cudaStreamSynchronize(st));
@@ -1054,7 +1059,8 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     int rc;
     const bool f16 = passes == 16, h16 = passes == 16 || passes == 48, three = passes == 3 || passes == 48;
     const size_t esz = h16 ? sizeof(__half) : sizeof(float);
-    const size_t per_a = (size_t)rows_a * TC_D * esz, per_b = (size_t)rows_b * TC_D * esz;
+    const int row_elems = src_u8 ? 32 : TC_D;  // stored elements per descriptor row
+    const size_t per_a = (size_t)rows_a * row_elems * esz, per_b = (size_t)rows_b * row_elems * esz;
     if ((rc = ws_get(ctx, WS_SPLIT_A, per_a * (three ? 2 : 1), (void **)&split_a))) return rc;
     const bool ext = !three && l2;  // B extension rows [rows_b][32] live behind B_hi
     const size_t per_ext = (size_t)rows_b * TC_KB * sizeof(float);
@@ -1073,9 +1079,9 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
         prep16x3_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, reinterpret_cast<__half *>(b_hi), reinterpret_cast<__half *>(b_lo), l2 ? col_norm : nullptr);
         VO_LAUNCH_CHECK(ctx);
     } else if (f16 && src_u8) {
-        prep16_u8_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(ref), rows_a, reinterpret_cast<__half *>(a_hi), row_norm, nullptr);
+        prep16_u8_kernel<<<(unsigned)((rows_a + 31) / 32), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(ref), rows_a, reinterpret_cast<__half *>(a_hi), row_norm, nullptr);
         VO_LAUNCH_CHECK(ctx);
-        prep16_u8_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(cur), rows_b, reinterpret_cast<__half *>(b_hi), col_norm, b_ext);
+        prep16_u8_kernel<<<(unsigned)((rows_b + 31) / 32), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(cur), rows_b, reinterpret_cast<__half *>(b_hi), col_norm, b_ext);
         VO_LAUNCH_CHECK(ctx);
     } else if (f16) {
         prep16_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, reinterpret_cast<__half *>(a_hi), l2 ? row_norm : nullptr, nullptr);
@@ -1091,7 +1097,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
 
     CUtensorMap mbh, mbl;
     const int bn = three ? TcCfg<3>::BN : (f16 ? TcCfg<16>::BN : TcCfg<1>::BN);
-    if ((rc = make_map(ctx, &mbh, b_hi, rows_b, bn, TC_D, h16))) return rc;
+    if ((rc = make_map(ctx, &mbh, b_hi, rows_b, bn, row_elems, h16))) return rc;
     if (ext) rc = make_map(ctx, &mbl, b_ext, rows_b, bn, TC_KB);
     else rc = make_map(ctx, &mbl, three ? b_lo : b_hi, rows_b, bn, TC_D, h16);
     if (rc) return rc;
@@ -1107,7 +1113,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
 #define TC_PICK(P, MET) (need_cols ? launch_tc<P, MET, true>(TC_ARGS) : launch_tc<P, MET, false>(TC_ARGS))
     if (passes == 3) rc = l2 ? TC_PICK(3, VO_METRIC_L2) : TC_PICK(3, VO_METRIC_COSINE);
     else if (passes == 48) rc = l2 ? TC_PICK(48, VO_METRIC_L2) : TC_PICK(48, VO_METRIC_COSINE);
-    else if (f16) rc = l2 ? launch_tc<16, VO_METRIC_L2, false>(TC_ARGS) : launch_tc<16, VO_METRIC_COSINE, false>(TC_ARGS);
+    else if (f16) rc = l2 ? launch_tc<16, VO_METRIC_L2, false>(TC_ARGS, row_elems) : launch_tc<16, VO_METRIC_COSINE, false>(TC_ARGS);
     else rc = l2 ? TC_PICK(1, VO_METRIC_L2) : TC_PICK(1, VO_METRIC_COSINE);
 #undef TC_PICK
 #undef TC_ARGS
