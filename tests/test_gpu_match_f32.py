@@ -171,3 +171,29 @@ def test_f16_pass_batched_ragged_and_mutual_fallback(orc):
     a = ops.match_f32(ref, cur, ops.VO_METRIC_L2, ops.VO_MODE_MUTUAL, 0.0, precision=ops.VO_PREC_F16X1, want_knn=True)
     t = ops.match_f32(ref, cur, ops.VO_METRIC_L2, ops.VO_MODE_MUTUAL, 0.0, precision=ops.VO_PREC_TF32X1, want_knn=True)
     assert torch.equal(a.pairs[0, :int(a.count[0])], t.pairs[0, :int(t.count[0])]) and torch.equal(a.col_idx, t.col_idx)
+
+
+@pytest.mark.parametrize("B", [3, 8, 11])
+def test_split_fp16_batch_equals_single_pair_calls(B):
+    """The split fp16 pass deals the clusters of up to 8 consecutive pairs round-robin over the pairs (so that the row
+    blocks of a pair run at different times and the column filter sees earlier results).  The remap is an index bijection:
+    a ragged batch (sizes that leave a partial last set) must give, pair by pair, exactly what a single-pair call gives."""
+    import torch
+    from vo_b200 import ops, synthetic
+    N = 900
+    batch = synthetic.make_batch(70, B, n_kp=N, kind="r2d2")
+    rng = np.random.default_rng(B)
+    n_ref = torch.from_numpy(rng.integers(1, N + 1, B).astype(np.int32)).cuda()
+    n_cur = torch.from_numpy(rng.integers(1, N + 1, B).astype(np.int32)).cuda()
+    ref, cur = _gpu(batch["ref_desc"]), _gpu(batch["cur_desc"])
+    r = ops.match_f32(ref, cur, ops.VO_METRIC_COSINE, ops.VO_MODE_RATIO_MUTUAL, 0.90, precision=ops.VO_PREC_F16X3,
+                      n_ref=n_ref, n_cur=n_cur, want_knn=True)
+    for b in range(B):
+        nr, nc = int(n_ref[b]), int(n_cur[b])
+        s = ops.match_f32(ref[b, :nr].contiguous(), cur[b, :nc].contiguous(), ops.VO_METRIC_COSINE, ops.VO_MODE_RATIO_MUTUAL,
+                          0.90, precision=ops.VO_PREC_F16X3, want_knn=True)
+        assert int(r.count[b]) == int(s.count[0]), b
+        k = int(s.count[0])
+        assert torch.equal(r.pairs[b, :k], s.pairs[0, :k]), b
+        assert torch.equal(r.knn_idx[b, :nr], s.knn_idx[0, :nr]) and torch.equal(r.knn_val[b, :nr], s.knn_val[0, :nr]), b
+        assert torch.equal(r.col_idx[b, :nc], s.col_idx[0, :nc]), b
