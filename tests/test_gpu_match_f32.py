@@ -197,3 +197,37 @@ def test_split_fp16_batch_equals_single_pair_calls(B):
         assert torch.equal(r.pairs[b, :k], s.pairs[0, :k]), b
         assert torch.equal(r.knn_idx[b, :nr], s.knn_idx[0, :nr]) and torch.equal(r.knn_val[b, :nr], s.knn_val[0, :nr]), b
         assert torch.equal(r.col_idx[b, :nc], s.col_idx[0, :nc]), b
+
+
+def test_fp16_passes_random_shapes_vs_oracle(orc):
+    """40 random (n, m) shapes around the tile boundaries (192-column tiles of the fp16 single pass, 128-column tiles of the
+    split pass, 128-row blocks, cluster pairs): fp16 single pass bit-exact on SIFT-like data, split fp16 near-tie aware
+    on R2D2-like data."""
+    from vo_b200 import ops, synthetic
+    rng = np.random.default_rng(2024)
+    edges = [1, 2, 31, 47, 48, 49, 127, 128, 129, 191, 192, 193, 255, 256, 257, 383, 384, 385, 575, 576, 577, 640]
+    sift = synthetic.make_pair(901, n_kp=700, n_cur=700, kind="sift")
+    r2d2 = synthetic.make_pair(902, n_kp=700, n_cur=700, kind="r2d2")
+    for it in range(40):
+        n = int(rng.choice(edges)) if it % 2 == 0 else int(rng.integers(1, 700))
+        m = int(rng.choice(edges)) if it % 3 == 0 else int(rng.integers(1, 700))
+        ref, cur = sift["ref_desc"][:n], sift["cur_desc"][:m]
+        r = ops.match_f32(_gpu(ref), _gpu(cur), ops.VO_METRIC_L2, ops.VO_MODE_RATIO, 0.85, precision=ops.VO_PREC_F16X1,
+                          want_knn="rows")
+        ridx, rval, cidx = orc.knn_f32(ref, cur, orc.METRIC_L2)
+        assert np.array_equal(r.knn_idx[0].cpu().numpy(), ridx), (n, m)
+        assert np.array_equal(r.knn_val[0].cpu().numpy(), rval), (n, m)
+        want, _ = orc.accept(ridx, rval, cidx, orc.MODE_RATIO, 0.85, orc.METRIC_L2)
+        assert np.array_equal(r.numpy(), want), (n, m)
+        ref, cur = r2d2["ref_desc"][:n], r2d2["cur_desc"][:m]
+        r = ops.match_f32(_gpu(ref), _gpu(cur), ops.VO_METRIC_COSINE, ops.VO_MODE_RATIO_MUTUAL, 0.90,
+                          precision=ops.VO_PREC_F16X3, want_knn=True)
+        ridx, rval, cidx = orc.knn_f32(ref, cur, orc.METRIC_COSINE)
+        gi, gc = r.knn_idx[0].cpu().numpy(), r.col_idx[0].cpu().numpy()
+        for row in np.nonzero(gi[:, 0] != ridx[:, 0])[0]:
+            s = orc.pair_scores_f64(ref, cur, [row, row], [gi[row, 0], ridx[row, 0]], orc.METRIC_COSINE)
+            assert abs(s[0] - s[1]) <= REL_TIE * abs(s).max(), (n, m, row, s)
+        for col in np.nonzero(gc != cidx)[0]:
+            s = orc.pair_scores_f64(ref, cur, [gc[col], cidx[col]], [col, col], orc.METRIC_COSINE)
+            assert abs(s[0] - s[1]) <= REL_TIE * abs(s).max(), (n, m, col, s)
+        assert np.allclose(r.knn_val[0].cpu().numpy()[:, 0], rval[:, 0], atol=2e-6, rtol=0), (n, m)

@@ -147,3 +147,21 @@ def test_l2_bytes_tensor_core_pass_ragged_batch(orc):
     for b in range(B):
         want, _ = orc.match_u8(ref[b, :n_ref[b]], cur[b, :n_cur[b]], orc.NORM_L2_U8, orc.MODE_RATIO, 0.85)
         assert np.array_equal(_pairs(r, b), want), b
+
+
+def test_l2_bytes_tensor_core_pass_random_shapes(orc):
+    """30 random (n, m) shapes around the tile / row-block boundaries, byte-wise L2 + ratio on the tensor-core pass."""
+    from vo_b200 import ops, synthetic
+    rng = np.random.default_rng(77)
+    edges = [1, 2, 47, 48, 49, 127, 128, 129, 191, 192, 193, 255, 256, 257, 383, 384, 385, 576, 577]
+    p = synthetic.make_pair(903, n_kp=700, n_cur=700, kind="orb")
+    for it in range(30):
+        n = int(rng.choice(edges)) if it % 2 == 0 else int(rng.integers(1, 700))
+        m = int(rng.choice(edges)) if it % 3 == 0 else int(rng.integers(1, 700))
+        ref, cur = p["ref_desc"][:n], p["cur_desc"][:m]
+        r = ops.match_u8(_gpu(ref), _gpu(cur), ops.VO_NORM_L2_U8, ops.VO_MODE_RATIO, 0.85, want_knn="rows")
+        ridx, rval, cidx = orc.knn_u8(ref, cur, ops.VO_NORM_L2_U8)
+        assert np.array_equal(r.knn_idx[0].cpu().numpy(), ridx), (n, m)
+        assert np.array_equal(r.knn_val[0].cpu().numpy(), rval), (n, m)
+        want, _ = orc.accept(ridx, rval, cidx, ops.VO_MODE_RATIO, 0.85)
+        assert np.array_equal(_pairs(r), want), (n, m)
