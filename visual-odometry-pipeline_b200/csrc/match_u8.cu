@@ -53,19 +53,37 @@ struct U8Mul {
     uint32_t m1, m2, m4, mrow, mcol;
 };
 
+// Carry of a full adder whose third input is known only through the sum: F(x, y, s) = maj(x, y, s ^ x ^ y)
+// = (x & y) | ((x ^ y) & ~s).
+__device__ __forceinline__ uint32_t carry_from_sum(uint32_t x, uint32_t y, uint32_t s) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD4;" : "=r"(d) : "r"(x), "r"(y), "r"(s));
+    return d;
+}
+
+// Hamming descriptors are kept in a prefix-XOR form (both frames alike): words 2, 5 and 6 hold w0^w1^w2, w3^w4^w5 and
+// w0^...^w6.  The XOR of two such descriptors then yields the SUM outputs of the first three carry-save adders
+// directly (sa = x0^x1^x2, sb = x3^x4^x5, sc = sa^sb^x6), and every carry follows from two inputs and the sum with one
+// LOP3: 13 logic operations per distance instead of 16 (8 XOR + 3 carries + the twos/fours adder), same 4 POPC.
+__device__ __forceinline__ void hamming_prefix_form(uint32_t (&w)[8]) {
+    w[2] ^= w[0] ^ w[1];
+    w[5] ^= w[3] ^ w[4];
+    w[6] ^= w[2] ^ w[5];
+}
+
 template <int NORM>
 __device__ __forceinline__ uint32_t dist256(const uint32_t (&a)[8], const uint4 b0, const uint4 b1, const U8Mul &mu) {
     const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     if (NORM == VO_NORM_HAMMING) {
-        uint32_t x[8];
+        uint32_t x[8];  // x[2], x[5], x[6] are the sums sa, sb, sc (prefix form)
 #pragma unroll
         for (int w = 0; w < 8; ++w) x[w] = a[w] ^ b[w];
-        const uint32_t sa = xor3(x[0], x[1], x[2]), ca = maj3(x[0], x[1], x[2]);
-        const uint32_t sb = xor3(x[3], x[4], x[5]), cb = maj3(x[3], x[4], x[5]);
-        const uint32_t sc = xor3(sa, sb, x[6]), cc = maj3(sa, sb, x[6]);
+        const uint32_t ca = carry_from_sum(x[0], x[1], x[2]);
+        const uint32_t cb = carry_from_sum(x[3], x[4], x[5]);
+        const uint32_t cc = carry_from_sum(x[2], x[5], x[6]);
         const uint32_t t = xor3(ca, cb, cc), f = maj3(ca, cb, cc);
-        // ones: sc, x7; twos: t; fours: f
-        const uint32_t t1 = (uint32_t)__popc(t) * mu.m2 + (uint32_t)__popc(sc);
+        // ones: sc = x[6], x7; twos: t; fours: f
+        const uint32_t t1 = (uint32_t)__popc(t) * mu.m2 + (uint32_t)__popc(x[6]);
         const uint32_t t2 = (uint32_t)__popc(f) * mu.m4 + (uint32_t)__popc(x[7]);
         return t1 * mu.m1 + t2;
     } else {
@@ -111,6 +129,7 @@ match_u8_kernel(const uint8_t *__restrict__ ref, const uint8_t *__restrict__ cur
         uint4 q0 = valid ? p[0] : make_uint4(0, 0, 0, 0), q1 = valid ? p[1] : make_uint4(0, 0, 0, 0);
         a[r][0] = q0.x; a[r][1] = q0.y; a[r][2] = q0.z; a[r][3] = q0.w;
         a[r][4] = q1.x; a[r][5] = q1.y; a[r][6] = q1.z; a[r][7] = q1.w;
+        if (NORM == VO_NORM_HAMMING) hamming_prefix_form(a[r]);
         rowid[r] = (uint32_t)(r * U8_THREADS + tid) + (valid ? 0u : U8_INVALID_ROW);
         s1[r] = s2[r] = 0xffffffffu;
         i1[r] = i2[r] = -1;
@@ -122,7 +141,17 @@ match_u8_kernel(const uint8_t *__restrict__ ref, const uint8_t *__restrict__ cur
         for (int c0 = c_begin; c0 < c_end; c0 += U8_CHUNK) {
             const int cnt = min(U8_CHUNK, c_end - c0);
             __syncthreads();  // previous chunk fully consumed
-            for (int t = tid; t < cnt * 2; t += U8_THREADS) sdesc[t] = cur4[(size_t)c0 * 2 + t];
+            if (NORM == VO_NORM_HAMMING) {
+                for (int t = tid; t < cnt; t += U8_THREADS) {
+                    const uint4 q0 = cur4[(size_t)(c0 + t) * 2], q1 = cur4[(size_t)(c0 + t) * 2 + 1];
+                    uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                    hamming_prefix_form(w);
+                    sdesc[2 * t] = make_uint4(w[0], w[1], w[2], w[3]);
+                    sdesc[2 * t + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+            } else {
+                for (int t = tid; t < cnt * 2; t += U8_THREADS) sdesc[t] = cur4[(size_t)c0 * 2 + t];
+            }
             __syncthreads();
 
             int j = 0;
