@@ -340,16 +340,18 @@ def run_ours(args, wl):
                 "traffic": ncu_traffic("match_u8_kernel", pairs_per_launch), "algorithmic_bytes": alg_bytes,
                 "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "note": "structurally << 1: all-pairs Hamming is bound by the integer pipes, not HBM (SURVEY D5); see binding_pipe"}
-        # carry-save popcount: 8 XOR + 8 LOP3 (4 full adders) + 4 POPC per 256-bit distance, + one 3-input minimum per
-        # distance on the same logic pipe (weights, adds and keys run as IMADs on the FMA pipe): 17 ALU-pipe
-        # instructions per distance at 64 lanes/clk/SM is the binding ceiling
+        # carry-save popcount on prefix-XOR descriptors: 8 XOR + 3 carries + the twos/fours adder = 13 LOP3, + 4 POPC per
+        # 256-bit distance, + one 3-input minimum per distance (weights, adds and keys run as IMADs on the FMA pipe).
+        # Four POPC per distance is the floor of the formulation (the eight XOR words of a distance hold 9 values per bit
+        # column); at 16 POPC lanes/clk/SM that pipe is the binding ceiling, the logic pipe (14 per distance at 64 lanes)
+        # sits 10 % below it
         dists = pairs_per_launch * N * M
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        alu_peak = 64.0 * 148 * sm_mhz * 1e6 / 17.0                                 # distances/s if the ALU pipe never idles
-        roof["binding_pipe"] = {"pipe": "alu (LOP3/VIMNMX3)", "achieved": dists / match_s / 1e12, "peak": alu_peak / 1e12,
-                                "unit": "Tdist/s", "frac": dists / match_s / alu_peak,
-                                "popc_pipe_frac": dists * 4.0 / match_s / (16.0 * 148 * sm_mhz * 1e6),
-                                "peak_source": "64 ALU lanes/clk/SM x 148 SM x sampled SM clock / 17 ALU instructions per distance"}
+        popc_peak = 16.0 * 148 * sm_mhz * 1e6 / 4.0                                 # distances/s if the POPC pipe never idles
+        roof["binding_pipe"] = {"pipe": "xu (POPC)", "achieved": dists / match_s / 1e12, "peak": popc_peak / 1e12,
+                                "unit": "Tdist/s", "frac": dists / match_s / popc_peak,
+                                "alu_pipe_frac": dists * 14.0 / match_s / (64.0 * 148 * sm_mhz * 1e6),
+                                "peak_source": "16 POPC lanes/clk/SM x 148 SM x sampled SM clock / 4 POPC per distance"}
     else:
         passes = 3 if mc["precision"] in (ops.VO_PREC_TF32X3, ops.VO_PREC_F16X3) else 1
         flops = pairs_per_launch * 2.0 * N * M * 128 * (passes if mc["precision"] != ops.VO_PREC_FP32_SIMT else 1)
