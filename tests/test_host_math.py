@@ -61,3 +61,28 @@ def test_p3p_and_scoring_bit_exact(hm, orc, golden):
         m = orc.inlier_mask(xyz, uv, K, poses[h])
         assert cnt == int(m[::7].sum())
     assert nvalid > 100
+
+
+def test_prefix_xor_hamming_tree_equals_popcount(hm):
+    """csrc/hamming_math.cuh (prefix-XOR descriptors, carries from two inputs and the sum, 4 weighted popcounts) must
+    give the plain 256-bit Hamming distance for every input: random words, sparse and dense differences, the extremes
+    (0 and 256) and single-bit differences in every position."""
+    rng = np.random.default_rng(8214)
+    n = 20000
+    a = rng.integers(0, 2 ** 32, (n, 8), dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 2 ** 32, (n, 8), dtype=np.uint64).astype(np.uint32)
+    sparse = (rng.integers(0, 2 ** 32, (n, 8), dtype=np.uint64) & rng.integers(0, 2 ** 32, (n, 8), dtype=np.uint64)
+              & rng.integers(0, 2 ** 32, (n, 8), dtype=np.uint64)).astype(np.uint32)
+    b[: n // 3] = a[: n // 3] ^ sparse[: n // 3]                       # matches: few differing bits
+    b[n // 3: n // 2] = ~(a[n // 3: n // 2] ^ sparse[n // 3: n // 2])  # nearly all bits differ (carries into the fours)
+    b[n // 2] = a[n // 2]                                              # distance 0
+    b[n // 2 + 1] = ~a[n // 2 + 1]                                     # distance 256: every bit column counts 8
+    for bit in range(256):                                             # one differing bit, every position
+        b[n // 2 + 2 + bit] = a[n // 2 + 2 + bit]
+        b[n // 2 + 2 + bit, bit // 32] ^= np.uint32(1 << (bit % 32))
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    got = np.zeros(n, np.int32)
+    hm.hm_hamming256_many(_p(a), _p(b), n, _p(got))
+    want = np.unpackbits((a ^ b).view(np.uint8), axis=1).sum(1)
+    assert np.array_equal(got, want)
+    assert got[n // 2] == 0 and got[n // 2 + 1] == 256 and (got[n // 2 + 2: n // 2 + 258] == 1).all()

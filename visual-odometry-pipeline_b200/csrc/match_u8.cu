@@ -13,10 +13,11 @@
 //
 // Hamming arithmetic: the POPC pipe issues 16 lanes/clk/SM, a quarter of the logic pipe, so a
 // plain 8 x (XOR, POPC) distance is POPC-bound.  The eight XOR words are first compressed by a
-// carry-save adder tree (4 full adders = 8 LOP3: 3-input XOR 0x96 and majority 0xE8) into two
-// words of weight 1, one of weight 2 and one of weight 4, which leaves 4 POPC per distance and
-// moves the bound to the logic pipe (16 LOP3 per distance at 64 lanes/clk/SM).
+// carry-save adder tree into two words of weight 1, one of weight 2 and one of weight 4, which
+// leaves 4 POPC per distance (the floor: a bit column of eight words takes nine values).  On
+// descriptors in prefix-XOR form (hamming_math.cuh) the tree costs 13 LOP3 instead of 16.
 #include "common.cuh"
+#include "hamming_math.cuh"
 #include <stdlib.h>
 
 namespace vo {
@@ -31,17 +32,6 @@ constexpr uint32_t U8_INVALID_ROW = 0x80000000u;      // added to the column key
 constexpr int U8_COL_BITS = 20;                       // Hamming row key = dist << 20 | column
 static_assert(U8_ROWS_CTA == (1 << U8_ROW_BITS), "row-in-CTA must fit the key");
 
-__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
 // Multipliers the compiler cannot see through: `x * opaque(4) + y` stays an IMAD (FMA pipe) instead of being strength-
 // reduced to LEA / IADD3 on the logic pipe, which is the pipe this kernel is bound by.
 __device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
@@ -53,38 +43,14 @@ struct U8Mul {
     uint32_t m1, m2, m4, mrow, mcol;
 };
 
-// Carry of a full adder whose third input is known only through the sum: F(x, y, s) = maj(x, y, s ^ x ^ y)
-// = (x & y) | ((x ^ y) & ~s).
-__device__ __forceinline__ uint32_t carry_from_sum(uint32_t x, uint32_t y, uint32_t s) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xD4;" : "=r"(d) : "r"(x), "r"(y), "r"(s));
-    return d;
-}
-
-// Hamming descriptors are kept in a prefix-XOR form (both frames alike): words 2, 5 and 6 hold w0^w1^w2, w3^w4^w5 and
-// w0^...^w6.  The XOR of two such descriptors then yields the SUM outputs of the first three carry-save adders
-// directly (sa = x0^x1^x2, sb = x3^x4^x5, sc = sa^sb^x6), and every carry follows from two inputs and the sum with one
-// LOP3: 13 logic operations per distance instead of 16 (8 XOR + 3 carries + the twos/fours adder), same 4 POPC.
-__device__ __forceinline__ void hamming_prefix_form(uint32_t (&w)[8]) {
-    w[2] ^= w[0] ^ w[1];
-    w[5] ^= w[3] ^ w[4];
-    w[6] ^= w[2] ^ w[5];
-}
-
 template <int NORM>
 __device__ __forceinline__ uint32_t dist256(const uint32_t (&a)[8], const uint4 b0, const uint4 b1, const U8Mul &mu) {
     const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     if (NORM == VO_NORM_HAMMING) {
-        uint32_t x[8];  // x[2], x[5], x[6] are the sums sa, sb, sc (prefix form)
-#pragma unroll
-        for (int w = 0; w < 8; ++w) x[w] = a[w] ^ b[w];
-        const uint32_t ca = carry_from_sum(x[0], x[1], x[2]);
-        const uint32_t cb = carry_from_sum(x[3], x[4], x[5]);
-        const uint32_t cc = carry_from_sum(x[2], x[5], x[6]);
-        const uint32_t t = xor3(ca, cb, cc), f = maj3(ca, cb, cc);
-        // ones: sc = x[6], x7; twos: t; fours: f
-        const uint32_t t1 = (uint32_t)__popc(t) * mu.m2 + (uint32_t)__popc(x[6]);
-        const uint32_t t2 = (uint32_t)__popc(f) * mu.m4 + (uint32_t)__popc(x[7]);
+        // a, b in prefix-XOR form (hamming_math.cuh): 13 LOP3 + 4 POPC; the weighted sum is three IMADs (FMA pipe)
+        const HammingPlanes p = hamming_planes(a, b);
+        const uint32_t t1 = (uint32_t)__popc(p.twos) * mu.m2 + (uint32_t)__popc(p.ones_a);
+        const uint32_t t2 = (uint32_t)__popc(p.fours) * mu.m4 + (uint32_t)__popc(p.ones_b);
         return t1 * mu.m1 + t2;
     } else {
         uint32_t d = 0;
