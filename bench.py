@@ -27,11 +27,11 @@ WORKLOADS = {
     # name: (descriptor kind, keypoints, hypotheses, matcher description, cpu matcher)
     "c1": dict(kind="sift", n_kp=2000, n_hyp=512, pairs=256, chunk=256, shape="kitti", cpu_matcher="knn_ratio",
                desc="SIFT 2k kp, L2 kNN-2 + ratio 0.85, PnP-RANSAC 512 hyp, KITTI 1241x376"),
-    "c2": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="hamming_mutual",
+    "c2": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="hamming_mutual", e2e_sampled_frac=0.4,
                desc="ORB 5k kp, 256-bit Hamming mutual-NN, PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
     # c2 with the reference's OWN ORB rule (feature_extractors/ORB.py: cv2.BFMatcher() = NORM_L2 over byte values, ratio 0.85;
     # SURVEY D2) instead of the north-star's Hamming / mutual rule: an exact fp16 tensor-core pass
-    "c2r": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="knn_ratio", orb_l2=True,
+    "c2r": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="knn_ratio", orb_l2=True, e2e_sampled_frac=0.4,
                 desc="ORB 5k kp, reference rule: byte-wise L2 kNN-2 + ratio 0.85, PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
     "c3": dict(kind="r2d2", n_kp=10000, n_hyp=4096, pairs=64, chunk=64, shape="kitti", cpu_matcher="r2d2",
                desc="R2D2 10k kp, cosine GEMM-argmin ratio+mutual, PnP-RANSAC 4096 hyp, KITTI 1241x376"),
@@ -283,7 +283,8 @@ def run_ours(args, wl):
     host_rep = {k: np.concatenate([host[k]] * reps, 0)[:P] for k in ("ref_desc", "cur_desc", "ref_kp", "cur_kp", "depth")}
     host_rep["K"] = host["K"]
     runner = sequence.HostPairRunner(host_rep, cfg, chunk=min(args.e2e_chunk or max(1, chunk // 2), P), device=dev,
-                                     depth_mode=args.e2e_depth, sampled_frac=args.e2e_sampled_frac)
+                                     depth_mode=args.e2e_depth,
+                                     sampled_frac=args.e2e_sampled_frac if args.e2e_sampled_frac is not None else wl.get("e2e_sampled_frac", 0.2))
     del host_rep
 
     def e2e_step():
@@ -471,7 +472,7 @@ def run_ours(args, wl):
                    "host_numa_binding": (f"rank 0 bound to {len(numa_cores)} GPU-local cores" if numa_cores else "none")},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": runner.h2d_bytes,
                 "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
-                "depth": args.e2e_depth},
+                "depth": args.e2e_depth, "sampled_frac": runner.frac},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -501,7 +502,8 @@ def main():
                     "(default: 40; 8 / 4 for c4 / c5)")
     ap.add_argument("--chunk", type=int, default=0, help="pairs per vo_pipeline call (default: workload's)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="pairs per H2D/compute chunk of the e2e run (default: chunk/2)")
-    ap.add_argument("--e2e-sampled-frac", type=float, default=0.2, help="hybrid: fraction of each chunk's maps sampled zero-copy")
+    ap.add_argument("--e2e-sampled-frac", type=float, default=None, help="hybrid: fraction of each chunk's maps sampled zero-copy "
+                    "(default: the workload's; 0.4 at ORB 5k — tools/e2e_sweep.py: 0.2 / 0.4 / 0.6 / 0.8 -> 25.3k / 26.6-27.0k / 25.7k / 24.8k pairs/s — else 0.2)")
     ap.add_argument("--e2e-depth", default="hybrid", choices=["sampled", "dense", "hybrid"],
                     help="e2e leg: copy whole depth maps (dense) or read depth at the reference keypoints zero-copy from "
                          "pinned host memory (sampled), or both concurrently (hybrid, default: measured c2 dense 21.5k, sampled 20.4k, hybrid 23.3k pairs/s)")
