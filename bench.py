@@ -470,7 +470,7 @@ def run_ours(args, wl):
                    f"{batch.nbytes() / 1e6:.0f} MB per GPU per step)", "parallelism": f"pairs sharded over {world} GPU(s), "
                    "1 NCCL all-gather of 4x4 poses per step" if world > 1 else "single GPU",
                    "host_numa_binding": (f"rank 0 bound to {len(numa_cores)} GPU-local cores" if numa_cores else "none")},
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": runner.h2d_bytes,
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": runner.count_matched_bytes(),
                 "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
                 "depth": args.e2e_depth, "sampled_frac": runner.frac},
         "gpu_launches": int(launches),
@@ -504,9 +504,10 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=0, help="pairs per H2D/compute chunk of the e2e run (default: chunk/2)")
     ap.add_argument("--e2e-sampled-frac", type=float, default=None, help="hybrid: fraction of each chunk's maps sampled zero-copy "
                     "(default: the workload's; 0.4 at ORB 5k — tools/e2e_sweep.py: 0.2 / 0.4 / 0.6 / 0.8 -> 25.3k / 26.6-27.0k / 25.7k / 24.8k pairs/s — else 0.2)")
-    ap.add_argument("--e2e-depth", default="hybrid", choices=["sampled", "dense", "hybrid"],
+    ap.add_argument("--e2e-depth", default="hybrid", choices=["sampled", "dense", "hybrid", "matched"],
                     help="e2e leg: copy whole depth maps (dense) or read depth at the reference keypoints zero-copy from "
-                         "pinned host memory (sampled), or both concurrently (hybrid, default: measured c2 dense 21.5k, sampled 20.4k, hybrid 23.3k pairs/s)")
+                         "pinned host memory (sampled), or both concurrently (hybrid, default), or hand vo_pipeline the pinned maps so that only matched "
+                         "keypoints are read (matched).  Measured at c2: dense 22.8k, sampled 25.1k, matched 26.1-26.5k, hybrid 27.0k pairs/s")
     ap.add_argument("--precision", type=int, default=None)
     ap.add_argument("--cpu-pairs", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

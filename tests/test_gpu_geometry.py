@@ -124,11 +124,13 @@ def test_host_runner_sampled_equals_dense():
     batch = synthetic.make_batch(40, B, n_kp=800, kind="orb")
     cfg = sequence.PipelineConfig(ops.VO_NORM_HAMMING, ops.VO_MODE_MUTUAL, 0.0, 0, n_hyp=256)
     outs = []
-    for mode in ("dense", "sampled", "hybrid"):
+    for mode in ("dense", "sampled", "hybrid", "matched"):   # matched: two lanes (stream + vo_ctx), maps read in place
         r = sequence.HostPairRunner(batch, cfg, chunk=5, device="cuda", depth_mode=mode)
-        T, st, inl = r.run(pair0=40)
-        torch.cuda.synchronize()
-        outs.append((T.clone(), st.clone(), inl.clone(), r.h2d_bytes))
+        for _ in range(2):                                    # second pass: stage buffers and lanes are reused
+            T, st, inl = r.run(pair0=40)
+            torch.cuda.synchronize()
+        outs.append((T.clone(), st.clone(), inl.clone(), r.count_matched_bytes()))
     for o in outs[1:]:
         assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) and torch.equal(outs[0][2], o[2])
     assert outs[1][3] < outs[0][3] / 3 and outs[1][3] < outs[2][3] < outs[0][3]
+    assert outs[3][3] < outs[1][3]                            # only the matched keypoints' pixels cross the bus

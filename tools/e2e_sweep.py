@@ -32,7 +32,8 @@ def main():
         e1.record(); torch.cuda.synchronize()
         print(f"resident chunk {chunk:4d}: {P / (e0.elapsed_time(e1) / 3) * 1e3:9.0f} pairs/s", flush=True)
     del dev_batch
-    for mode, frac_list in (("dense", [0.0]), ("hybrid", fracs), ("sampled", [1.0])):
+    ref_T = None
+    for mode, frac_list in (("dense", [0.0]), ("hybrid", fracs), ("sampled", [1.0]), ("matched", [1.0])):
         for frac in frac_list:
             for chunk in chunks:
                 r = sequence.HostPairRunner(rep, cfg, chunk=chunk, device="cuda", depth_mode=mode, sampled_frac=frac)
@@ -44,7 +45,10 @@ def main():
                 e1.record(); torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 3
                 ok = float((r.host_status.numpy() == 0).mean())
-                print(f"{mode:8s} frac {frac:.2f} chunk {chunk:4d}: {P / ms * 1e3:9.0f} pairs/s, {r.h2d_bytes / ms / 1e6:6.1f} GB/s H2D, ok {ok:.3f}", flush=True)
+                T = r.host_T.numpy().copy()
+                ref_T = T if ref_T is None else ref_T
+                same = bool(np.array_equal(T, ref_T))
+                print(f"{mode:8s} frac {frac:.2f} chunk {chunk:4d}: {P / ms * 1e3:9.0f} pairs/s, {r.count_matched_bytes() / ms / 1e6:6.1f} GB/s H2D, ok {ok:.3f}, poses equal to the first setting: {same}", flush=True)
                 del r
 
 if __name__ == "__main__":

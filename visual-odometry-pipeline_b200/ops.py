@@ -15,15 +15,17 @@ from ._lib import (KnnOut, PipelineArgs, VO_METRIC_COSINE, VO_METRIC_L2, VO_MODE
 _contexts = {}
 
 
-def context(device=None):
-    """Per-device vo_ctx (created on first use)."""
+def context(device=None, lane=0):
+    """Per-device vo_ctx (created on first use).  A vo_ctx owns one workspace, so calls that are to run concurrently on
+    different streams of a device use different lanes (lane 0 is the one the profiling / launch counters read)."""
     if not torch.cuda.is_available():
         raise _lib.VoError("no CUDA device: libvo_b200 has no CPU fallback")
     dev = torch.cuda.current_device() if device is None else torch.device(device).index
     dev = 0 if dev is None else dev
-    if dev not in _contexts:
-        _contexts[dev] = _lib.Context(dev)
-    return _contexts[dev]
+    key = dev if lane == 0 else (dev, int(lane))
+    if key not in _contexts:
+        _contexts[key] = _lib.Context(dev)
+    return _contexts[key]
 
 
 def launch_count(device=None):
@@ -287,18 +289,20 @@ class PipelineBuffers:
 
 def pipeline(ref_desc, cur_desc, ref_kp, cur_kp, depth, K, *, norm_or_metric, mode, match_param=0.85,
              precision=VO_PREC_TF32X3, n_ref=None, n_cur=None, n_hyp=1024, seed=8214, pair0=0, thr_px=1.5,
-             min_inliers=20, refine_iters=10, min_flow_px=3.0, z_min=0.0, z_max=50.0, out=None, depth_kp=None, hw=None):
+             min_inliers=20, refine_iters=10, min_flow_px=3.0, z_min=0.0, z_max=50.0, out=None, depth_kp=None, hw=None,
+             lane=0):
     """match -> gather/back-project -> hypotheses -> PnP-RANSAC -> T_rel for a batch of pairs (vo_pipeline).
-    `depth` is the reference frames' dense map [B,H,W]; alternatively pass `depth_kp` [B,N] (sample_depth) and
-    `hw=(H, W)`."""
+    `depth` is the reference frames' dense map [B,H,W], on the device or in pinned host memory (then only the pixels
+    under the matched reference keypoints cross the bus, read zero-copy by the gather kernel); alternatively pass
+    `depth_kp` [B,N] (sample_depth) and `hw=(H, W)`.  `lane` selects the vo_ctx (see context())."""
     _chk(ref_kp, torch.float32, "ref_kp")
     _chk(cur_kp, torch.float32, "cur_kp")
     if depth_kp is not None:
         _chk(depth_kp, torch.float32, "depth_kp")
         if hw is None and depth is None:
             raise ValueError("pipeline: depth_kp needs hw=(H, W)")
-    else:
-        _chk(depth, torch.float32, "depth")
+    elif depth.dtype != torch.float32 or not depth.is_contiguous() or not (depth.is_cuda or depth.is_pinned()):
+        raise ValueError("pipeline: depth must be contiguous float32 on the device or in pinned host memory")
     if not ref_desc.is_contiguous() or not cur_desc.is_contiguous():
         raise ValueError("pipeline: descriptors must be contiguous")
     B, N, M = ref_desc.shape[0], ref_desc.shape[1], cur_desc.shape[1]
@@ -328,7 +332,7 @@ def pipeline(ref_desc, cur_desc, ref_kp, cur_kp, depth, K, *, norm_or_metric, mo
     a.T_rel, a.rt = out.T_rel.data_ptr(), out.rt.data_ptr()
     a.n_matches, a.n_corr = out.n_matches.data_ptr(), out.n_corr.data_ptr()
     a.n_inl, a.status = out.n_inl.data_ptr(), out.status.data_ptr()
-    ctx = context(dev)
+    ctx = context(dev, lane)
     with torch.cuda.device(dev):
         check(ctx.lib.vo_pipeline(ctx.handle, ctypes.byref(a), _stream()), "vo_pipeline")
     return PipelineResult(out.T_rel, out.rt, out.n_matches, out.n_corr, out.n_inl, out.status)

@@ -165,10 +165,14 @@ class HostPairRunner:
       "hybrid"   both at once: the first (1 - sampled_frac) of each chunk's maps go by DMA on the copy stream while the
                  SMs pull the samples of the rest zero-copy on a third stream — the two paths are limited by different
                  things (link bandwidth vs outstanding small reads), so together they move a chunk faster than either.
-    In the last two modes vo_pipeline consumes the compact depth_kp array (sampled on the device for DMA'd maps)."""
+      "matched"  maps stay in pinned host memory and vo_pipeline gets the mapped pointer: the gather kernel reads only
+                 the pixels under the MATCHED reference keypoints that pass the flow filter (~3.6 k of 5 k at ORB 5k).
+                 Those reads sit inside the pipeline (after the matcher), so consecutive chunks alternate between two
+                 lanes (stream + vo_ctx each): one chunk's reads are in flight while the next chunk's matcher runs.
+    In "sampled" / "hybrid" vo_pipeline consumes the compact depth_kp array (sampled on the device for DMA'd maps)."""
 
     def __init__(self, host_batch, cfg, chunk, device="cuda", depth_mode="dense", sampled_frac=0.2):
-        if depth_mode not in ("dense", "sampled", "hybrid"):
+        if depth_mode not in ("dense", "sampled", "hybrid", "matched"):
             raise ValueError(depth_mode)
         self.depth_mode = depth_mode
         self.cfg, self.chunk, self.device = cfg, chunk, torch.device(device)
@@ -177,26 +181,28 @@ class HostPairRunner:
         self.host = {k: torch.from_numpy(np.ascontiguousarray(host_batch[k])).pin_memory() for k in keys}
         self.B = self.host["ref_desc"].shape[0]
         # pairs [0, n_dma) of a chunk send their map by DMA, pairs [n_dma, chunk) are sampled from host memory
-        self.frac = {"dense": 0.0, "sampled": 1.0, "hybrid": float(sampled_frac)}[depth_mode]
+        self.frac = {"dense": 0.0, "sampled": 1.0, "hybrid": float(sampled_frac), "matched": 1.0}[depth_mode]
         self.n_dma = chunk - int(round(chunk * self.frac))
         self.schedule = chunk_schedule(self.B, chunk)
         self.hw = tuple(self.host["depth"].shape[1:])
         N = self.host["ref_kp"].shape[1]
         self.stage = []
-        for _ in range(2):
+        self.n_stage = 4 if depth_mode == "matched" else 2   # matched: two chunks computing + one copying
+        for _ in range(self.n_stage):
             st = {k: torch.empty((chunk,) + tuple(self.host[k].shape[1:]), dtype=self.host[k].dtype, device=self.device)
                   for k in keys if k != "depth"}
-            if self.n_dma:
+            if self.n_dma and depth_mode != "matched":
                 st["depth"] = torch.empty((self.n_dma,) + self.hw, dtype=torch.float32, device=self.device)
-            if depth_mode != "dense":
+            if depth_mode in ("sampled", "hybrid"):
                 st["depth_kp"] = torch.empty((chunk, N), dtype=torch.float32, device=self.device)
             self.stage.append(st)
+        self.lanes = [torch.cuda.Stream(device=self.device) for _ in range(2)] if depth_mode == "matched" else []
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.sample_stream = torch.cuda.Stream(device=self.device)
-        self.copied = [torch.cuda.Event() for _ in range(2)]
-        self.kp_ready = [torch.cuda.Event() for _ in range(2)]
-        self.sampled = [torch.cuda.Event() for _ in range(2)]
-        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.copied = [torch.cuda.Event() for _ in range(self.n_stage)]
+        self.kp_ready = [torch.cuda.Event() for _ in range(self.n_stage)]
+        self.sampled = [torch.cuda.Event() for _ in range(self.n_stage)]
+        self.consumed = [torch.cuda.Event() for _ in range(self.n_stage)]
         self.out = ops.PipelineBuffers(self.B, self.device)
         self.host_T = torch.empty((self.B, 4, 4), dtype=torch.float64).pin_memory()
         self.host_status = torch.empty((self.B,), dtype=torch.int32).pin_memory()
@@ -206,6 +212,47 @@ class HostPairRunner:
         self.h2d_bytes = self.B * sum(b for k, b in per_pair.items() if k != "depth") + dma_pairs * per_pair["depth"] \
             + (self.B - dma_pairs) * N * 32          # one 32-byte sector per zero-copy sample
         self.d2h_bytes = self.host_T.numel() * 8 + self.host_status.numel() * 4 + self.host_inl.numel() * 4
+        self._base_bytes = self.B * sum(b for k, b in per_pair.items() if k != "depth")
+
+    def count_matched_bytes(self):
+        """matched mode, after a run: h2d_bytes = descriptors / keypoints + one 32-byte sector per match (every match
+        reads at most one depth pixel; those under the flow filter read none, so this is an upper bound)."""
+        if self.depth_mode == "matched":
+            self.h2d_bytes = self._base_bytes + int(self.out.n_matches.sum().item()) * 32
+        return self.h2d_bytes
+
+    def _view(self, lo, hi):
+        view = ops.PipelineBuffers.__new__(ops.PipelineBuffers)
+        view.T_rel, view.rt = self.out.T_rel[lo:hi], self.out.rt[lo:hi]
+        view.n_matches, view.n_corr = self.out.n_matches[lo:hi], self.out.n_corr[lo:hi]
+        view.n_inl, view.status = self.out.n_inl[lo:hi], self.out.status[lo:hi]
+        return view
+
+    def _run_matched(self, pair0):
+        compute = torch.cuda.current_stream(self.device)
+        for ls in self.lanes:
+            ls.wait_stream(compute)
+        for c, (lo, hi) in enumerate(self.schedule):
+            n, buf, lane = hi - lo, c % self.n_stage, c % 2
+            st = self.stage[buf]
+            with torch.cuda.stream(self.copy_stream):
+                if c >= self.n_stage:
+                    self.copy_stream.wait_event(self.consumed[buf])
+                for k in ("ref_kp", "cur_kp", "ref_desc", "cur_desc"):
+                    st[k][:n].copy_(self.host[k][lo:hi], non_blocking=True)
+                self.copied[buf].record(self.copy_stream)
+            with torch.cuda.stream(self.lanes[lane]):
+                self.lanes[lane].wait_event(self.copied[buf])
+                ops.pipeline(st["ref_desc"][:n], st["cur_desc"][:n], st["ref_kp"][:n], st["cur_kp"][:n],
+                             self.host["depth"][lo:hi], self.K, pair0=pair0 + lo, out=self._view(lo, hi), lane=lane,
+                             **self.cfg.kw)
+                self.consumed[buf].record(self.lanes[lane])
+        for ls in self.lanes:
+            compute.wait_stream(ls)
+        self.host_T.copy_(self.out.T_rel, non_blocking=True)
+        self.host_status.copy_(self.out.status, non_blocking=True)
+        self.host_inl.copy_(self.out.n_inl, non_blocking=True)
+        return self.host_T, self.host_status, self.host_inl
 
     def _n_dma(self, n):
         """pairs of an n-pair chunk whose depth map travels by DMA (the rest is sampled zero-copy)"""
@@ -213,6 +260,8 @@ class HostPairRunner:
 
     def run(self, pair0=0):
         """One pass over all pairs.  Returns after the D2H copies were enqueued; caller synchronises."""
+        if self.depth_mode == "matched":
+            return self._run_matched(pair0)
         compute = torch.cuda.current_stream(self.device)
         for c, (lo, hi) in enumerate(self.schedule):
             n, buf = hi - lo, c % 2
