@@ -219,7 +219,8 @@ typedef struct vo_pipeline_args {
     /* keypoints + depth */
     const float *ref_kp, *cur_kp;
     int kp_stride;
-    const float *depth;
+    const float *depth; /* float [B][H][W] of the reference frames; device memory, or pinned host memory mapped into the
+                         * device address space (then only the pixels under matched keypoints cross the bus) */
     int H, W;
     const double *K_h; /* host double[9] */
     float min_flow_px, z_min, z_max;
