@@ -19,6 +19,9 @@ def hm():
                            os.path.join(HERE, "host_math_shim.cpp")])
     lib = ctypes.CDLL(so)
     lib.hm_is_inlier.restype = ctypes.c_int
+    lib.hm_orb_harris.restype = ctypes.c_float
+    lib.hm_orb_atan2.restype = ctypes.c_float
+    lib.hm_orb_atan2.argtypes = [ctypes.c_float, ctypes.c_float]
     return lib
 
 
@@ -86,3 +89,46 @@ def test_prefix_xor_hamming_tree_equals_popcount(hm):
     want = np.unpackbits((a ^ b).view(np.uint8), axis=1).sum(1)
     assert np.array_equal(got, want)
     assert got[n // 2] == 0 and got[n // 2 + 1] == 256 and (got[n // 2 + 2: n // 2 + 258] == 1).all()
+
+
+def test_orb_math_header_equals_oracle(hm):
+    """csrc/orb_math.cuh (the arithmetic the ORB front-end kernels will run) against oracle/orb_frontend.py, which is
+    pinned against OpenCV: gray weights, INTER_LINEAR_EXACT, FAST corner score, Harris response, fastAtan2, the float
+    Gaussian, the rotated rBRIEF pattern, the circular-patch table."""
+    from oracle import orb_frontend as of
+    rng = np.random.default_rng(8214)
+    assert [hm.hm_orb_umax(v) for v in range(16)] == [int(u) for u in of.umax_table(15)[:16]]
+    bgr = rng.integers(0, 256, (64, 3), dtype=np.uint8)
+    assert [hm.hm_orb_gray(int(b), int(g), int(r)) for b, g, r in bgr] == [int(v) for v in of.bgr_to_gray(bgr[None])[0]]
+    # resize cascade of a KITTI-wide strip
+    img = rng.integers(0, 256, (60, 1241), dtype=np.uint8)
+    for dw, dh in ((1034, 50), (862, 42), (97, 7), (1241, 60), (2000, 90)):
+        out = np.zeros((dh, dw), np.uint8)
+        hm.hm_orb_resize(_p(img), 1241, 60, _p(out), dw, dh)
+        assert np.array_equal(out, of.resize_linear_exact(img, dw, dh)), (dw, dh)
+    # FAST score map: noise (dense corners) and a smooth image with flat rectangles (ties, non-corners)
+    smooth = np.kron(rng.integers(0, 256, (12, 20), dtype=np.uint8), np.ones((8, 8), np.uint8))
+    for im in (rng.integers(0, 256, (70, 90), dtype=np.uint8), np.ascontiguousarray(smooth)):
+        got = np.zeros(im.shape, np.int32)
+        hm.hm_orb_fast_map(_p(im), im.shape[1], im.shape[0], 20, _p(got))
+        want = of.fast_scores(im, 20)
+        assert np.array_equal(got, want) and (want > 0).any()
+    # Harris response from integer sums (incl. the magnitudes a 7x7 block of extreme gradients reaches)
+    for a, b, c in np.concatenate([rng.integers(0, 49 * 1020 * 1020, (200, 3)), [[0, 0, 0], [49 * 1020 * 1020] * 3]]):
+        c = int(c) - 20_000_000
+        fa, fb, fc = np.float32(int(a)), np.float32(int(b)), np.float32(c)
+        scale = np.float32(1.0) / np.float32(28 * np.float32(255.0))
+        want = (fa * fb - fc * fc - np.float32(0.04) * (fa + fb) * (fa + fb)) * (scale * scale * scale * scale)
+        assert np.float32(hm.hm_orb_harris(int(a), int(b), c)) == want
+    for y, x in np.concatenate([rng.integers(-60000, 60000, (400, 2)), [[0, 0], [0, 5], [5, 0], [-5, 0], [0, -5], [7, 7], [-7, 7]]]):
+        assert np.float32(hm.hm_orb_atan2(float(y), float(x))) == of.fast_atan2(y, x), (y, x)
+    tex = rng.integers(0, 256, (40, 57), dtype=np.uint8)
+    out = np.zeros_like(tex)
+    hm.hm_orb_blur(_p(tex), 57, 40, _p(out))
+    assert np.array_equal(out, of.blur_7x7(tex))
+    pat = np.ascontiguousarray(of.pattern().astype(np.int32))
+    for ang in np.concatenate([rng.uniform(0, 360, 100).astype(np.float32), np.float32([0, 90, 180, 270, 359.99])]):
+        ix, iy = np.zeros(512, np.int32), np.zeros(512, np.int32)
+        hm.hm_orb_rotate(ctypes.c_float(float(ang)), _p(pat), 512, _p(ix), _p(iy))
+        wx, wy = of.rotated_pattern(ang, pat)
+        assert np.array_equal(ix, wx) and np.array_equal(iy, wy), ang
