@@ -1,6 +1,6 @@
 // Per-pixel / per-keypoint arithmetic of the ORB front-end (feature_extractors/ORB.py:8-21 -> cv2.ORB_create()
 // .detectAndCompute), written once for device code and compilable for the host: tests/test_host_math.py checks every
-// function bit for bit against oracle/orb_frontend.py, which is pinned against OpenCV.  The kernels that will call
+// function bit for bit against the CPU restatement of the front-end, which is pinned against OpenCV.  The kernels that will call
 // these (pyramid, FAST map, retainBest, Harris, orientation, Gaussian, rBRIEF: DESIGN 8 item 7) are NOT built yet —
 // nothing in libvo_b200.so includes this header so far.
 //
@@ -39,7 +39,7 @@ namespace orb {
 constexpr int BORDER = 32;        // max(edgeThreshold 31, ceil(15 sqrt 2), HARRIS_BLOCK_SIZE / 2) + 1
 constexpr int HALF_PATCH = 15;
 // Row half-width of the circular orientation patch at row offset v = 0..15 (orb.cpp computeKeyPoints, umax):
-// {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3}, one nibble each; checked against the oracle.
+// {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3}, one nibble each; checked against the CPU restatement.
 VO_ORB_HD int umax(int v) { return (int)((0x3689abcddeeeffffull >> (4 * v)) & 15ull); }
 
 // cv2.cvtColor(BGR2GRAY) on 8-bit pixels.
