@@ -336,6 +336,31 @@ VO_API int vo_r2d2_out_shape(const vo_r2d2 *net, int *Ho, int *Wo);
 VO_API int vo_r2d2_extract(vo_r2d2 *net, const uint8_t *rgb, float rel_thr, float rep_thr, float score_thr, float *xys,
                     float *desc, float *scores, int32_t *count, float *rel_map, float *rep_map, void *stream);
 
+/*
+ * ORB front-end: `extract_features_and_desc` of feature_extractors/ORB.py:10-21, i.e.
+ * cv2.ORB_create() (ORB.py:8, all defaults: scale 1.2f, edge 31, patch 31, Harris score, WTA_K 2) followed by
+ * detectAndCompute: gray conversion, INTER_LINEAR_EXACT pyramid, FAST-9/16 + non-maximum suppression, retainBest on
+ * the FAST score and on the Harris response (ties kept), intensity-centroid orientation, 7x7 Gaussian, rBRIEF.
+ * NOT YET RUN ON A GPU (see csrc/orb.cu): the arithmetic is host-verified against the pinned CPU restatement.
+ *   vo_orb_extract: image uint8 [H][W] (channels = 1) or [H][W][3] BGR (channels = 3), device-accessible.
+ *   Outputs (device), vo_orb_capacity() rows each: kp float [cap][2] = KeyPoint.pt; desc uint8 [cap][32];
+ *   aux float [cap][4] = (octave, angle in degrees, response, size), optional; count int32[2] = (keypoints written,
+ *   overflow flag: a level kept more than its share of ties).  Order: level-major, then row-major (OpenCV's own
+ *   order is unspecified: it depends on std::nth_element).
+ */
+typedef struct vo_orb_config {
+    int H, W;
+    int nfeatures;       /* 500 */
+    int nlevels;         /* 8 (at most 8) */
+    int fast_threshold;  /* 20 */
+} vo_orb_config;
+typedef struct vo_orb vo_orb;
+VO_API int vo_orb_create(vo_ctx *ctx, const vo_orb_config *cfg, vo_orb **out);
+VO_API void vo_orb_destroy(vo_orb *orb);
+VO_API int vo_orb_capacity(const vo_orb *orb);
+VO_API int vo_orb_extract(vo_orb *orb, const uint8_t *image, int channels, float *kp, uint8_t *desc, float *aux,
+                   int32_t *count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,10 @@ class R2d2Config(ctypes.Structure):
                 ("max_kp", c_int)]
 
 
+class OrbConfig(ctypes.Structure):
+    _fields_ = [("H", c_int), ("W", c_int), ("nfeatures", c_int), ("nlevels", c_int), ("fast_threshold", c_int)]
+
+
 PROTOTYPES = {
     "vo_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     "vo_destroy": (None, [c_void_p]),
@@ -117,6 +121,10 @@ PROTOTYPES = {
     "vo_r2d2_out_shape": (c_int, [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "vo_r2d2_extract": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
+    "vo_orb_create": (c_int, [c_void_p, ctypes.POINTER(OrbConfig), ctypes.POINTER(c_void_p)]),
+    "vo_orb_destroy": (None, [c_void_p]),
+    "vo_orb_capacity": (c_int, [c_void_p]),
+    "vo_orb_extract": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vo_profile_enable": (c_int, [c_void_p, c_int]),
     "vo_profile_collect": (c_int, [c_void_p, c_void_p, c_void_p]),
 }

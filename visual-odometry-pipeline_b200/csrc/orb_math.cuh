@@ -52,7 +52,11 @@ VO_ORB_HD uint8_t bgr_to_gray(uint8_t b, uint8_t g, uint8_t r) {
 // the destination pixel copies source pixel `ofs` (clamped edge).
 VO_ORB_HD void linear_exact_coeff(int x, int dst, int src, int &ofs, int &c1, bool &inside) {
     const double scale = 1.0 / ((double)dst / (double)src);
+#if defined(__CUDA_ARCH__)   // OpenCV's softdouble rounds the product and the difference separately: no contraction
+    const double fval = __dsub_rn(__dmul_rn(scale, (double)x + 0.5), 0.5);
+#else
     const double fval = scale * ((double)x + 0.5) - 0.5;
+#endif
     const int iv = (int)floor(fval);
     inside = iv >= 0 && iv < src - 1 && src > 1;
     if (inside) {
