@@ -1,6 +1,10 @@
 // Shared host/device helpers for libvo_b200 (sm_100a only).
 #pragma once
+#ifdef VO_HOST_EMU          // test builds only: the host emulation of the execution model (tests/cuda_emu.h)
+#include VO_HOST_EMU
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -68,6 +72,16 @@ __host__ __device__ inline float ordered_to_float(uint32_t k) {
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Kernel launch on stream `st` with no dynamic shared memory.  VO_LAUNCH_BAR marks kernels that use __syncthreads: on
+// the device the two are the same; the host emulation used by the tests gives those kernels real threads.
+#ifdef VO_HOST_EMU
+#define VO_LAUNCH(kernel, grid, block, st, ...) vo_emu::launch((grid), (block), false, [&]() { kernel(__VA_ARGS__); })
+#define VO_LAUNCH_BAR(kernel, grid, block, st, ...) vo_emu::launch((grid), (block), true, [&]() { kernel(__VA_ARGS__); })
+#else
+#define VO_LAUNCH(kernel, grid, block, st, ...) kernel<<<(grid), (block), 0, (st)>>>(__VA_ARGS__)
+#define VO_LAUNCH_BAR(kernel, grid, block, st, ...) kernel<<<(grid), (block), 0, (st)>>>(__VA_ARGS__)
+#endif
 
 }  // namespace vo
 

@@ -3,8 +3,9 @@
 // 1.2f, 8 levels, edge 31, patch 31, FAST threshold 20, Harris score.  SURVEY 8(f) rank 1.
 //
 // STATUS: compiled for sm_100a; every arithmetic routine it calls (orb_math.cuh) is checked bit for bit on the host
-// against the CPU restatement that is pinned against OpenCV; the kernels themselves have NOT run on a GPU yet
-// (tests/test_gpu_orb.py is ready and opt-in, VO_ORB_GPU=1).  No product path calls this file so far.
+// against the CPU restatement that is pinned against OpenCV, and this very file — kernels and launch sequence — runs
+// bit-identical to it under the host emulation of tests/cuda_emu.h (tests/test_orb_emulation.py).  The kernels have
+// NOT run on a GPU yet (tests/test_gpu_orb.py is ready and opt-in, VO_ORB_GPU=1); no product path calls this file.
 //
 // Data layout: one unbordered 8-bit image per pyramid level, back to back in one buffer (keypoints stay >= 31 pixels
 // from the border, so orientation / Harris / rBRIEF never leave a level; the Gaussian reflects indices).  Per level:
@@ -428,7 +429,7 @@ extern "C" int vo_orb_extract(vo_orb *o, const uint8_t *image, int channels, flo
     VO_CUDA(cudaMemsetAsync(o->counts, 0, sizeof(int32_t) * 32, st));
     const int n_px = o->W * o->H;
     if (channels == 3) {
-        orb_gray_kernel<<<ceil_div(n_px, 256), 256, 0, st>>>(image, o->pyr, n_px);
+        VO_LAUNCH(orb_gray_kernel, ceil_div(n_px, 256), 256, st, image, o->pyr, n_px);
         VO_LAUNCH_CHECK(ctx);
     } else {
         VO_CUDA(cudaMemcpyAsync(o->pyr, image, (size_t)n_px, cudaMemcpyDefault, st));
@@ -438,32 +439,32 @@ extern "C" int vo_orb_extract(vo_orb *o, const uint8_t *image, int channels, flo
         const dim3 grid(ceil_div(lv.w, 128), lv.h);
         if (l > 0) {   // every level is resized from the previous one
             const OrbLevel &pv = L.l[l - 1];
-            orb_resize_kernel<<<grid, 128, 0, st>>>(o->pyr + pv.img_ofs, pv.w, pv.h, o->pyr + lv.img_ofs, lv.w, lv.h);
+            VO_LAUNCH(orb_resize_kernel, grid, 128, st, o->pyr + pv.img_ofs, pv.w, pv.h, o->pyr + lv.img_ofs, lv.w, lv.h);
             VO_LAUNCH_CHECK(ctx);
         }
         if (lv.w < 2 * ORB_EDGE + 1 || lv.h < 2 * ORB_EDGE + 1) continue;   // no pixel survives the border filter
-        orb_fast_kernel<<<grid, 128, 0, st>>>(o->pyr + lv.img_ofs, lv.w, lv.h, o->fast_thr, o->score + lv.img_ofs);
+        VO_LAUNCH(orb_fast_kernel, grid, 128, st, o->pyr + lv.img_ofs, lv.w, lv.h, o->fast_thr, o->score + lv.img_ofs);
         VO_LAUNCH_CHECK(ctx);
-        orb_nms_kernel<<<grid, 128, 0, st>>>(o->score + lv.img_ofs, lv.w, lv.h, o->cand_xy + lv.cand_ofs,
-                                             o->cand_s + lv.cand_ofs, cand_count + l, lv.cand_cap);
+        VO_LAUNCH(orb_nms_kernel, grid, 128, st, o->score + lv.img_ofs, lv.w, lv.h, o->cand_xy + lv.cand_ofs,
+                  o->cand_s + lv.cand_ofs, cand_count + l, lv.cand_cap);
         VO_LAUNCH_CHECK(ctx);
-        orb_blur_row_kernel<<<grid, 128, 0, st>>>(o->pyr + lv.img_ofs, lv.w, lv.h, o->g, o->tmp + lv.img_ofs);
+        VO_LAUNCH(orb_blur_row_kernel, grid, 128, st, o->pyr + lv.img_ofs, lv.w, lv.h, o->g, o->tmp + lv.img_ofs);
         VO_LAUNCH_CHECK(ctx);
-        orb_blur_col_kernel<<<grid, 128, 0, st>>>(o->tmp + lv.img_ofs, lv.w, lv.h, o->g, o->blurred + lv.img_ofs);
+        VO_LAUNCH(orb_blur_col_kernel, grid, 128, st, o->tmp + lv.img_ofs, lv.w, lv.h, o->g, o->blurred + lv.img_ofs);
         VO_LAUNCH_CHECK(ctx);
     }
-    orb_select_fast_kernel<<<L.n, 1024, 0, st>>>(L, o->cand_xy, o->cand_s, cand_count, o->surv_xy, surv_count);
+    VO_LAUNCH_BAR(orb_select_fast_kernel, L.n, 1024, st, L, o->cand_xy, o->cand_s, cand_count, o->surv_xy, surv_count);
     VO_LAUNCH_CHECK(ctx);
     int max_cap = 0;
     for (int l = 0; l < L.n; ++l) max_cap = L.l[l].cand_cap > max_cap ? L.l[l].cand_cap : max_cap;
-    orb_harris_kernel<<<dim3(ceil_div(max_cap, 256), L.n), 256, 0, st>>>(L, o->pyr, o->surv_xy, surv_count, o->resp);
+    VO_LAUNCH(orb_harris_kernel, dim3(ceil_div(max_cap, 256), L.n), 256, st, L, o->pyr, o->surv_xy, surv_count, o->resp);
     VO_LAUNCH_CHECK(ctx);
-    orb_select_harris_kernel<<<L.n, 1024, 0, st>>>(L, o->surv_xy, o->resp, surv_count, o->fin_xy, o->fin_resp, fin_count, overflow);
+    VO_LAUNCH_BAR(orb_select_harris_kernel, L.n, 1024, st, L, o->surv_xy, o->resp, surv_count, o->fin_xy, o->fin_resp, fin_count, overflow);
     VO_LAUNCH_CHECK(ctx);
-    orb_finish_kernel<<<dim3(ceil_div(ORB_FINAL_CAP, 128), L.n), 128, 0, st>>>(L, o->pyr, o->fin_xy, o->fin_resp, fin_count, overflow,
-                                                                             kp, aux, o->angle, count);
+    VO_LAUNCH(orb_finish_kernel, dim3(ceil_div(ORB_FINAL_CAP, 128), L.n), 128, st, L, o->pyr, o->fin_xy, o->fin_resp, fin_count,
+              overflow, kp, aux, o->angle, count);
     VO_LAUNCH_CHECK(ctx);
-    orb_desc_kernel<<<dim3(ceil_div(ORB_FINAL_CAP, 8), L.n), 256, 0, st>>>(L, o->blurred, o->fin_xy, fin_count, o->angle, desc);
+    VO_LAUNCH(orb_desc_kernel, dim3(ceil_div(ORB_FINAL_CAP, 8), L.n), 256, st, L, o->blurred, o->fin_xy, fin_count, o->angle, desc);
     VO_LAUNCH_CHECK(ctx);
     return VO_OK;
 }
