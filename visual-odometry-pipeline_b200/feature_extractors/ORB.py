@@ -10,7 +10,12 @@ import numpy as np
 from feature_extractors import _gpu_match
 
 MATCHER = "l2_ratio"  # or "hamming_mutual"
+# Extraction: "opencv" (cv2 on the CPU, as the reference) or "gpu" (vo_orb_extract: the same keypoint set and bit-identical
+# descriptors, in level-major / row-major order instead of OpenCV's unspecified one).  "gpu" stays opt-in until
+# tests/test_gpu_orb.py has been run on a B200 (csrc/orb.cu is so far verified under the host emulation only).
+EXTRACTOR = "opencv"
 _orb = None
+_gpu_orb = {}
 
 
 def _detector():
@@ -21,6 +26,13 @@ def _detector():
 
 
 def extract_features_and_desc(image):
+    if EXTRACTOR == "gpu":
+        from vo_b200.orb_frontend import OrbExtractor
+        key = tuple(image.shape[:2])
+        if key not in _gpu_orb:
+            _gpu_orb[key] = OrbExtractor(*key)
+        kp, desc, _ = _gpu_orb[key].extract(np.ascontiguousarray(image))
+        return kp.cpu().numpy().astype(np.float64), desc.cpu().numpy()
     gray = cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)
     kps, desc = _detector().detectAndCompute(gray, None)
     return np.asarray([[k.pt[0], k.pt[1]] for k in kps]), desc
