@@ -13,7 +13,8 @@
 // retainBest(2 n) on the integer score (256-bin histogram), their Harris responses, the survivors of retainBest(n) on
 // the response (4-pass radix select on the ordered float bits; ties kept, as OpenCV does), ranked by (y, x) so that the
 // output order is deterministic: level-major, then row-major (OpenCV's own order depends on std::nth_element).
-// Everything is HBM-bound integer / byte work: ~1.1 M pixels per 1241 x 376 frame over the 8 levels.
+// Everything is HBM-bound integer / byte work: ~1.1 M pixels per 1241 x 376 frame over the 8 levels; the per-pixel
+// kernels cover all levels in one launch each (17 launches per BGR frame, 7 of them the resize cascade).
 //
 // The rBRIEF point pairs below are OpenCV's learned pattern (modules/features2d/src/orb.cpp, bit_pattern_31_,
 // Apache-2.0): data of the third-party library whose arithmetic the reference's plug-in runs.
@@ -75,7 +76,17 @@ struct OrbLevel {
 struct OrbLevels {
     OrbLevel l[ORB_MAX_LEVELS];
     int n;
+    int total_rows;      // sum of the level heights: per-pixel kernels run over all levels in one launch
 };
+
+// blockIdx.y of an all-level launch -> (level, row inside it).  The grid is as wide as level 0.
+__device__ __forceinline__ bool orb_locate_row(const OrbLevels &L, int gy, int &lev, int &y) {
+    for (lev = 0; lev < L.n; ++lev) {
+        if (gy < L.l[lev].h) { y = gy; return true; }
+        gy -= L.l[lev].h;
+    }
+    return false;
+}
 
 __global__ void orb_gray_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ gray, int n_px) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,10 +105,14 @@ __global__ void orb_resize_kernel(const uint8_t *__restrict__ src, int W, int H,
                                                       src[(size_t)oy1 * W + ox], src[(size_t)oy1 * W + ox1], cx, inx, cy, iny);
 }
 
-// FAST-9/16 corner score of every pixel (0 in the 3-pixel frame and for non-corners).
-__global__ void orb_fast_kernel(const uint8_t *__restrict__ img, int w, int h, int thr, uint8_t *__restrict__ score) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+// FAST-9/16 corner score of every pixel of every level (0 in the 3-pixel frame and for non-corners).
+__global__ void orb_fast_kernel(OrbLevels L, const uint8_t *__restrict__ pyr, int thr, uint8_t *__restrict__ score_all) {
+    int lev, y;
+    if (!orb_locate_row(L, blockIdx.y, lev, y)) return;
+    const int w = L.l[lev].w, h = L.l[lev].h;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
+    const uint8_t *img = pyr + L.l[lev].img_ofs;
     int s = 0;
     if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
         const uint8_t *p = img + (size_t)y * w + x;
@@ -115,20 +130,24 @@ __global__ void orb_fast_kernel(const uint8_t *__restrict__ img, int w, int h, i
             s = orb::fast_corner_score(v, ring, thr);
         }
     }
-    score[(size_t)y * w + x] = (uint8_t)s;
+    score_all[L.l[lev].img_ofs + (size_t)y * w + x] = (uint8_t)s;
 }
 
-// Corners that are strict maxima of the score in their 3x3 neighbourhood and lie >= 31 pixels inside the level.
-__global__ void orb_nms_kernel(const uint8_t *__restrict__ score, int w, int h, uint32_t *__restrict__ cand_xy,
-                               uint8_t *__restrict__ cand_s, int32_t *__restrict__ count, int cap) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+// Corners that are strict maxima of the score in their 3x3 neighbourhood and lie >= 31 pixels inside their level.
+__global__ void orb_nms_kernel(OrbLevels L, const uint8_t *__restrict__ score_all, uint32_t *__restrict__ cand_xy,
+                               uint8_t *__restrict__ cand_s, int32_t *__restrict__ cand_count) {
+    int lev, y;
+    if (!orb_locate_row(L, blockIdx.y, lev, y)) return;
+    const OrbLevel lv = L.l[lev];
+    const int w = lv.w, h = lv.h;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x < ORB_EDGE || x >= w - ORB_EDGE || y < ORB_EDGE || y >= h - ORB_EDGE) return;
-    const uint8_t *p = score + (size_t)y * w + x;
+    const uint8_t *p = score_all + lv.img_ofs + (size_t)y * w + x;
     const int s = p[0];
     if (s == 0) return;
     if (s > p[-1] && s > p[1] && s > p[-w - 1] && s > p[-w] && s > p[-w + 1] && s > p[w - 1] && s > p[w] && s > p[w + 1]) {
-        const int i = atomicAdd(count, 1);
-        if (i < cap) { cand_xy[i] = (uint32_t)x | ((uint32_t)y << 16); cand_s[i] = (uint8_t)s; }
+        const int i = atomicAdd(cand_count + lev, 1);
+        if (i < lv.cand_cap) { cand_xy[lv.cand_ofs + i] = (uint32_t)x | ((uint32_t)y << 16); cand_s[lv.cand_ofs + i] = (uint8_t)s; }
     }
 }
 
@@ -292,21 +311,29 @@ __device__ __forceinline__ int reflect101(int i, int n) { return i < 0 ? -i : (i
 
 struct GaussK { float k[7]; };
 
-__global__ void orb_blur_row_kernel(const uint8_t *__restrict__ img, int w, int h, GaussK g, float *__restrict__ tmp) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+__global__ void orb_blur_row_kernel(OrbLevels L, const uint8_t *__restrict__ pyr, GaussK g, float *__restrict__ tmp_all) {
+    int lev, y;
+    if (!orb_locate_row(L, blockIdx.y, lev, y)) return;
+    const int w = L.l[lev].w;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
+    const uint8_t *img = pyr + L.l[lev].img_ofs;
     uint8_t p[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) p[i] = img[(size_t)y * w + reflect101(x + i - 3, w)];
-    tmp[(size_t)y * w + x] = orb::blur_row(g.k, p);
+    tmp_all[L.l[lev].img_ofs + (size_t)y * w + x] = orb::blur_row(g.k, p);
 }
-__global__ void orb_blur_col_kernel(const float *__restrict__ tmp, int w, int h, GaussK g, uint8_t *__restrict__ out) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+__global__ void orb_blur_col_kernel(OrbLevels L, const float *__restrict__ tmp_all, GaussK g, uint8_t *__restrict__ blurred) {
+    int lev, y;
+    if (!orb_locate_row(L, blockIdx.y, lev, y)) return;
+    const int w = L.l[lev].w, h = L.l[lev].h;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
+    const float *tmp = tmp_all + L.l[lev].img_ofs;
     float c[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) c[i] = tmp[(size_t)reflect101(y + i - 3, h) * w + x];
-    out[(size_t)y * w + x] = orb::blur_col(g.k, c);
+    blurred[L.l[lev].img_ofs + (size_t)y * w + x] = orb::blur_col(g.k, c);
 }
 
 // rBRIEF: one warp per keypoint, lane = descriptor byte (8 point pairs = 16 pattern points).
@@ -397,6 +424,8 @@ extern "C" int vo_orb_create(vo_ctx *ctx, const vo_orb_config *cfg, vo_orb **out
         cand_ofs += ((size_t)lv.cand_cap + 63) & ~(size_t)63;
     }
     o->pyr_bytes = img_ofs; o->cand_total = cand_ofs;
+    o->L.total_rows = 0;
+    for (int l = 0; l < cfg->nlevels; ++l) o->L.total_rows += o->L.l[l].h;
     orb::gaussian_kernel(o->g.k);
     const size_t fin = (size_t)cfg->nlevels * ORB_FINAL_CAP;
     cudaError_t e = cudaSuccess;
@@ -434,25 +463,22 @@ extern "C" int vo_orb_extract(vo_orb *o, const uint8_t *image, int channels, flo
     } else {
         VO_CUDA(cudaMemcpyAsync(o->pyr, image, (size_t)n_px, cudaMemcpyDefault, st));
     }
-    for (int l = 0; l < L.n; ++l) {
-        const OrbLevel &lv = L.l[l];
-        const dim3 grid(ceil_div(lv.w, 128), lv.h);
-        if (l > 0) {   // every level is resized from the previous one
-            const OrbLevel &pv = L.l[l - 1];
-            VO_LAUNCH(orb_resize_kernel, grid, 128, st, o->pyr + pv.img_ofs, pv.w, pv.h, o->pyr + lv.img_ofs, lv.w, lv.h);
-            VO_LAUNCH_CHECK(ctx);
-        }
-        if (lv.w < 2 * ORB_EDGE + 1 || lv.h < 2 * ORB_EDGE + 1) continue;   // no pixel survives the border filter
-        VO_LAUNCH(orb_fast_kernel, grid, 128, st, o->pyr + lv.img_ofs, lv.w, lv.h, o->fast_thr, o->score + lv.img_ofs);
-        VO_LAUNCH_CHECK(ctx);
-        VO_LAUNCH(orb_nms_kernel, grid, 128, st, o->score + lv.img_ofs, lv.w, lv.h, o->cand_xy + lv.cand_ofs,
-                  o->cand_s + lv.cand_ofs, cand_count + l, lv.cand_cap);
-        VO_LAUNCH_CHECK(ctx);
-        VO_LAUNCH(orb_blur_row_kernel, grid, 128, st, o->pyr + lv.img_ofs, lv.w, lv.h, o->g, o->tmp + lv.img_ofs);
-        VO_LAUNCH_CHECK(ctx);
-        VO_LAUNCH(orb_blur_col_kernel, grid, 128, st, o->tmp + lv.img_ofs, lv.w, lv.h, o->g, o->blurred + lv.img_ofs);
+    for (int l = 1; l < L.n; ++l) {   // every level is resized from the previous one
+        const OrbLevel &lv = L.l[l], &pv = L.l[l - 1];
+        VO_LAUNCH(orb_resize_kernel, dim3(ceil_div(lv.w, 128), lv.h), 128, st, o->pyr + pv.img_ofs, pv.w, pv.h,
+                  o->pyr + lv.img_ofs, lv.w, lv.h);
         VO_LAUNCH_CHECK(ctx);
     }
+    // per-pixel work of all levels in one launch each (levels too small for the 31-pixel border yield no candidate)
+    const dim3 grid_all(ceil_div(L.l[0].w, 128), L.total_rows);
+    VO_LAUNCH(orb_fast_kernel, grid_all, 128, st, L, o->pyr, o->fast_thr, o->score);
+    VO_LAUNCH_CHECK(ctx);
+    VO_LAUNCH(orb_nms_kernel, grid_all, 128, st, L, o->score, o->cand_xy, o->cand_s, cand_count);
+    VO_LAUNCH_CHECK(ctx);
+    VO_LAUNCH(orb_blur_row_kernel, grid_all, 128, st, L, o->pyr, o->g, o->tmp);
+    VO_LAUNCH_CHECK(ctx);
+    VO_LAUNCH(orb_blur_col_kernel, grid_all, 128, st, L, o->tmp, o->g, o->blurred);
+    VO_LAUNCH_CHECK(ctx);
     VO_LAUNCH_BAR(orb_select_fast_kernel, L.n, 1024, st, L, o->cand_xy, o->cand_s, cand_count, o->surv_xy, surv_count);
     VO_LAUNCH_CHECK(ctx);
     int max_cap = 0;
