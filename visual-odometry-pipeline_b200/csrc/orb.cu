@@ -423,6 +423,13 @@ extern "C" int vo_orb_create(vo_ctx *ctx, const vo_orb_config *cfg, vo_orb **out
         img_ofs += ((size_t)lv.w * lv.h + 255) & ~(size_t)255;
         cand_ofs += ((size_t)lv.cand_cap + 63) & ~(size_t)63;
     }
+    for (int l = 0; l < cfg->nlevels; ++l)
+        if (o->L.l[l].n_feat > ORB_FINAL_CAP / 2) {   // leave room for ties with the n-th response
+            set_error("vo_orb_create: nfeatures %d asks level %d for %d keypoints (at most %d per level)", cfg->nfeatures, l,
+                      o->L.l[l].n_feat, ORB_FINAL_CAP / 2);
+            delete o;
+            return VO_ERR_ARG;
+        }
     o->pyr_bytes = img_ofs; o->cand_total = cand_ofs;
     o->L.total_rows = 0;
     for (int l = 0; l < cfg->nlevels; ++l) o->L.total_rows += o->L.l[l].h;
