@@ -97,3 +97,25 @@ def test_whole_front_end_equals_opencv_on_other_images():
         for key, (p, a, r, d) in want.items():
             p2, a2, r2, d2 = got[key]
             assert np.array_equal(p, p2) and a == a2 and r == r2 and np.array_equal(d, d2), key
+
+
+def test_non_default_quotas_and_level_counts_equal_opencv():
+    """nfeatures / nlevels other than the defaults (the bench's ORB-5k setting among them)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (180, 300), dtype=np.uint8)
+    scales = of.level_scales()
+    for nfeatures, nlevels in ((5000, 8), (1500, 5), (60, 3)):
+        kps, desc = cv2.ORB_create(nfeatures=nfeatures, nlevels=nlevels).detectAndCompute(img, None)
+        out = of.detect_and_compute(img, nfeatures=nfeatures, nlevels=nlevels)
+        assert len(kps) == len(out["level"]) > 0
+        pt = np.array([k.pt for k in kps], np.float32)
+        octave = np.array([k.octave for k in kps])
+        gx, gy = _cv_keys(pt, octave, scales)
+        want = _by_key(octave, gx, gy, pt, np.array([k.angle for k in kps], np.float32),
+                       np.array([k.response for k in kps], np.float32), desc)
+        got = _by_key(out["level"], out["xl"], out["yl"], out["pt"], out["angle"], out["response"], out["desc"])
+        assert set(want) == set(got)
+        for key, (p, a, r, d) in want.items():
+            p2, a2, r2, d2 = got[key]
+            assert np.array_equal(p, p2) and a == a2 and r == r2 and np.array_equal(d, d2), key

@@ -46,7 +46,7 @@ def _sets(level, x, y, *fields):
 
 
 def _check(emu, image, gray, **kw):
-    want = of.detect_and_compute(gray, **({"nfeatures": kw["nfeatures"]} if "nfeatures" in kw else {}))
+    want = of.detect_and_compute(gray, **{k: v for k, v in kw.items() if k in ("nfeatures", "nlevels")})
     kp, desc, aux = _run(emu, image, **kw)
     assert len(kp) == len(want["level"])
     if not len(kp):
@@ -81,6 +81,7 @@ def test_emulated_kernels_edge_cases(emu):
     assert _check(emu, *(2 * [rng.integers(0, 256, (97, 163), dtype=np.uint8)])) > 0      # top levels below the border
     noise = rng.integers(0, 256, (130, 170), dtype=np.uint8)
     assert _check(emu, noise, noise, nfeatures=40) > 0                          # small quotas: both retainBest cuts bite
+    assert _check(emu, noise, noise, nfeatures=300, nlevels=3) > 0              # fewer pyramid levels
 
 
 def test_emulated_kernels_kitti_shaped_frame(emu):
