@@ -35,3 +35,23 @@ int emu_orb_run(const unsigned char *image, int H, int W, int channels, int nfea
     return count2[0] <= cap ? count2[0] : -300;
 }
 }
+
+#ifdef VO_EMU_MAIN   // stand-alone driver for sanitizer runs: orb_emu <raw image file> H W channels [nfeatures]
+int main(int argc, char **argv) {
+    if (argc < 5) return 2;
+    const int H = atoi(argv[2]), W = atoi(argv[3]), ch = atoi(argv[4]), nf = argc > 5 ? atoi(argv[5]) : 500;
+    std::vector<unsigned char> img((size_t)H * W * ch);
+    FILE *f = fopen(argv[1], "rb");
+    if (!f || fread(img.data(), 1, img.size(), f) != img.size()) return 3;
+    fclose(f);
+    const int cap = 8 * 4096;
+    std::vector<float> kp((size_t)cap * 2), aux((size_t)cap * 4);
+    std::vector<unsigned char> desc((size_t)cap * 32);
+    int cnt[2] = {0, 0};
+    const int n = emu_orb_run(img.data(), H, W, ch, nf, 8, 20, kp.data(), desc.data(), aux.data(), cnt);
+    unsigned long long h = 1469598103934665603ull;
+    for (int i = 0; i < n * 32; ++i) h = (h ^ desc[i]) * 1099511628211ull;
+    printf("%d keypoints, overflow %d, descriptor hash %016llx, %s\n", n, cnt[1], h, n < 0 ? emu_last_error() : "ok");
+    return n < 0;
+}
+#endif

@@ -1,13 +1,19 @@
 """GPU ORB front-end (vo_orb_extract) against the pinned CPU restatement (oracle/orb_frontend.py) and the golden output
-of the reference's own plug-in.  OPT-IN (VO_ORB_GPU=1): csrc/orb.cu has not run on a GPU yet, and an unverified
-kernel must not be able to turn the suite red; its arithmetic is already covered on the host by test_host_math.py."""
+of the reference's own plug-in.
+
+csrc/orb.cu was written after the round's GPU budget was spent: it is verified under the host emulation
+(tests/test_orb_emulation.py; AddressSanitizer / UBSan / ThreadSanitizer clean) but had not run on a GPU when this was
+committed.  Until it has, these tests are NON-STRICT XFAIL: they run wherever the GPU suite runs (last, hence the file
+name), a pass shows up as XPASS, a failure cannot turn the suite red.  VO_ORB_GPU=1 makes them ordinary tests — set it,
+see them pass on a B200, then delete the marker."""
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("VO_ORB_GPU"), reason="csrc/orb.cu not yet verified on a GPU: set VO_ORB_GPU=1")]
+pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("VO_ORB_GPU") else [pytest.mark.xfail(
+    reason="csrc/orb.cu is verified under the host emulation only; first GPU run pending (VO_ORB_GPU=1 makes this strict)",
+    strict=False)])
 
 
 def _sets(level, x, y, *fields):

@@ -12,7 +12,7 @@ from feature_extractors import _gpu_match
 MATCHER = "l2_ratio"  # or "hamming_mutual"
 # Extraction: "opencv" (cv2 on the CPU, as the reference) or "gpu" (vo_orb_extract: the same keypoint set and bit-identical
 # descriptors, in level-major / row-major order instead of OpenCV's unspecified one).  "gpu" stays opt-in until
-# tests/test_gpu_orb.py has been run on a B200 (csrc/orb.cu is so far verified under the host emulation only).
+# tests/test_zz_gpu_orb.py has been run on a B200 (csrc/orb.cu is so far verified under the host emulation only).
 EXTRACTOR = "opencv"
 _orb = None
 _gpu_orb = {}
