@@ -59,3 +59,31 @@ def test_orb_equals_oracle_kitti_shaped_and_edge_cases():
                  np.full((120, 200), 77, np.uint8),                           # flat: no keypoints at all
                  rng.integers(0, 256, (97, 163), dtype=np.uint8)):            # top levels smaller than the border
         _check(gray, gray)
+
+
+def test_device_loop_push_image_equals_push_of_extracted_features(golden):
+    import torch
+    import vo_b200  # noqa: F401
+    from vo_b200 import synthetic
+    from vo_b200.device_loop import DeviceLoop
+    from vo_b200.orb_frontend import OrbExtractor
+    img = golden("orb_golden.npz")["image"]
+    H, W = img.shape[:2]
+    depth = np.full((H, W), 10.0, np.float32)
+    shifted = np.roll(img, 4, axis=1)                     # second frame: 4-pixel pan
+    orb = OrbExtractor(H, W)
+    poses = []
+    for use_image in (True, False):
+        loop = DeviceLoop(synthetic.KITTI_K, (W, H), 1024, kind="orb", n_hyp=128)
+        for i, frame in enumerate((img, shifted)):
+            if use_image:
+                loop.push_image(frame, depth, i)
+            else:
+                kp, desc, _ = orb.extract(frame)
+                loop.push(kp.clone(), desc.clone(), depth, i)
+        p, info = loop.poses()
+        poses.append((p, info))
+        loop.close()
+    torch.cuda.synchronize()
+    assert np.array_equal(poses[0][0], poses[1][0]) and np.array_equal(poses[0][1], poses[1][1])
+    assert poses[0][1][1, 1] > 50                         # the panned frame matches the first one
