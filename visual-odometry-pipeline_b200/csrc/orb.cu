@@ -185,11 +185,11 @@ orb_select_fast_kernel(OrbLevels L, const uint32_t *__restrict__ cand_xy, const 
 __global__ void orb_harris_kernel(OrbLevels L, const uint8_t *__restrict__ pyr, const uint32_t *__restrict__ surv_xy,
                                   const int32_t *__restrict__ surv_count, float *__restrict__ resp) {
     const OrbLevel lv = L.l[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= surv_count[blockIdx.y]) return;
-    const uint32_t xy = surv_xy[lv.cand_ofs + i];
-    const int x = xy & 0xffff, y = xy >> 16, w = lv.w;
+    const int m = surv_count[blockIdx.y], w = lv.w;
     const uint8_t *img = pyr + lv.img_ofs;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const uint32_t xy = surv_xy[lv.cand_ofs + i];
+    const int x = xy & 0xffff, y = xy >> 16;
     int a = 0, b = 0, c = 0;
     for (int dy = -3; dy <= 3; ++dy)
         for (int dx = -3; dx <= 3; ++dx) {
@@ -199,6 +199,7 @@ __global__ void orb_harris_kernel(OrbLevels L, const uint8_t *__restrict__ pyr, 
             a += ix * ix; b += iy * iy; c += ix * iy;
         }
     resp[lv.cand_ofs + i] = orb::harris_response(a, b, c);
+    }
 }
 
 // retainBest(n) on the Harris response: exact n-th largest by a 4-pass radix select over the ordered float bits, every
@@ -277,10 +278,10 @@ __global__ void orb_finish_kernel(OrbLevels L, const uint8_t *__restrict__ pyr, 
     int base = 0, total = 0;
     for (int j = 0; j < L.n; ++j) { if (j < lev) base += fin_count[j]; total += fin_count[j]; }
     if (lev == 0 && blockIdx.x == 0 && threadIdx.x == 0) { count_out[0] = total; count_out[1] = overflow[0]; }
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= fin_count[lev]) return;
+    const int n_lev = fin_count[lev], w = lv.w;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_lev; i += gridDim.x * blockDim.x) {
     const uint32_t xy = fin_xy[(size_t)lev * ORB_FINAL_CAP + i];
-    const int x = xy & 0xffff, y = xy >> 16, w = lv.w;
+    const int x = xy & 0xffff, y = xy >> 16;
     const uint8_t *c = pyr + lv.img_ofs + (size_t)y * w + x;
     int m01 = 0, m10 = 0;
     for (int u = -orb::HALF_PATCH; u <= orb::HALF_PATCH; ++u) m10 += u * (int)c[u];
@@ -304,6 +305,7 @@ __global__ void orb_finish_kernel(OrbLevels L, const uint8_t *__restrict__ pyr, 
         aux[4 * o + 1] = ang;
         aux[4 * o + 2] = fin_resp[(size_t)lev * ORB_FINAL_CAP + i];
         aux[4 * o + 3] = __fmul_rn(31.0f, lv.scale);
+    }
     }
 }
 
@@ -341,13 +343,13 @@ __global__ void orb_desc_kernel(OrbLevels L, const uint8_t *__restrict__ blurred
                                 const int32_t *__restrict__ fin_count, const float *__restrict__ angle,
                                 uint8_t *__restrict__ desc) {
     const int lev = blockIdx.y, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= fin_count[lev]) return;
     const OrbLevel lv = L.l[lev];
+    const int n_lev = fin_count[lev], w = lv.w;
     int base = 0;
     for (int j = 0; j < lev; ++j) base += fin_count[j];
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_lev; i += gridDim.x * (blockDim.x >> 5)) {
     const uint32_t xy = fin_xy[(size_t)lev * ORB_FINAL_CAP + i];
-    const int x = xy & 0xffff, y = xy >> 16, w = lv.w;
+    const int x = xy & 0xffff, y = xy >> 16;
     const uint8_t *c = blurred + lv.img_ofs + (size_t)y * w + x;
     float ca, sb;
     orb::angle_cos_sin(angle[base + i], ca, sb);
@@ -361,6 +363,7 @@ __global__ void orb_desc_kernel(OrbLevels L, const uint8_t *__restrict__ blurred
         val |= ((int)c[iy0 * w + ix0] < (int)c[iy1 * w + ix1]) << b;
     }
     desc[(size_t)(base + i) * 32 + lane] = (uint8_t)val;
+    }
 }
 
 }  // namespace
@@ -488,16 +491,15 @@ extern "C" int vo_orb_extract(vo_orb *o, const uint8_t *image, int channels, flo
     VO_LAUNCH_CHECK(ctx);
     VO_LAUNCH_BAR(orb_select_fast_kernel, L.n, 1024, st, L, o->cand_xy, o->cand_s, cand_count, o->surv_xy, surv_count);
     VO_LAUNCH_CHECK(ctx);
-    int max_cap = 0;
-    for (int l = 0; l < L.n; ++l) max_cap = L.l[l].cand_cap > max_cap ? L.l[l].cand_cap : max_cap;
-    VO_LAUNCH(orb_harris_kernel, dim3(ceil_div(max_cap, 256), L.n), 256, st, L, o->pyr, o->surv_xy, surv_count, o->resp);
+    // keypoint-list kernels: a few CTAs per level striding over lists whose lengths only the device knows
+    VO_LAUNCH(orb_harris_kernel, dim3(8, L.n), 256, st, L, o->pyr, o->surv_xy, surv_count, o->resp);
     VO_LAUNCH_CHECK(ctx);
     VO_LAUNCH_BAR(orb_select_harris_kernel, L.n, 1024, st, L, o->surv_xy, o->resp, surv_count, o->fin_xy, o->fin_resp, fin_count, overflow);
     VO_LAUNCH_CHECK(ctx);
-    VO_LAUNCH(orb_finish_kernel, dim3(ceil_div(ORB_FINAL_CAP, 128), L.n), 128, st, L, o->pyr, o->fin_xy, o->fin_resp, fin_count,
+    VO_LAUNCH(orb_finish_kernel, dim3(4, L.n), 128, st, L, o->pyr, o->fin_xy, o->fin_resp, fin_count,
               overflow, kp, aux, o->angle, count);
     VO_LAUNCH_CHECK(ctx);
-    VO_LAUNCH(orb_desc_kernel, dim3(ceil_div(ORB_FINAL_CAP, 8), L.n), 256, st, L, o->blurred, o->fin_xy, fin_count, o->angle, desc);
+    VO_LAUNCH(orb_desc_kernel, dim3(16, L.n), 256, st, L, o->blurred, o->fin_xy, fin_count, o->angle, desc);
     VO_LAUNCH_CHECK(ctx);
     return VO_OK;
 }
