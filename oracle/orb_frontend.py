@@ -21,6 +21,10 @@ Pipeline (defaults: 500 features, scale 1.2f, 8 levels, edge 31, patch 31, FAST 
   6. rBRIEF: the 256 learned point pairs (bit_pattern_31_) rotated by the angle in fp32, cvRound of each coordinate,
      bit = I(p0) < I(p1)
 
+Host dependence: every stage is integer / explicitly rounded except the Gaussian, which follows the FMA-chained row pass
+of the AVX2 object of OpenCV's filter code (the path every AVX2-capable x86 host takes; an SSE-only host would differ in
+rare pixels by one grey level).
+
 Keypoint ORDER: OpenCV's depends on the internals of std::nth_element inside KeyPointsFilter::retainBest; only the SET
 is defined by the algorithm.  This oracle emits level-major, then row-major order; comparisons are made as sets.
 """
