@@ -1,0 +1,74 @@
+"""The SIFT front-end oracle (oracle/sift_frontend.py) against the reference's own plug-in (golden fixture) and live OpenCV.
+
+SIFT's low-order bits depend on which SIMD object OpenCV dispatches to on the host (oracle/sift_frontend.py), so
+the comparison is to a tolerance, written here: every oracle keypoint has an OpenCV partner within 1e-2 px / 1e-2 in size /
+0.25 degrees, the keypoint counts differ by at most 0.5 % (decision-boundary cases), descriptor entries agree within 1 for
+>= 99 % of the keypoints and within 2 for all."""
+import numpy as np
+import pytest
+
+from oracle import sift_frontend as sf
+
+
+def _match(ref, got):
+    """ref / got: dicts of pt (N,2), size, angle, desc.  Returns (pairs, max angle error, per-pair max descriptor error)."""
+    used, pairs = set(), []
+    for j in range(len(got["size"])):
+        d = np.abs(ref["pt"] - got["pt"][j]).max(1) + np.abs(ref["size"] - got["size"][j])
+        da = np.abs(ref["angle"] - got["angle"][j])
+        d = d + np.minimum(da, 360 - da) * 0.01
+        i = int(np.argmin(d))
+        assert d[i] < 0.02 and i not in used, (j, float(d[i]))
+        used.add(i)
+        pairs.append((i, j))
+    i, j = np.array(pairs).T
+    da = np.abs(ref["angle"][i] - got["angle"][j])
+    return pairs, float(np.minimum(da, 360 - da).max()), np.abs(ref["desc"][i].astype(np.float32) - got["desc"][j]).max(1)
+
+
+def _check(ref, got):
+    n_ref, n_got = len(ref["size"]), len(got["size"])
+    assert abs(n_ref - n_got) <= max(1, int(0.005 * n_ref)), (n_ref, n_got)
+    pairs, ang, derr = _match(ref, got)
+    assert ang < 0.25
+    assert (derr <= 1).mean() >= 0.99 and derr.max() <= 2, (float((derr <= 1).mean()), float(derr.max()))
+    return len(pairs)
+
+
+def test_extract_features_and_desc_matches_reference_plugin(golden):
+    g = golden("sift_golden.npz")
+    kp, desc = sf.extract_features_and_desc(g["image"])
+    assert kp.dtype == np.float64 and desc.dtype == np.float32 and desc.shape[1] == 128
+    got = sf.detect_and_compute(sf.bgr_to_gray(g["image"]))
+    ref = {"pt": g["kp"].astype(np.float32), "size": g["size"], "angle": g["angle"], "desc": g["desc"]}
+    assert _check(ref, got) >= 480
+    # the list is sorted the way OpenCV leaves it (x ascending first), so matched rows come in the same order
+    assert np.all(np.diff(got["pt"][:, 0]) >= 0)
+
+
+def test_matches_live_opencv_on_other_images():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    smooth = cv2.add(cv2.resize(rng.integers(0, 256, (30, 50), dtype=np.uint8), (400, 240), interpolation=cv2.INTER_CUBIC),
+                     rng.integers(0, 12, (240, 400), dtype=np.uint8))
+    rect = np.full((200, 300), 90, np.uint8)
+    for _ in range(30):
+        x, y = int(rng.integers(10, 250)), int(rng.integers(10, 150))
+        cv2.rectangle(rect, (x, y), (x + int(rng.integers(8, 50)), y + int(rng.integers(8, 35))), int(rng.integers(0, 256)), -1)
+    for img in (smooth, rng.integers(0, 256, (120, 160), dtype=np.uint8), rect):
+        kps, desc = cv2.SIFT_create().detectAndCompute(img, None)
+        ref = {"pt": np.array([k.pt for k in kps], np.float32), "size": np.array([k.size for k in kps], np.float32),
+               "angle": np.array([k.angle for k in kps], np.float32), "desc": desc}
+        assert _check(ref, sf.detect_and_compute(img)) > 50
+
+
+def test_building_blocks_match_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    img = rng.random((90, 130), dtype=np.float32) * 255
+    up = cv2.resize(img, (260, 180), interpolation=cv2.INTER_LINEAR)
+    assert np.abs(sf.upsample2(img) - up).max() < 1e-3
+    for sigma in (1.2489996, 1.6, 2.0158738, 3.2):
+        assert np.abs(sf.gaussian_blur(up, sigma) - cv2.GaussianBlur(up, (0, 0), sigmaX=sigma, sigmaY=sigma)).max() < 2e-3
+    y, x = rng.normal(size=1000).astype(np.float32), rng.normal(size=1000).astype(np.float32)
+    assert np.abs(sf.fast_atan2_deg(y, x) - cv2.phase(x, y, angleInDegrees=True)[:, 0]).max() < 1e-3
