@@ -361,6 +361,28 @@ VO_API int vo_orb_capacity(const vo_orb *orb);
 VO_API int vo_orb_extract(vo_orb *orb, const uint8_t *image, int channels, float *kp, uint8_t *desc, float *aux,
                    int32_t *count, void *stream);
 
+/*
+ * SIFT front-end: `extract_features_and_desc` of feature_extractors/SIFT.py:14-23, i.e.
+ * cv2.xfeatures2d.SIFT_create() (SIFT.py:10, all defaults) followed by detectAndCompute.  Parity is held to a tolerance
+ * (same keypoints to 1e-2 px / 0.25 degrees, descriptor entries within 1): OpenCV's own low-order bits depend on the
+ * host CPU.  First version, NOT YET RUN ON A GPU (see csrc/sift.cu); verified under the host emulation.
+ *   vo_sift_extract: image uint8 [H][W] (channels = 1) or [H][W][3] BGR (channels = 3), device-accessible.
+ *   Outputs (device), max_keypoints rows each: kp float [cap][2] = KeyPoint.pt; desc float [cap][128] (values 0..255);
+ *   aux float [cap][4] = (size, angle in degrees, response, packed octave word), optional; count int32[2] =
+ *   (keypoints written, raw candidates found: more than max_keypoints means the list was cut).  Rows are in OpenCV's
+ *   order (sorted by x, y, ...; duplicates removed).
+ */
+typedef struct vo_sift_config {
+    int H, W;
+    int max_keypoints;
+} vo_sift_config;
+typedef struct vo_sift vo_sift;
+VO_API int vo_sift_create(vo_ctx *ctx, const vo_sift_config *cfg, vo_sift **out);
+VO_API void vo_sift_destroy(vo_sift *sift);
+VO_API int vo_sift_capacity(const vo_sift *sift);
+VO_API int vo_sift_extract(vo_sift *sift, const uint8_t *image, int channels, float *kp, float *desc, float *aux,
+                    int32_t *count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,8 @@ using std::min;
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline float __fmul_rn(float a, float b) { return a * b; }
+inline int __float2int_rn(float x) { return (int)lrintf(x); }
+inline int __double2int_rn(double x) { return (int)lrint(x); }
 
 namespace vo_emu {
 struct Barrier {

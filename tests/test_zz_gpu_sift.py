@@ -1,0 +1,43 @@
+"""GPU SIFT front-end (vo_sift_extract) against the CPU restatement and the golden output of the reference's own plug-in,
+to the tolerance of tests/test_oracle_sift.py.
+
+csrc/sift.cu was written after the round's GPU budget was spent: it is verified under the host emulation
+(tests/test_sift_emulation.py; AddressSanitizer / UBSan clean) but had not run on a GPU when this was committed.  Until it
+has, these tests are NON-STRICT XFAIL (they run last; a pass shows up as XPASS, a failure cannot turn the suite red).
+VO_SIFT_GPU=1 makes them ordinary tests."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("VO_SIFT_GPU") else [pytest.mark.xfail(
+    reason="csrc/sift.cu is verified under the host emulation only; first GPU run pending (VO_SIFT_GPU=1 makes this strict)",
+    strict=False)])
+
+
+def _run(image):
+    import vo_b200  # noqa: F401
+    from vo_b200.sift_frontend import SiftExtractor
+    sift = SiftExtractor(*image.shape[:2])
+    kp, desc, aux = (t.cpu().numpy() for t in sift.extract(image))
+    sift.close()
+    return {"pt": kp, "size": aux[:, 0], "angle": aux[:, 1], "desc": desc}
+
+
+def test_sift_matches_oracle_and_reference_plugin(golden):
+    from oracle import sift_frontend as sf
+    from test_oracle_sift import _check
+    g = golden("sift_golden.npz")
+    got = _run(g["image"])
+    assert _check(sf.detect_and_compute(sf.bgr_to_gray(g["image"])), got) >= 480
+    assert _check({"pt": g["kp"].astype(np.float32), "size": g["size"], "angle": g["angle"], "desc": g["desc"]}, got) >= 480
+
+
+def test_sift_kitti_shaped_and_flat():
+    from oracle import sift_frontend as sf
+    from test_oracle_sift import _check
+    rng = np.random.default_rng(8214)
+    tex = np.kron(rng.integers(0, 256, (47, 156), dtype=np.uint8), np.ones((8, 8), np.uint8))[:376, :1241]
+    tex = np.ascontiguousarray((tex.astype(np.int32) + rng.integers(0, 25, tex.shape)).clip(0, 255).astype(np.uint8))
+    assert _check(sf.detect_and_compute(tex), _run(tex)) > 500
+    assert len(_run(np.full((120, 200), 77, np.uint8))["size"]) == 0

@@ -87,6 +87,10 @@ class OrbConfig(ctypes.Structure):
     _fields_ = [("H", c_int), ("W", c_int), ("nfeatures", c_int), ("nlevels", c_int), ("fast_threshold", c_int)]
 
 
+class SiftConfig(ctypes.Structure):
+    _fields_ = [("H", c_int), ("W", c_int), ("max_keypoints", c_int)]
+
+
 PROTOTYPES = {
     "vo_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     "vo_destroy": (None, [c_void_p]),
@@ -125,6 +129,10 @@ PROTOTYPES = {
     "vo_orb_destroy": (None, [c_void_p]),
     "vo_orb_capacity": (c_int, [c_void_p]),
     "vo_orb_extract": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vo_sift_create": (c_int, [c_void_p, ctypes.POINTER(SiftConfig), ctypes.POINTER(c_void_p)]),
+    "vo_sift_destroy": (None, [c_void_p]),
+    "vo_sift_capacity": (c_int, [c_void_p]),
+    "vo_sift_extract": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vo_profile_enable": (c_int, [c_void_p, c_int]),
     "vo_profile_collect": (c_int, [c_void_p, c_void_p, c_void_p]),
 }

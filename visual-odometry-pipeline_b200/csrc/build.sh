@@ -10,7 +10,7 @@ COMMON=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompi
         -Xptxas -v --expt-relaxed-constexpr)
 declare -A EXTRA=( [pnp]="-fmad=false" )
 pids=()
-for src in api match_finalize match_u8 match_f32_simt match_f32_tc geometry pnp sequence conv_tc r2d2_net orb; do
+for src in api match_finalize match_u8 match_f32_simt match_f32_tc geometry pnp sequence conv_tc r2d2_net orb sift; do
   (
     "${NVCC}" "${COMMON[@]}" ${EXTRA[$src]:-} -c "${here}/${src}.cu" -o "${obj}/${src}.o" > "${obj}/${src}.log" 2>&1 \
       || { cat "${obj}/${src}.log"; exit 1; }

@@ -1,7 +1,8 @@
 """SIFT plug-in — same module-level interface as the reference's feature_extractors/SIFT.py
 (`extract_features_and_desc(image) -> (kp, desc)` :14-23, `get_matches(...) -> int[K,2]` :25-34).
 
-Detection / description stays on OpenCV (the front-end is outside the accelerated path); matching —
+Detection / description runs on OpenCV by default; EXTRACTOR = "gpu" switches to vo_sift_extract (same keypoints and
+descriptors to the tolerance of sift_frontend.py), opt-in until tests/test_zz_gpu_sift.py has passed on a B200.  Matching —
 brute-force 2-NN in L2 plus Lowe's 0.85 ratio test — runs on the tensor cores through vo_match_f32.
 """
 import cv2
@@ -9,7 +10,9 @@ import numpy as np
 
 from feature_extractors import _gpu_match
 
+EXTRACTOR = "opencv"  # or "gpu"
 _sift = None
+_gpu_sift = {}
 
 
 def _detector():
@@ -21,6 +24,13 @@ def _detector():
 
 
 def extract_features_and_desc(image):
+    if EXTRACTOR == "gpu":
+        from vo_b200.sift_frontend import SiftExtractor
+        key = tuple(image.shape[:2])
+        if key not in _gpu_sift:
+            _gpu_sift[key] = SiftExtractor(*key)
+        kp, desc, _ = _gpu_sift[key].extract(np.ascontiguousarray(image))
+        return kp.cpu().numpy().astype(np.float64), desc.cpu().numpy()
     gray = cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)
     kps, desc = _detector().detectAndCompute(gray, None)
     return np.asarray([[k.pt[0], k.pt[1]] for k in kps]), desc
