@@ -45,7 +45,8 @@ struct SiftKp {            // one record per (extremum, orientation peak); coord
 };
 
 __device__ __forceinline__ int reflect101i(int i, int n) {
-    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;   // kernels longer than the image reflect more than once
     return i;
 }
 
