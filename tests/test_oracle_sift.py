@@ -11,27 +11,35 @@ from oracle import sift_frontend as sf
 
 
 def _match(ref, got):
-    """ref / got: dicts of pt (N,2), size, angle, desc.  Returns (pairs, max angle error, per-pair max descriptor error)."""
+    """ref / got: dicts of pt (N,2), size, angle, desc.  Greedy one-to-one pairing of keypoints that agree within 1e-2 px in
+    position, 1e-2 in size and (loosely) in angle.  Returns (pairs, max angle error, per-pair max descriptor error)."""
     used, pairs = set(), []
     for j in range(len(got["size"])):
         d = np.abs(ref["pt"] - got["pt"][j]).max(1) + np.abs(ref["size"] - got["size"][j])
         da = np.abs(ref["angle"] - got["angle"][j])
         d = d + np.minimum(da, 360 - da) * 0.01
-        i = int(np.argmin(d))
-        assert d[i] < 0.02 and i not in used, (j, float(d[i]))
-        used.add(i)
-        pairs.append((i, j))
+        for i in np.argsort(d)[:4]:
+            if d[i] < 0.02 and int(i) not in used:
+                used.add(int(i))
+                pairs.append((int(i), j))
+                break
+    if not pairs:
+        return pairs, 0.0, np.zeros(0, np.float32)
     i, j = np.array(pairs).T
     da = np.abs(ref["angle"][i] - got["angle"][j])
     return pairs, float(np.minimum(da, 360 - da).max()), np.abs(ref["desc"][i].astype(np.float32) - got["desc"][j]).max(1)
 
 
 def _check(ref, got):
+    """Asserts the tolerance of the module docstring; returns the number of paired keypoints."""
     n_ref, n_got = len(ref["size"]), len(got["size"])
-    assert abs(n_ref - n_got) <= max(1, int(0.005 * n_ref)), (n_ref, n_got)
+    slack = max(1, int(0.005 * max(n_ref, n_got)))          # decision-boundary keypoints present on one side only
+    assert abs(n_ref - n_got) <= slack, (n_ref, n_got)
     pairs, ang, derr = _match(ref, got)
-    assert ang < 0.25
-    assert (derr <= 1).mean() >= 0.99 and derr.max() <= 2, (float((derr <= 1).mean()), float(derr.max()))
+    assert min(n_ref, n_got) - len(pairs) <= slack, (n_ref, n_got, len(pairs))
+    if pairs:
+        assert ang < 0.25
+        assert (derr <= 1).mean() >= 0.99 and derr.max() <= 2, (float((derr <= 1).mean()), float(derr.max()))
     return len(pairs)
 
 
