@@ -11,7 +11,7 @@
 // the x2 bilinear up-sampling of the image; octave o + 1 starts from every second pixel of layer 3 of octave o.
 // Candidates (26-neighbour extrema of the DoG stack) are refined, tested and given their orientations by one thread
 // each; the keypoint list is then sorted exactly as OpenCV's KeyPointsFilter::removeDuplicatedSorted does (rank by
-// counting), duplicates are dropped, and one thread per keypoint accumulates the 4 x 4 x 8 descriptor.
+// counting), duplicates are dropped, and one warp per keypoint accumulates the 4 x 4 x 8 descriptor.
 #include "common.cuh"
 #include "orb_math.cuh"
 #include <math.h>
@@ -293,15 +293,22 @@ sift_unique_kernel(const SiftKp *__restrict__ sorted, const int32_t *__restrict_
     if (threadIdx.x == 0) out_count[0] = base_s;
 }
 
-// calcSIFTDescriptor, one thread per keypoint (first version).
-__global__ void sift_desc_kernel(SiftGeom G, const float *__restrict__ gauss, const SiftKp *__restrict__ kps,
-                                 const int32_t *__restrict__ n_kp, float *__restrict__ kp_out, float *__restrict__ aux,
-                                 float *__restrict__ desc) {
-    const int n = n_kp[0];
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+// calcSIFTDescriptor, one warp (= one CTA of 32 threads) per keypoint.  The (2 r + 1)^2 samples are dealt to the lanes by
+// row; every lane accumulates its own 6 x 6 x 10 partial histogram in shared memory (bin-major, lane-minor: no bank
+// conflicts, no atomics), the 32 partials are summed in lane order, and lane 0 finishes (circular wrap, clipping,
+// normalisation): the result does not depend on scheduling.
+constexpr int SIFT_HIST = 6 * 6 * 10;
+__global__ void __launch_bounds__(32)
+sift_desc_kernel(SiftGeom G, const float *__restrict__ gauss, const SiftKp *__restrict__ kps, const int32_t *__restrict__ n_kp,
+                 float *__restrict__ kp_out, float *__restrict__ aux, float *__restrict__ desc) {
+    __shared__ float part[SIFT_HIST * 32];
+    const int n = n_kp[0], lane = threadIdx.x;
+    for (int idx = blockIdx.x; idx < n; idx += gridDim.x) {
         const SiftKp k = kps[idx];
-        kp_out[2 * idx] = k.x; kp_out[2 * idx + 1] = k.y;
-        if (aux) { aux[4 * idx] = k.size; aux[4 * idx + 1] = k.angle; aux[4 * idx + 2] = k.resp; aux[4 * idx + 3] = (float)k.octave; }
+        if (lane == 0) {
+            kp_out[2 * idx] = k.x; kp_out[2 * idx + 1] = k.y;
+            if (aux) { aux[4 * idx] = k.size; aux[4 * idx + 1] = k.angle; aux[4 * idx + 2] = k.resp; aux[4 * idx + 3] = (float)k.octave; }
+        }
         int octave = k.octave & 255;
         const int layer = (k.octave >> 8) & 255;
         octave = octave < 128 ? octave : (-128 | octave);
@@ -319,9 +326,8 @@ __global__ void sift_desc_kernel(SiftGeom G, const float *__restrict__ gauss, co
         int radius = __float2int_rn(hist_width * 1.4142135623730951f * 5.f * 0.5f);
         radius = min(radius, (int)sqrt((double)cols * cols + (double)rows * rows));
         cos_t /= hist_width; sin_t /= hist_width;
-        float hist[6 * 6 * 10];
-        for (int i = 0; i < 360; ++i) hist[i] = 0.f;
-        for (int i = -radius; i <= radius; ++i)
+        for (int b = 0; b < SIFT_HIST; ++b) part[b * 32 + lane] = 0.f;
+        for (int i = -radius + lane; i <= radius; i += 32)
             for (int j = -radius; j <= radius; ++j) {
                 const float c_rot = j * cos_t - i * sin_t, r_rot = j * sin_t + i * cos_t;
                 float rbin = r_rot + 2 - 0.5f, cbin = c_rot + 2 - 0.5f;
@@ -341,23 +347,37 @@ __global__ void sift_desc_kernel(SiftGeom G, const float *__restrict__ gauss, co
                 const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11, v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
                 const float v111 = v_rc11 * obin, v110 = v_rc11 - v111, v101 = v_rc10 * obin, v100 = v_rc10 - v101;
                 const float v011 = v_rc01 * obin, v010 = v_rc01 - v011, v001 = v_rc00 * obin, v000 = v_rc00 - v001;
-                const int h = ((r0 + 1) * 6 + c0 + 1) * 10 + o0;
-                hist[h] += v000; hist[h + 1] += v001; hist[h + 10] += v010; hist[h + 11] += v011;
-                hist[h + 60] += v100; hist[h + 61] += v101; hist[h + 70] += v110; hist[h + 71] += v111;
+                float *hp = part + (((r0 + 1) * 6 + c0 + 1) * 10 + o0) * 32 + lane;
+                hp[0] += v000; hp[32] += v001; hp[10 * 32] += v010; hp[11 * 32] += v011;
+                hp[60 * 32] += v100; hp[61 * 32] += v101; hp[70 * 32] += v110; hp[71 * 32] += v111;
             }
-        float *dst = desc + (size_t)idx * 128;
-        float nrm2 = 0.f;
-        for (int i = 0; i < 4; ++i)
-            for (int j = 0; j < 4; ++j) {
-                const int h = ((i + 1) * 6 + (j + 1)) * 10;
-                hist[h] += hist[h + 8]; hist[h + 1] += hist[h + 9];
-                for (int b = 0; b < 8; ++b) { const float v = hist[h + b]; dst[(i * 4 + j) * 8 + b] = v; nrm2 += v * v; }
-            }
-        const float thr = sqrtf(nrm2) * 0.2f;
-        nrm2 = 0.f;
-        for (int i = 0; i < 128; ++i) { const float v = fminf(dst[i], thr); dst[i] = v; nrm2 += v * v; }
-        const float f = 512.f / fmaxf(sqrtf(nrm2), 1.1920929e-07f);
-        for (int i = 0; i < 128; ++i) { const int q = __float2int_rn(dst[i] * f); dst[i] = (float)(q < 0 ? 0 : (q > 255 ? 255 : q)); }
+        __syncthreads();
+        for (int b = lane; b < SIFT_HIST; b += 32) {   // the 32 partials of a bin, in lane order
+            float sum = 0.f;
+            for (int l = 0; l < 32; ++l) sum += part[b * 32 + l];
+            part[b * 32] = sum;
+        }
+        __syncthreads();
+        if (lane == 0) {
+            float *dst = desc + (size_t)idx * 128;
+            float nrm2 = 0.f;
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) {
+                    const int h = ((i + 1) * 6 + (j + 1)) * 10;
+                    const float b0 = part[h * 32] + part[(h + 8) * 32], b1 = part[(h + 1) * 32] + part[(h + 9) * 32];
+                    for (int b = 0; b < 8; ++b) {
+                        const float v = b == 0 ? b0 : (b == 1 ? b1 : part[(h + b) * 32]);
+                        dst[(i * 4 + j) * 8 + b] = v;
+                        nrm2 += v * v;
+                    }
+                }
+            const float thr = sqrtf(nrm2) * 0.2f;
+            nrm2 = 0.f;
+            for (int i = 0; i < 128; ++i) { const float v = fminf(dst[i], thr); dst[i] = v; nrm2 += v * v; }
+            const float f = 512.f / fmaxf(sqrtf(nrm2), 1.1920929e-07f);
+            for (int i = 0; i < 128; ++i) { const int q = __float2int_rn(dst[i] * f); dst[i] = (float)(q < 0 ? 0 : (q > 255 ? 255 : q)); }
+        }
+        __syncthreads();   // part[] is reused by the next keypoint of this CTA
     }
 }
 
@@ -489,7 +509,7 @@ extern "C" int vo_sift_extract(vo_sift *s, const uint8_t *image, int channels, f
     VO_LAUNCH_CHECK(ctx);
     VO_LAUNCH_BAR(sift_unique_kernel, 1, 1024, st, s->sorted, s->counts, s->cap, s->uniq, s->counts + 1);
     VO_LAUNCH_CHECK(ctx);
-    VO_LAUNCH(sift_desc_kernel, 64, 128, st, G, s->gauss, s->uniq, s->counts + 1, kp, aux, desc);
+    VO_LAUNCH_BAR(sift_desc_kernel, 1184, 32, st, G, s->gauss, s->uniq, s->counts + 1, kp, aux, desc);   // 8 CTAs per SM, striding
     VO_LAUNCH_CHECK(ctx);
     // count[0] = keypoints written, count[1] = raw candidates found (> max_keypoints: the list was cut)
     VO_CUDA(cudaMemcpyAsync(count, s->counts + 1, sizeof(int32_t), cudaMemcpyDefault, st));
