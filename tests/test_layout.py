@@ -29,5 +29,6 @@ def test_no_compat_layers_in_product():
 
 def test_required_files_exist():
     for rel in ("include/vo_b200.h", "oracle/vo_oracle.c", "oracle/oracle.py", "bench.py", "__graft_entry__.py",
-                "DESIGN.md", "INTEGRATION.md", "tests/golden/make_golden.py"):
+                "DESIGN.md", "INTEGRATION.md", "tests/golden/make_golden.py", "oracle/orb_frontend.py", "oracle/sift_frontend.py",
+                "tests/golden/make_orb_golden.py", "tests/golden/make_sift_golden.py", "tests/golden/orb_pattern.npy"):
         assert os.path.exists(os.path.join(ROOT, rel)), rel
