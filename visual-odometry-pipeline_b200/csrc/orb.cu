@@ -5,7 +5,8 @@
 // STATUS: compiled for sm_100a; every arithmetic routine it calls (orb_math.cuh) is checked bit for bit on the host
 // against the CPU restatement that is pinned against OpenCV, and this very file — kernels and launch sequence — runs
 // bit-identical to it under the host emulation of tests/cuda_emu.h (tests/test_orb_emulation.py).  The kernels have
-// NOT run on a GPU yet (tests/test_zz_gpu_orb.py: non-strict xfail until its first pass on a B200); no product path calls this file.
+// NOT run on a GPU yet (tests/test_zz_gpu_orb.py: non-strict xfail until its first pass on a B200); nothing calls it unless asked to
+// (EXTRACTOR = "gpu" in feature_extractors/ORB.py, DeviceLoop.push_image).
 //
 // Data layout: one unbordered 8-bit image per pyramid level, back to back in one buffer (keypoints stay >= 31 pixels
 // from the border, so orientation / Harris / rBRIEF never leave a level; the Gaussian reflects indices).  Per level:

@@ -5,7 +5,8 @@
 // PARITY BAR: a tolerance, not bit-exactness — OpenCV's own low-order bits depend on the SIMD object the host CPU
 // selects: same keypoints to 1e-2 px / 0.25 degrees, descriptor entries within 1.
 // STATUS: first version, written for correctness: verified against the CPU restatement under the host emulation of
-// tests/cuda_emu.h (tests/test_sift_emulation.py); NOT yet run on a GPU, no product path calls it.
+// tests/cuda_emu.h (tests/test_sift_emulation.py); NOT yet run on a GPU; nothing calls it unless asked to
+// (EXTRACTOR = "gpu" in feature_extractors/SIFT.py).
 //
 // Data layout: per octave six Gaussian layers and five difference-of-Gaussian layers, fp32, back to back.  Octave 0 is
 // the x2 bilinear up-sampling of the image; octave o + 1 starts from every second pixel of layer 3 of octave o.
