@@ -60,3 +60,9 @@ def test_emulated_sift_edge_cases(emu):
     assert len(_run(emu, flat)["size"]) == 0 == len(sf.detect_and_compute(flat)["size"])
     tiny = rng.integers(0, 256, (17, 23), dtype=np.uint8)                   # fewer octaves, every layer near the border
     assert abs(len(_run(emu, tiny)["size"]) - len(sf.detect_and_compute(tiny)["size"])) <= 1
+
+
+def test_emulated_sift_kitti_shaped_frame(emu):
+    from test_zz_gpu_sift import _kitti_like
+    img = _kitti_like()
+    assert _check(sf.detect_and_compute(img), _run(emu, img)) > 500
