@@ -8,7 +8,9 @@ mkdir -p "${obj}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 COMMON=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
         -Xptxas -v --expt-relaxed-constexpr)
-declare -A EXTRA=( [pnp]="-fmad=false" )
+# pnp / orb / sift: no implicit FMA contraction, so the device rounds like the host restatements the parity tests use
+# (explicit fused operations, where OpenCV itself fuses, are spelled out with __fmaf_rn)
+declare -A EXTRA=( [pnp]="-fmad=false" [orb]="-fmad=false" [sift]="-fmad=false" )
 pids=()
 for src in api match_finalize match_u8 match_f32_simt match_f32_tc geometry pnp sequence conv_tc r2d2_net orb sift; do
   (
