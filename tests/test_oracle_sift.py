@@ -2,7 +2,7 @@
 
 SIFT's low-order bits depend on which SIMD object OpenCV dispatches to on the host (oracle/sift_frontend.py), so
 the comparison is to a tolerance, written here: every oracle keypoint has an OpenCV partner within 1e-2 px / 1e-2 in size /
-0.25 degrees, the keypoint counts differ by at most 0.5 % (decision-boundary cases), descriptor entries agree within 1 for
+0.25 degrees, the keypoint counts differ by at most 0.5 % (at least 2: decision-boundary cases), descriptor entries agree within 1 for
 >= 99 % of the keypoints and within 2 for all."""
 import numpy as np
 import pytest
@@ -33,7 +33,7 @@ def _match(ref, got):
 def _check(ref, got):
     """Asserts the tolerance of the module docstring; returns the number of paired keypoints."""
     n_ref, n_got = len(ref["size"]), len(got["size"])
-    slack = max(1, int(0.005 * max(n_ref, n_got)))          # decision-boundary keypoints present on one side only
+    slack = max(2, int(0.005 * max(n_ref, n_got)))          # decision-boundary keypoints present on one side only
     assert abs(n_ref - n_got) <= slack, (n_ref, n_got)
     pairs, ang, derr = _match(ref, got)
     assert min(n_ref, n_got) - len(pairs) <= slack, (n_ref, n_got, len(pairs))
