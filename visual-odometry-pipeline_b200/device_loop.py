@@ -79,16 +79,22 @@ class DeviceLoop:
             check(self.ctx.lib.vo_seq_push(self.handle, self._ptr(desc_a), self._ptr(kp_a), n, self._ptr(depth_a),
                                            int(frame_no), stream), "vo_seq_push")
 
-    def push_image(self, image, depth, frame_no, nfeatures=500):
-        """ORB loops only: extract on the device (orb_frontend.OrbExtractor, cv2.ORB_create(nfeatures) semantics) and push —
-        the image is the only per-frame upload besides the depth map.  One host read of the keypoint count per frame.
-        (The extractor's first GPU run is still pending, see orb_frontend.py; `push` with OpenCV features is the verified path.)"""
-        if self.desc_cols != 32:
-            raise ValueError("DeviceLoop.push_image: only the ORB loop has a device front-end here")
-        if getattr(self, "_orb", None) is None:
-            from .orb_frontend import OrbExtractor
-            self._orb = OrbExtractor(self.cfg.H, self.cfg.W, nfeatures=nfeatures, device=self.device)
-        kp, desc, _ = self._orb.extract(image)
+    def push_image(self, image, depth, frame_no, nfeatures=500, frontend=None):
+        """Extract on the device and push — the image is the only per-frame upload besides the depth map; one host read of
+        the keypoint count per frame.  frontend: "orb" (orb_frontend.OrbExtractor, cv2.ORB_create(nfeatures) semantics; the
+        default of a byte-descriptor loop) or "sift" (sift_frontend.SiftExtractor; the default of a float-descriptor loop).
+        (Both extractors' first GPU run is still pending; `push` with OpenCV features is the verified path.)"""
+        frontend = frontend or ("orb" if self.desc_cols == 32 else "sift")
+        if (frontend == "orb") != (self.desc_cols == 32) or frontend not in ("orb", "sift"):
+            raise ValueError(f"DeviceLoop.push_image: front-end {frontend!r} does not produce this loop's descriptors")
+        if getattr(self, "_extractor", None) is None:
+            if frontend == "orb":
+                from .orb_frontend import OrbExtractor
+                self._extractor = OrbExtractor(self.cfg.H, self.cfg.W, nfeatures=nfeatures, device=self.device)
+            else:
+                from .sift_frontend import SiftExtractor
+                self._extractor = SiftExtractor(self.cfg.H, self.cfg.W, max_keypoints=self.cfg.n_cap, device=self.device)
+        kp, desc, _ = self._extractor.extract(image)
         return self.push(kp, desc, depth, frame_no)
 
     def __len__(self):
