@@ -341,7 +341,7 @@ VO_API int vo_r2d2_extract(vo_r2d2 *net, const uint8_t *rgb, float rel_thr, floa
  * cv2.ORB_create() (ORB.py:8, all defaults: scale 1.2f, edge 31, patch 31, Harris score, WTA_K 2) followed by
  * detectAndCompute: gray conversion, INTER_LINEAR_EXACT pyramid, FAST-9/16 + non-maximum suppression, retainBest on
  * the FAST score and on the Harris response (ties kept), intensity-centroid orientation, 7x7 Gaussian, rBRIEF.
- * NOT YET RUN ON A GPU (see csrc/orb.cu): the arithmetic is host-verified against the pinned CPU restatement.
+ * Bit-identical to the pinned CPU restatement on a B200 (tests/test_gpu_orb_frontend.py).
  *   vo_orb_extract: image uint8 [H][W] (channels = 1) or [H][W][3] BGR (channels = 3), device-accessible.
  *   Outputs (device), vo_orb_capacity() rows each: kp float [cap][2] = KeyPoint.pt; desc uint8 [cap][32];
  *   aux float [cap][4] = (octave, angle in degrees, response, size), optional; count int32[2] = (keypoints written,
@@ -360,12 +360,15 @@ VO_API void vo_orb_destroy(vo_orb *orb);
 VO_API int vo_orb_capacity(const vo_orb *orb);
 VO_API int vo_orb_extract(vo_orb *orb, const uint8_t *image, int channels, float *kp, uint8_t *desc, float *aux,
                    int32_t *count, void *stream);
+/* Diagnostic: copy one intermediate buffer of the last vo_orb_extract to host memory (synchronises; buffer ids in
+ * csrc/orb.cu).  Used by tools/orb_bisect.py to compare the extractor stage by stage with the CPU restatement. */
+VO_API int vo_orb_debug_read(vo_orb *orb, int what, int level, void *host_dst, size_t cap_bytes, size_t *out_bytes);
 
 /*
  * SIFT front-end: `extract_features_and_desc` of feature_extractors/SIFT.py:14-23, i.e.
  * cv2.xfeatures2d.SIFT_create() (SIFT.py:10, all defaults) followed by detectAndCompute.  Parity is held to a tolerance
  * (same keypoints to 1e-2 px / 0.25 degrees, descriptor entries within 1): OpenCV's own low-order bits depend on the
- * host CPU.  First version, NOT YET RUN ON A GPU (see csrc/sift.cu); verified under the host emulation.
+ * host CPU.  Verified under the host emulation and on a B200 (tests/test_gpu_sift_frontend.py).
  *   vo_sift_extract: image uint8 [H][W] (channels = 1) or [H][W][3] BGR (channels = 3), device-accessible.
  *   Outputs (device), max_keypoints rows each: kp float [cap][2] = KeyPoint.pt; desc float [cap][128] (values 0..255);
  *   aux float [cap][4] = (size, angle in degrees, response, packed octave word), optional; count int32[2] =

@@ -1,19 +1,11 @@
 """GPU ORB front-end (vo_orb_extract) against the pinned CPU restatement (oracle/orb_frontend.py) and the golden output
-of the reference's own plug-in.
-
-csrc/orb.cu was written after the round's GPU budget was spent: it is verified under the host emulation
-(tests/test_orb_emulation.py; AddressSanitizer / UBSan / ThreadSanitizer clean) but had not run on a GPU when this was
-committed.  Until it has, these tests are NON-STRICT XFAIL: they run wherever the GPU suite runs (last, hence the file
-name), a pass shows up as XPASS, a failure cannot turn the suite red.  VO_ORB_GPU=1 makes them ordinary tests — set it,
-see them pass on a B200, then delete the marker."""
-import os
-
+of the reference's own plug-in: identical keypoint sets, bit-identical pt / angle / response / size / descriptors.
+Strict since its first pass on a B200 (round 2; the first hardware run exposed a ptxas miscompilation of the FAST corner
+score that the host emulation could not see — csrc/orb_math.cuh fast_corner_score, tools/probe/fast_probe.cu)."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("VO_ORB_GPU") else [pytest.mark.xfail(
-    reason="csrc/orb.cu is verified under the host emulation only; first GPU run pending (VO_ORB_GPU=1 makes this strict)",
-    strict=False)])
+pytestmark = [pytest.mark.gpu]
 
 
 def _sets(level, x, y, *fields):

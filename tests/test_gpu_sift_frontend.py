@@ -1,18 +1,9 @@
 """GPU SIFT front-end (vo_sift_extract) against the CPU restatement and the golden output of the reference's own plug-in,
-to the tolerance of tests/test_oracle_sift.py.
-
-csrc/sift.cu was written after the round's GPU budget was spent: it is verified under the host emulation
-(tests/test_sift_emulation.py; AddressSanitizer / UBSan clean) but had not run on a GPU when this was committed.  Until it
-has, these tests are NON-STRICT XFAIL (they run last; a pass shows up as XPASS, a failure cannot turn the suite red).
-VO_SIFT_GPU=1 makes them ordinary tests."""
-import os
-
+to the tolerance of tests/test_oracle_sift.py.  Strict since its first pass on a B200."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("VO_SIFT_GPU") else [pytest.mark.xfail(
-    reason="csrc/sift.cu is verified under the host emulation only; first GPU run pending (VO_SIFT_GPU=1 makes this strict)",
-    strict=False)])
+pytestmark = [pytest.mark.gpu]
 
 
 def _run(image):

@@ -1,6 +1,6 @@
 """csrc/orb.cu — kernels AND launch sequence — executed on the host through tests/cuda_emu.h (blocks one after another,
 barrier kernels on real threads) and compared with the pinned CPU restatement (oracle/orb_frontend.py): the CPU-side
-half of the ORB front-end's parity claim; tests/test_zz_gpu_orb.py is the device half."""
+half of the ORB front-end's parity claim; tests/test_gpu_orb_frontend.py is the device half."""
 import ctypes
 import os
 import subprocess

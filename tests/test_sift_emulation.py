@@ -63,6 +63,6 @@ def test_emulated_sift_edge_cases(emu):
 
 
 def test_emulated_sift_kitti_shaped_frame(emu):
-    from test_zz_gpu_sift import _kitti_like
+    from test_gpu_sift_frontend import _kitti_like
     img = _kitti_like()
     assert _check(sf.detect_and_compute(img), _run(emu, img)) > 500

@@ -1,7 +1,7 @@
 """GPU-box helper: ORB front-end (vo_orb_extract) on a KITTI-shaped frame — parity against the CPU restatement,
 frames/s with the image resident in HBM and from pinned host memory, and the same frame through cv2.ORB_create() on the
 host cores.  First thing to run on a B200 for csrc/orb.cu:
-    VO_ORB_GPU=1 python -m pytest tests/test_zz_gpu_orb.py -q && python tools/orb_bench.py"""
+    python -m pytest tests/test_gpu_orb_frontend.py -q && python tools/orb_bench.py"""
 import json
 import os
 import sys

@@ -1,6 +1,6 @@
 """GPU-box helper: SIFT front-end (vo_sift_extract) on a KITTI-shaped frame — parity (to the tolerance of
 tests/test_oracle_sift.py) against OpenCV on the host, frames/s resident and from pinned host memory, OpenCV's own time.
-    VO_SIFT_GPU=1 python -m pytest tests/test_zz_gpu_sift.py -q && python tools/sift_bench.py"""
+    python -m pytest tests/test_gpu_sift_frontend.py -q && python tools/sift_bench.py"""
 import json
 import os
 import sys

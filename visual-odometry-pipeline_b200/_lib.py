@@ -129,6 +129,7 @@ PROTOTYPES = {
     "vo_orb_destroy": (None, [c_void_p]),
     "vo_orb_capacity": (c_int, [c_void_p]),
     "vo_orb_extract": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vo_orb_debug_read": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "vo_sift_create": (c_int, [c_void_p, ctypes.POINTER(SiftConfig), ctypes.POINTER(c_void_p)]),
     "vo_sift_destroy": (None, [c_void_p]),
     "vo_sift_capacity": (c_int, [c_void_p]),

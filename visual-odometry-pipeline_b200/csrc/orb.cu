@@ -2,11 +2,9 @@
 // (feature_extractors/ORB.py:8 `orb = cv2.ORB_create()`, :10-21 extract_features_and_desc) — 500 features, scale
 // 1.2f, 8 levels, edge 31, patch 31, FAST threshold 20, Harris score.  SURVEY 8(f) rank 1.
 //
-// STATUS: compiled for sm_100a; every arithmetic routine it calls (orb_math.cuh) is checked bit for bit on the host
-// against the CPU restatement that is pinned against OpenCV, and this very file — kernels and launch sequence — runs
-// bit-identical to it under the host emulation of tests/cuda_emu.h (tests/test_orb_emulation.py).  The kernels have
-// NOT run on a GPU yet (tests/test_zz_gpu_orb.py: non-strict xfail until its first pass on a B200); nothing calls it unless asked to
-// (EXTRACTOR = "gpu" in feature_extractors/ORB.py, DeviceLoop.push_image).
+// STATUS: bit-identical to the CPU restatement pinned against OpenCV — on the host emulation of tests/cuda_emu.h
+// (tests/test_orb_emulation.py) and on a B200 (tests/test_gpu_orb_frontend.py, tools/orb_bisect.py stage by stage).  Default
+// extractor of feature_extractors/ORB.py and of DeviceLoop.push_image for byte-descriptor loops.
 //
 // Data layout: one unbordered 8-bit image per pyramid level, back to back in one buffer (keypoints stay >= 31 pixels
 // from the border, so orientation / Harris / rBRIEF never leave a level; the Gaussian reflects indices).  Per level:
@@ -454,6 +452,48 @@ extern "C" int vo_orb_create(vo_ctx *ctx, const vo_orb_config *cfg, vo_orb **out
         return VO_ERR_CUDA;
     }
     *out = o;
+    return VO_OK;
+}
+
+// Diagnostic read-back of the extractor's intermediate buffers (tools/orb_bisect.py compares them stage by stage with
+// the CPU restatement).  Synchronises the device.  what: 0 level geometry (int32 {w, h, n_feat, cand_cap} per level),
+// 1 pyramid level, 2 FAST score map, 3 blurred level, 4 candidate xy (u32), 5 candidate score (u8), 6 survivor xy (u32),
+// 7 survivor Harris response (f32), 8 kept xy (u32), 9 kept response (f32), 10 counts (int32[32]), 11 angles (f32, all levels).
+extern "C" int vo_orb_debug_read(vo_orb *o, int what, int level, void *host_dst, size_t cap_bytes, size_t *out_bytes) {
+    using namespace vo;
+    VO_REQUIRE(o && host_dst && out_bytes, "vo_orb_debug_read: null argument");
+    VO_REQUIRE(level >= 0 && level < o->L.n, "vo_orb_debug_read: level %d out of range", level);
+    const OrbLevel &lv = o->L.l[level];
+    const size_t px = (size_t)lv.w * lv.h;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    int32_t geo[4 * ORB_MAX_LEVELS];
+    switch (what) {
+    case 0:
+        for (int l = 0; l < o->L.n; ++l) { geo[4 * l] = o->L.l[l].w; geo[4 * l + 1] = o->L.l[l].h; geo[4 * l + 2] = o->L.l[l].n_feat; geo[4 * l + 3] = o->L.l[l].cand_cap; }
+        bytes = sizeof(int32_t) * 4 * o->L.n;
+        VO_REQUIRE(bytes <= cap_bytes, "vo_orb_debug_read: buffer too small");
+        memcpy(host_dst, geo, bytes);
+        *out_bytes = bytes;
+        return VO_OK;
+    case 1: src = o->pyr + lv.img_ofs; bytes = px; break;
+    case 2: src = o->score + lv.img_ofs; bytes = px; break;
+    case 3: src = o->blurred + lv.img_ofs; bytes = px; break;
+    case 4: src = o->cand_xy + lv.cand_ofs; bytes = (size_t)lv.cand_cap * 4; break;
+    case 5: src = o->cand_s + lv.cand_ofs; bytes = (size_t)lv.cand_cap; break;
+    case 6: src = o->surv_xy + lv.cand_ofs; bytes = (size_t)lv.cand_cap * 4; break;
+    case 7: src = o->resp + lv.cand_ofs; bytes = (size_t)lv.cand_cap * 4; break;
+    case 8: src = o->fin_xy + (size_t)level * ORB_FINAL_CAP; bytes = (size_t)ORB_FINAL_CAP * 4; break;
+    case 9: src = o->fin_resp + (size_t)level * ORB_FINAL_CAP; bytes = (size_t)ORB_FINAL_CAP * 4; break;
+    case 10: src = o->counts; bytes = sizeof(int32_t) * 32; break;
+    case 11: src = o->angle; bytes = (size_t)o->L.n * ORB_FINAL_CAP * 4; break;
+    default: set_error("vo_orb_debug_read: unknown buffer %d", what); return VO_ERR_ARG;
+    }
+    VO_REQUIRE(bytes <= cap_bytes, "vo_orb_debug_read: buffer too small (%zu > %zu)", bytes, cap_bytes);
+    cudaSetDevice(o->ctx->device);
+    VO_CUDA(cudaDeviceSynchronize());
+    VO_CUDA(cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));
+    *out_bytes = bytes;
     return VO_OK;
 }
 

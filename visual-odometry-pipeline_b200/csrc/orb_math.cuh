@@ -79,23 +79,38 @@ VO_ORB_HD uint8_t linear_exact_pixel(int p00, int p01, int p10, int p11, int cx,
 // nine contiguous ring pixels is uniformly brighter than v + thr or darker than v - thr, else the largest threshold
 // for which the pixel stays a corner (fast_score.cpp cornerScore<16>): max over the 16 arcs of min |v - p|, minus 1.
 VO_ORB_HD int fast_corner_score(int v, const uint8_t (&ring)[16], int thr) {
-    int d[24];
+    // Sliding-window form: lo9[k] / hi9[k] = min / max of d over the arc k..k+8, built from windows of 2, 4, 8.  The
+    // darker-arc score is max_k lo9[k]; the brighter-arc score is max_k min(p - v) = -(min_k hi9[k]): ONE negation at
+    // the end.  (The direct form, max(lo, -hi) per arc, is miscompiled by ptxas 12.9 for sm_100a: it folds 15 of the
+    // 16 negations away when it fuses the min / max chains into VIMNMX3 — found with tools/orb_bisect.py on a B200;
+    // tools/probe/fast_probe.cu keeps the reproducer.)
+    int d[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) d[k] = v - (int)ring[k];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) d[16 + k] = d[k];
-    int best = -256;
+    int lo2[16], hi2[16], lo4[16], hi4[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        int lo = d[k], hi = d[k];
-#pragma unroll
-        for (int j = 1; j < 9; ++j) {
-            lo = d[k + j] < lo ? d[k + j] : lo;
-            hi = d[k + j] > hi ? d[k + j] : hi;
-        }
-        const int m = lo > -hi ? lo : -hi;     // darker arc: min(v - p); brighter arc: min(p - v) = -max(v - p)
-        best = m > best ? m : best;
+        const int a = d[k], b = d[(k + 1) & 15];
+        lo2[k] = a < b ? a : b;
+        hi2[k] = a > b ? a : b;
     }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        lo4[k] = lo2[k] < lo2[(k + 2) & 15] ? lo2[k] : lo2[(k + 2) & 15];
+        hi4[k] = hi2[k] > hi2[(k + 2) & 15] ? hi2[k] : hi2[(k + 2) & 15];
+    }
+    int dark = -256, nbright = 256;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        int lo = lo4[k] < lo4[(k + 4) & 15] ? lo4[k] : lo4[(k + 4) & 15];
+        int hi = hi4[k] > hi4[(k + 4) & 15] ? hi4[k] : hi4[(k + 4) & 15];
+        lo = lo < d[(k + 8) & 15] ? lo : d[(k + 8) & 15];
+        hi = hi > d[(k + 8) & 15] ? hi : d[(k + 8) & 15];
+        dark = lo > dark ? lo : dark;
+        nbright = hi < nbright ? hi : nbright;
+    }
+    const int bright = 0 - nbright;
+    const int best = dark > bright ? dark : bright;
     return best > thr ? best - 1 : 0;
 }
 

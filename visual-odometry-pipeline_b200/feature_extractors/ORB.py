@@ -9,11 +9,13 @@ import numpy as np
 
 from feature_extractors import _gpu_match
 
+import os
+
 MATCHER = "l2_ratio"  # or "hamming_mutual"
-# Extraction: "opencv" (cv2 on the CPU, as the reference) or "gpu" (vo_orb_extract: the same keypoint set and bit-identical
-# descriptors, in level-major / row-major order instead of OpenCV's unspecified one).  "gpu" stays opt-in until
-# tests/test_zz_gpu_orb.py has been run on a B200 (csrc/orb.cu is so far verified under the host emulation only).
-EXTRACTOR = "opencv"
+# Extraction: "gpu" (vo_orb_extract, csrc/orb.cu: the same keypoint set, bit-identical pt / angle / response /
+# descriptors as cv2.ORB_create().detectAndCompute — tests/test_gpu_orb_frontend.py on a B200 — in level-major /
+# row-major order instead of OpenCV's unspecified one) or "opencv" (cv2 on the CPU, as the reference; VO_EXTRACTOR=opencv).
+EXTRACTOR = os.environ.get("VO_EXTRACTOR", "gpu")
 _orb = None
 _gpu_orb = {}
 

@@ -1,16 +1,18 @@
 """SIFT plug-in — same module-level interface as the reference's feature_extractors/SIFT.py
 (`extract_features_and_desc(image) -> (kp, desc)` :14-23, `get_matches(...) -> int[K,2]` :25-34).
 
-Detection / description runs on OpenCV by default; EXTRACTOR = "gpu" switches to vo_sift_extract (same keypoints and
-descriptors to the tolerance of sift_frontend.py), opt-in until tests/test_zz_gpu_sift.py has passed on a B200.  Matching —
+Detection / description runs on the GPU (vo_sift_extract, csrc/sift.cu: same keypoints and descriptors as OpenCV to the
+tolerance of sift_frontend.py, tests/test_gpu_sift_frontend.py); VO_EXTRACTOR=opencv keeps cv2 on the CPU.  Matching —
 brute-force 2-NN in L2 plus Lowe's 0.85 ratio test — runs on the tensor cores through vo_match_f32.
 """
+import os
+
 import cv2
 import numpy as np
 
 from feature_extractors import _gpu_match
 
-EXTRACTOR = "opencv"  # or "gpu"
+EXTRACTOR = os.environ.get("VO_EXTRACTOR", "gpu")  # or "opencv"
 _sift = None
 _gpu_sift = {}
 

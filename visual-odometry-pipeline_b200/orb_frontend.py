@@ -1,9 +1,8 @@
 """ORB front-end on the GPU (vo_orb_create / vo_orb_extract): cv2.ORB_create().detectAndCompute with the reference's
 default parameters (feature_extractors/ORB.py:8-21).
 
-STATUS: the kernels are compiled and their arithmetic is host-verified against the CPU restatement pinned on OpenCV,
-but they have not run on a GPU yet (tests/test_zz_gpu_orb.py, a non-strict xfail until its first pass on a B200).  The drop-in plug-in
-feature_extractors/ORB.py therefore still extracts with OpenCV; switch it over once that test is green."""
+Bit-identical to the CPU restatement pinned on OpenCV (identical keypoint set, pt, angle, response, descriptors) on a B200:
+tests/test_gpu_orb_frontend.py; tools/orb_bisect.py compares every stage.  Default extractor of feature_extractors/ORB.py."""
 import ctypes
 
 import numpy as np

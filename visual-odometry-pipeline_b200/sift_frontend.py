@@ -2,9 +2,8 @@
 default parameters (feature_extractors/SIFT.py:10-23), held to a tolerance (same keypoints to 1e-2 px / 0.25 degrees,
 descriptor entries within 1 — OpenCV's own low-order bits depend on the host CPU).
 
-STATUS: first version, verified against the CPU restatement under the host emulation only (tests/test_sift_emulation.py);
-it has not run on a GPU yet (tests/test_zz_gpu_sift.py is a non-strict xfail until its first pass on a B200), and the
-drop-in plug-in feature_extractors/SIFT.py therefore still extracts with OpenCV by default."""
+Verified against the CPU restatement under the host emulation (tests/test_sift_emulation.py) and on a B200
+(tests/test_gpu_sift_frontend.py, strict).  Default extractor of the drop-in plug-in feature_extractors/SIFT.py."""
 import ctypes
 
 import numpy as np
