@@ -175,7 +175,7 @@ class VisualOdometry:
         try:
             retval, framepair, common_pts, best_inliers = self.computepose_3D_2D(framepair)
             dist_scale = float(np.linalg.norm(framepair.pose.t))
-            if dist_scale > self.MAX_STEP_M * (frame2.id - frame1.id):
+            if not dist_scale <= self.MAX_STEP_M * (frame2.id - frame1.id):   # NaN-safe form of the reference's `>` (:271)
                 retval = False
                 self.bad_pnp += 1
                 print("Inside false PnP condition")

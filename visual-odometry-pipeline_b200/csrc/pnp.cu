@@ -460,9 +460,9 @@ refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
     const float *pxyz = xyz + (size_t)b * cap * 3;
     const float *puv = uv + (size_t)b * cap * 2;
 
-    __shared__ double sR[9], st[3];
+    __shared__ double sR[9], st[3], sRp[9], stp[3], s_cost;
     __shared__ double sacc[RF_THREADS / 32][RF_ACC];
-    __shared__ int s_stop;
+    __shared__ int s_stop, s_bad;
 
     if (!have) {
         if (mask_out)
@@ -511,6 +511,7 @@ refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
         for (int j = 0; j < 9; ++j) sR[j] = R[j];
         for (int j = 0; j < 3; ++j) st[j] = (double)p.t[j];
         s_stop = 0;
+        s_bad = 0;
     }
     // inlier mask of the winning minimal model: identical arithmetic to score_kernel
     // (per-thread flags are recomputed in the refit loop instead of being stored per point)
@@ -526,7 +527,11 @@ refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
     }
     __syncthreads();
 
-    for (int it = 0; it < iters; ++it) {
+    // Gauss-Newton with a guard (the refined pose is chained into every later global pose, so it must never be worse
+    // than what RANSAC found): every pass evaluates the cost at the current pose first; a pose that is not finite or
+    // whose cost exceeds that of the last accepted pose is dropped for the last accepted one (at worst the minimal
+    // model itself) and the iteration stops.  One extra evaluate-only pass checks the last step.
+    for (int it = 0; it <= iters; ++it) {
         double acc[RF_ACC];
 #pragma unroll
         for (int j = 0; j < RF_ACC; ++j) acc[j] = 0.0;
@@ -572,6 +577,23 @@ refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
                 for (int w = 0; w < RF_THREADS / 32; ++w) s += sacc[w][j];
                 tot[j] = s;
             }
+            const double cost = tot[27];
+            bool finite = cost == cost && cost < 1e300;
+            for (int j = 0; j < 9; ++j) finite = finite && sR[j] == sR[j] && fabs(sR[j]) < 2.0;
+            for (int j = 0; j < 3; ++j) finite = finite && st[j] == st[j] && fabs(st[j]) < 1e300;
+            if (it == 0 && !finite) {        // the minimal model itself is unusable: report "no model" below
+                s_bad = 1;
+                s_stop = 1;
+            } else if (it > 0 && !(finite && cost <= s_cost * (1.0 + 1e-12))) {   // worse than the last accepted pose: take that one back
+                for (int j = 0; j < 9; ++j) sR[j] = sRp[j];
+                for (int j = 0; j < 3; ++j) st[j] = stp[j];
+                s_stop = 1;
+            } else {
+                s_cost = cost;
+                for (int j = 0; j < 9; ++j) sRp[j] = sR[j];
+                for (int j = 0; j < 3; ++j) stp[j] = st[j];
+                if (it == iters) s_stop = 1;
+            }
             double g[6], d[6];
             for (int j = 0; j < 6; ++j) g[j] = -tot[21 + j];
             // tiny relative damping keeps the factorisation defined for planar / weak geometry
@@ -580,7 +602,8 @@ refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
                 tot[dq] += 1e-12 * tot[dq] + 1e-300;
                 dq += 6 - r;
             }
-            if (solve6(tot, g, d)) {
+            if (s_stop) {
+            } else if (solve6(tot, g, d)) {
                 double dR[9], Rn[9];
                 so3_exp(d, dR);
                 for (int i = 0; i < 3; ++i)
@@ -600,7 +623,11 @@ refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
     }
 
     if (threadIdx.x == 0) {
-        if (status && !accumulate_status) status[b] = VO_ST_OK;  // else: keep the soft bits set upstream
+        if (s_bad) {                                              // non-finite minimal model: identity + VO_ST_NO_MODEL
+            for (int j = 0; j < 9; ++j) sR[j] = (j % 4 == 0) ? 1.0 : 0.0;
+            for (int j = 0; j < 3; ++j) st[j] = 0.0;
+            if (status) status[b] = (accumulate_status ? status[b] : 0) | VO_ST_NO_MODEL;
+        } else if (status && !accumulate_status) status[b] = VO_ST_OK;  // else: keep the soft bits set upstream
         if (n_inl_out) n_inl_out[b] = count;
         if (best_h_out) best_h_out[b] = h;
         if (rt_out) {

@@ -63,7 +63,7 @@ __global__ void seq_policy_kernel(vo_seq_state *st, const double *__restrict__ T
     if (ok) {
         const double x = T_rel[3], y = T_rel[7], z = T_rel[11];
         dist = sqrt(x * x + y * y + z * z);
-        if (dist > max_step_m * (double)(st->cur_id - st->key_id)) {  // "Inside false PnP condition" (:271-274)
+        if (!(dist <= max_step_m * (double)(st->cur_id - st->key_id))) {  // "Inside false PnP condition" (:271-274); written NaN-safe
             ok = false;
             ++bad;
         }

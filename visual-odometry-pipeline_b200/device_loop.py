@@ -17,7 +17,7 @@ from ._lib import SeqConfig, check
 
 class DeviceLoop:
     def __init__(self, K, wh, n_cap, *, kind="orb", kp_stride=2, norm_or_metric=None, mode=None, match_param=0.85,
-                 precision=ops.VO_PREC_TF32X1, n_hyp=512, seed=8214, thr_px=1.5, min_inliers=20, refine_iters=10,
+                 precision=None, allow_inexact=False, n_hyp=512, seed=8214, thr_px=1.5, min_inliers=20, refine_iters=10,
                  min_flow_px=3.0, z_range=(0.0, 50.0), max_step_m=1.5, kf_min_common=200, kf_min_inliers=100,
                  kf_max_dist=1.5, bad_pnp_limit=3, max_frames=4096, device=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -27,6 +27,15 @@ class DeviceLoop:
             norm_or_metric = {"orb": ops.VO_NORM_L2_U8, "sift": ops.VO_METRIC_L2}.get(kind, ops.VO_METRIC_COSINE)
         if mode is None:
             mode = ops.VO_MODE_RATIO_MUTUAL if kind == "r2d2" else ops.VO_MODE_RATIO
+        if precision is None:
+            # one 11-bit pass is exact only on integer-valued descriptors (OpenCV SIFT); unit-norm R2D2 descriptors need
+            # the split passes to reproduce the reference's fp32 `d1 @ d2.t()` decisions (R2D2.py:56-65)
+            precision = ops.VO_PREC_F16X1 if kind == "sift" else ops.VO_PREC_TF32X3
+        if (f32 and norm_or_metric == ops.VO_METRIC_COSINE and precision in (ops.VO_PREC_TF32X1, ops.VO_PREC_F16X1)
+                and not allow_inexact):
+            raise ValueError("DeviceLoop: a single 11-bit pass (TF32X1 / F16X1) on cosine similarities of real-valued "
+                             "descriptors changes ratio / mutual decisions (~1e-3 similarity error); use TF32X3 / F16X3 "
+                             "or pass allow_inexact=True")
         c = SeqConfig()
         c.desc_is_f32, c.n_cap, c.kp_stride, c.H, c.W = int(f32), int(n_cap), int(kp_stride), int(wh[1]), int(wh[0])
         c.K = (ctypes.c_double * 9)(*np.asarray(K, np.float64).reshape(9))
@@ -83,7 +92,7 @@ class DeviceLoop:
         """Extract on the device and push — the image is the only per-frame upload besides the depth map; one host read of
         the keypoint count per frame.  frontend: "orb" (orb_frontend.OrbExtractor, cv2.ORB_create(nfeatures) semantics; the
         default of a byte-descriptor loop) or "sift" (sift_frontend.SiftExtractor; the default of a float-descriptor loop).
-        (Both extractors' first GPU run is still pending; `push` with OpenCV features is the verified path.)"""
+        Both extractors are parity-tested on a B200 (tests/test_gpu_orb_frontend.py, tests/test_gpu_sift_frontend.py)."""
         frontend = frontend or ("orb" if self.desc_cols == 32 else "sift")
         if (frontend == "orb") != (self.desc_cols == 32) or frontend not in ("orb", "sift"):
             raise ValueError(f"DeviceLoop.push_image: front-end {frontend!r} does not produce this loop's descriptors")

@@ -6,8 +6,6 @@ import torch
 import _bootstrap  # noqa: F401
 from vo_b200 import ops
 
-_int_valued = {}
-
 
 def _dev(a, dtype):
     if isinstance(a, torch.Tensor):
@@ -29,11 +27,12 @@ def mutual_u8(ref_desc, cur_desc, norm=ops.VO_NORM_HAMMING):
 
 def knn_ratio_f32(ref_desc, cur_desc, ratio=0.85, tag="sift"):
     a, b = _dev(ref_desc, torch.float32), _dev(cur_desc, torch.float32)
-    if tag not in _int_valued:
-        # OpenCV SIFT descriptors are integer-valued in [0,255]: one fp16 pass (11 significant bits) is then exact, and
-        # so is the fp32 accumulation (128 x 255 x 510 < 2^24).  Checked once per run, on both frames.
-        _int_valued[tag] = all(bool(((t == t.round()) & (t.abs() <= 255)).all().item()) for t in (a, b))
-    prec = ops.VO_PREC_F16X1 if _int_valued[tag] else ops.VO_PREC_TF32X3
+    # OpenCV SIFT descriptors are integer-valued in [0,255]: one fp16 pass (11 significant bits) is then exact, and so is
+    # the fp32 accumulation (128 x 255 x 510 < 2^24).  Checked on EVERY call, on both frames (one fused reduction each):
+    # RootSIFT / normalised descriptors or another extractor under the same tag take the split 3xTF32 pass instead.
+    exact = a.numel() > 0 and b.numel() > 0 and all(
+        bool(((t == t.round()) & (t >= 0) & (t <= 255)).all().item()) for t in (a, b))
+    prec = ops.VO_PREC_F16X1 if exact else ops.VO_PREC_TF32X3
     if a.shape[-1] != 128:
         prec = ops.VO_PREC_FP32_SIMT
     res = ops.match_f32(a, b, ops.VO_METRIC_L2, ops.VO_MODE_RATIO, ratio, precision=prec, want_dist=False)
