@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """bench.py — frame-pairs/sec of the hot path (match -> gather/back-project -> PnP-RANSAC -> pose).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c2r|c2tc|c3|c4|c5|default]
 
-A step = one pass of the hot path over `--pairs` synthetic frame pairs per GPU (weak scaling: every rank owns
-its own block of the pre-declared pair list), followed under N>1 by one NCCL all-gather of the
-4x4 relative poses.  Default workload c2 = BASELINE.json configs[1]: ORB 5k keypoints/frame, 256-bit Hamming
-mutual-NN + PnP-RANSAC (1024 hypotheses), 1000-pair sequence, KITTI-shaped frames.
-Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU path (oracle/reference_path.py:
-the same OpenCV calls the reference makes) on the host cores instead.
+Input = one synthetic SEQUENCE of P + 1 frames per GPU (synthetic.make_chain): pair i = (frame i, frame i+1), so a frame's
+descriptors / keypoints / depth map exist (and, in the e2e leg, cross the bus) once.  A step = R passes of the hot path
+over the rank's P consecutive pairs (weak scaling: every rank owns its own block of the pre-declared pair list, SURVEY
+D3/8(e)); R is chosen once, before timing, so that the K timed steps last >= ~2.5 s; under N>1 every pass ends with one
+NCCL all-gather of the 4x4 relative poses.
+Default = BASELINE.json's metric in full: the HEADLINE line is workload c3 (configs[2], the largest single-GPU
+configuration: R2D2 10k keypoints, the tcgen05 3xTF32 GEMM-argmin the metric's "matching GEMM % TC peak" names, 4096
+hypotheses), and the complete line of c2 (configs[1]: ORB 5k, Hamming mutual-NN, 1024 hypotheses, 1000-pair sequence) rides
+in `extra.c2`.  `--workload X` or VO_BENCH_WORKLOAD=X selects a single workload (c4 / c5 for the multi-GPU configs).
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU path (oracle/reference_path.py: the same
+OpenCV / torch calls the reference makes) on the host cores instead, on the same workload(s).
 """
 import argparse
 import json
@@ -33,7 +38,7 @@ WORKLOADS = {
     # SURVEY D2) instead of the north-star's Hamming / mutual rule: an exact fp16 tensor-core pass
     "c2r": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="knn_ratio", orb_l2=True, e2e_sampled_frac=0.4,
                 desc="ORB 5k kp, reference rule: byte-wise L2 kNN-2 + ratio 0.85, PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
-    "c3": dict(kind="r2d2", n_kp=10000, n_hyp=4096, pairs=64, chunk=64, shape="kitti", cpu_matcher="r2d2",
+    "c3": dict(kind="r2d2", n_kp=10000, n_hyp=4096, pairs=128, chunk=64, shape="kitti", cpu_matcher="r2d2",
                desc="R2D2 10k kp, cosine GEMM-argmin ratio+mutual, PnP-RANSAC 4096 hyp, KITTI 1241x376"),
     # the two multi-GPU configurations of BASELINE.json (per-GPU block of the sharded sequence; weak scaling)
     "c4": dict(kind="sift", n_kp=20000, n_hyp=16384, pairs=32, chunk=32, shape="kitti", cpu_matcher="knn_ratio", unique=8,
@@ -47,7 +52,8 @@ def env_rank():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def matcher_cfg(kind, ops, orb_l2=False):
+def matcher_cfg(kind, ops, wl=None):
+    orb_l2 = bool(wl and wl.get("orb_l2"))
     if kind == "orb" and orb_l2:
         return dict(norm_or_metric=ops.VO_NORM_L2_U8, mode=ops.VO_MODE_RATIO, match_param=0.85, precision=0)
     if kind == "orb":
@@ -57,10 +63,24 @@ def matcher_cfg(kind, ops, orb_l2=False):
     return dict(norm_or_metric=ops.VO_METRIC_COSINE, mode=ops.VO_MODE_RATIO_MUTUAL, match_param=0.90, precision=ops.VO_PREC_TF32X3)
 
 
-def make_host_batch(wl, unique, first_index):
+def make_host_chain(wl, n_pairs, first_index, pinned=False):
+    """P + 1 consecutive synthetic frames (synthetic.make_chain), optionally generated straight into pinned host memory."""
     from vo_b200 import synthetic
     K, wh = (synthetic.KITTI_K, synthetic.KITTI_WH) if wl["shape"] == "kitti" else (synthetic.ZED_K, synthetic.ZED_WH)
-    return synthetic.make_batch(first_index, unique, n_kp=wl["n_kp"], kind=wl["kind"], K=K, wh=wh)
+    out = None
+    if pinned:
+        import torch
+        F, N = n_pairs + 1, wl["n_kp"]
+        ddt, dd = (torch.uint8, 32) if wl["kind"] == "orb" else (torch.float32, 128)
+        t = {"desc": torch.empty((F, N, dd), dtype=ddt).pin_memory(), "kp": torch.empty((F, N, 2), dtype=torch.float32).pin_memory(),
+             "depth": torch.empty((F, wh[1], wh[0]), dtype=torch.float32).pin_memory()}
+        out = {k: v.numpy() for k, v in t.items()}
+        out["_pinned"] = t
+    ch = synthetic.make_chain(first_index, n_pairs, n_kp=wl["n_kp"], kind=wl["kind"], K=K, wh=wh,
+                              out=None if out is None else {k: out[k] for k in ("desc", "kp", "depth")})
+    if out is not None:
+        ch["_pinned"] = out["_pinned"]
+    return ch
 
 
 class ClockSampler:
@@ -156,11 +176,12 @@ def ncu_traffic(kernel_key, pairs_per_launch):
 def time_cpu_pairs(wl, n_pairs, first_index=0, warm=1):
     """Runs the reference's CPU path over `n_pairs` synthetic pairs; returns (pairs/s, seconds, threads)."""
     from oracle import reference_path as rp
+    from vo_b200 import synthetic
     threads = rp.set_threads(os.cpu_count() or 1)
-    batch = make_host_batch(wl, n_pairs + warm, first_index)
+    chain = make_host_chain(wl, n_pairs + warm, first_index)
     rng = np.random.RandomState(8214)          # vo_stereo_runner.py:20-24
     def run(i):
-        p = batch["pairs"][i]
+        p = synthetic.chain_pair(chain, i)
         return rp.process_pair(p["ref_desc"], p["cur_desc"], p["ref_kp"], p["cur_kp"], p["depth"], p["K"],
                                matcher=wl["cpu_matcher"], rng=rng)
     for i in range(warm):
@@ -173,29 +194,28 @@ def time_cpu_pairs(wl, n_pairs, first_index=0, warm=1):
     return n_pairs / dt, dt, threads, ok
 
 
-def run_reference(args, wl):
-    rank, _, world = env_rank()
-    if rank != 0:
-        return
-    sample = args.cpu_pairs or {"c1": 24, "c2": 16, "c2r": 16, "c3": 4, "c4": 2, "c5": 1}[args.workload]
+def run_reference(args, name):
+    """--impl reference: the reference's CPU path on the host cores, bounded sample per step (rank 0 only)."""
+    wl = WORKLOADS[name]
+    sample = args.cpu_pairs or {"c1": 24, "c2": 16, "c2r": 16, "c2tc": 16, "c3": 4, "c4": 2, "c5": 1}[name]
     vals, secs = [], []
     for s in range(args.warmup + args.steps):
-        v, dt, threads, ok = time_cpu_pairs(wl, sample, first_index=s * (sample + 1))
+        v, dt, threads, ok = time_cpu_pairs(wl, sample, first_index=s)
         if s >= args.warmup:
             vals.append(v); secs.append(dt)
     value = float(np.mean(vals))
-    line = {
+    return {
         "impl": "reference", "metric": "frame-pairs/sec (match+PnP)", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs) * 1e3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_of(wl), "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "pairs_per_step": sample,
-                   "path": "cv2.BFMatcher + depthTo3d restatement + 3x cv2.solvePnPRansac(100, 1.5) (oracle/reference_path.py)"},
+        "config": {"workload": f"{name}: {wl['desc']}", "pairs_per_step": sample,
+                   "path": "cv2.BFMatcher / torch matmul+topk + depthTo3d restatement + 3x cv2.solvePnPRansac(100, 1.5) "
+                           "(oracle/reference_path.py: the reference's own third-party calls)"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} pairs/step x {args.steps} steps of the same synthetic workload"},
+                         "sample": f"{sample} consecutive pairs/step x {args.steps} steps of the same synthetic workload"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
 
 
 def dtype_of(wl):
@@ -206,34 +226,36 @@ def dtype_of(wl):
 
 
 # --------------------------------------------------------------------------------------- our arm
-def run_ours(args, wl):
+_DIST = {"init": False}
+
+
+def run_ours(args, name):
     import torch
     import torch.distributed as dist
     import vo_b200  # noqa: F401
-    from vo_b200 import ops, sequence
+    from vo_b200 import ops, sequence, synthetic
 
+    wl = WORKLOADS[name]
     rank, local_rank, world = env_rank()
     numa_cores = sequence.bind_to_gpu_numa(local_rank) if world > 1 else None   # pinned buffers on the GPU's NUMA node
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and not _DIST["init"]:
         dist.init_process_group("nccl", device_id=dev)
+        _DIST["init"] = True
 
-    P = args.pairs or wl["pairs"]                      # pairs per GPU per step
-    unique = min(args.unique or wl.get("unique", 40), P)
-    reps = (P + unique - 1) // unique
-    host = make_host_batch(wl, unique, first_index=rank * P)
-    batch_full = sequence.PairBatch.from_numpy(host, dev, repeat=reps)
-    batch = batch_full.slice(0, P)                     # distinct memory per pair: inputs >> L2
-    mc = matcher_cfg(wl["kind"], ops, wl.get("orb_l2", False))
+    P = args.pairs or wl["pairs"]                      # pairs per GPU per pass
+    host = make_host_chain(wl, P, first_index=rank, pinned=True)    # P + 1 frames, straight into pinned host memory
+    seq = sequence.FrameSequence.from_numpy({**host["_pinned"], "K": host["K"]}, dev)   # every frame resident once: >> L2
+    mc = matcher_cfg(wl["kind"], ops, wl)
     if args.precision is not None:
         mc["precision"] = args.precision
     cfg = sequence.PipelineConfig(n_hyp=wl["n_hyp"], **mc)
     chunk = min(args.chunk or wl["chunk"], P)
     out = ops.PipelineBuffers(P, dev)
 
-    def step():
-        sequence.run_resident(batch, cfg, pair0=rank * P, chunk=chunk, out=out)
+    def one_pass():
+        sequence.run_resident(seq, cfg, pair0=rank * P, chunk=chunk, out=out)
         if world > 1:
             return sequence.all_gather_poses(out.T_rel, out.status, world)
         return out.T_rel, out.status
@@ -242,6 +264,25 @@ def run_ours(args, wl):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def agree_max(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # passes per step: chosen once, outside the timed region, so that the K timed steps last >= ~2.5 s
+    one_pass(); barrier()
+    e0.record(); one_pass(); one_pass(); e1.record(); barrier()
+    pass_ms = agree_max(e0.elapsed_time(e1) / 2.0)
+    R = args.passes or int(min(256, max(1, np.ceil(args.min_timed_ms / (args.steps * pass_ms)))))
+
+    def step():
+        for _ in range(R):
+            r = one_pass()
+        return r
 
     for _ in range(args.warmup):
         step()
@@ -252,7 +293,6 @@ def run_ours(args, wl):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
@@ -264,56 +304,67 @@ def run_ours(args, wl):
     stages = ops.profile_collect()
     ops.profile_enable(False)
     launches = ops.launch_count() - l0
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * P * args.steps / (ms / 1e3)
+    ms = agree_max(ms)
+    value = world * P * R * args.steps / (ms / 1e3)
 
     # sanity of the work done inside the timed region (not a parity test: tests/ does that)
     st = out.status.cpu().numpy()
     ok_frac = float((st == 0).mean())
     n_inl = out.n_inl.cpu().numpy()
-    from vo_b200 import synthetic
     Tn = out.T_rel.cpu().numpy()
-    errs = [synthetic.pose_errors(Tn[i], host["pairs"][i % unique]["T_rel"]) for i in range(min(P, unique))]
+    errs = [synthetic.pose_errors(Tn[i], host["T_rel"][i]) for i in range(P)]
     chain = sequence.chain_poses(T_all.cpu().numpy(), sequence.gate_poses(T_all.cpu().numpy(), st_all.cpu().numpy()))
 
-    # ---- e2e: host buffers in, poses out, H2D/D2H inside the timed region
-    host_rep = {k: np.concatenate([host[k]] * reps, 0)[:P] for k in ("ref_desc", "cur_desc", "ref_kp", "cur_kp", "depth")}
-    host_rep["K"] = host["K"]
-    runner = sequence.HostPairRunner(host_rep, cfg, chunk=min(args.e2e_chunk or max(1, chunk // 2), P), device=dev,
-                                     depth_mode=args.e2e_depth,
-                                     sampled_frac=args.e2e_sampled_frac if args.e2e_sampled_frac is not None else wl.get("e2e_sampled_frac", 0.2))
-    del host_rep
+    # ---- e2e: the same sequence from pinned HOST memory through sequence.HostSequenceRunner (the call a user with frames in
+    # host memory makes): H2D of every frame, D2H of the poses and the host-side pose chaining inside the timed region
+    runner = sequence.HostSequenceRunner({**host["_pinned"], "K": host["K"]}, cfg,
+                                         chunk=min(args.e2e_chunk or max(1, chunk // 2), P), device=dev, depth_mode=args.e2e_depth,
+                                         sampled_frac=args.e2e_sampled_frac if args.e2e_sampled_frac is not None else wl.get("e2e_sampled_frac", 0.4))
+    tune = {}
+    if args.e2e_depth == "hybrid" and args.e2e_sampled_frac is None:
+        tune = runner.autotune(sync=barrier)             # untimed: which DMA / zero-copy split suits this host with `world` ranks pulling
+        if world > 1:                                    # every rank runs the same split (the slowest rank sets the time anyway)
+            votes = torch.tensor([tune[f] for f in sorted(tune)], dtype=torch.float64, device=dev)
+            dist.all_reduce(votes, op=dist.ReduceOp.MAX)
+            runner.frac = sorted(tune)[int(votes.argmin().item())]
+            tune = {f: float(v) for f, v in zip(sorted(tune), votes.tolist())}
 
-    def e2e_step():
-        T_h, st_h, inl_h = runner.run(pair0=rank * P)
-        if world > 1:
-            sequence.all_gather_poses(runner.out.T_rel, runner.out.status, world)
+    def e2e_passes(count):
+        """`count` passes, software-pipelined: pass r+1 is submitted (its uploads start at once) before the host waits for,
+        reads back and chains the poses of pass r.  Every pass's H2D, compute, D2H and host chaining lie inside the caller's
+        timed region; the function returns with the last pass's results read."""
+        pending = None
+        for _ in range(count):
+            t = runner.submit(pair0=rank * P)
+            if world > 1:
+                sequence.all_gather_poses(runner.out.T_rel, runner.out.status, world)
+            if pending is not None:
+                T_h, st_h, _ = runner.collect(pending)
+                sequence.chain_poses(T_h.numpy(), sequence.gate_poses(T_h.numpy(), st_h.numpy()))
+            pending = t
+        T_h, st_h, _ = runner.collect(pending)
+        sequence.chain_poses(T_h.numpy(), sequence.gate_poses(T_h.numpy(), st_h.numpy()))
         torch.cuda.synchronize()
         return T_h, st_h
 
+    e2e_passes(2); barrier()
+    e0.record(); e2e_passes(4); e1.record(); barrier()
+    Re = args.passes or int(min(256, max(1, np.ceil(args.min_timed_ms / (args.steps * agree_max(e0.elapsed_time(e1)) / 4.0)))))
     for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
+        e2e_passes(Re)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        T_h, st_h = e2e_step()
-        sequence.chain_poses(T_h.numpy(), sequence.gate_poses(T_h.numpy(), st_h.numpy()))
+    T_h, st_h = e2e_passes(args.steps * Re)
     e1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * P * args.steps / (float(t.item()) / 1e3)
+    e2e_ms = agree_max(e0.elapsed_time(e1))
+    e2e_value = world * P * Re * args.steps / (e2e_ms / 1e3)
+    e2e_same = bool(np.array_equal(T_h.numpy(), Tn) and np.array_equal(st_h.numpy(), st))   # host path == resident path, bit for bit
+    h2d_pass, d2h_pass = runner.h2d_bytes, runner.d2h_bytes
+    del runner
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---- roofline of the dominant kernel, from the per-stage event times of the timed region
     hbm_peak, bf16_peak, peak_kind = peaks()
@@ -322,7 +373,7 @@ def run_ours(args, wl):
     total_stage = sum(v[0] for v in stages.values())
     share = {k: (v[0] / total_stage if total_stage else 0.0) for k, v in stages.items() if v[1]}
     launches_match = stages["match"][1]
-    pairs_per_launch = P * args.steps / max(launches_match, 1)
+    pairs_per_launch = P * R * args.steps / max(launches_match, 1)
     match_s = stage_ms.get("match", float("nan")) / 1e3
     if wl.get("orb_l2"):
         # bytes widened to fp16 and zero-padded to 128 dimensions: the pass SIFT runs (kind::f16, exact integers)
@@ -374,13 +425,18 @@ def run_ours(args, wl):
                             "sm__pipe_tensor_cycles_active 50-54 %, ALU pipe 61-65 % (profiles/r01i_ncu_raw_match_f16*.csv)"}
         else:
             tf32_cublas = measure_tf32_peak(dev)
+            sm_mhz_r = (clocks or {}).get("sm_mhz") or 1965.0
+            pipe_tf32 = 4055.0 * 148 * sm_mhz_r * 1e6 / 1e12        # tools/probe/mma_issue_probe.cu: tf32 FLOP/clk/SM the pipe retires
+            ach = flops / match_s / 1e12
             roof = {"kernel": "match_f32_tc_kernel (tcgen05 kind::tf32 fused GEMM + row top-2 / column arg-max)",
-                    "bound": "tensor", "achieved": flops / match_s / 1e12, "peak": tf32_half_bf16, "unit": "TFLOP/s",
+                    "bound": "tensor", "achieved": ach, "peak": pipe_tf32, "unit": "TFLOP/s",
                     "traffic": ncu_traffic("match_f32_tc_kernel", pairs_per_launch),
-                    "peak_source": f"0.5 x bf16 cuBLAS burst peak of MEASURED_PEAKS.json ({peak_kind}); MEASURED_PEAKS has no "
-                                   "TF32 entry, so cuBLAS TF32 was also measured in this run: see peak_cublas_tf32",
-                    "peak_cublas_tf32": tf32_cublas, "frac_of_cublas_tf32": flops / match_s / 1e12 / tf32_cublas,
-                    "frac_of_nominal_1100": flops / match_s / 1e12 / 1100.0,
+                    "peak_source": "tensor-pipe tf32 rate measured on this GPU model (tools/probe/mma_issue_probe.cu: 4055 FLOP/clk/SM, "
+                                   "half the fp16 rate) x 148 SM x the SM clock sampled in this run.  MEASURED_PEAKS.json has no TF32 "
+                                   "entry; the two other yardsticks are printed beside it: cuBLAS TF32 measured in this run "
+                                   "(peak_cublas_tf32, power-limited like any long GEMM) and 0.5 x the bf16 burst peak of MEASURED_PEAKS.json",
+                    "peak_cublas_tf32": tf32_cublas, "frac_of_cublas_tf32": ach / tf32_cublas,
+                    "peak_half_bf16_measured": tf32_half_bf16, "frac_of_half_bf16_measured": ach / tf32_half_bf16,
                     "issued_passes": passes, "algorithmic_flops": flops / passes,
                     "note": "achieved counts ISSUED tensor FLOPs (3 tf32 MMAs per k-step for 3xTF32), as BASELINE.md section 3 specifies"}
     roof["frac"] = roof["achieved"] / roof["peak"]
@@ -393,7 +449,7 @@ def run_ours(args, wl):
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12                              # FFMA lanes x 2 FLOP, TFLOP/s
     n_corr = out.n_corr.cpu().numpy().astype(np.float64)
     n_match = out.n_matches.cpu().numpy().astype(np.float64)
-    launches_per_step = max(stages["score"][1], 1) / args.steps
+    launches_per_step = max(stages["score"][1], 1) / (args.steps * R)      # per pass over the P pairs
     corr_per_launch = float(n_corr.sum()) / launches_per_step
     match_per_launch = float(n_match.sum()) / launches_per_step
     Hh = wl["n_hyp"]
@@ -435,12 +491,12 @@ def run_ours(args, wl):
     # dense back-projection (cv2.rgbd.depthTo3d replacement): not on the fused pipeline's critical path, timed here on
     # the same depth maps, L2-cold (every launch reads / writes frames no earlier launch of the loop touched)
     try:
-        nfr = int(min(batch.depth.shape[0], max(8, (2 << 30) // (batch.depth[0].numel() * 16))))
-        frames = batch.depth[:nfr]
-        ops.backproject_dense(frames[:2], batch.K)
+        nfr = int(min(seq.depth.shape[0], max(8, (2 << 30) // (seq.depth[0].numel() * 16))))
+        frames = seq.depth[:nfr]
+        ops.backproject_dense(frames[:2], seq.K)
         torch.cuda.synchronize()
         ops.profile_enable(True); ops.profile_collect()
-        xyz_dense = ops.backproject_dense(frames, batch.K)
+        xyz_dense = ops.backproject_dense(frames, seq.K)
         st_d = ops.profile_collect(); ops.profile_enable(False)
         t = st_d["dense"][0] / max(st_d["dense"][1], 1) / 1e3
         db = float(frames.numel()) * 16.0
@@ -455,24 +511,35 @@ def run_ours(args, wl):
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
-        sample = args.cpu_pairs or {"c1": 48, "c2": 24, "c2r": 24, "c3": 6, "c4": 2, "c5": 1}[args.workload]
+        sample = args.cpu_pairs or {"c1": 48, "c2": 24, "c2r": 24, "c2tc": 24, "c3": 6, "c4": 2, "c5": 1}[name]
         v, dt, threads, okc = time_cpu_pairs(wl, sample, first_index=0)
         cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-               "sample": f"first {sample} pairs of the same synthetic workload, {dt:.1f} s, reference CPU path "
+               "sample": f"first {sample} consecutive pairs of the same synthetic workload, {dt:.1f} s, reference CPU path "
                          f"(cv2 {wl['cpu_matcher']} + 3x solvePnPRansac), {okc}/{sample} poses found"}
 
+    if clocks is not None and not clocks.get("samples") and not args.allow_no_clocks:
+        raise SystemExit("bench.py: no nvidia-smi clock sample fell inside the timed region; the line would be unverifiable "
+                         "(--allow-no-clocks to print it anyway)")
     line = {
         "metric": "frame-pairs/sec (match+PnP)", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": dtype_of(wl), "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "pairs_per_gpu_per_step": P, "unique_pairs": unique,
-                   "chunk": chunk, "l2": "inputs larger than L2 (every pair has its own HBM copy: "
-                   f"{batch.nbytes() / 1e6:.0f} MB per GPU per step)", "parallelism": f"pairs sharded over {world} GPU(s), "
-                   "1 NCCL all-gather of 4x4 poses per step" if world > 1 else "single GPU",
+        "config": {"workload": f"{name}: {wl['desc']}", "pairs_per_gpu_per_step": P * R, "passes_per_step": R,
+                   "pairs_per_pass": P, "frames_per_gpu": P + 1, "chunk": chunk, "timed_region_s": ms / 1e3,
+                   "sequence": "consecutive pairs of one synthetic sequence per GPU: frame i+1 is the current frame of pair i and "
+                               "the reference frame of pair i+1 (synthetic.make_chain; no pair or frame is repeated inside a pass)",
+                   "l2": f"inputs larger than L2: {seq.nbytes() / 1e6:.0f} MB of frames per GPU are streamed from HBM in every pass",
+                   "parallelism": f"pairs sharded over {world} GPU(s), 1 NCCL all-gather of 4x4 poses per pass" if world > 1 else "single GPU",
                    "host_numa_binding": (f"rank 0 bound to {len(numa_cores)} GPU-local cores" if numa_cores else "none")},
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": runner.count_matched_bytes(),
-                "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
-                "depth": args.e2e_depth, "sampled_frac": runner.frac},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_pass * Re),
+                "d2h_bytes_per_step": int(d2h_pass * Re), "ms_per_step": e2e_ms / args.steps, "passes_per_step": Re,
+                "timed_region_s": e2e_ms / 1e3, "frac_of_resident": e2e_value / value,
+                "depth": args.e2e_depth, "sampled_frac": tune and min(tune, key=tune.get) or (args.e2e_sampled_frac if args.e2e_sampled_frac is not None else wl.get("e2e_sampled_frac", 0.4)),
+                "sampled_frac_autotune_ms_per_pass": tune or None, "equals_resident_bitwise": e2e_same,
+                "precondition": "frames (descriptors, keypoints, depth maps) are in PINNED host memory when the timed region starts; "
+                                "every frame crosses the bus once per pass, poses / status / inlier counts come back, host-side "
+                                "gating + pose chaining included",
+                "h2d_gbs_per_gpu": h2d_pass * Re * args.steps / (e2e_ms / 1e3) / 1e9},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -485,9 +552,9 @@ def run_ours(args, wl):
                   "median_trans_err_m": float(np.median([e[1] for e in errs])),
                   "chained_poses": int(chain.shape[0])},
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del seq, out
+    torch.cuda.empty_cache()
+    return line
 
 
 def main():
@@ -496,27 +563,43 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: workload's)")
-    ap.add_argument("--unique", type=int, default=0, help="distinct synthetic pairs generated per rank, tiled to --pairs "
-                    "(default: 40; 8 / 4 for c4 / c5)")
+    ap.add_argument("--workload", default=os.environ.get("VO_BENCH_WORKLOAD", "default"), choices=sorted(WORKLOADS) + ["default"],
+                    help="default = headline c3 (the tcgen05 GEMM of BASELINE.json's metric) with the c2 line in extra.c2; "
+                         "VO_BENCH_WORKLOAD sets it for driver-launched runs")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per pass (default: workload's)")
+    ap.add_argument("--passes", type=int, default=0, help="passes over the sequence per step (default: sized for --min-timed-ms)")
+    ap.add_argument("--min-timed-ms", type=float, default=2500.0, help="lower bound of the timed region the pass count is sized for")
     ap.add_argument("--chunk", type=int, default=0, help="pairs per vo_pipeline call (default: workload's)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="pairs per H2D/compute chunk of the e2e run (default: chunk/2)")
     ap.add_argument("--e2e-sampled-frac", type=float, default=None, help="hybrid: fraction of each chunk's maps sampled zero-copy "
-                    "(default: the workload's; 0.4 at ORB 5k — tools/e2e_sweep.py: 0.2 / 0.4 / 0.6 / 0.8 -> 25.3k / 26.6-27.0k / 25.7k / 24.8k pairs/s — else 0.2)")
-    ap.add_argument("--e2e-depth", default="hybrid", choices=["sampled", "dense", "hybrid", "matched"],
-                    help="e2e leg: copy whole depth maps (dense) or read depth at the reference keypoints zero-copy from "
-                         "pinned host memory (sampled), or both concurrently (hybrid, default), or hand vo_pipeline the pinned maps so that only matched "
-                         "keypoints are read (matched).  Measured at c2: dense 22.8k, sampled 25.1k, matched 26.1-26.5k, hybrid 27.0k pairs/s")
+                    "(default: autotuned before timing over 0.2 / 0.4 / 0.6 / 0.8 / 1.0)")
+    ap.add_argument("--e2e-depth", default="hybrid", choices=["sampled", "dense", "hybrid"],
+                    help="e2e leg: copy whole depth maps (dense), read depth at the reference keypoints zero-copy from pinned "
+                         "host memory (sampled), or both concurrently (hybrid, default)")
     ap.add_argument("--precision", type=int, default=None)
     ap.add_argument("--cpu-pairs", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--allow-no-clocks", action="store_true")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    rank, _, world = env_rank()
+    names = ["c2", "c3"] if args.workload == "default" else [args.workload]     # headline last
     if args.impl == "reference":
-        run_reference(args, wl)
+        if rank != 0:
+            return                                                             # N > 1: rank 0 alone runs and prints it
+        lines = [run_reference(args, n) for n in names]
     else:
-        run_ours(args, wl)
+        lines = [run_ours(args, n) for n in names]
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank != 0:
+            return
+    line = lines[-1]
+    if len(lines) > 1:
+        line["extra"] = {n: l for n, l in zip(names[:-1], lines[:-1])}
+        line["config"]["also_measured"] = "extra.c2 = the complete line of workload c2 (BASELINE.json configs[1]) from the same run"
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -25,7 +25,9 @@ def test_reference_arm_prints_one_contract_line():
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
     assert d["metric"].startswith("frame-pairs/sec") and d["unit"] == "pairs/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic" and d["scaling"] == "weak"
-    assert d["config"]["workload"].startswith("c2:")                    # BASELINE.json configs[1]
+    assert d["config"]["workload"].startswith("c3:")                    # headline: BASELINE.json configs[2], the GEMM of the metric
+    assert d["extra"]["c2"]["config"]["workload"].startswith("c2:")     # BASELINE.json configs[1] rides along, complete line
+    assert BASE_KEYS <= set(d["extra"]["c2"])
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -26,6 +26,8 @@ def match_f32():
         for prec in (ops.VO_PREC_TF32X3, ops.VO_PREC_TF32X1, ops.VO_PREC_F16X1, ops.VO_PREC_F16X3, ops.VO_PREC_FP32_SIMT):
             for mode, param in ((ops.VO_MODE_RATIO, 0.85), (ops.VO_MODE_MUTUAL, 0.0), (ops.VO_MODE_RATIO_MUTUAL, 0.9),
                                 (ops.VO_MODE_THRESH_MUTUAL, 0.9), (ops.VO_MODE_THRESH, 0.9), (ops.VO_MODE_NN, 0.0)):
+                if metric == ops.VO_METRIC_L2 and mode in (ops.VO_MODE_THRESH_MUTUAL, ops.VO_MODE_THRESH):
+                    continue                       # similarity thresholds are defined on cosine similarities only
                 for ragged in (False, True):
                     r = ops.match_f32(ref, cur, metric, mode, param, precision=prec, n_ref=n_ref if ragged else None,
                                       n_cur=n_cur if ragged else None, want_knn=(mode == ops.VO_MODE_MUTUAL))

@@ -101,21 +101,45 @@ constexpr uint32_t VO_DEPTH_OOB_BITS = 0xffc0b200u;  // quiet NaN with a payload
 // Depth at every keypoint's truncated pixel, depth[int(y), int(x)] (VisualOdometry_Stereo.py:97), as a compact
 // [B][n_stride] array.  `depth` only has to be device-ACCESSIBLE: reading a pinned host image through the mapped
 // pointer moves one 32-byte sector per keypoint over PCIe instead of the whole H x W map (1.87 MB at 1241 x 376).
-__global__ void __launch_bounds__(256)
+// Thin and persistent on purpose: a zero-copy read takes ~2 us of link latency and the link sustains only a few hundred
+// reads in flight (tools/h2d_wall.py: ~366 M sector reads/s), so a few thousand resident threads with SD_ILP independent loads
+// each saturate it.  64-thread CTAs with a small register footprint co-reside with the CTAs of a matcher launch that is
+// running on another stream (which leaves only a few thousand free registers per SM), instead of queueing behind them:
+// the e2e path overlaps the sampling of the next chunk with the matcher of the current one.
+// <= 32 registers per thread: three 80-register matcher CTAs leave 1024 registers per SM sub-partition, one such warp.
+constexpr int SD_THREADS = 64, SD_ILP = 4;
+__global__ void __launch_bounds__(SD_THREADS, 32)
 sample_depth_kernel(const float *__restrict__ kp, int n_stride, int kp_stride, const int32_t *__restrict__ n_kp,
                     const float *__restrict__ depth, int H, int W, long long total, float *__restrict__ z_kp) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
-    const int b = (int)(gid / n_stride), i = (int)(gid % n_stride);
-    const int n = n_kp ? min(n_kp[b], n_stride) : n_stride;
-    float z = __int_as_float(0x7fc00000);
-    if (i < n) {
-        const float *p = kp + (size_t)gid * kp_stride;
-        const int u = (int)p[0], v = (int)p[1];
-        if (u < 0 || u >= W || v < 0 || v >= H) z = __uint_as_float(VO_DEPTH_OOB_BITS);
-        else z = depth[(size_t)b * H * W + (size_t)v * W + u];
+    const long long step = (long long)gridDim.x * SD_THREADS * SD_ILP;
+    for (long long base = (long long)blockIdx.x * SD_THREADS * SD_ILP + threadIdx.x; base < total; base += step) {
+        float z[SD_ILP];
+        const float *src[SD_ILP];
+#pragma unroll
+        for (int q = 0; q < SD_ILP; ++q) {
+            const long long gid = base + (long long)q * SD_THREADS;
+            src[q] = nullptr;
+            z[q] = __int_as_float(0x7fc00000);
+            if (gid < total) {
+                const int b = (int)(gid / n_stride), i = (int)(gid % n_stride);
+                const int n = n_kp ? min(n_kp[b], n_stride) : n_stride;
+                if (i < n) {
+                    const float *p = kp + (size_t)gid * kp_stride;
+                    const int u = (int)p[0], v = (int)p[1];
+                    if (u < 0 || u >= W || v < 0 || v >= H) z[q] = __uint_as_float(VO_DEPTH_OOB_BITS);
+                    else src[q] = depth + (size_t)b * H * W + (size_t)v * W + u;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SD_ILP; ++q)                       // all loads issued before the first use
+            if (src[q]) z[q] = __ldg(src[q]);
+#pragma unroll
+        for (int q = 0; q < SD_ILP; ++q) {
+            const long long gid = base + (long long)q * SD_THREADS;
+            if (gid < total) z_kp[gid] = z[q];
+        }
     }
-    z_kp[gid] = z;
 }
 
 // Sparse fused path: one CTA per frame pair, chunks of GB_THREADS matches, ballot + warp-count
@@ -254,8 +278,9 @@ extern "C" int vo_sample_depth(vo_ctx *ctx, const float *kp, int B, int n_stride
     VO_REQUIRE(B >= 0 && n_stride >= 0 && kp_stride >= 2 && H > 0 && W > 0, "vo_sample_depth: bad shape");
     const long long total = (long long)B * n_stride;
     if (total == 0) return VO_OK;
-    sample_depth_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kp, n_stride, kp_stride, n_kp, depth,
-                                                                                          H, W, total, depth_kp);
+    const long long want = (total + SD_THREADS * SD_ILP - 1) / (SD_THREADS * SD_ILP);
+    const unsigned grid = (unsigned)(want < 148 ? want : 148);     // persistent, one thin CTA per SM: all resident in the leftover registers at once
+    sample_depth_kernel<<<grid, SD_THREADS, 0, (cudaStream_t)stream>>>(kp, n_stride, kp_stride, n_kp, depth, H, W, total, depth_kp);
     VO_LAUNCH_CHECK(ctx);
     return VO_OK;
 }

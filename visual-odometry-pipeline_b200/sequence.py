@@ -108,6 +108,30 @@ class PairBatch:
         return sum(t.numel() * t.element_size() for t in (self.ref_desc, self.cur_desc, self.ref_kp, self.cur_kp, self.depth))
 
 
+class FrameSequence:
+    """Device-resident frames of one sequence: desc [F,N,..], kp [F,N,s], depth [F,H,W].  Pair i = (frame i, frame i+1):
+    frame i+1 is the current frame of pair i and the reference frame of pair i+1 (as in VisualOdometry.process_frame when
+    every frame becomes the keyframe), so every frame is resident once and the two sides of a pair batch are views of the
+    same arrays shifted by one frame."""
+
+    def __init__(self, desc, kp, depth, K):
+        self.desc, self.kp, self.depth = desc, kp, depth
+        self.K = np.asarray(K, np.float64)
+        self.B = desc.shape[0] - 1
+
+    @staticmethod
+    def from_numpy(chain, device="cuda"):
+        up = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(device)  # noqa: E731
+        return FrameSequence(up(chain["desc"]), up(chain["kp"]), up(chain["depth"]), chain["K"])
+
+    def slice(self, lo, hi):
+        return PairBatch(self.desc[lo:hi], self.desc[lo + 1:hi + 1], self.kp[lo:hi], self.kp[lo + 1:hi + 1],
+                         self.depth[lo:hi], self.K)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.desc, self.kp, self.depth))
+
+
 class PipelineConfig:
     def __init__(self, norm_or_metric, mode, match_param=0.85, precision=ops.VO_PREC_TF32X3, n_hyp=1024, seed=8214,
                  thr_px=1.5, min_inliers=20, refine_iters=10):
@@ -119,7 +143,7 @@ def run_resident(batch, cfg, pair0=0, chunk=None, out=None):
     """vo_pipeline over device-resident pairs, in chunks; returns a PipelineBuffers covering the whole block."""
     B = batch.B
     chunk = chunk or B
-    out = out or ops.PipelineBuffers(B, batch.ref_desc.device)
+    out = out or ops.PipelineBuffers(B, batch.slice(0, 1).ref_desc.device)
     for lo in range(0, B, chunk):
         hi = min(B, lo + chunk)
         sub = batch.slice(lo, hi)
@@ -301,3 +325,163 @@ class HostPairRunner:
         self.host_status.copy_(self.out.status, non_blocking=True)
         self.host_inl.copy_(self.out.n_inl, non_blocking=True)
         return self.host_T, self.host_status, self.host_inl
+
+
+class HostSequenceRunner:
+    """End-to-end path for a SEQUENCE held in pinned host memory: frames desc [F,N,..], kp [F,N,s], depth [F,H,W]; pair i =
+    (frame i, frame i+1).  Every frame crosses the bus once: a chunk of n pairs uploads its n+1 frames' descriptors and
+    keypoints (the first frame of a chunk is copied device-to-device from the previous chunk's last one) on a copy
+    stream, double-buffered against vo_pipeline on the compute stream; poses, status and inlier counts come back with one
+    D2H copy per pass.  Depth maps are needed for reference frames only, and only under their keypoints:
+      "dense"    whole maps by DMA;
+      "sampled"  maps stay in pinned host memory, vo_sample_depth reads depth[int(y), int(x)] of every reference keypoint
+                 zero-copy through the mapped pointer (one 32 B sector per keypoint);
+      "hybrid"   the first (1 - sampled_frac) of a chunk's maps by DMA while the SMs pull the samples of the rest on a
+                 third stream.  `autotune()` picks sampled_frac by timing whole passes (the best split depends on how many
+                 GPUs share the host's memory system).
+    Precondition: the frames are already in pinned host memory (numpy inputs are pinned here, outside any timed region)."""
+
+    def __init__(self, host_seq, cfg, chunk, device="cuda", depth_mode="hybrid", sampled_frac=0.4):
+        if depth_mode not in ("dense", "sampled", "hybrid"):
+            raise ValueError(depth_mode)
+        self.depth_mode = depth_mode
+        self.cfg, self.chunk, self.device = cfg, int(chunk), torch.device(device)
+        self.K = np.asarray(host_seq["K"], np.float64)
+
+        def pinned(a):
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+            return t if t.is_pinned() else t.pin_memory()
+        self.host = {k: pinned(host_seq[k]) for k in ("desc", "kp", "depth")}
+        self.B = self.host["desc"].shape[0] - 1
+        self.hw = tuple(self.host["depth"].shape[1:])
+        self.N = self.host["kp"].shape[1]
+        self.frac = {"dense": 0.0, "sampled": 1.0, "hybrid": float(sampled_frac)}[depth_mode]
+        self.schedule = chunk_schedule(self.B, self.chunk)
+        c = self.chunk
+        self.stage = []
+        for _ in range(2):
+            st = {k: torch.empty((c + 1,) + tuple(self.host[k].shape[1:]), dtype=self.host[k].dtype, device=self.device)
+                  for k in ("desc", "kp")}
+            if depth_mode != "sampled":
+                st["depth"] = torch.empty((c,) + self.hw, dtype=torch.float32, device=self.device)
+            if depth_mode != "dense":
+                st["depth_kp"] = torch.empty((c, self.N), dtype=torch.float32, device=self.device)
+            self.stage.append(st)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.sample_stream = torch.cuda.Stream(device=self.device, priority=-1)   # its thin CTAs go ahead of pending matcher CTAs
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.kp_ready = [torch.cuda.Event() for _ in range(2)]
+        self.sampled = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.out = ops.PipelineBuffers(self.B, self.device)
+        self.host_out = [(torch.empty((self.B, 4, 4), dtype=torch.float64).pin_memory(),
+                          torch.empty((self.B,), dtype=torch.int32).pin_memory(),
+                          torch.empty((self.B,), dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+        self.d2h_bytes = self.B * (128 + 4 + 4)
+        self._issued = 0                                   # chunks submitted so far (stage buffers alternate across passes too)
+        self._passes = 0
+
+    def _n_dma(self, n):
+        return n - int(round(n * self.frac))
+
+    @property
+    def h2d_bytes(self):
+        """bytes that cross the bus per pass: every frame's descriptors + keypoints once (+ the first frame of the pass),
+        whole maps for the DMA share, one 32-byte sector per reference keypoint for the sampled share."""
+        per = {k: v[0].numel() * v.element_size() for k, v in self.host.items()}
+        dma = sum(self._n_dma(hi - lo) for lo, hi in self.schedule)
+        return (self.B + 1) * (per["desc"] + per["kp"]) + dma * per["depth"] + (self.B - dma) * self.N * 32
+
+    def _view(self, lo, hi):
+        view = ops.PipelineBuffers.__new__(ops.PipelineBuffers)
+        view.T_rel, view.rt = self.out.T_rel[lo:hi], self.out.rt[lo:hi]
+        view.n_matches, view.n_corr = self.out.n_matches[lo:hi], self.out.n_corr[lo:hi]
+        view.n_inl, view.status = self.out.n_inl[lo:hi], self.out.status[lo:hi]
+        return view
+
+    def submit(self, pair0=0):
+        """Enqueue one pass over all pairs (copies, sampling, vo_pipeline per chunk, D2H of the results) and return a ticket
+        for `collect`.  Nothing here waits for the GPU: the next pass can be submitted while this one runs, its first
+        chunks' copies then overlap this pass's last chunks (two passes' results may be in flight: ping-pong host buffers)."""
+        compute = torch.cuda.current_stream(self.device)
+        prev = None                                        # (stage index, pairs) of the previous chunk of THIS pass
+        for lo, hi in self.schedule:
+            n, buf = hi - lo, self._issued % 2
+            reuse = self._issued >= 2                      # the stage buffer was used by an earlier chunk (of this or the last pass)
+            self._issued += 1
+            st = self.stage[buf]
+            n_dma = self._n_dma(n)
+            with torch.cuda.stream(self.copy_stream):
+                if reuse:
+                    self.copy_stream.wait_event(self.consumed[buf])
+                first = 0
+                if prev is not None:                       # frame lo is already on the device: last frame of the previous chunk
+                    pst, pn = self.stage[prev[0]], prev[1]
+                    st["kp"][0].copy_(pst["kp"][pn], non_blocking=True)
+                    st["desc"][0].copy_(pst["desc"][pn], non_blocking=True)
+                    first = 1
+                st["kp"][first:n + 1].copy_(self.host["kp"][lo + first:hi + 1], non_blocking=True)
+                self.kp_ready[buf].record(self.copy_stream)
+                st["desc"][first:n + 1].copy_(self.host["desc"][lo + first:hi + 1], non_blocking=True)
+                if n_dma:
+                    st["depth"][:n_dma].copy_(self.host["depth"][lo:lo + n_dma], non_blocking=True)
+                    if self.depth_mode != "dense":         # maps that came by DMA are sampled from HBM
+                        ops.sample_depth(st["kp"][:n_dma], st["depth"][:n_dma], out=st["depth_kp"][:n_dma])
+                self.copied[buf].record(self.copy_stream)
+            if n > n_dma:
+                with torch.cuda.stream(self.sample_stream):   # zero-copy samples, concurrent with the DMA above and the matcher
+                    self.sample_stream.wait_event(self.kp_ready[buf])
+                    ops.sample_depth(st["kp"][n_dma:n], self.host["depth"][lo + n_dma:hi], out=st["depth_kp"][n_dma:n])
+                    self.sampled[buf].record(self.sample_stream)
+                compute.wait_event(self.sampled[buf])
+            compute.wait_event(self.copied[buf])
+            if self.depth_mode == "dense":
+                ops.pipeline(st["desc"][:n], st["desc"][1:n + 1], st["kp"][:n], st["kp"][1:n + 1], st["depth"][:n], self.K,
+                             pair0=pair0 + lo, out=self._view(lo, hi), **self.cfg.kw)
+            else:
+                ops.pipeline(st["desc"][:n], st["desc"][1:n + 1], st["kp"][:n], st["kp"][1:n + 1], None, self.K,
+                             pair0=pair0 + lo, out=self._view(lo, hi), depth_kp=st["depth_kp"][:n], hw=self.hw, **self.cfg.kw)
+            self.consumed[buf].record(compute)
+            prev = (buf, n)
+        slot = self._passes % 2
+        self._passes += 1
+        T_h, st_h, inl_h, done = self.host_out[slot]
+        T_h.copy_(self.out.T_rel, non_blocking=True)
+        st_h.copy_(self.out.status, non_blocking=True)
+        inl_h.copy_(self.out.n_inl, non_blocking=True)
+        done.record(compute)
+        return slot
+
+    def collect(self, ticket):
+        """Wait for a submitted pass; returns its pinned host results (T_rel [B,4,4] f64, status, n_inl), valid until the
+        pass after the next one is submitted."""
+        T_h, st_h, inl_h, done = self.host_out[ticket]
+        done.synchronize()
+        return T_h, st_h, inl_h
+
+    def run(self, pair0=0):
+        """One pass over all pairs.  Returns after the D2H copies were enqueued; the caller synchronises."""
+        T_h, st_h, inl_h, _ = self.host_out[self.submit(pair0)]
+        return T_h, st_h, inl_h
+
+    def autotune(self, fracs=(0.2, 0.4, 0.6, 0.8, 1.0), sync=None):
+        """hybrid only: time one pass per candidate sampled_frac (after one warm pass) and keep the fastest.  `sync` is
+        called before every timed pass (a barrier under torch.distributed, so that all ranks load the host together).
+        Returns {frac: ms}."""
+        if self.depth_mode != "hybrid":
+            return {}
+        res = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.run()
+        torch.cuda.synchronize(self.device)
+        for f in fracs:
+            self.frac = float(f)
+            if sync:
+                sync()
+            e0.record()
+            self.run()
+            e1.record()
+            torch.cuda.synchronize(self.device)
+            res[float(f)] = e0.elapsed_time(e1)
+        self.frac = min(res, key=res.get)
+        return res
