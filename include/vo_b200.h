@@ -51,6 +51,9 @@ extern "C" {
 /* byte descriptors (ORB) */
 #define VO_NORM_HAMMING 0 /* popcount(a xor b): cv2.NORM_HAMMING (north-star semantics)          */
 #define VO_NORM_L2_U8 1   /* sqrt(sum (a_k-b_k)^2) over byte VALUES: what ORB.py:8 really builds  */
+#define VO_NORM_HAMMING_TC 2 /* VO_NORM_HAMMING computed on the tensor cores (bits as fp16 -1/+1, K = 256 tcgen05 GEMM, exact integers;
+                                a second pass with the roles swapped supplies the column arg-min): bit-identical results, opt-in;
+                                VO_NORM_HAMMING itself stays XOR + POPC */
 /* float descriptors */
 #define VO_METRIC_L2 0     /* d = sqrt(sum (a-b)^2)            : SIFT.py:11,27                    */
 #define VO_METRIC_COSINE 1 /* s = a.b, d = sqrt(2-2s)          : R2D2.py:56-59                    */

@@ -39,7 +39,7 @@ def test_binding_prototypes_cover_the_header_and_abi_version():
     assert lib.vo_abi_version() == _lib.VO_ABI_VERSION
     src = open(HEADER).read()
     for name in ("VO_MODE_RATIO", "VO_MODE_MUTUAL", "VO_MODE_RATIO_MUTUAL", "VO_MODE_THRESH_MUTUAL", "VO_MODE_THRESH",
-                 "VO_MODE_NN", "VO_NORM_HAMMING", "VO_NORM_L2_U8", "VO_METRIC_L2", "VO_METRIC_COSINE", "VO_PREC_TF32X3",
+                 "VO_MODE_NN", "VO_NORM_HAMMING", "VO_NORM_L2_U8", "VO_NORM_HAMMING_TC", "VO_METRIC_L2", "VO_METRIC_COSINE", "VO_PREC_TF32X3",
                  "VO_PREC_TF32X1", "VO_PREC_FP32_SIMT", "VO_PREC_F16X1", "VO_PREC_F16X3", "VO_ST_NO_MODEL", "VO_ST_TOO_FEW_POINTS", "VO_ST_KP_OUT_OF_IMAGE"):
         m = re.search(rf"#define {name} \(?(-?\d+)\)?", src)
         assert m and int(m.group(1)) == getattr(_lib, name), name

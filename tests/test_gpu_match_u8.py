@@ -165,3 +165,50 @@ def test_l2_bytes_tensor_core_pass_random_shapes(orc):
         assert np.array_equal(r.knn_val[0].cpu().numpy(), rval), (n, m)
         want, _ = orc.accept(ridx, rval, cidx, ops.VO_MODE_RATIO, 0.85)
         assert np.array_equal(_pairs(r), want), (n, m)
+
+
+@pytest.mark.parametrize("n,m", [(5000, 5000), (1237, 3001), (513, 255), (129, 700), (700, 1)])
+def test_tensor_core_hamming_is_bit_identical_to_xor_popc(orc, golden, n, m):
+    """VO_NORM_HAMMING_TC (bits as fp16 -1 / +1, K = 256 tcgen05 GEMM, row top-2; roles swapped for the column arg-min) against the XOR + POPC
+    kernel and the CPU oracle: same neighbours, same distances, same column arg-min, same accepted pairs, every rule."""
+    import torch
+    from vo_b200 import ops, synthetic
+    p = synthetic.make_pair(3 * n + m, n_kp=max(n, 8), n_cur=max(m, 8), kind="orb")
+    ref, cur = p["ref_desc"][:n].copy(), p["cur_desc"][:m].copy()
+    if n > 40 and m > 40:   # tie-heavy block: duplicated descriptors on both sides
+        ref[7:27] = ref[3]
+        cur[11:31] = cur[5]
+    ridx, rval, cidx = orc.knn_u8(ref, cur, ops.VO_NORM_HAMMING)
+    for mode, param in ((ops.VO_MODE_MUTUAL, 0.0), (ops.VO_MODE_RATIO, 0.85), (ops.VO_MODE_NN, 0.0)):
+        for knn in (True, "rows", False):
+            a = ops.match_u8(_gpu(ref), _gpu(cur), ops.VO_NORM_HAMMING, mode, param, want_knn=knn)
+            b = ops.match_u8(_gpu(ref), _gpu(cur), ops.VO_NORM_HAMMING_TC, mode, param, want_knn=knn)
+            torch.cuda.synchronize()
+            assert np.array_equal(_pairs(a), _pairs(b)), (mode, knn)
+            k = int(a.count[0])
+            assert np.array_equal(a.dist[0, :k].cpu().numpy(), b.dist[0, :k].cpu().numpy())
+            if knn:
+                assert np.array_equal(b.knn_idx[0].cpu().numpy(), ridx)
+                assert np.array_equal(b.knn_val[0].cpu().numpy(), rval)
+            if knn is True:
+                assert np.array_equal(b.col_idx[0].cpu().numpy(), cidx)
+    g = golden("match_u8.npz")   # cv2.BFMatcher(NORM_HAMMING, crossCheck=True) on the tie-heavy golden pair
+    r = ops.match_u8(_gpu(g["ref"]), _gpu(g["cur"]), ops.VO_NORM_HAMMING_TC, ops.VO_MODE_MUTUAL, want_knn=True)
+    assert np.array_equal(r.knn_idx[0].cpu().numpy(), g["ham_idx"]) and np.array_equal(r.knn_val[0].cpu().numpy(), g["ham_dist"])
+    assert np.array_equal(r.col_idx[0].cpu().numpy(), g["col_idx"]) and np.array_equal(_pairs(r), g["cc_pairs"])
+
+
+def test_tensor_core_hamming_ragged_batch(orc):
+    import torch
+    from vo_b200 import ops, synthetic
+    b = synthetic.make_batch(5, 3, n_kp=900, kind="orb", n_cur=777)
+    n_ref = torch.tensor([900, 513, 1], dtype=torch.int32, device="cuda")
+    n_cur = torch.tensor([777, 129, 300], dtype=torch.int32, device="cuda")
+    a = ops.match_u8(_gpu(b["ref_desc"]), _gpu(b["cur_desc"]), ops.VO_NORM_HAMMING, ops.VO_MODE_MUTUAL, n_ref=n_ref, n_cur=n_cur, want_knn=True)
+    t = ops.match_u8(_gpu(b["ref_desc"]), _gpu(b["cur_desc"]), ops.VO_NORM_HAMMING_TC, ops.VO_MODE_MUTUAL, n_ref=n_ref, n_cur=n_cur, want_knn=True)
+    for i in range(3):
+        assert np.array_equal(a.numpy(i), t.numpy(i))
+        nr, nc = int(n_ref[i]), int(n_cur[i])
+        assert np.array_equal(a.knn_idx[i, :nr].cpu().numpy(), t.knn_idx[i, :nr].cpu().numpy())
+        assert np.array_equal(a.knn_val[i, :nr].cpu().numpy(), t.knn_val[i, :nr].cpu().numpy())
+        assert np.array_equal(a.col_idx[i, :nc].cpu().numpy(), t.col_idx[i, :nc].cpu().numpy())

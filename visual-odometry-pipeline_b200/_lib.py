@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libvo_b200.so")
 VO_ABI_VERSION = 1
 VO_OK, VO_ERR_ARG, VO_ERR_CUDA, VO_ERR_UNSUPPORTED = 0, -1, -2, -3
 VO_ST_OK, VO_ST_NO_MODEL, VO_ST_TOO_FEW_POINTS, VO_ST_KP_OUT_OF_IMAGE = 0, 1, 2, 4
-VO_NORM_HAMMING, VO_NORM_L2_U8 = 0, 1
+VO_NORM_HAMMING, VO_NORM_L2_U8, VO_NORM_HAMMING_TC = 0, 1, 2
 VO_METRIC_L2, VO_METRIC_COSINE = 0, 1
 (VO_MODE_RATIO, VO_MODE_MUTUAL, VO_MODE_RATIO_MUTUAL, VO_MODE_THRESH_MUTUAL, VO_MODE_THRESH,
  VO_MODE_NN) = range(6)

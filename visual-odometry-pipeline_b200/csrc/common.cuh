@@ -94,13 +94,14 @@ struct __align__(16) vo_row_partial {
 };
 
 // ---- context ---------------------------------------------------------------
+#define VO_WS_SLOTS 10   /* = vo::WS_SLOTS (static_assert below) */
 struct vo_ctx {
     int device;
     int sm_count;
     long long launches;
     // growable workspace regions (device)
-    void *ws[9];
-    size_t ws_bytes[9];
+    void *ws[VO_WS_SLOTS];
+    size_t ws_bytes[VO_WS_SLOTS];
     int tc_ready;  // tcgen05 path initialised (driver entry point resolved)
     void *encode_tiled;  // PFN_cuTensorMapEncodeTiled
     void *prof;          // vo::Profiler* when profiling was ever enabled
@@ -108,7 +109,8 @@ struct vo_ctx {
 };
 
 namespace vo {
-enum WsSlot { WS_ROWPART = 0, WS_COLKEY = 1, WS_POSES = 2, WS_BESTKEY = 3, WS_SPLIT_A = 4, WS_SPLIT_B = 5, WS_PIPE = 6, WS_NORMS = 7, WS_FIN = 8, WS_SLOTS = 9 };
+enum WsSlot { WS_ROWPART = 0, WS_COLKEY = 1, WS_POSES = 2, WS_BESTKEY = 3, WS_SPLIT_A = 4, WS_SPLIT_B = 5, WS_PIPE = 6, WS_NORMS = 7, WS_FIN = 8, WS_ROWPART2 = 9, WS_SLOTS = 10 };
+static_assert(WS_SLOTS == VO_WS_SLOTS, "vo_ctx::ws holds one pointer per workspace slot");
 // Returns a device buffer of at least `bytes` for `slot`, reallocating (stream-ordered
 // free of the old block) only when it must grow.
 int ws_get(vo_ctx *ctx, int slot, size_t bytes, void **out);
@@ -134,6 +136,10 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
                  const int32_t *n_ref, const int32_t *n_cur, int metric, int passes, int need_cols,
                  vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey, const float **row_norm_out,
                  cudaStream_t st, int src_u8 = 0);
+// tensor-core Hamming (VO_NORM_HAMMING_TC): row partials of the 256-bit descriptors and, if need_cols, the column keys
+int match_bits_tc(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, int n_stride, int m_stride, const int32_t *n_ref,
+                  const int32_t *n_cur, int need_cols, vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey,
+                  cudaStream_t st);
 int pick_split(vo_ctx *ctx, int B, int row_blocks, int col_tiles, int min_tiles_per_split);
 int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_t *n_pts, int B, int cap,
                     const double *K_h, const int32_t *hyp, int H, float thr_px, int min_inliers, int refine_iters,
@@ -152,6 +158,7 @@ enum ScoreKind {
     SCORE_HAMMING = 0,   // s = integer Hamming distance, dist = (float)s
     SCORE_L2SQ_U32 = 1,  // s = integer squared L2, dist = sqrtf((float)s)
     SCORE_L2SQ_F32 = 2,  // s = ordered key of fp32 squared L2, dist = sqrtf
-    SCORE_NEGSIM_F32 = 3 // s = ordered key of -similarity, value = sim, dist = sqrtf(2-2 sim)
+    SCORE_NEGSIM_F32 = 3, // s = ordered key of -similarity, value = sim, dist = sqrtf(2-2 sim)
+    SCORE_HAMMING_F32 = 4 // s = ordered key of -(a.b) over -1 / +1 bit vectors = 2 Hamming - 256 (exact fp32): tensor-core Hamming
 };
 }  // namespace vo

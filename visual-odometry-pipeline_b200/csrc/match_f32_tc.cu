@@ -28,6 +28,7 @@
 //    1  1xTF32      single tf32 pass, column norm as an extra K-step           integer-valued data, rules with a column side
 //   16  1xFP16      single fp16 pass (kind::f16, K = 16), 192-column tiles     integer-valued data: SIFT, ORB bytes (exact)
 //   48  3xFP16      x * 2^8 = hi + lo in fp16, three kind::f16 MMAs per 16 k   the 22 operand bits of 3xTF32 at twice the rate
+//  256  1xFP16/256  256-bit descriptors as 256-d rows of fp16 -1 / +1          a.b = 256 - 2 Hamming (exact), K = 256, no norms
 // The two fp16 modes use the all-warp epilogue (16 warps on every tile, accumulator released right after the TMEM read,
 // the four threads of a row share their filter threshold); tools/probe/mma_issue_probe.cu has the pipe rates.
 #include "common.cuh"
@@ -57,20 +58,23 @@ constexpr int TC_NKB = TC_D / TC_KB;
 // three kind::tf32 MMAs per 8 k.  Tile geometry, ring and epilogue are those of 3xTF32.
 template <int PASSES>
 struct TcCfg {
-    static constexpr bool F16 = PASSES == 16;                     // fp16 single pass (own epilogue)
-    static constexpr bool H16 = PASSES == 16 || PASSES == 48;     // fp16 operands
+    static constexpr bool K256 = PASSES == 256;                   // fp16 single pass over 256-d rows (bit descriptors as -1 / +1)
+    static constexpr bool F16 = PASSES == 16 || K256;             // fp16 single pass (own epilogue)
+    static constexpr bool H16 = F16 || PASSES == 48;              // fp16 operands
     static constexpr bool THREE = PASSES == 3 || PASSES == 48;    // hi/lo split, three MMAs per k-step
+    static constexpr bool ALLWARP_COLS = PASSES == 48;            // all-warp epilogue with the column side
+    static constexpr int KDIM = K256 ? 256 : TC_D;                // descriptor length the kernel contracts over
     static constexpr bool SINGLE = !THREE;
     static constexpr int ALO = H16 ? 64 : TC_D;                   // TMEM columns from A_hi to A_lo
     static constexpr int BN = F16 ? 192 : (SINGLE ? 160 : 128);
     static constexpr int STAGES = F16 ? 9 : (SINGLE ? 10 : 13);
     static constexpr int BLOCK_BYTES = BN * 128;                  // one [BN rows x 128 B] box: 32 fp32 or 64 fp16 along k
-    static constexpr int TMEM_A = F16 ? 416 : (SINGLE ? 384 : 256);  // first column of A_hi (A_lo follows in 3xTF32)
+    static constexpr int TMEM_A = K256 ? 384 : (F16 ? 416 : (SINGLE ? 384 : 256));  // first column of A_hi (A_lo follows in 3xTF32)
     static constexpr int TMEM_EXT = F16 ? 384 : 320;              // single pass only
     static constexpr int OFF_SCOL = STAGES * BLOCK_BYTES;         // [2 groups][2 bufs][4 quarters][BN] x (float, u32)
     // column scratch, (float, u32) per entry: [2 groups][2 bufs][4 quarters][BN]; the all-warp epilogue of the split fp16
     // pass needs [2 bufs][4][BN]; the fp16 single pass has no column side
-    static constexpr int SCOL_N = F16 ? 0 : (PASSES == 48 ? 2 * 4 * BN : 2 * 2 * 4 * BN);
+    static constexpr int SCOL_N = F16 ? 0 : (ALLWARP_COLS ? 2 * 4 * BN : 2 * 2 * 4 * BN);
     static constexpr int OFF_ROW2 = OFF_SCOL + SCOL_N * 8;
     static constexpr int OFF_BAR = OFF_ROW2 + (H16 ? 4 * TC_BM * 4 : 0);        // [4 column quarters][128 rows] shared second-bests
     static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;       // barriers + alignment slack
@@ -188,6 +192,43 @@ prep16_u8_kernel(const uint8_t *__restrict__ x, long long rows, __half *__restri
         }
         reinterpret_cast<float4 *>(ext)[row * 8 + sub] = e;
     }
+}
+
+// 256-bit descriptors (VO_NORM_HAMMING_TC) as 256-d fp16 rows of -1 / +1: a.b = (#equal bits) - (#different bits) =
+// 256 - 2 popcount(a xor b), an exact small integer in the fp32 accumulator, and no norm enters: the matcher's cosine
+// machinery (larger is closer) orders by Hamming distance.  One warp per descriptor, one byte (8 halves, 16 B) per lane.
+__global__ void __launch_bounds__(256)
+prep_bits_kernel(const uint8_t *__restrict__ x, long long rows, __half *__restrict__ h16) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t v = x[row * 32 + lane];
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)   // fp16 +1.0 = 0x3c00, -1.0 = 0xbc00
+        w[i] = (((v >> (2 * i)) & 1u) ? 0x3c00u : 0xbc00u) | (((v >> (2 * i + 1)) & 1u) ? 0x3c000000u : 0xbc000000u);
+    *reinterpret_cast<uint4 *>(h16 + row * 256 + lane * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Second pass of the tensor-core Hamming matcher (roles swapped: current-frame descriptors as rows): the row arg-max of every
+// current descriptor IS the column arg-min of the first pass.  Merges the per-split partials (ties -> lower reference row,
+// the rule of the fused column arg-min) into the colkey format finalize reads: ordered(-score) << 32 | reference row.
+__global__ void __launch_bounds__(256)
+colkey_from_partials_kernel(const vo_row_partial *__restrict__ part, int n_split, int m_stride, const int32_t *__restrict__ n_cur,
+                            unsigned long long *__restrict__ colkey) {
+    const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m_stride) return;
+    const int M = n_cur ? min(n_cur[b], m_stride) : m_stride;
+    unsigned long long best = ~0ull;
+    if (j < M)
+        for (int sp = 0; sp < n_split; ++sp) {
+            const vo_row_partial p = part[((size_t)b * n_split + sp) * m_stride + j];
+            if (p.i1 >= 0) {
+                const unsigned long long key = ((unsigned long long)p.s1 << 32) | (unsigned long long)(uint32_t)p.i1;
+                best = key < best ? key : best;
+            }
+        }
+    colkey[(size_t)b * m_stride + j] = best;
 }
 
 // split fp16 (VO_PREC_F16X3): x * 2^8 = hi + lo, both fp16; squared norms of the unscaled rows
@@ -396,7 +437,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     constexpr bool F16 = Cfg::F16;
     constexpr bool H16 = Cfg::H16, THREE = Cfg::THREE, SCALED = PASSES == 48;
     constexpr bool EXT = !THREE && (METRIC == VO_METRIC_L2);
-    constexpr int NKB = H16 ? TC_D / 64 : TC_NKB;                                // k boxes per tile (128 B of k each)
+    constexpr int NKB = H16 ? Cfg::KDIM / 64 : TC_NKB;                           // k boxes per tile (128 B of k each)
     constexpr int ITEMS = THREE ? 2 * NKB : (EXT ? NKB + 1 : NKB);               // B boxes streamed per tile
     const uint32_t s_b = base;
     float *scol_v = reinterpret_cast<float *>(smem + Cfg::OFF_SCOL);                      // [2 groups][2 bufs][4][BN]
@@ -417,7 +458,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             mbar_init(bar_full(s), 1);            // this CTA's producer arms it; TMA bytes complete it
             mbar_init(bar_empty(s), TC_CLUSTER);  // one commit from each CTA of the cluster
         }
-        mbar_init(bar_a, THREE ? 16 : (EXT ? 12 : 8));
+        mbar_init(bar_a, (THREE || Cfg::K256) ? 16 : (EXT ? 12 : 8));   // warps that store a part of A (or the ones block)
         for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull(g), 1); mbar_init(bar_tempty(g), H16 ? 16 : 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -535,7 +576,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         const bool row_ok = row < N;
         const bool partial_rows = row0 + TC_BM > N;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (n_tiles > 0 && cq < 2) {  // A -> tensor memory, once: 64 k (one 32-column chunk of packed halves) per warp
+        if (n_tiles > 0 && cq < Cfg::KDIM / 64) {  // A -> tensor memory, once: 64 k (one 32-column chunk of packed halves) per warp
             // row_elems < 128: compact rows (byte descriptors: 32 values), the missing dimensions are zero
             const __half *src = reinterpret_cast<const __half *>(a_hi) + ((size_t)b * n_stride + min(row, n_stride - 1)) * row_elems + cq * 64;
             const bool have = row < n_stride;
@@ -620,7 +661,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             p.i1 = i1; p.i2 = i2;
             part[((size_t)b * (n_split * 4) + split * 4 + cq) * n_stride + row] = p;
         }
-        } else if constexpr (PASSES == 48) {
+        } else if constexpr (Cfg::ALLWARP_COLS) {
         // ===================== split-fp16 epilogue: all 16 warps on every tile, with the column side =====================
         // Same idea as the fp16 single pass: lane quarter q x column quarter cq (32 columns per thread), the tile slice
         // goes to registers, the accumulator is released, then the fold.  Column arg-max: per warp and column
@@ -701,7 +742,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                                                        \
         float v[8];                                                                                                        \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[8 * u + i]);                              \
-        epi_group8<METRIC, MASKC, MASKR, COLS, false, true, true>(v, col0 + (J0) + 8 * u, M, row_ok, na, cn, cn_vec, lane, \
+        epi_group8<METRIC, MASKC, MASKR, COLS, false, SCALED, true>(v, col0 + (J0) + 8 * u, M, row_ok, na, cn, cn_vec, lane, \
                                                                   my_cv + (J0) + 8 * u, my_cb + (J0) + 8 * u, s1, s2, i1,  \
                                                                   i2, thr, colthr, &col_any);                              \
     }
@@ -987,7 +1028,7 @@ int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &
     VO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<PASSES>::SMEM_BYTES));
     // split fp16 with the column side: interleave as many pairs as keep their current-frame descriptors (hi + lo fp16) in L2
     int pair_group = 1;
-    if (PASSES == 48 && COLS && !getenv("VO_TC_NO_INTERLEAVE"))
+    if (TcCfg<PASSES>::ALLWARP_COLS && COLS && !getenv("VO_TC_NO_INTERLEAVE"))
         pair_group = (int)max(1ll, min(8ll, (64ll << 20) / ((long long)m_stride * TC_D * 4)));
     kern<<<grid, TC_THREADS, TcCfg<PASSES>::SMEM_BYTES, st>>>(bh, bl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm,
                                                   n_split, part, colkey, dbg, pair_group, row_elems);
@@ -1121,6 +1162,62 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     *part_out = part;
     *n_split_out = n_split * 4;  // 2 epilogue groups x 2 column halves -> four partials per (row, split)
     *row_norm_out = nullptr;     // scores already carry -|a-b|^2 in full
+    return VO_OK;
+}
+
+// Tensor-core Hamming matcher (VO_NORM_HAMMING_TC): 256-bit descriptors -> fp16 rows of -1 / +1 (once per frame set), then the
+// fp16 single pass over K = 256 (row top-2, thread-private: with 16 MMAs of N = 192 per tile the pass is bound by the tensor
+// pipe, not by its epilogue) — once with the reference descriptors as rows, and, when the acceptance rule needs the column
+// arg-min (mutual nearest neighbours, raw column output), once more with the roles swapped.  Scores are exact integers.
+int match_bits_tc(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, int n_stride, int m_stride, const int32_t *n_ref,
+                  const int32_t *n_cur, int need_cols, vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey,
+                  cudaStream_t st) {
+    if (!ctx->tc_ready) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        VO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return VO_ERR_UNSUPPORTED;
+        }
+        ctx->encode_tiled = fn;
+        ctx->tc_ready = 1;
+    }
+    constexpr int KD = 256, BN = TcCfg<256>::BN;
+    const long long rows_a = (long long)B * n_stride, rows_b = (long long)B * m_stride;
+    __half *a16, *b16;
+    int rc;
+    if ((rc = ws_get(ctx, WS_SPLIT_A, (size_t)rows_a * KD * sizeof(__half), (void **)&a16))) return rc;
+    if ((rc = ws_get(ctx, WS_SPLIT_B, (size_t)rows_b * KD * sizeof(__half), (void **)&b16))) return rc;
+    VO_PROF(ctx, st, VO_STAGE_PREP);
+    prep_bits_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, a16);
+    VO_LAUNCH_CHECK(ctx);
+    prep_bits_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b16);
+    VO_LAUNCH_CHECK(ctx);
+
+    auto pass = [&](const __half *A, const __half *Bm, int ns, int ms, const int32_t *na, const int32_t *nb, int slot,
+                    vo_row_partial **part, int *n_split) -> int {
+        CUtensorMap map;
+        int r;
+        if ((r = make_map(ctx, &map, Bm, (long long)B * ms, BN, KD, true))) return r;
+        const int row_blocks = ceil_div(ns, TC_BM);
+        const int grid_x = ceil_div(row_blocks, TC_CLUSTER) * TC_CLUSTER;
+        const int ns_split = pick_split(ctx, B, grid_x, ceil_div(ms, BN), 4);
+        if ((r = ws_get(ctx, slot, sizeof(vo_row_partial) * (size_t)B * ns_split * 4 * ns, (void **)part))) return r;
+        dim3 grid(grid_x, ns_split, B);
+        *n_split = ns_split * 4;
+        return launch_tc<256, VO_METRIC_COSINE, false>(ctx, grid, map, map, reinterpret_cast<const float *>(A), nullptr, ns, ms, na, nb,
+                                                       nullptr, nullptr, ns_split, *part, nullptr, st, KD);
+    };
+    VO_PROF(ctx, st, VO_STAGE_MATCH);
+    if ((rc = pass(a16, b16, n_stride, m_stride, n_ref, n_cur, WS_ROWPART, part_out, n_split_out))) return rc;
+    if (need_cols) {
+        vo_row_partial *part2;
+        int n_split2;
+        if ((rc = pass(b16, a16, m_stride, n_stride, n_cur, n_ref, WS_ROWPART2, &part2, &n_split2))) return rc;
+        colkey_from_partials_kernel<<<dim3(ceil_div(m_stride, 256), B), 256, 0, st>>>(part2, n_split2, m_stride, n_cur, colkey);
+        VO_LAUNCH_CHECK(ctx);
+    }
     return VO_OK;
 }
 

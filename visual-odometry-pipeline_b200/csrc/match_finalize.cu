@@ -41,6 +41,7 @@ __device__ __forceinline__ float score_value(int kind, uint32_t s, float rn) {
             float d2 = __fadd_rn(ordered_to_float(s), rn);
             return __fsqrt_rn(fmaxf(d2, 0.0f));
         }
+        case SCORE_HAMMING_F32: return __fmul_rn(0.5f, __fadd_rn(256.0f, ordered_to_float(s)));   // key = -(a.b) = 2 Hamming - 256
         default: return -ordered_to_float(s);  // SCORE_NEGSIM_F32 -> similarity
     }
 }

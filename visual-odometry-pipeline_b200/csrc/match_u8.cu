@@ -228,7 +228,7 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
     using namespace vo;
     VO_REQUIRE(ctx, "vo_match_u8: null ctx");
     VO_REQUIRE(bytes == 32, "vo_match_u8: only 32-byte (256-bit) descriptors are supported, got %d", bytes);
-    VO_REQUIRE(norm == VO_NORM_HAMMING || norm == VO_NORM_L2_U8, "vo_match_u8: bad norm %d", norm);
+    VO_REQUIRE(norm == VO_NORM_HAMMING || norm == VO_NORM_L2_U8 || norm == VO_NORM_HAMMING_TC, "vo_match_u8: bad norm %d", norm);
     VO_REQUIRE(mode >= VO_MODE_RATIO && mode <= VO_MODE_NN, "vo_match_u8: bad mode %d", mode);
     VO_REQUIRE(mode != VO_MODE_THRESH && mode != VO_MODE_THRESH_MUTUAL && mode != VO_MODE_RATIO_MUTUAL,
                "vo_match_u8: similarity modes need float descriptors");
@@ -260,6 +260,21 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
             return rc;
         return match_finalize(ctx, part_tc, n_split_tc, colkey_tc, B, n_stride, m_stride, n_ref, n_cur, SCORE_L2SQ_F32, mode,
                               ratio, row_norm_tc, out_pairs, out_dist, out_count, knn, nullptr, st);
+    }
+    // Opt-in tensor-core Hamming (VO_NORM_HAMMING_TC; VO_NORM_HAMMING stays XOR + POPC, what the north-star prescribes): with the
+    // 256 bits as fp16 -1 / +1, a.b = 256 - 2 popcount(a xor b), so the fp16 single pass of the tcgen05 matcher over K = 256 orders
+    // by Hamming distance (match_bits_tc, csrc/match_f32_tc.cu).  Exact integers throughout, same tie rules, same finalize:
+    // results are bit-identical to the XOR + POPC kernel (tests/test_gpu_match_u8.py).
+    if (norm == VO_NORM_HAMMING_TC) {
+        int rc;
+        unsigned long long *colkey_tc;
+        if ((rc = ws_get(ctx, WS_COLKEY, sizeof(unsigned long long) * (size_t)B * m_stride, (void **)&colkey_tc))) return rc;
+        vo_row_partial *part_tc;
+        int n_split_tc;
+        if ((rc = match_bits_tc(ctx, ref, cur, B, n_stride, m_stride, n_ref, n_cur, need_cols ? 1 : 0, &part_tc, &n_split_tc, colkey_tc, st)))
+            return rc;
+        return match_finalize(ctx, part_tc, n_split_tc, colkey_tc, B, n_stride, m_stride, n_ref, n_cur, SCORE_HAMMING_F32, mode,
+                              ratio, nullptr, out_pairs, out_dist, out_count, knn, nullptr, st);
     }
     const int row_blocks = ceil_div(n_stride, U8_ROWS_CTA);
     // Column splits: every CTA costs the same, so pick the smallest split count whose CTA total fills the

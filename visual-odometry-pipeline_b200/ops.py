@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import (KnnOut, PipelineArgs, VO_METRIC_COSINE, VO_METRIC_L2, VO_MODE_MUTUAL, VO_MODE_NN, VO_MODE_RATIO,
-                   VO_MODE_RATIO_MUTUAL, VO_MODE_THRESH, VO_MODE_THRESH_MUTUAL, VO_NORM_HAMMING, VO_NORM_L2_U8,
+                   VO_MODE_RATIO_MUTUAL, VO_MODE_THRESH, VO_MODE_THRESH_MUTUAL, VO_NORM_HAMMING, VO_NORM_HAMMING_TC, VO_NORM_L2_U8,
                    VO_PREC_F16X1, VO_PREC_F16X3, VO_PREC_FP32_SIMT, VO_PREC_TF32X1, VO_PREC_TF32X3, check)
 
 _contexts = {}
