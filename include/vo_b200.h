@@ -340,6 +340,27 @@ VO_API int vo_r2d2_extract(vo_r2d2 *net, const uint8_t *rgb, float rel_thr, floa
                     float *desc, float *scores, int32_t *count, float *rel_map, float *rep_map, void *stream);
 
 /*
+ * Reference-sampler PnP-RANSAC ("Mode R", the drop-in's default): VisualOdometry_Stereo.py:120-135 as the reference runs them.
+ * `boot_idx` int32 [restarts][n] (device) are the bootstrap index rows the caller drew with np.random.randint(0, n, n) (:122);
+ * every row goes through the inside of cv2.solvePnPRansac(iterationsCount = iters, reprojectionError = thr_px, confidence):
+ * OpenCV's own sample table (its RNG is re-seeded per call, so the table is a function of n), EPnP on five points,
+ * projectPoints-style fp32 scoring (err <= thr_px^2), the adaptive iteration count, a Gauss-Newton refit on the inliers of the
+ * best minimal model (cv2.solvePnP(ITERATIVE)'s fixed point); the best restart by inlier count (strictly more than
+ * min_inliers) wins, the first one on ties (:132-135).  One frame pair per call (B = 1): xyz float [>= max idx + 1][3],
+ * uv float [..][2] are the gathered / gated correspondences (vo_gather_backproject).
+ * Outputs (device, all optional except T_rel / status): rt [12], rvec_tvec [6], T_rel [16] as vo_pnp_ransac; n_inl [1] = inliers
+ * of the winning minimal model; best int32 [3] = (restart, iteration, iterations the stopping rule ran); inlier_mask uint8 [n]
+ * over the winning restart's resample; hyp_counts int32 [restarts][iters] (-1: no model), hyp_poses double [restarts][iters][12].
+ * Parity: sampler, scoring and stopping rule reproduce cv2.solvePnPRansac exactly when driven with OpenCV's minimal solver
+ * (tests/test_oracle_pnp_ref.py); OpenCV's five-point EPnP itself depends on an arbitrary null-space basis and is matched
+ * statistically (csrc/pnp_ref_math.cuh).
+ */
+VO_API int vo_pnp_ransac_ref(vo_ctx *ctx, const float *xyz, const float *uv, int n, const double *K_h, const int32_t *boot_idx,
+                      int restarts, int iters, float thr_px, double confidence, int min_inliers, int refine_iters, double *rt,
+                      double *rvec_tvec, double *T_rel, int32_t *n_inl, int32_t *best, uint8_t *inlier_mask, int32_t *hyp_counts,
+                      double *hyp_poses, int32_t *status, void *stream);
+
+/*
  * ORB front-end: `extract_features_and_desc` of feature_extractors/ORB.py:10-21, i.e.
  * cv2.ORB_create() (ORB.py:8, all defaults: scale 1.2f, edge 31, patch 31, Harris score, WTA_K 2) followed by
  * detectAndCompute: gray conversion, INTER_LINEAR_EXACT pyramid, FAST-9/16 + non-maximum suppression, retainBest on

@@ -3,6 +3,7 @@
 #include "../visual-odometry-pipeline_b200/csrc/pnp_math.cuh"
 #include "../visual-odometry-pipeline_b200/csrc/hamming_math.cuh"
 #include "../visual-odometry-pipeline_b200/csrc/orb_math.cuh"
+#include "../visual-odometry-pipeline_b200/csrc/pnp_ref_math.cuh"
 extern "C" {
 int hm_p3p4(const double *P, const double *uv, const double *K, double *out) {
     double Pm[4][3], uvm[4][2];
@@ -91,5 +92,28 @@ void hm_orb_blur(const unsigned char *img, int W, int H, unsigned char *out) {  
 void hm_orb_rotate(float angle_deg, const int *pat, int n, int *ix, int *iy) {
     float ca, sb; vo::orb::angle_cos_sin(angle_deg, ca, sb);
     for (int i = 0; i < n; ++i) vo::orb::rotate_pattern_point(pat[2 * i], pat[2 * i + 1], ca, sb, ix[i], iy[i]);
+}
+// ---- reference-sampler PnP-RANSAC arithmetic (csrc/pnp_ref_math.cuh)
+void hm_ref_table(int n, int iters, int *out) { vo::refpnp::mwc_table(n, iters, out); }
+int hm_ref_epnp5(const double *X, const double *uv, const double *K, double *out) {
+    double Xm[5][3], uvm[5][2];
+    for (int i = 0; i < 5; ++i) {
+        for (int j = 0; j < 3; ++j) Xm[i][j] = X[3 * i + j];
+        uvm[i][0] = uv[2 * i]; uvm[i][1] = uv[2 * i + 1];
+    }
+    vo::refpnp::Pose p;
+    if (!vo::refpnp::epnp5(Xm, uvm, K[0], K[1], K[2], K[3], p)) return 0;
+    for (int j = 0; j < 9; ++j) out[j] = p.R[j];
+    for (int j = 0; j < 3; ++j) out[9 + j] = p.t[j];
+    return 1;
+}
+void hm_ref_err2(const double *pose, const double *K, const float *xyz, const float *uv, int n, float *out) {
+    vo::refpnp::Pose p;
+    for (int j = 0; j < 9; ++j) p.R[j] = pose[j];
+    for (int j = 0; j < 3; ++j) p.t[j] = pose[9 + j];
+    for (int i = 0; i < n; ++i) out[i] = vo::refpnp::reproj_err2(p, K[0], K[1], K[2], K[3], xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], uv[2 * i], uv[2 * i + 1]);
+}
+int hm_ref_scan(const int *counts, int n, int iters, double conf, int *iters_run, int *best_count) {
+    return vo::refpnp::ransac_scan(counts, n, iters, conf, iters_run, best_count);
 }
 }

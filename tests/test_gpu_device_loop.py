@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def _run_dropin(tmp_path, kind, frames, extra=""):
     from test_gpu_dropin import _load_dropin
     from vo_b200 import synthetic
-    vos = _load_dropin(tmp_path, kind, extra)
+    vos = _load_dropin(tmp_path, kind, extra + "\npnp_mode: throughput\n")   # the device loop runs the throughput sampler
     feed = {}
     vos.extract_features_and_desc = lambda img: feed["cur"]
     vo = vos.VisualOdometry(synthetic.KITTI_K, seq=0)

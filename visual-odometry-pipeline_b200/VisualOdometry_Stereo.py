@@ -64,6 +64,13 @@ class VisualOdometry:
         self.method = "r2d2"
         self.find_ps_homography = False
         self.midpoint_3D = None
+        # PnP-RANSAC mode.  "reference" (default): the reference's own sampler — three np.random.randint bootstraps (:122), each
+        # through the inside of cv2.solvePnPRansac(100, 1.5): OpenCV's sample table, EPnP-5, adaptive stop, refit on the best
+        # minimal model's inliers (vo_pnp_ransac_ref).  "throughput": a fixed budget of counter-based P3P hypotheses over the
+        # un-resampled correspondences (vo_pnp_ransac): more accurate and what the batched / device-resident paths run.
+        self.pnp_mode = str(vo_params.get("pnp_mode", "reference")).lower()
+        if self.pnp_mode not in ("reference", "throughput"):
+            raise ValueError(f"pnp_mode must be reference or throughput (got {self.pnp_mode!r})")
         self.n_hyp = int(vo_params.get("ransac_hypotheses", 512))
         self.seed = int(vo_params.get("ransac_seed", 8214))
         self.device = torch.device("cuda", int(vo_params.get("device", 0)))
@@ -108,12 +115,26 @@ class VisualOdometry:
         n_pairs = torch.tensor([K], dtype=torch.int32, device=dev)
         corr = ops.gather_backproject(pairs, n_pairs, lk, rk, self._depth_on_device(framepair.frame1), self.cam_intr,
                                       min_flow_px=-1.0, z_min=self.Z_RANGE[0], z_max=self.Z_RANGE[1])
-        hyp = ops.hypotheses(corr.count, self.n_hyp, self.seed, self._pair_ctr)
-        self._pair_ctr += 1
-        res = ops.pnp_ransac(corr.xyz, corr.cur_uv, corr.count, self.cam_intr, hyp, self.REPROJ_PX, self.MIN_INLIERS, 10)
-        status = int(corr.status.item()) | int(res.status.item())   # one small D2H round trip per pair
-        n_common = int(corr.count.item())
-        best_inlier = int(res.n_inl.item())
+        if self.pnp_mode == "reference":
+            n_common = int(corr.count.item())                        # the bootstrap needs the count on the host (:122)
+            if n_common <= 0:
+                raise ValueError("no correspondence with 0 < Z < 50")  # np.random.randint(0, 0, 0) raises in the reference too
+            # essentialMat['iter'] = 3 restarts (:76, :120); drawing the three rows up front consumes the global numpy stream
+            # exactly like the loop does (nothing else on the path draws from it)
+            boot = np.stack([np.random.randint(0, n_common, n_common) for _ in range(3)]).astype(np.int32)
+            res = ops.pnp_ransac_ref(corr.xyz[0], corr.cur_uv[0], n_common, self.cam_intr, torch.from_numpy(boot).to(dev),
+                                     iters=100, thr_px=self.REPROJ_PX, min_inliers=self.MIN_INLIERS)
+            status = int(corr.status.item()) | int(res.status.item())
+            best_inlier = int(res.n_inl.item())
+            T_rel = res.T_rel
+        else:
+            hyp = ops.hypotheses(corr.count, self.n_hyp, self.seed, self._pair_ctr)
+            self._pair_ctr += 1
+            res = ops.pnp_ransac(corr.xyz, corr.cur_uv, corr.count, self.cam_intr, hyp, self.REPROJ_PX, self.MIN_INLIERS, 10)
+            status = int(corr.status.item()) | int(res.status.item())   # one small D2H round trip per pair
+            n_common = int(corr.count.item())
+            best_inlier = int(res.n_inl.item())
+            T_rel = res.T_rel[0]
         keep = corr.src[0, :n_common].cpu().numpy()
         framepair.left_kp = left_kp[keep].copy()
         framepair.right_kp = right_kp[keep].copy()
@@ -124,7 +145,7 @@ class VisualOdometry:
             self.bad_pnp += 1
             return False, framepair, n_common, best_inlier
         pose = SE3()
-        pose.pose = res.T_rel[0].cpu().numpy().copy()
+        pose.pose = T_rel.cpu().numpy().copy()
         framepair.pose = pose
         framepair.inlier_pts_ct = best_inlier
         return True, framepair, n_common, best_inlier

@@ -763,3 +763,312 @@ extern "C" int vo_pnp_ransac(vo_ctx *ctx, const float *xyz, const float *uv, con
     return vo::pnp_ransac_impl(ctx, xyz, uv, n_pts, B, cap, K_h, hyp, H, thr_px, min_inliers, refine_iters, rt,
                                rvec_tvec, T_rel, n_inl, best_h, inlier_mask, hyp_counts, status, 0, stream);
 }
+
+// =====================================================================================================================
+// Reference-sampler PnP-RANSAC ("Mode R"): computepose_3D_2D lines :120-135 as the reference runs them — three bootstrap
+// resamples (the index rows are an INPUT: the drop-in draws them with np.random.randint exactly like :122), each through
+// the inside of cv2.solvePnPRansac(iterationsCount = 100, reprojectionError = 1.5): OpenCV's own sample table, EPnP on five
+// points, projectPoints-style fp32 scoring, the adaptive iteration count, and the refit on the inliers of the best MINIMAL
+// model (duplicates of the resample included); best of three by inlier count, > min_inliers.  Arithmetic: pnp_ref_math.cuh.
+// All restarts x iterations minimal models are solved and scored in parallel; the sequential loop with its early stop is
+// replayed over the counts afterwards (a model's count does not depend on the iterations before it).
+// =====================================================================================================================
+#include "pnp_ref_math.cuh"
+
+namespace vo {
+namespace {
+
+constexpr int RP_MAX_RESTARTS = 8, RP_MAX_ITERS = 1024;
+
+__global__ void ref_table_kernel(int n, int iters, int32_t *__restrict__ table) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) refpnp::mwc_table(n, iters, table);
+}
+
+// one thread per (restart, iteration): the f64 EPnP solve is a long dependent chain with large local arrays; 32-thread
+// blocks spread the few hundred solves over the SMs
+__global__ void __launch_bounds__(32)
+ref_epnp_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ boot, int n,
+                const int32_t *__restrict__ table, int restarts, int iters, IntrD kd, double *__restrict__ poses,
+                int32_t *__restrict__ valid) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= restarts * iters) return;
+    const int r = id / iters, h = id % iters;
+    double X[refpnp::EP_N][3], q[refpnp::EP_N][2];
+    int src[refpnp::EP_N];
+    bool repeated = false;
+    for (int j = 0; j < refpnp::EP_N; ++j) {
+        const int idx = boot[(size_t)r * n + table[h * refpnp::EP_N + j]];
+        for (int k = 0; k < j; ++k) repeated = repeated || (src[k] == idx);
+        src[j] = idx;
+        for (int k = 0; k < 3; ++k) X[j][k] = (double)xyz[(size_t)idx * 3 + k];
+        q[j][0] = (double)uv[(size_t)idx * 2];
+        q[j][1] = (double)uv[(size_t)idx * 2 + 1];
+    }
+    // The five sampled positions are distinct, but a bootstrap resample repeats points: a sample that holds the same
+    // correspondence twice has four distinct points, M^T M a four-dimensional null space, and what OpenCV's EPnP returns for
+    // it is arbitrary.  Such an iteration is spent without a model (0.7 % of the iterations at n = 1500) — deterministic, and
+    // the same in the oracle.
+    refpnp::Pose p;
+    const bool ok = !repeated && refpnp::epnp5(X, q, kd.fx, kd.fy, kd.cx, kd.cy, p);
+    valid[id] = ok ? 1 : 0;
+    if (ok) {
+        for (int k = 0; k < 9; ++k) poses[(size_t)id * 12 + k] = p.R[k];
+        for (int k = 0; k < 3; ++k) poses[(size_t)id * 12 + 9 + k] = p.t[k];
+    }
+}
+
+// one warp per (restart, iteration): inlier count over the n points of the restart's resample
+__global__ void __launch_bounds__(256)
+ref_score_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ boot, int n,
+                 int restarts, int iters, IntrD kd, float thr2, const double *__restrict__ poses,
+                 const int32_t *__restrict__ valid, int32_t *__restrict__ counts) {
+    const int id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (id >= restarts * iters) return;
+    if (!valid[id]) {
+        if (lane == 0) counts[id] = -1;
+        return;
+    }
+    refpnp::Pose p;
+    for (int k = 0; k < 9; ++k) p.R[k] = poses[(size_t)id * 12 + k];
+    for (int k = 0; k < 3; ++k) p.t[k] = poses[(size_t)id * 12 + 9 + k];
+    const int32_t *b = boot + (size_t)(id / iters) * n;
+    int c = 0;
+    for (int i = lane; i < n; i += 32) {
+        const int idx = b[i];
+        c += refpnp::reproj_err2(p, kd.fx, kd.fy, kd.cx, kd.cy, xyz[(size_t)idx * 3], xyz[(size_t)idx * 3 + 1], xyz[(size_t)idx * 3 + 2],
+                                 uv[(size_t)idx * 2], uv[(size_t)idx * 2 + 1]) <= thr2 ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) counts[id] = c;
+}
+
+// stopping rule per restart, best of the restarts, inlier mask of the winning minimal model, Gauss-Newton refit on those
+// inliers (what cv2.solvePnP(ITERATIVE) converges to), Rodrigues vector and the pose the reference stores
+__global__ void __launch_bounds__(RF_THREADS)
+ref_select_refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ boot, int n,
+                        int restarts, int iters, IntrD kd, float thr2, double confidence, int min_inliers, int refine_iters,
+                        const double *__restrict__ poses, const int32_t *__restrict__ counts, double *__restrict__ rt_out,
+                        double *__restrict__ rvec_tvec, double *__restrict__ T_rel, int32_t *__restrict__ n_inl_out,
+                        int32_t *__restrict__ best_out, uint8_t *__restrict__ mask_out, int32_t *__restrict__ status) {
+    __shared__ int s_best[RP_MAX_RESTARTS], s_cnt[RP_MAX_RESTARTS], s_run[RP_MAX_RESTARTS];
+    __shared__ int s_r, s_h, s_stop, s_bad;
+    __shared__ double sR[9], st[3], sRp[9], stp[3], s_cost;
+    __shared__ double sacc[RF_THREADS / 32][RF_ACC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < restarts) {
+        int run = 0, cnt = 0;
+        s_best[threadIdx.x] = refpnp::ransac_scan(counts + threadIdx.x * iters, n, iters, confidence, &run, &cnt);
+        s_cnt[threadIdx.x] = cnt;
+        s_run[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0, rsel = -1;                             // :132-135: flag and inliers > best and inliers > 20, first restart keeps ties
+        for (int r = 0; r < restarts; ++r)
+            if (s_best[r] >= 0 && s_cnt[r] > best && s_cnt[r] > min_inliers) { best = s_cnt[r]; rsel = r; }
+        s_r = rsel;
+        s_h = rsel >= 0 ? s_best[rsel] : -1;
+        s_stop = 0;
+        s_bad = 0;
+        if (rsel >= 0) {
+            const double *p = poses + ((size_t)rsel * iters + s_h) * 12;
+            for (int j = 0; j < 9; ++j) sR[j] = p[j];
+            for (int j = 0; j < 3; ++j) st[j] = p[9 + j];
+        }
+    }
+    __syncthreads();
+    const int rsel = s_r, hsel = s_h;
+    if (rsel < 0) {
+        if (mask_out)
+            for (int i = threadIdx.x; i < n; i += RF_THREADS) mask_out[i] = 0;
+        if (threadIdx.x == 0) {
+            if (status) status[0] = VO_ST_NO_MODEL;
+            if (n_inl_out) n_inl_out[0] = 0;
+            if (best_out) { best_out[0] = -1; best_out[1] = -1; best_out[2] = 0; }
+            for (int j = 0; j < 16; ++j)
+                if (T_rel) T_rel[j] = (j % 5 == 0) ? 1.0 : 0.0;
+            for (int j = 0; j < 12; ++j)
+                if (rt_out) rt_out[j] = (j == 0 || j == 4 || j == 8) ? 1.0 : 0.0;
+            for (int j = 0; j < 6; ++j)
+                if (rvec_tvec) rvec_tvec[j] = 0.0;
+        }
+        return;
+    }
+    const int32_t *b = boot + (size_t)rsel * n;
+    refpnp::Pose pm;                                        // the winning minimal model: its mask selects the refit's points
+    for (int j = 0; j < 9; ++j) pm.R[j] = sR[j];
+    for (int j = 0; j < 3; ++j) pm.t[j] = st[j];
+    auto inlier = [&](int i, float &X, float &Y, float &Z, float &u, float &v) {
+        const int idx = b[i];
+        X = xyz[(size_t)idx * 3]; Y = xyz[(size_t)idx * 3 + 1]; Z = xyz[(size_t)idx * 3 + 2];
+        u = uv[(size_t)idx * 2]; v = uv[(size_t)idx * 2 + 1];
+        return refpnp::reproj_err2(pm, kd.fx, kd.fy, kd.cx, kd.cy, X, Y, Z, u, v) <= thr2;
+    };
+    if (mask_out)
+        for (int i = threadIdx.x; i < n; i += RF_THREADS) {
+            float X, Y, Z, u, v;
+            mask_out[i] = inlier(i, X, Y, Z, u, v) ? 1 : 0;
+        }
+    for (int it = 0; it <= refine_iters; ++it) {             // same guarded Gauss-Newton as refit_kernel
+        double acc[RF_ACC];
+#pragma unroll
+        for (int j = 0; j < RF_ACC; ++j) acc[j] = 0.0;
+        double R[9], t[3];
+        for (int j = 0; j < 9; ++j) R[j] = sR[j];
+        for (int j = 0; j < 3; ++j) t[j] = st[j];
+        for (int i = threadIdx.x; i < n; i += RF_THREADS) {
+            float Xf, Yf, Zf, uf, vf;
+            if (!inlier(i, Xf, Yf, Zf, uf, vf)) continue;
+            const double X = Xf, Y = Yf, Z = Zf;
+            const double xr = R[0] * X + R[1] * Y + R[2] * Z;
+            const double yr = R[3] * X + R[4] * Y + R[5] * Z;
+            const double zr = R[6] * X + R[7] * Y + R[8] * Z;
+            const double xc = xr + t[0], yc = yr + t[1], zc = zr + t[2];
+            const double iz = 1.0 / zc;
+            const double x = xc * iz, y = yc * iz;
+            const double ru = kd.fx * x + kd.cx - (double)uf;
+            const double rv = kd.fy * y + kd.cy - (double)vf;
+            const double a0 = kd.fx * iz, a2 = -kd.fx * x * iz;
+            const double b1 = kd.fy * iz, b2 = -kd.fy * y * iz;
+            const double ju[6] = {a2 * yr, a0 * zr - a2 * xr, -a0 * yr, a0, 0.0, a2};
+            const double jv[6] = {-b1 * zr + b2 * yr, -b2 * xr, b1 * xr, 0.0, b1, b2};
+            int q = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = r; c < 6; ++c) acc[q++] += ju[r] * ju[c] + jv[r] * jv[c];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) acc[21 + r] += ju[r] * ru + jv[r] * rv;
+            acc[27] += ru * ru + rv * rv;
+        }
+#pragma unroll
+        for (int j = 0; j < RF_ACC; ++j) {
+            const double s = warp_sum(acc[j]);
+            if (lane == 0) sacc[warp][j] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot[RF_ACC];
+            for (int j = 0; j < RF_ACC; ++j) {
+                double s = 0.0;
+                for (int w = 0; w < RF_THREADS / 32; ++w) s += sacc[w][j];
+                tot[j] = s;
+            }
+            const double cost = tot[27];
+            bool finite = cost == cost && cost < 1e300;
+            for (int j = 0; j < 9; ++j) finite = finite && sR[j] == sR[j] && fabs(sR[j]) < 2.0;
+            for (int j = 0; j < 3; ++j) finite = finite && st[j] == st[j] && fabs(st[j]) < 1e300;
+            if (it == 0 && !finite) {
+                s_bad = 1;
+                s_stop = 1;
+            } else if (it > 0 && !(finite && cost <= s_cost * (1.0 + 1e-12))) {
+                for (int j = 0; j < 9; ++j) sR[j] = sRp[j];
+                for (int j = 0; j < 3; ++j) st[j] = stp[j];
+                s_stop = 1;
+            } else {
+                s_cost = cost;
+                for (int j = 0; j < 9; ++j) sRp[j] = sR[j];
+                for (int j = 0; j < 3; ++j) stp[j] = st[j];
+                if (it == refine_iters) s_stop = 1;
+            }
+            double g[6], d[6];
+            for (int j = 0; j < 6; ++j) g[j] = -tot[21 + j];
+            int dq = 0;
+            for (int r = 0; r < 6; ++r) {
+                tot[dq] += 1e-12 * tot[dq] + 1e-300;
+                dq += 6 - r;
+            }
+            if (s_stop) {
+            } else if (solve6(tot, g, d)) {
+                double dR[9], Rn[9];
+                so3_exp(d, dR);
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j)
+                        Rn[3 * i + j] = dR[3 * i] * sR[j] + dR[3 * i + 1] * sR[3 + j] + dR[3 * i + 2] * sR[6 + j];
+                for (int j = 0; j < 9; ++j) sR[j] = Rn[j];
+                for (int j = 0; j < 3; ++j) st[j] += d[3 + j];
+                double mx = 0.0;
+                for (int j = 0; j < 6; ++j) mx = fmax(mx, fabs(d[j]));
+                if (mx < 1e-11) s_stop = 1;
+            } else {
+                s_stop = 1;
+            }
+        }
+        __syncthreads();
+        if (s_stop) break;
+    }
+    if (threadIdx.x == 0) {
+        if (s_bad) {
+            for (int j = 0; j < 9; ++j) sR[j] = (j % 4 == 0) ? 1.0 : 0.0;
+            for (int j = 0; j < 3; ++j) st[j] = 0.0;
+        }
+        if (status) status[0] = s_bad ? VO_ST_NO_MODEL : VO_ST_OK;
+        if (n_inl_out) n_inl_out[0] = s_cnt[rsel];
+        if (best_out) { best_out[0] = rsel; best_out[1] = hsel; best_out[2] = s_run[rsel]; }
+        if (rt_out) {
+            for (int j = 0; j < 9; ++j) rt_out[j] = sR[j];
+            for (int j = 0; j < 3; ++j) rt_out[9 + j] = st[j];
+        }
+        if (rvec_tvec) {
+            double w[3];
+            so3_log(sR, w);
+            for (int j = 0; j < 3; ++j) rvec_tvec[j] = w[j];
+            for (int j = 0; j < 3; ++j) rvec_tvec[3 + j] = st[j];
+        }
+        if (T_rel) {  // inverse of [R|t]: [R^T | -R^T t]  (pose.pose = pose.inv_pose, :143)
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) T_rel[4 * i + j] = sR[3 * j + i];
+                T_rel[4 * i + 3] = -(sR[i] * st[0] + sR[3 + i] * st[1] + sR[6 + i] * st[2]);
+            }
+            T_rel[12] = 0.0; T_rel[13] = 0.0; T_rel[14] = 0.0; T_rel[15] = 1.0;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace vo
+
+extern "C" int vo_pnp_ransac_ref(vo_ctx *ctx, const float *xyz, const float *uv, int n, const double *K_h, const int32_t *boot_idx,
+                                 int restarts, int iters, float thr_px, double confidence, int min_inliers, int refine_iters,
+                                 double *rt, double *rvec_tvec, double *T_rel, int32_t *n_inl, int32_t *best, uint8_t *inlier_mask,
+                                 int32_t *hyp_counts, double *hyp_poses, int32_t *status, void *stream) {
+    using namespace vo;
+    VO_REQUIRE(ctx && xyz && uv && K_h && boot_idx, "vo_pnp_ransac_ref: null argument");
+    VO_REQUIRE(n >= 0 && restarts >= 1 && restarts <= RP_MAX_RESTARTS && iters >= 1 && iters <= RP_MAX_ITERS,
+               "vo_pnp_ransac_ref: bad size (n %d, restarts %d, iterations %d)", n, restarts, iters);
+    VO_REQUIRE(K_h[0] != 0.0 && K_h[4] != 0.0, "vo_pnp_ransac_ref: zero focal length");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int total = restarts * iters;
+    // workspace: sample table | validity | counts | poses
+    char *ws;
+    int rc;
+    const size_t off_valid = sizeof(int32_t) * (size_t)iters * refpnp::EP_N, off_counts = off_valid + sizeof(int32_t) * total;
+    const size_t off_poses = (off_counts + sizeof(int32_t) * total + 15) & ~(size_t)15;
+    if ((rc = ws_get(ctx, WS_POSES, off_poses + sizeof(double) * 12 * (size_t)total, (void **)&ws))) return rc;
+    int32_t *table = reinterpret_cast<int32_t *>(ws), *valid = reinterpret_cast<int32_t *>(ws + off_valid);
+    int32_t *counts = reinterpret_cast<int32_t *>(ws + off_counts);
+    double *poses = reinterpret_cast<double *>(ws + off_poses);
+    const IntrD kd{K_h[0], K_h[4], K_h[2], K_h[5]};
+    const float thr2 = (float)((double)thr_px * (double)thr_px);      // findInliers: float t = (float)(thresh * thresh)
+    if (n < refpnp::EP_N) {                                            // RANSAC needs at least the model points: "no model"
+        VO_CUDA(cudaMemsetAsync(counts, 0xff, sizeof(int32_t) * total, st));
+    } else {
+        VO_PROF(ctx, st, VO_STAGE_P3P);
+        ref_table_kernel<<<1, 32, 0, st>>>(n, iters, table);
+        VO_LAUNCH_CHECK(ctx);
+        ref_epnp_kernel<<<ceil_div(total, 32), 32, 0, st>>>(xyz, uv, boot_idx, n, table, restarts, iters, kd, poses, valid);
+        VO_LAUNCH_CHECK(ctx);
+        VO_PROF(ctx, st, VO_STAGE_SCORE);
+        ref_score_kernel<<<ceil_div(total, 8), 256, 0, st>>>(xyz, uv, boot_idx, n, restarts, iters, kd, thr2, poses, valid, counts);
+        VO_LAUNCH_CHECK(ctx);
+    }
+    VO_PROF(ctx, st, VO_STAGE_REFIT);
+    ref_select_refit_kernel<<<1, RF_THREADS, 0, st>>>(xyz, uv, boot_idx, n, restarts, iters, kd, thr2, confidence, min_inliers, refine_iters,
+                                                      poses, counts, rt, rvec_tvec, T_rel, n_inl, best, inlier_mask, status);
+    VO_LAUNCH_CHECK(ctx);
+    VO_PROF(ctx, st, -1);
+    if (hyp_counts) VO_CUDA(cudaMemcpyAsync(hyp_counts, counts, sizeof(int32_t) * total, cudaMemcpyDeviceToDevice, st));
+    if (hyp_poses) VO_CUDA(cudaMemcpyAsync(hyp_poses, poses, sizeof(double) * 12 * (size_t)total, cudaMemcpyDeviceToDevice, st));
+    return VO_OK;
+}

@@ -270,6 +270,43 @@ def pnp_ransac(xyz, uv, n_pts, K, hyp, thr_px=1.5, min_inliers=20, refine_iters=
     return PnpResult(rt, rv, T, n_inl, best_h, mask, counts, status)
 
 
+class PnpRefResult:
+    def __init__(self, rt, rvec_tvec, T_rel, n_inl, best, mask, hyp_counts, hyp_poses, status):
+        self.rt, self.rvec_tvec, self.T_rel, self.n_inl, self.best = rt, rvec_tvec, T_rel, n_inl, best
+        self.mask, self.hyp_counts, self.hyp_poses, self.status = mask, hyp_counts, hyp_poses, status
+
+
+def pnp_ransac_ref(xyz, uv, n, K, boot_idx, iters=100, thr_px=1.5, confidence=0.99, min_inliers=20, refine_iters=20,
+                   want_hyp=False):
+    """Reference-sampler PnP-RANSAC (vo_pnp_ransac_ref): xyz [cap,3], uv [cap,2] float32 (one pair's correspondences), n of
+    them valid; boot_idx int32 [restarts, n] = the bootstrap rows np.random.randint(0, n, n) (VisualOdometry_Stereo.py:122)."""
+    xyz, uv = xyz.reshape(-1, 3), uv.reshape(-1, 2)
+    _chk(xyz, torch.float32, "xyz")
+    _chk(uv, torch.float32, "uv")
+    _chk(boot_idx, torch.int32, "boot_idx")
+    if boot_idx.dim() != 2 or boot_idx.shape[1] != n:
+        raise ValueError(f"pnp_ransac_ref: boot_idx must be [restarts, {n}], got {tuple(boot_idx.shape)}")
+    restarts = int(boot_idx.shape[0])
+    dev = xyz.device
+    rt = torch.empty((12,), dtype=torch.float64, device=dev)
+    rv = torch.empty((6,), dtype=torch.float64, device=dev)
+    T = torch.empty((4, 4), dtype=torch.float64, device=dev)
+    n_inl = torch.zeros((1,), dtype=torch.int32, device=dev)
+    best = torch.zeros((3,), dtype=torch.int32, device=dev)
+    mask = torch.zeros((max(n, 1),), dtype=torch.uint8, device=dev)
+    counts = torch.zeros((restarts, iters), dtype=torch.int32, device=dev) if want_hyp else None
+    poses = torch.zeros((restarts, iters, 12), dtype=torch.float64, device=dev) if want_hyp else None
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ctx = context(dev)
+    kh, kp = _k_host(K)
+    with torch.cuda.device(dev):
+        check(ctx.lib.vo_pnp_ransac_ref(ctx.handle, _ptr(xyz), _ptr(uv), int(n), kp, _ptr(boot_idx), restarts, int(iters),
+                                        float(thr_px), float(confidence), int(min_inliers), int(refine_iters), _ptr(rt), _ptr(rv),
+                                        _ptr(T), _ptr(n_inl), _ptr(best), _ptr(mask), _ptr(counts), _ptr(poses), _ptr(status),
+                                        _stream()), "vo_pnp_ransac_ref")
+    return PnpRefResult(rt, rv, T, n_inl, best, mask, counts, poses, status)
+
+
 class PipelineResult:
     def __init__(self, T_rel, rt, n_matches, n_corr, n_inl, status):
         self.T_rel, self.rt, self.n_matches, self.n_corr, self.n_inl, self.status = T_rel, rt, n_matches, n_corr, n_inl, status
