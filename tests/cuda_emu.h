@@ -27,7 +27,7 @@
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 enum { cudaSuccess = 0 };
-enum cudaMemcpyKind { cudaMemcpyDefault = 4 };
+enum cudaMemcpyKind { cudaMemcpyDeviceToHost = 2, cudaMemcpyDefault = 4 };
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
@@ -36,6 +36,7 @@ inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n); return *p
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 
 struct dim3 {
     unsigned x, y, z;

@@ -27,7 +27,7 @@ def main():
         frames, gt = synthetic_sequence.make_sequence(n_frames=n_frames, n_kp=n_kp, kind=kind, seed=3)
         cwd = os.getcwd()
         tmp = pathlib.Path(tempfile.mkdtemp())
-        vos = _load_dropin(tmp, kind, extra)
+        vos = _load_dropin(tmp, kind, extra + "\npnp_mode: throughput\n")      # the sampler the device loop runs (comparable poses)
         feed = {}
         vos.extract_features_and_desc = lambda img: feed["cur"]
         img = np.zeros((synthetic.KITTI_WH[1], synthetic.KITTI_WH[0], 3), np.uint8)
@@ -48,11 +48,16 @@ def main():
         pinned = [(torch.from_numpy(np.ascontiguousarray(f["kp"], dtype=np.float32)).pin_memory(),
                    torch.from_numpy(f["desc"]).pin_memory(), torch.from_numpy(f["depth"]).pin_memory()) for f in frames]
 
+        enqueue_s = []
+
         def run_dev():
             loop = DeviceLoop(synthetic.KITTI_K, synthetic.KITTI_WH, n_kp, kind=kind, norm_or_metric=norm, mode=mode,
                               match_param=0.85, precision=prec, n_hyp=vo.n_hyp, seed=vo.seed)
+            torch.cuda.synchronize()
+            t_e = time.perf_counter()
             for i, (kp, d, z) in enumerate(pinned):
                 loop.push(kp, d, z, i)
+            enqueue_s.append(time.perf_counter() - t_e)      # host time to enqueue the whole sequence (no synchronisation inside)
             return loop.poses()
         from vo_b200 import ops
         run_dev()
@@ -67,7 +72,8 @@ def main():
         ops.profile_enable(False)
         print(json.dumps({"kind": kind, "device_loop_stage_ms_per_frame": stages, "profiled_run_s": t_prof}), flush=True)
         print(json.dumps({"kind": kind, "n_kp": n_kp, "frames": n_frames, "host_policy_fps": n_frames / t_host,
-                          "device_loop_fps": n_frames / t_dev, "device_loop_fps_median_of_5": n_frames / float(np.median(t_devs)), "max_abs_pose_diff": float(np.abs(got - want).max()),
+                          "device_loop_fps": n_frames / t_dev, "host_enqueue_us_per_frame": 1e6 * min(enqueue_s) / n_frames,
+                          "gpu_us_per_frame": 1e6 * t_dev / n_frames, "device_loop_fps_median_of_5": n_frames / float(np.median(t_devs)), "max_abs_pose_diff": float(np.abs(got - want).max()),
                           "keyframes": int(info[:, 5].sum()), "bad_pnp": int((info[1:, 0] != 0).sum()),
                           "max_pos_err_m": float(np.linalg.norm(got[:, :3, 3] - gt[:, :3, 3], axis=1).max())}), flush=True)
 

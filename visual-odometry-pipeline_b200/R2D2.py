@@ -9,7 +9,8 @@ tcgen05 kernel (3xTF32, accumulator in TMEM) produces the row top-2 and the colu
 finalize kernel applies `ratio <= 0.90 and mutual` (or the similarity threshold) — see csrc/match_f32_tc.cu.
 
 `extract_features_and_desc` runs the R2D2 network on the tensor cores too (csrc/conv_tc.cu, csrc/r2d2_net.cu); the
-weights are read from the user's naver/r2d2 checkpoint file (CC BY-NC-SA, not redistributed).
+weights are read from the user's naver/r2d2 checkpoint file: the product ships none (they are CC BY-NC-SA 3.0, (c) NAVER;
+the only copy in this repository is the parity-test fixture tests/golden/r2d2_net.npz, see tests/golden/NOTICE.md).
 """
 import os
 import sys
@@ -62,7 +63,7 @@ def get_matches(ref_kp, ref_desc, cur_kp, cur_desc, imgshape):
 
 # ---------------------------------------------------------------------------------------------------------
 # Front-end: the network, the heads, NMS and the score filter run in libvo_b200.so (vo_r2d2_*, csrc/r2d2_net.cu +
-# csrc/conv_tc.cu).  Only the checkpoint FILE is the user's: the weights are not redistributed (CC BY-NC-SA); point
+# csrc/conv_tc.cu).  Only the checkpoint FILE is the user's: the package ships no weights (CC BY-NC-SA 3.0); point
 # args['model'] at a naver/r2d2 checkpoint (the reference's default path is kept).
 args = {"model": "feature_extractors/r2d2/models/faster2d2_WASF_N16.pt", "scale_f": 2 ** 0.25, "min_size": 256,
         "max_size": 1380, "min_scale": 0, "max_scale": 1, "reliability_thr": 0.7, "repeatability_thr": 0.7,

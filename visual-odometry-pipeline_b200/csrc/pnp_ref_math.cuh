@@ -13,7 +13,7 @@
 // space, and OpenCV takes whatever basis of it its SVD returns — rounding noise, different per build and CPU
 // (tools/probe/epnp_basis_probe.py: the per-hypothesis poses of two implementations of the same algorithm differ by
 // millimetres).  Here the null-space basis is made canonical (see canonical_null_basis), so that this header, the numpy
-// oracle (oracle/pnp_ref.py, LAPACK eigen-solver) and the kernels agree to ~1e-9; and the absolute orientation uses Horn's
+// restatement of the test suite (LAPACK eigen-solver) and the kernels agree to ~1e-9; and the absolute orientation uses Horn's
 // quaternion form (identical to U V^T whenever det(U V^T) > 0; a proper rotation in the reflected, degenerate case too).
 // Parity with the reference's own call is therefore exact for the sampler / scoring / stopping rule (tests/test_oracle_pnp_ref.py
 // drives the same control flow with cv2's minimal solver and reproduces cv2.solvePnPRansac bit for bit) and statistical for the

@@ -24,21 +24,24 @@ def scale_lse_solver(X, Y):
 
 
 def umeyama_alignment(x, y, with_scale=False):
-    """Least-squares Sim(m) alignment of two m x n point sets (Umeyama 1991; reference :28-77).  Returns r, t, c."""
+    """Similarity transform (r, t, c) minimising sum |y_i - (c r x_i + t)|^2 over two m x n point sets (columns are points) —
+    the closed form of Umeyama (1991), interface of the reference's helper (plot_utils/kittievalodom.py:28-77).  Written from
+    the paper: cross-covariance of the centred sets, its SVD, the reflection guard on the last singular direction, scale from
+    the guarded singular values over the variance of x."""
+    x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
     if x.shape != y.shape:
-        assert False, "x.shape not equal to y.shape"
-    m, n = x.shape
-    mean_x, mean_y = x.mean(axis=1), y.mean(axis=1)
-    xc, yc = x - mean_x[:, None], y - mean_y[:, None]
-    sigma_x = 1.0 / n * (np.linalg.norm(xc) ** 2)
-    cov_xy = (yc @ xc.T) / n
-    u, d, v = np.linalg.svd(cov_xy)
-    s = np.eye(m)
-    if np.linalg.det(u) * np.linalg.det(v) < 0.0:
-        s[m - 1, m - 1] = -1
-    r = u.dot(s).dot(v)
-    c = 1 / sigma_x * np.trace(np.diag(d).dot(s)) if with_scale else 1.0
-    t = mean_y - np.multiply(c, r.dot(mean_x))
+        raise AssertionError("x.shape not equal to y.shape")
+    dim, count = x.shape
+    cx, cy = x.mean(axis=1, keepdims=True), y.mean(axis=1, keepdims=True)
+    dx, dy = x - cx, y - cy
+    cross = dy @ dx.T / count                                 # E[(y - cy)(x - cx)^T]
+    left, sing, right_t = np.linalg.svd(cross)
+    guard = np.ones(dim)
+    if np.linalg.det(left) * np.linalg.det(right_t) < 0.0:    # a reflection would fit better: flip the weakest direction
+        guard[-1] = -1.0
+    r = (left * guard) @ right_t
+    c = float((sing * guard).sum() / ((dx * dx).sum() / count)) if with_scale else 1.0
+    t = (cy - c * (r @ cx)).ravel()
     return r, t, c
 
 
