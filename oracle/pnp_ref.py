@@ -70,11 +70,16 @@ def epnp5(X, uv, K):
     cws[0] = pws.sum(0) / n
     d0 = pws - cws[0]
     dc, uc_ = _eigh_desc(d0.T @ d0)
+    axes = np.stack([_fix_sign(uc_[:, i]) for i in range(3)])         # principal directions (rows), orthonormal
+    ks = np.sqrt(np.maximum(dc, 0.0) / n)
     for i in range(1, 4):
-        cws[i] = cws[0] + np.sqrt(max(dc[i - 1], 0.0) / n) * _fix_sign(uc_[:, i - 1])
-    ci = np.linalg.inv((cws[1:] - cws[0]).T)
+        cws[i] = cws[0] + ks[i - 1] * axes[i - 1]
+    # barycentric coordinates: the control vectors are k_i * (orthonormal axis i), so the inverse of [c1-c0 c2-c0 c3-c0] is
+    # axis_i / k_i row by row; a vanishing k_i (planar or collinear points) gives a zero row — the pseudo-inverse
+    # cvInvert(CV_SVD) returns in epnp.cpp (singular values <= 2 eps * sum are dropped, SVD::backSubst)
+    inv_k = np.where(ks > 2 * np.finfo(np.float64).eps * ks.sum(), 1.0 / np.where(ks > 0, ks, 1.0), 0.0)
     al = np.zeros((n, 4))
-    al[:, 1:] = d0 @ ci.T
+    al[:, 1:] = (d0 @ axes.T) * inv_k
     al[:, 0] = 1.0 - al[:, 1] - al[:, 2] - al[:, 3]
     M = np.zeros((2 * n, 12))
     for j in range(4):
@@ -82,9 +87,19 @@ def epnp5(X, uv, K):
         M[0::2, 3 * j + 2] = al[:, j] * (uc - us[:, 0])
         M[1::2, 3 * j + 1] = al[:, j] * fv
         M[1::2, 3 * j + 2] = al[:, j] * (vc - us[:, 1])
-    _, V = _eigh_desc(M.T @ M)
-    v0, v1 = _canonical_null_basis(V[:, 11], V[:, 10])
-    v = [v0, v1, _fix_sign(V[:, 9]), _fix_sign(V[:, 8])]
+    MtM = M.T @ M
+    if inv_k[2] == 0.0 and inv_k[1] != 0.0:
+        # coplanar points: the fourth control point coincides with the centroid, its three columns of M vanish and e9, e10, e11
+        # span an exactly-null eigenspace (OpenCV gets an arbitrary basis of it from its SVD).  Canonical choice: those unit
+        # vectors as v[0..2], and the weakest direction of the 9 x 9 block of the three real control points as v[3]
+        _, V9 = _eigh_desc(MtM[:9, :9])
+        x = np.zeros(12)
+        x[:9] = V9[:, 8]
+        v = [np.eye(12)[11], np.eye(12)[10], np.eye(12)[9], _fix_sign(x)]
+    else:
+        _, V = _eigh_desc(MtM)
+        v0, v1 = _canonical_null_basis(V[:, 11], V[:, 10])
+        v = [v0, v1, _fix_sign(V[:, 9]), _fix_sign(V[:, 8])]
     dv = np.zeros((4, 6, 3))
     pairs = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
     for i in range(4):

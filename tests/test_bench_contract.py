@@ -40,17 +40,26 @@ def test_reference_arm_is_silent_on_other_ranks():
 
 
 def test_committed_b200_line_has_the_roofline_and_clock_keys():
-    d = json.loads(open(os.path.join(ROOT, "profiles", "bench_c2_r01m.json")).read().strip().splitlines()[-1])
-    assert BASE_KEYS <= set(d) and "impl" not in d
-    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    """The default line of this round as measured on a B200 (profiles/bench_default_r02c.json): the headline is workload c3 —
+    the tcgen05 GEMM BASELINE.json's metric names — and the complete line of c2 rides in extra.c2."""
+    d = json.loads(open(os.path.join(ROOT, "profiles", "bench_default_r02c.json")).read().strip().splitlines()[-1])
+    for line, wl in ((d, "c3:"), (d["extra"]["c2"], "c2:")):
+        assert BASE_KEYS <= set(line) and "impl" not in line
+        assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["gpu_launches"] > 0
+        assert line["config"]["workload"].startswith(wl) and "l2" in line["config"]
+        assert line["config"]["timed_region_s"] >= 2.0 and line["e2e"]["timed_region_s"] >= 2.0
+        roof = line["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(roof) and roof["bound"] in ("hbm", "tensor")
+        assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+        e2e = line["e2e"]
+        assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and 0 < e2e["value"] < line["value"]
+        assert e2e["equals_resident_bitwise"] is True and "precondition" in e2e
+        clocks = line["clocks"]
+        assert clocks["samples"] > 0 and clocks["sm_mhz"] and clocks["sm_max_mhz"]
+        assert not set(clocks["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        cb = line["cpu_baseline"]
+        assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "pairs" in cb["sample"]
     roof = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(roof) and roof["bound"] in ("hbm", "tensor")
-    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
-    assert 0.5 < roof["binding_pipe"]["frac"] < 1.0                      # the pipe that really bounds the Hamming kernel
-    e2e = d["e2e"]
-    assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and 0 < e2e["value"] < d["value"]
-    clocks = d["clocks"]
-    assert clocks["sm_mhz"] and clocks["sm_max_mhz"] and not set(clocks["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "pairs" in cb["sample"]
-    assert "l2" in d["config"] and d["config"]["workload"].startswith("c2:")
+    assert "match_f32_tc_kernel" in roof["kernel"] and roof["bound"] == "tensor" and roof["unit"] == "TFLOP/s"
+    assert 0.5 < roof["frac"] < 1.0 and roof["frac_of_cublas_tf32"] > 0.9                # tensor pipe rate, and cuBLAS TF32 of the same run
+    assert 0.5 < d["extra"]["c2"]["roofline"]["binding_pipe"]["frac"] < 1.0                 # the POPC pipe bounds the Hamming kernel

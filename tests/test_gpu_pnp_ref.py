@@ -17,14 +17,15 @@ def _gpu(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-@pytest.mark.parametrize("seed,n,outliers", [(1, 900, 0.35), (2, 300, 0.2), (3, 2000, 0.5), (4, 60, 0.1), (5, 1500, 0.0)])
-def test_gpu_equals_restatement_under_shared_bootstrap(seed, n, outliers):
+@pytest.mark.parametrize("seed,n,outliers,planar", [(1, 900, 0.35, False), (2, 300, 0.2, False), (3, 2000, 0.5, False), (4, 60, 0.1, False),
+                                                    (5, 1500, 0.0, False), (6, 800, 0.2, True)])
+def test_gpu_equals_restatement_under_shared_bootstrap(seed, n, outliers, planar):
     import cv2
     import torch
     from vo_b200 import ops
     from oracle import pnp_ref
     from test_oracle_pnp_ref import _scene
-    X, uv, K = _scene(seed, n, outliers)
+    X, uv, K = _scene(seed, n, outliers, planar=planar)
     rng = np.random.RandomState(8214 + seed)
     boot = np.stack([rng.randint(0, n, n) for _ in range(3)]).astype(np.int32)
     want = pnp_ref.pose_3d_2d_ref(X, uv, K, boot, solver="epnp")
@@ -43,8 +44,12 @@ def test_gpu_equals_restatement_under_shared_bootstrap(seed, n, outliers):
             if c_o[h] < 0:
                 continue
             e_o = pnp_ref.reproj_err2(p_o[h][0], p_o[h][1], K, obj, img)
-            straddlers = int((np.abs(e_o - thr) < 1e-3).sum())
-            if c_o[h] > 0.3 * n:                                   # a usable model: poses agree closely, counts up to straddlers
+            straddlers = int((np.abs(e_o - thr) < (0.2 if planar else 1e-3)).sum())
+            if planar:                                             # coplanar points: millimetre-level agreement only (ill-conditioned 9 x 9 block)
+                if c_o[h] > 0.3 * n:
+                    n_good += 1
+                    assert abs(int(counts[r, h]) - int(c_o[h])) <= 0.05 * n, (r, h, counts[r, h], c_o[h])
+            elif c_o[h] > 0.3 * n:                                 # a usable model: poses agree closely, counts up to straddlers
                 n_good += 1
                 d = max(np.abs(poses[r, h, :9] - p_o[h][0].ravel()).max(), np.abs(poses[r, h, 9:] - p_o[h][1]).max())
                 assert d < 1e-6, (r, h, d)
@@ -52,17 +57,21 @@ def test_gpu_equals_restatement_under_shared_bootstrap(seed, n, outliers):
         # the stopping rule replayed over the GPU's own counts gives the GPU's decision
         assert pnp_ref.ransac_scan(counts[r], n)[0] == (int(res.best[1]) if r == int(res.best[0]) else pnp_ref.ransac_scan(counts[r], n)[0])
     assert n_good >= 3
+    if planar:
+        assert abs(int(res.n_inl.item()) - want["n_inl"]) <= 0.02 * n
+        assert np.abs(res.T_rel.cpu().numpy() - want["T_rel"]).max() < 5e-3
+        return
     assert (int(res.best[0]), int(res.best[1])) == (want["restart"], want["iteration"])
     assert int(res.n_inl.item()) == want["n_inl"] or abs(int(res.n_inl.item()) - want["n_inl"]) <= 2
     mask = res.mask.cpu().numpy()[:n].astype(bool)
     inl_o = np.zeros(n, bool)
     inl_o[want["inliers"]] = True
     e_w = pnp_ref.reproj_err2(want["minimal"][0], want["minimal"][1], K, X[boot[want["restart"]]], uv[boot[want["restart"]]])
-    off = np.abs(e_w - thr) >= 1e-3
+    off = np.abs(e_w - thr) >= (0.2 if planar else 1e-3)
     assert np.array_equal(mask[off], inl_o[off])
     # refit: Gauss-Newton on the device vs cv2.solvePnP(ITERATIVE) on the same inliers (DLT + LM inside OpenCV)
     rv = res.rvec_tvec.cpu().numpy()
-    if np.array_equal(mask, inl_o):
+    if np.array_equal(mask, inl_o) and not planar:          # (cv2's ITERATIVE starts from a homography on coplanar points: its LM stops earlier)
         assert np.abs(rv[:3] - want["rvec"]).max() < 1e-6 and np.abs(rv[3:] - want["tvec"]).max() < 1e-6
         assert np.abs(res.T_rel.cpu().numpy() - want["T_rel"]).max() < 1e-6
     M = np.eye(4)

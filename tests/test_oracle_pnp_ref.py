@@ -31,12 +31,15 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def _scene(seed, n=900, outliers=0.35, noise=0.3):
+def _scene(seed, n=900, outliers=0.35, noise=0.3, planar=False):
     import cv2
     from vo_b200 import synthetic
     rng = np.random.default_rng(seed)
     K = synthetic.KITTI_K
     X = np.stack([rng.uniform(-12, 12, n), rng.uniform(-3, 3, n), rng.uniform(4, 45, n)], 1).astype(np.float32)
+    if planar:                                   # a fronto-parallel wall: the third principal direction vanishes exactly
+        X[:, 0] *= 0.3
+        X[:, 2] = 5.0
     R = cv2.Rodrigues(rng.normal(0, 0.01, 3))[0]
     t = np.array([rng.normal(0, 0.02), rng.normal(0, 0.01), -0.67])
     Xc = X.astype(np.float64) @ R.T + t
@@ -46,11 +49,12 @@ def _scene(seed, n=900, outliers=0.35, noise=0.3):
     return X, uv.astype(np.float32), K
 
 
-@pytest.mark.parametrize("seed,n,outliers", [(1, 900, 0.35), (2, 300, 0.2), (3, 2000, 0.5), (4, 60, 0.1)])
-def test_replica_with_cv_minimal_solver_equals_solvepnpransac(seed, n, outliers):
+@pytest.mark.parametrize("seed,n,outliers,planar", [(1, 900, 0.35, False), (2, 300, 0.2, False), (3, 2000, 0.5, False), (4, 60, 0.1, False),
+                                                    (5, 800, 0.2, True)])
+def test_replica_with_cv_minimal_solver_equals_solvepnpransac(seed, n, outliers, planar):
     import cv2
     from oracle import pnp_ref
-    X, uv, K = _scene(seed, n, outliers)
+    X, uv, K = _scene(seed, n, outliers, planar=planar)
     ok, rv, tv, inl = cv2.solvePnPRansac(objectPoints=X, imagePoints=np.ascontiguousarray(uv).reshape(-1, 1, 2), cameraMatrix=K,
                                          distCoeffs=None, iterationsCount=100, reprojectionError=1.5)
     ok2, rv2, tv2, inl2, counts, poses, best, iters_run = pnp_ref.ransac_replica(X, uv, K, solver="cv")
@@ -67,7 +71,13 @@ def test_header_equals_numpy_restatement(hm):
         hm.hm_ref_table(n, 100, _p(got))
         assert np.array_equal(got, pnp_ref.mwc_table(n, 100))
         assert all(len(set(r.tolist())) == 5 for r in got) and got.max() < n
-    X, uv, K = _scene(11, 1200, 0.3)
+    _header_vs_numpy_on_scene(hm, pnp_ref, *_scene(11, 1200, 0.3), tol=1e-6)
+    # coplanar points (three effective control points): the weakest direction of the 9 x 9 block is poorly conditioned, the two
+    # eigen-solvers agree to millimetres only — the same models for RANSAC's purposes (counts within a few percent)
+    _header_vs_numpy_on_scene(hm, pnp_ref, *_scene(11, 1200, 0.3, planar=True), tol=2e-2)
+
+
+def _header_vs_numpy_on_scene(hm, pnp_ref, X, uv, K, tol):
     kv = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]])
     tab = pnp_ref.mwc_table(len(X), 100)
     thr = np.float32(2.25)
@@ -93,9 +103,12 @@ def test_header_equals_numpy_restatement(hm):
         if counts_o[h] > 0.3 * len(X):                                    # a usable model: the two eigen-solvers must agree closely
             n_good += 1
             d = max(np.abs(out[:9] - want[0].ravel()).max(), np.abs(out[9:] - want[1]).max())
-            assert d < 1e-6, (h, d)
-            straddle = np.abs(e_o - thr) < 1e-3
-            assert np.array_equal((e_hh <= thr)[~straddle], (e_o <= thr)[~straddle])
+            assert d < tol, (h, d)
+            if tol <= 1e-6:
+                straddle = np.abs(e_o - thr) < 1e-3
+                assert np.array_equal((e_hh <= thr)[~straddle], (e_o <= thr)[~straddle])
+            else:
+                assert abs(int(counts_h[h]) - int(counts_o[h])) <= 0.05 * len(X)
             n_cmp += 1
     assert n_good >= 5 and n_cmp == n_good
     for c in (counts_o, counts_h, np.array([-1] * 100, np.int32), np.arange(100, dtype=np.int32) * 9 + 5):

@@ -41,8 +41,8 @@ def match_u8():
     ref, cur = g(b["ref_desc"]), g(b["cur_desc"])
     n_ref = torch.tensor([300, 131], dtype=torch.int32, device="cuda")
     n_cur = torch.tensor([333, 200], dtype=torch.int32, device="cuda")
-    for norm in (ops.VO_NORM_HAMMING, ops.VO_NORM_L2_U8):
-        for mode, param in ((ops.VO_MODE_RATIO, 0.85), (ops.VO_MODE_MUTUAL, 0.0), (ops.VO_MODE_RATIO_MUTUAL, 0.9), (ops.VO_MODE_NN, 0.0)):
+    for norm in (ops.VO_NORM_HAMMING, ops.VO_NORM_HAMMING_TC, ops.VO_NORM_L2_U8):
+        for mode, param in ((ops.VO_MODE_RATIO, 0.85), (ops.VO_MODE_MUTUAL, 0.0), (ops.VO_MODE_NN, 0.0)):
             for ragged in (False, True):
                 for knn in (False, True, "rows"):
                     ops.match_u8(ref, cur, norm, mode, param, n_ref=n_ref if ragged else None, n_cur=n_cur if ragged else None,

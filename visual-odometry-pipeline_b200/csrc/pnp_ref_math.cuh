@@ -199,6 +199,7 @@ VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], d
         for (int i = 0; i < n; ++i) s += X[i][j];
         cws[0][j] = s / n;
     }
+    double axes[3][3], ks[3];                       // principal directions (orthonormal, sign-fixed) and their scales
     {
         double C[3][3], V[3][3], d[3];
         for (int a = 0; a < 3; ++a)
@@ -208,35 +209,22 @@ VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], d
                 C[a][b] = s;
             }
         jacobi_eig<3>(C, V, d);
-        for (int i = 1; i < 4; ++i) {
-            double v[3] = {V[0][i - 1], V[1][i - 1], V[2][i - 1]};
+        for (int i = 0; i < 3; ++i) {
+            double v[3] = {V[0][i], V[1][i], V[2][i]};
             fix_sign(v);
-            const double k = sqrt(fmax(d[i - 1], 0.0) / n);
-            for (int j = 0; j < 3; ++j) cws[i][j] = cws[0][j] + k * v[j];
+            ks[i] = sqrt(fmax(d[i], 0.0) / n);
+            for (int j = 0; j < 3; ++j) { axes[i][j] = v[j]; cws[i + 1][j] = cws[0][j] + ks[i] * v[j]; }
         }
     }
-    // barycentric coordinates
+    // barycentric coordinates: the control vectors are k_i * (orthonormal axis i), so the inverse of [c1-c0 c2-c0 c3-c0] is
+    // axis_i / k_i row by row; a vanishing k_i (planar or collinear points) gives a zero row — the pseudo-inverse
+    // cvInvert(CV_SVD) returns in epnp.cpp (singular values <= 2 eps * sum are dropped, SVD::backSubst)
     double al[n][4];
+    const double cut = 2.0 * 2.220446049250313e-16 * (ks[0] + ks[1] + ks[2]);
     {
-        double cc[3][3];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 1; j < 4; ++j) cc[i][j - 1] = cws[j][i] - cws[0][i];
-        const double det = cc[0][0] * (cc[1][1] * cc[2][2] - cc[1][2] * cc[2][1]) - cc[0][1] * (cc[1][0] * cc[2][2] - cc[1][2] * cc[2][0]) +
-                           cc[0][2] * (cc[1][0] * cc[2][1] - cc[1][1] * cc[2][0]);
-        const double id = 1.0 / det;
-        double ci[3][3];
-        ci[0][0] = (cc[1][1] * cc[2][2] - cc[1][2] * cc[2][1]) * id;
-        ci[0][1] = (cc[0][2] * cc[2][1] - cc[0][1] * cc[2][2]) * id;
-        ci[0][2] = (cc[0][1] * cc[1][2] - cc[0][2] * cc[1][1]) * id;
-        ci[1][0] = (cc[1][2] * cc[2][0] - cc[1][0] * cc[2][2]) * id;
-        ci[1][1] = (cc[0][0] * cc[2][2] - cc[0][2] * cc[2][0]) * id;
-        ci[1][2] = (cc[0][2] * cc[1][0] - cc[0][0] * cc[1][2]) * id;
-        ci[2][0] = (cc[1][0] * cc[2][1] - cc[1][1] * cc[2][0]) * id;
-        ci[2][1] = (cc[0][1] * cc[2][0] - cc[0][0] * cc[2][1]) * id;
-        ci[2][2] = (cc[0][0] * cc[1][1] - cc[0][1] * cc[1][0]) * id;
         for (int i = 0; i < n; ++i) {
             const double p[3] = {X[i][0] - cws[0][0], X[i][1] - cws[0][1], X[i][2] - cws[0][2]};
-            for (int j = 0; j < 3; ++j) al[i][1 + j] = ci[j][0] * p[0] + ci[j][1] * p[1] + ci[j][2] * p[2];
+            for (int j = 0; j < 3; ++j) al[i][1 + j] = (ks[j] > cut) ? dot3(axes[j], p) / ks[j] : 0.0;
             al[i][0] = 1.0 - al[i][1] - al[i][2] - al[i][3];
         }
     }
@@ -254,7 +242,20 @@ VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], d
             for (int b = 0; b < 12; ++b) MtM[a][b] += m1[a] * m1[b] + m2[a] * m2[b];
     }
     double v[4][12];                    // v[0] = ut[11] ... v[3] = ut[8] of epnp.cpp
-    {
+    if (!(ks[2] > cut) && ks[1] > cut) {
+        // coplanar points: the fourth control point coincides with the centroid, its three columns of M vanish and e9, e10, e11
+        // span an exactly-null eigenspace (OpenCV gets an arbitrary basis of it from its SVD).  Canonical choice: those unit
+        // vectors as v[0..2], and the weakest direction of the 9 x 9 block of the three real control points as v[3]
+        double B[9][9], V9[9][9], d9[9];
+        for (int a = 0; a < 9; ++a)
+            for (int b = 0; b < 9; ++b) B[a][b] = MtM[a][b];
+        jacobi_eig<9>(B, V9, d9);
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 12; ++k) v[i][k] = 0.0;
+        v[0][11] = 1.0; v[1][10] = 1.0; v[2][9] = 1.0;
+        for (int k = 0; k < 9; ++k) v[3][k] = V9[k][8];
+        fix_sign(v[3]);
+    } else {
         double V[12][12], d[12];
         jacobi_eig<12>(MtM, V, d);
         for (int i = 0; i < 4; ++i)

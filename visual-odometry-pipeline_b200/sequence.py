@@ -339,7 +339,10 @@ class HostSequenceRunner:
       "hybrid"   the first (1 - sampled_frac) of a chunk's maps by DMA while the SMs pull the samples of the rest on a
                  third stream.  `autotune()` picks sampled_frac by timing whole passes (the best split depends on how many
                  GPUs share the host's memory system).
-    Precondition: the frames are already in pinned host memory (numpy inputs are pinned here, outside any timed region)."""
+    Precondition: the frames are already in pinned host memory (numpy inputs are pinned here, outside any timed region).
+    `host_seq["desc"]` may be a CUDA tensor instead: descriptors that never left the device — how the reference holds R2D2
+    descriptors (R2D2.py:224-232 keeps them CUDA tensors, the network runs on the GPU) — are used in place; only keypoints and
+    depth then cross the bus."""
 
     def __init__(self, host_seq, cfg, chunk, device="cuda", depth_mode="hybrid", sampled_frac=0.4):
         if depth_mode not in ("dense", "sampled", "hybrid"):
@@ -351,8 +354,9 @@ class HostSequenceRunner:
         def pinned(a):
             t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
             return t if t.is_pinned() else t.pin_memory()
-        self.host = {k: pinned(host_seq[k]) for k in ("desc", "kp", "depth")}
-        self.B = self.host["desc"].shape[0] - 1
+        self.dev_desc = host_seq["desc"] if isinstance(host_seq["desc"], torch.Tensor) and host_seq["desc"].is_cuda else None
+        self.host = {k: pinned(host_seq[k]) for k in (("kp", "depth") if self.dev_desc is not None else ("desc", "kp", "depth"))}
+        self.B = self.host["kp"].shape[0] - 1
         self.hw = tuple(self.host["depth"].shape[1:])
         self.N = self.host["kp"].shape[1]
         self.frac = {"dense": 0.0, "sampled": 1.0, "hybrid": float(sampled_frac)}[depth_mode]
@@ -361,7 +365,7 @@ class HostSequenceRunner:
         self.stage = []
         for _ in range(2):
             st = {k: torch.empty((c + 1,) + tuple(self.host[k].shape[1:]), dtype=self.host[k].dtype, device=self.device)
-                  for k in ("desc", "kp")}
+                  for k in ("desc", "kp") if k in self.host}
             if depth_mode != "sampled":
                 st["depth"] = torch.empty((c,) + self.hw, dtype=torch.float32, device=self.device)
             if depth_mode != "dense":
@@ -390,7 +394,7 @@ class HostSequenceRunner:
         whole maps for the DMA share, one 32-byte sector per reference keypoint for the sampled share."""
         per = {k: v[0].numel() * v.element_size() for k, v in self.host.items()}
         dma = sum(self._n_dma(hi - lo) for lo, hi in self.schedule)
-        return (self.B + 1) * (per["desc"] + per["kp"]) + dma * per["depth"] + (self.B - dma) * self.N * 32
+        return (self.B + 1) * (per.get("desc", 0) + per["kp"]) + dma * per["depth"] + (self.B - dma) * self.N * 32
 
     def _view(self, lo, hi):
         view = ops.PipelineBuffers.__new__(ops.PipelineBuffers)
@@ -418,11 +422,13 @@ class HostSequenceRunner:
                 if prev is not None:                       # frame lo is already on the device: last frame of the previous chunk
                     pst, pn = self.stage[prev[0]], prev[1]
                     st["kp"][0].copy_(pst["kp"][pn], non_blocking=True)
-                    st["desc"][0].copy_(pst["desc"][pn], non_blocking=True)
+                    if self.dev_desc is None:
+                        st["desc"][0].copy_(pst["desc"][pn], non_blocking=True)
                     first = 1
                 st["kp"][first:n + 1].copy_(self.host["kp"][lo + first:hi + 1], non_blocking=True)
                 self.kp_ready[buf].record(self.copy_stream)
-                st["desc"][first:n + 1].copy_(self.host["desc"][lo + first:hi + 1], non_blocking=True)
+                if self.dev_desc is None:
+                    st["desc"][first:n + 1].copy_(self.host["desc"][lo + first:hi + 1], non_blocking=True)
                 if n_dma:
                     st["depth"][:n_dma].copy_(self.host["depth"][lo:lo + n_dma], non_blocking=True)
                     if self.depth_mode != "dense":         # maps that came by DMA are sampled from HBM
@@ -435,11 +441,13 @@ class HostSequenceRunner:
                     self.sampled[buf].record(self.sample_stream)
                 compute.wait_event(self.sampled[buf])
             compute.wait_event(self.copied[buf])
+            d_ref, d_cur = (st["desc"][:n], st["desc"][1:n + 1]) if self.dev_desc is None else \
+                (self.dev_desc[lo:hi], self.dev_desc[lo + 1:hi + 1])
             if self.depth_mode == "dense":
-                ops.pipeline(st["desc"][:n], st["desc"][1:n + 1], st["kp"][:n], st["kp"][1:n + 1], st["depth"][:n], self.K,
+                ops.pipeline(d_ref, d_cur, st["kp"][:n], st["kp"][1:n + 1], st["depth"][:n], self.K,
                              pair0=pair0 + lo, out=self._view(lo, hi), **self.cfg.kw)
             else:
-                ops.pipeline(st["desc"][:n], st["desc"][1:n + 1], st["kp"][:n], st["kp"][1:n + 1], None, self.K,
+                ops.pipeline(d_ref, d_cur, st["kp"][:n], st["kp"][1:n + 1], None, self.K,
                              pair0=pair0 + lo, out=self._view(lo, hi), depth_kp=st["depth_kp"][:n], hw=self.hw, **self.cfg.kw)
             self.consumed[buf].record(compute)
             prev = (buf, n)
