@@ -188,7 +188,10 @@ extern "C" int vo_match_f32(vo_ctx *ctx, const float *ref, const float *cur, int
 }
 
 // ---------------------------------------------------------------- whole-path pipeline
-extern "C" int vo_pipeline(vo_ctx *ctx, const vo_pipeline_args *a, void *stream) {
+extern "C" int vo_pipeline(vo_ctx *ctx, const vo_pipeline_args *a, void *stream) { return vo::pipeline_impl(ctx, a, stream, nullptr); }
+
+// pair0_dev (optional, device): the hypothesis generator's pair offset read on the device instead of a->pair0 (vo_seq_*'s graph)
+int vo::pipeline_impl(vo_ctx *ctx, const vo_pipeline_args *a, void *stream, const long long *pair0_dev) {
     using namespace vo;
     VO_REQUIRE(ctx && a, "vo_pipeline: null argument");
     const bool u8 = a->ref_u8 && a->cur_u8, f32 = a->ref_f32 && a->cur_f32;
@@ -226,7 +229,7 @@ extern "C" int vo_pipeline(vo_ctx *ctx, const vo_pipeline_args *a, void *stream)
                                       a->min_flow_px, a->z_min, a->z_max, xyz, ruv, cuv, nullptr, a->n_corr, a->status,
                                       stream)))
         return rc;
-    if ((rc = vo_hypotheses(ctx, a->n_corr, B, H, a->seed, a->pair0, hyp, stream))) return rc;
+    if ((rc = hypotheses_impl(ctx, a->n_corr, B, H, a->seed, a->pair0, pair0_dev, hyp, stream))) return rc;
     return pnp_ransac_impl(ctx, xyz, cuv, a->n_corr, B, cap, a->K_h, hyp, H, a->thr_px, a->min_inliers,
                            a->refine_iters, a->rt, nullptr, a->T_rel, a->n_inl, nullptr, nullptr, nullptr, a->status,
                            1, stream);

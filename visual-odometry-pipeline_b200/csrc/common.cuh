@@ -141,6 +141,9 @@ int match_bits_tc(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, in
                   const int32_t *n_cur, int need_cols, vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey,
                   cudaStream_t st);
 int pick_split(vo_ctx *ctx, int B, int row_blocks, int col_tiles, int min_tiles_per_split);
+int hypotheses_impl(vo_ctx *ctx, const int32_t *n_pts, int B, int H, uint64_t seed, int64_t pair0, const long long *pair0_dev,
+                    int32_t *hyp, void *stream);
+int pipeline_impl(vo_ctx *ctx, const vo_pipeline_args *a, void *stream, const long long *pair0_dev);
 int pnp_ransac_impl(vo_ctx *ctx, const float *xyz, const float *uv, const int32_t *n_pts, int B, int cap,
                     const double *K_h, const int32_t *hyp, int H, float thr_px, int min_inliers, int refine_iters,
                     double *rt, double *rvec_tvec, double *T_rel, int32_t *n_inl, int32_t *best_h,

@@ -21,13 +21,15 @@ struct IntrD {
 };
 
 // ---------------------------------------------------------------- hypothesis table
+// pair0_dev (optional): the pair offset read from device memory — a CUDA graph of the keyframe loop replays with a fresh offset
 __global__ void hypotheses_kernel(const int32_t *__restrict__ n_pts, int B, int H, uint64_t seed, int64_t pair0,
-                                  int32_t *__restrict__ hyp) {
+                                  const long long *__restrict__ pair0_dev, int32_t *__restrict__ hyp) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * H) return;
     const int b = (int)(gid / H), h = (int)(gid % H);
     const int n = n_pts[b];
     int32_t idx[4] = {-1, -1, -1, -1};
+    if (pair0_dev) pair0 = (int64_t)*pair0_dev;
     if (n >= 4) draw_hypothesis(seed, pair0 + b, h, n, idx);
     reinterpret_cast<int4 *>(hyp)[gid] = make_int4(idx[0], idx[1], idx[2], idx[3]);
 }
@@ -654,19 +656,25 @@ refit_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const 
 }  // namespace
 }  // namespace vo
 
-extern "C" int vo_hypotheses(vo_ctx *ctx, const int32_t *n_pts, int B, int H, uint64_t seed, int64_t pair0,
-                             int32_t *hyp, void *stream) {
-    using namespace vo;
+namespace vo {
+int hypotheses_impl(vo_ctx *ctx, const int32_t *n_pts, int B, int H, uint64_t seed, int64_t pair0, const long long *pair0_dev,
+                    int32_t *hyp, void *stream) {
     VO_REQUIRE(ctx && n_pts && hyp, "vo_hypotheses: null argument");
     VO_REQUIRE(B >= 0 && H >= 0, "vo_hypotheses: negative size");
     VO_REQUIRE(((uintptr_t)hyp % 16) == 0, "vo_hypotheses: table must be 16B aligned");
     const long long total = (long long)B * H;
     if (total == 0) return VO_OK;
     VO_PROF(ctx, (cudaStream_t)stream, VO_STAGE_HYP);
-    hypotheses_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_pts, B, H, seed, pair0, hyp);
+    hypotheses_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_pts, B, H, seed, pair0, pair0_dev, hyp);
     VO_LAUNCH_CHECK(ctx);
     VO_PROF(ctx, (cudaStream_t)stream, -1);
     return VO_OK;
+}
+}  // namespace vo
+
+extern "C" int vo_hypotheses(vo_ctx *ctx, const int32_t *n_pts, int B, int H, uint64_t seed, int64_t pair0,
+                             int32_t *hyp, void *stream) {
+    return vo::hypotheses_impl(ctx, n_pts, B, H, seed, pair0, nullptr, hyp, stream);
 }
 
 namespace vo {

@@ -4,6 +4,12 @@
 // Two frame slots live in HBM (keyframe, current frame).  Per pushed frame the stream carries:
 //   copy inputs -> current slot | begin_kernel | vo_pipeline(keyframe slot, current slot, B = 1) | policy_kernel |
 //   promote_kernel
+// With VO_SEQ_GRAPH=1, from the third frame on everything after begin_kernel is ONE CUDA-graph launch: the pipeline's ~16
+// kernels, the policy and the promotion are captured once per loop (all per-frame values they need — keypoint counts, frame
+// numbers, the history slot, the hypothesis generator's pair offset — live in device memory, written by begin_kernel) and
+// replayed.  Opt-in because it buys nothing (measured on a B200, tools/seq_bench.py, identical poses): the loop is bound by the
+// latencies of its small kernels and the 1.87 MB depth upload, not by launches — host enqueue 54-62 us per frame against
+// 231 (SIFT 2k) / 291-306 us (ORB 5k) of GPU time; graph replay 233 / 306 us per frame against 231 / 291 us with plain launches.
 // policy_kernel is one thread of fp64: the 1.5 m x (frame gap) plausibility gate (:270-274), the bad-PnP counter
 // (:273, :279, :282, :295), T_cur = T_key @ T_rel (:283) or T_cur = T_key (:290), the keyframe rule
 // common_pts < 200 or inliers < 100 or dist > 1.5 (:285-287) and the history entry (:292-293).  promote_kernel copies
@@ -16,6 +22,9 @@ struct vo_seq_state {  // device-resident loop state
     int32_t key_id, cur_id;  // reference frame numbers
     int32_t bad_pnp;
     int32_t promote;         // current frame becomes the keyframe
+    int32_t slot;            // history index of the current frame (pose / info row the policy writes)
+    int32_t pad_;
+    long long pair0;         // pair offset of the hypothesis generator for this frame (= slot - 1)
     double T_key[16];        // global pose of the keyframe
 };
 
@@ -31,14 +40,19 @@ struct vo_seq {
     double *poses;  // [max_frames][16]
     int32_t *info;  // [max_frames][6]
     int pushed;
+    cudaGraphExec_t graph;     // pipeline + policy + promotion of one frame, captured at the third push
+    int graph_state;           // 0 not tried yet, 1 captured, -1 capture failed / disabled (plain launches)
+    long long graph_kernels;   // kernel launches one replay stands for (keeps vo_launch_count meaningful)
 };
 
 namespace vo {
 namespace {
 
-__global__ void seq_begin_kernel(vo_seq_state *st, int n_kp, int frame_id, int first, double *poses, int32_t *info) {
+__global__ void seq_begin_kernel(vo_seq_state *st, int n_kp, int frame_id, int first, int slot, double *poses, int32_t *info) {
     st->cur_n = n_kp;
     st->cur_id = frame_id;
+    st->slot = slot;
+    st->pair0 = (long long)slot - 1;
     if (first) {  // frame 0: identity pose, becomes the keyframe (:233-239)
         st->bad_pnp = 0;
         st->promote = 1;
@@ -55,7 +69,9 @@ __global__ void seq_begin_kernel(vo_seq_state *st, int n_kp, int frame_id, int f
 
 __global__ void seq_policy_kernel(vo_seq_state *st, const double *__restrict__ T_rel, const int32_t *__restrict__ out4,
                                   double max_step_m, int kf_min_common, int kf_min_inliers, double kf_max_dist,
-                                  int bad_pnp_limit, double *pose_out, int32_t *info_out) {
+                                  int bad_pnp_limit, double *poses, int32_t *infos) {
+    double *pose_out = poses + 16 * (size_t)st->slot;      // the history row of the current frame
+    int32_t *info_out = infos + 6 * (size_t)st->slot;
     const int n_matches = out4[0], n_corr = out4[1], n_inl = out4[2], status = out4[3];
     bool ok = status == 0;
     int bad = st->bad_pnp;
@@ -156,6 +172,7 @@ extern "C" int vo_seq_create(vo_ctx *ctx, const vo_seq_config *cfg, vo_seq **out
 extern "C" void vo_seq_destroy(vo_seq *seq) {
     if (!seq) return;
     cudaDeviceSynchronize();
+    if (seq->graph) cudaGraphExecDestroy(seq->graph);
     cudaFree(seq->key_desc);  // base of the single allocation
     free(seq);
 }
@@ -178,36 +195,63 @@ extern "C" int vo_seq_push(vo_seq *seq, const void *desc, const float *kp, int n
         VO_CUDA(cudaMemcpyAsync(seq->cur_kp, kp, sizeof(float) * c.kp_stride * n_kp, cudaMemcpyDefault, st));
     }
     VO_CUDA(cudaMemcpyAsync(seq->cur_depth, depth, nz, cudaMemcpyDefault, st));
-    seq_begin_kernel<<<1, 1, 0, st>>>(seq->st, n_kp, frame_id, slot == 0 ? 1 : 0, seq->poses, seq->info);
+    seq_begin_kernel<<<1, 1, 0, st>>>(seq->st, n_kp, frame_id, slot == 0 ? 1 : 0, slot, seq->poses, seq->info);
     VO_LAUNCH_CHECK(ctx);
-    if (slot > 0) {
-        vo_pipeline_args a;
-        memset(&a, 0, sizeof(a));
-        a.B = 1; a.n_stride = c.n_cap; a.m_stride = c.n_cap;
-        a.n_ref = &seq->st->key_n; a.n_cur = &seq->st->cur_n;
-        if (c.desc_is_f32) { a.ref_f32 = (const float *)seq->key_desc; a.cur_f32 = (const float *)seq->cur_desc; }
-        else { a.ref_u8 = seq->key_desc; a.cur_u8 = seq->cur_desc; }
-        a.norm_or_metric = c.norm_or_metric; a.mode = c.mode; a.precision = c.precision; a.match_param = c.match_param;
-        a.ref_kp = seq->key_kp; a.cur_kp = seq->cur_kp; a.kp_stride = c.kp_stride;
-        a.depth = seq->key_depth; a.H = c.H; a.W = c.W; a.K_h = c.K;
-        a.min_flow_px = c.min_flow_px; a.z_min = c.z_min; a.z_max = c.z_max;
-        a.n_hyp = c.n_hyp; a.seed = c.seed; a.pair0 = slot - 1;
-        a.thr_px = c.thr_px; a.min_inliers = c.min_inliers; a.refine_iters = c.refine_iters;
-        a.T_rel = seq->T_rel; a.rt = seq->rt;
-        a.n_matches = seq->out4 + 0; a.n_corr = seq->out4 + 1; a.n_inl = seq->out4 + 2; a.status = seq->out4 + 3;
-        int rc = vo_pipeline(ctx, &a, stream);
-        if (rc) return rc;
-        seq_policy_kernel<<<1, 1, 0, st>>>(seq->st, seq->T_rel, seq->out4, c.max_step_m, c.kf_min_common,
-                                           c.kf_min_inliers, c.kf_max_dist, c.bad_pnp_limit,
-                                           seq->poses + 16 * (size_t)slot, seq->info + 6 * (size_t)slot);
-        VO_LAUNCH_CHECK(ctx);
-    }
     const size_t nd16 = round16(seq->desc_row * c.n_cap) / 16, nk16 = round16(sizeof(float) * c.kp_stride * c.n_cap) / 16,
                  nz16 = round16(nz) / 16;
-    seq_promote_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(seq->st, (uint4 *)seq->key_desc, (const uint4 *)seq->cur_desc, nd16,
-                                                         (uint4 *)seq->key_kp, (const uint4 *)seq->cur_kp, nk16,
-                                                         (uint4 *)seq->key_depth, (const uint4 *)seq->cur_depth, nz16);
-    VO_LAUNCH_CHECK(ctx);
+    // everything after begin_kernel: identical launches for every frame (per-frame values are read from seq->st)
+    auto body = [&]() -> int {
+        if (slot > 0) {
+            vo_pipeline_args a;
+            memset(&a, 0, sizeof(a));
+            a.B = 1; a.n_stride = c.n_cap; a.m_stride = c.n_cap;
+            a.n_ref = &seq->st->key_n; a.n_cur = &seq->st->cur_n;
+            if (c.desc_is_f32) { a.ref_f32 = (const float *)seq->key_desc; a.cur_f32 = (const float *)seq->cur_desc; }
+            else { a.ref_u8 = seq->key_desc; a.cur_u8 = seq->cur_desc; }
+            a.norm_or_metric = c.norm_or_metric; a.mode = c.mode; a.precision = c.precision; a.match_param = c.match_param;
+            a.ref_kp = seq->key_kp; a.cur_kp = seq->cur_kp; a.kp_stride = c.kp_stride;
+            a.depth = seq->key_depth; a.H = c.H; a.W = c.W; a.K_h = c.K;
+            a.min_flow_px = c.min_flow_px; a.z_min = c.z_min; a.z_max = c.z_max;
+            a.n_hyp = c.n_hyp; a.seed = c.seed; a.pair0 = slot - 1;
+            a.thr_px = c.thr_px; a.min_inliers = c.min_inliers; a.refine_iters = c.refine_iters;
+            a.T_rel = seq->T_rel; a.rt = seq->rt;
+            a.n_matches = seq->out4 + 0; a.n_corr = seq->out4 + 1; a.n_inl = seq->out4 + 2; a.status = seq->out4 + 3;
+            int rc = pipeline_impl(ctx, &a, stream, &seq->st->pair0);
+            if (rc) return rc;
+            seq_policy_kernel<<<1, 1, 0, st>>>(seq->st, seq->T_rel, seq->out4, c.max_step_m, c.kf_min_common,
+                                               c.kf_min_inliers, c.kf_max_dist, c.bad_pnp_limit, seq->poses, seq->info);
+            VO_LAUNCH_CHECK(ctx);
+        }
+        seq_promote_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(seq->st, (uint4 *)seq->key_desc, (const uint4 *)seq->cur_desc, nd16,
+                                                             (uint4 *)seq->key_kp, (const uint4 *)seq->cur_kp, nk16,
+                                                             (uint4 *)seq->key_depth, (const uint4 *)seq->cur_depth, nz16);
+        VO_LAUNCH_CHECK(ctx);
+        return VO_OK;
+    };
+    // frames 0 and 1 run plainly (frame 1 sizes every workspace: nothing may allocate during capture); frame 2 captures
+    if (slot >= 2 && seq->graph_state == 0 && !ctx->prof_on && getenv("VO_SEQ_GRAPH")) {
+        cudaGraph_t g = nullptr;
+        const long long l0 = ctx->launches;
+        seq->graph_state = -1;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = body();
+            const cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (rc == VO_OK && e == cudaSuccess && g && cudaGraphInstantiate(&seq->graph, g, 0) == cudaSuccess) {
+                seq->graph_state = 1;
+                seq->graph_kernels = ctx->launches - l0;
+            }
+            if (g) cudaGraphDestroy(g);
+        }
+        (void)cudaGetLastError();          // a failed capture must not poison the next launch check
+        ctx->launches = l0;                // (captured launches did not run; the replay below counts them)
+    }
+    if (seq->graph_state == 1 && slot >= 2 && !ctx->prof_on) {
+        VO_CUDA(cudaGraphLaunch(seq->graph, st));
+        ctx->launches += seq->graph_kernels;
+    } else {
+        const int rc = body();
+        if (rc) return rc;
+    }
     seq->pushed = slot + 1;
     return VO_OK;
 }

@@ -71,20 +71,47 @@ __global__ void sift_upsample_kernel(const uint8_t *__restrict__ img, int channe
     out[(size_t)y * (2 * W) + x] = top * (1.f - wy) + bot * wy;
 }
 
-__global__ void sift_blur_row_kernel(const float *__restrict__ src, int w, int h, SiftKernels K, int ki, float *__restrict__ dst) {
+// Separable Gaussian, one thread per pixel.  The tap count is a template parameter (the five kernel lengths of the scale space:
+// 11, 13, 17, 21, 27): the unrolled loop lets all loads of a pixel issue before the first use, and interior pixels skip the
+// border reflection.  The products and the left-to-right sum are rounded one by one as before (-fmad=false): same bits as
+// the generic loop, which stays for other lengths.  (Generic loop on a B200: 18-50 us per 2482 x 752 layer, latency-bound;
+// the blur passes were 52 % of the front-end after the orientation kernel got its warps.)
+template <int N>
+__global__ void __launch_bounds__(128)
+sift_blur_row_kernel(const float *__restrict__ src, int w, int h, SiftKernels K, int ki, float *__restrict__ dst) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
-    const int n = K.ksize[ki], r = n / 2;
+    const int n = N > 0 ? N : K.ksize[ki], r = n / 2;
+    const float *row = src + (size_t)y * w;
     float s = 0.f;
-    for (int i = 0; i < n; ++i) s += K.k[ki][i] * src[(size_t)y * w + reflect101i(x + i - r, w)];
+    if (N > 0 && x >= r && x + r < w) {
+        float v[N > 0 ? N : 1];
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = row[x + i - r];
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += K.k[ki][i] * v[i];
+    } else {
+        for (int i = 0; i < n; ++i) s += K.k[ki][i] * row[reflect101i(x + i - r, w)];
+    }
     dst[(size_t)y * w + x] = s;
 }
-__global__ void sift_blur_col_kernel(const float *__restrict__ src, int w, int h, SiftKernels K, int ki, float *__restrict__ dst) {
+template <int N>
+__global__ void __launch_bounds__(128)
+sift_blur_col_kernel(const float *__restrict__ src, int w, int h, SiftKernels K, int ki, float *__restrict__ dst) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
-    const int n = K.ksize[ki], r = n / 2;
+    const int n = N > 0 ? N : K.ksize[ki], r = n / 2;
     float s = 0.f;
-    for (int i = 0; i < n; ++i) s += K.k[ki][i] * src[(size_t)reflect101i(y + i - r, h) * w + x];
+    if (N > 0 && y >= r && y + r < h) {
+        float v[N > 0 ? N : 1];
+        const float *col = src + (size_t)(y - r) * w + x;
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = col[(size_t)i * w];
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += K.k[ki][i] * v[i];
+    } else {
+        for (int i = 0; i < n; ++i) s += K.k[ki][i] * src[(size_t)reflect101i(y + i - r, h) * w + x];
+    }
     dst[(size_t)y * w + x] = s;
 }
 __global__ void sift_decimate_kernel(const float *__restrict__ src, int sw, float *__restrict__ dst, int w, int h) {
@@ -115,10 +142,16 @@ __device__ __forceinline__ void sift_solve3(const float a[3][3], const float b[3
     x[2] = d * (a[0][0] * (a[1][1] * b[2] - b[1] * a[2][1]) - a[0][1] * (a[1][0] * b[2] - b[1] * a[2][0]) + b[0] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]));
 }
 
-// 26-neighbour extremum -> adjustLocalExtrema -> orientation histogram -> one record per peak.  One thread per pixel of
-// the three inner DoG layers of one octave (grid.y = 3 * h).
-__global__ void sift_extrema_kernel(const float *__restrict__ dog, const float *__restrict__ gauss, int w, int h, int octv,
-                                    int threshold, SiftKp *__restrict__ kps, int32_t *__restrict__ count, int cap) {
+// 26-neighbour extremum -> adjustLocalExtrema -> one candidate record.  One thread per pixel of the three inner DoG layers
+// of one octave (grid.y = 3 * h).  The orientation histogram of a candidate covers (2 r + 1)^2 = 360 .. 840 pixels with an
+// exp, an atan2 and a sqrt each: run in the pixel's own thread it left 31 lanes of the warp idle for ~40 us per keypoint
+// (48 % of the whole front-end, ncu launch list r02); sift_orient_kernel now gives every candidate a warp.
+struct SiftCand {
+    int32_t r, c, layer, octave;
+    float xc, xr, contr, size;
+};
+__global__ void sift_extrema_kernel(const float *__restrict__ dog, int w, int h, int octv, int threshold,
+                                    SiftCand *__restrict__ cands, int32_t *__restrict__ n_cand, int cap) {
     const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int layer0 = 1 + blockIdx.y / h, r0 = blockIdx.y % h;
     if (c0 < SIFT_BORDER || c0 >= w - SIFT_BORDER || r0 < SIFT_BORDER || r0 >= h - SIFT_BORDER) return;
@@ -180,49 +213,82 @@ __global__ void sift_extrema_kernel(const float *__restrict__ dog, const float *
     const float oscale = (float)(1 << octv);
     const float size = 1.6f * powf(2.f, (layer + xi) / SIFT_LAYERS) * oscale * 2.f;
     const int octave = octv + (layer << 8) + (__double2int_rn(((double)xi + 0.5) * 255.0) << 16);
-    // ---- calcOrientationHist on Gaussian layer `layer`
-    const float scl_octv = size * 0.5f / oscale;
-    const int radius = __float2int_rn(4.5f * scl_octv);
-    const float sigma = 1.5f * scl_octv, expf_scale = -1.f / (2.f * sigma * sigma);
-    const float *gimg = gauss + layer * plane;
-    float temp[36 + 4];
-    for (int i = 0; i < 40; ++i) temp[i] = 0.f;
-    for (int i = -radius; i <= radius; ++i) {
-        const int y = r + i;
-        if (y <= 0 || y >= h - 1) continue;
-        for (int j = -radius; j <= radius; ++j) {
-            const int x = c + j;
-            if (x <= 0 || x >= w - 1) continue;
-            const float dx = gimg[(size_t)y * w + x + 1] - gimg[(size_t)y * w + x - 1];
-            const float dy = gimg[(size_t)(y - 1) * w + x] - gimg[(size_t)(y + 1) * w + x];
-            const float wgt = expf((float)(i * i + j * j) * expf_scale);
-            int bin = __float2int_rn((36.f / 360.f) * orb::fast_atan2(dy, dx));
-            if (bin >= 36) bin -= 36;
-            if (bin < 0) bin += 36;
-            temp[2 + bin] += wgt * sqrtf(dx * dx + dy * dy);
-        }
+    const int o = atomicAdd(n_cand, 1);
+    if (o < cap) {
+        SiftCand k;
+        k.r = r; k.c = c; k.layer = layer; k.octave = octave; k.xc = xc; k.xr = xr; k.contr = contr; k.size = size;
+        cands[o] = k;
     }
-    temp[0] = temp[36]; temp[1] = temp[37]; temp[38] = temp[2]; temp[39] = temp[3];
-    float hist[36], omax = 0.f;
-    for (int i = 0; i < 36; ++i) {
-        hist[i] = (temp[i] + temp[i + 4]) * (1.f / 16.f) + (temp[i + 1] + temp[i + 3]) * (4.f / 16.f) + temp[i + 2] * (6.f / 16.f);
-        omax = i == 0 ? hist[0] : fmaxf(omax, hist[i]);
-    }
-    const float mag_thr = omax * 0.8f;
-    for (int j = 0; j < 36; ++j) {
-        const int l = j > 0 ? j - 1 : 35, r2 = j < 35 ? j + 1 : 0;
-        if (hist[j] > hist[l] && hist[j] > hist[r2] && hist[j] >= mag_thr) {
-            float bin = j + 0.5f * (hist[l] - hist[r2]) / (hist[l] - 2.f * hist[j] + hist[r2]);
-            bin = bin < 0.f ? 36.f + bin : (bin >= 36.f ? bin - 36.f : bin);
-            float ang = 360.f - (360.f / 36.f) * bin;
-            if (fabsf(ang - 360.f) < 1.1920929e-07f) ang = 0.f;
-            const int o = atomicAdd(count, 1);
-            if (o < cap) {
-                SiftKp k;
-                k.x = (c + xc) * oscale; k.y = (r + xr) * oscale; k.size = size; k.angle = ang; k.resp = fabsf(contr); k.octave = octave;
-                kps[o] = k;
+}
+
+// calcOrientationHist + the peak loop of findScaleSpaceExtrema, one warp (= one CTA of 32 threads) per candidate: the rows of
+// the (2 r + 1)^2 window are dealt to the lanes, every lane accumulates its own 36-bin partial histogram in shared memory
+// (bin-major, lane-minor: no bank conflicts, no atomics), the 32 partials of a bin are summed in lane order, and lane 0
+// smooths, finds the peaks and appends one keypoint per peak: the result does not depend on scheduling.
+__global__ void __launch_bounds__(32)
+sift_orient_kernel(const float *__restrict__ gauss, int w, int h, int octv, const SiftCand *__restrict__ cands,
+                   const int32_t *__restrict__ n_cand, int cand_cap, SiftKp *__restrict__ kps, int32_t *__restrict__ count, int cap) {
+    __shared__ float part[36 * 32];
+    __shared__ float temp[36 + 4];
+    const int n = min(n_cand[0], cand_cap), lane = threadIdx.x;
+    const size_t plane = (size_t)w * h;
+    const float oscale = (float)(1 << octv);
+    for (int idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        const SiftCand k = cands[idx];
+        const int r = k.r, c = k.c;
+        const float scl_octv = k.size * 0.5f / oscale;
+        const int radius = __float2int_rn(4.5f * scl_octv);
+        const float sigma = 1.5f * scl_octv, expf_scale = -1.f / (2.f * sigma * sigma);
+        const float *gimg = gauss + k.layer * plane;
+        for (int b = 0; b < 36; ++b) part[b * 32 + lane] = 0.f;
+        for (int i = -radius + lane; i <= radius; i += 32) {
+            const int y = r + i;
+            if (y <= 0 || y >= h - 1) continue;
+            for (int j = -radius; j <= radius; ++j) {
+                const int x = c + j;
+                if (x <= 0 || x >= w - 1) continue;
+                const float dx = gimg[(size_t)y * w + x + 1] - gimg[(size_t)y * w + x - 1];
+                const float dy = gimg[(size_t)(y - 1) * w + x] - gimg[(size_t)(y + 1) * w + x];
+                const float wgt = expf((float)(i * i + j * j) * expf_scale);
+                int bin = __float2int_rn((36.f / 360.f) * orb::fast_atan2(dy, dx));
+                if (bin >= 36) bin -= 36;
+                if (bin < 0) bin += 36;
+                part[bin * 32 + lane] += wgt * sqrtf(dx * dx + dy * dy);
             }
         }
+        __syncthreads();
+        for (int b = lane; b < 36; b += 32) {   // the 32 partials of a bin, in lane order
+            float sum = 0.f;
+            for (int l = 0; l < 32; ++l) sum += part[b * 32 + l];
+            temp[2 + b] = sum;
+        }
+        __syncthreads();
+        if (lane == 0) {
+            temp[0] = temp[36]; temp[1] = temp[37]; temp[38] = temp[2]; temp[39] = temp[3];
+            float hist[36], omax = 0.f;
+            for (int i = 0; i < 36; ++i) {
+                hist[i] = (temp[i] + temp[i + 4]) * (1.f / 16.f) + (temp[i + 1] + temp[i + 3]) * (4.f / 16.f) + temp[i + 2] * (6.f / 16.f);
+                omax = i == 0 ? hist[0] : fmaxf(omax, hist[i]);
+            }
+            const float mag_thr = omax * 0.8f;
+            for (int j = 0; j < 36; ++j) {
+                const int l = j > 0 ? j - 1 : 35, r2 = j < 35 ? j + 1 : 0;
+                if (hist[j] > hist[l] && hist[j] > hist[r2] && hist[j] >= mag_thr) {
+                    float bin = j + 0.5f * (hist[l] - hist[r2]) / (hist[l] - 2.f * hist[j] + hist[r2]);
+                    bin = bin < 0.f ? 36.f + bin : (bin >= 36.f ? bin - 36.f : bin);
+                    float ang = 360.f - (360.f / 36.f) * bin;
+                    if (fabsf(ang - 360.f) < 1.1920929e-07f) ang = 0.f;
+                    const int o = atomicAdd(count, 1);
+                    if (o < cap) {
+                        SiftKp q;
+                        q.x = (c + k.xc) * oscale; q.y = (r + k.xr) * oscale; q.size = k.size; q.angle = ang; q.resp = fabsf(k.contr);
+                        q.octave = k.octave;
+                        kps[o] = q;
+                    }
+                }
+            }
+        }
+        __syncthreads();   // part[] / temp[] are reused by the next candidate of this CTA
     }
 }
 
@@ -248,13 +314,26 @@ __device__ __forceinline__ bool sift_before(const SiftKp &a, int ia, const SiftK
     if (a.octave != b.octave) return a.octave > b.octave;
     return ia < ib;
 }
-__global__ void sift_rank_kernel(const SiftKp *__restrict__ kps, const int32_t *__restrict__ count, int cap, SiftKp *__restrict__ sorted) {
+// rank = number of records ordered before this one; the list is streamed through shared-memory tiles (a thread compared its
+// record with 3000 others straight from global memory before: 410 us per frame, latency-bound)
+constexpr int SIFT_RANK_T = 256;
+__global__ void __launch_bounds__(SIFT_RANK_T)
+sift_rank_kernel(const SiftKp *__restrict__ kps, const int32_t *__restrict__ count, int cap, SiftKp *__restrict__ sorted) {
+    __shared__ SiftKp tile[SIFT_RANK_T];
     const int n = min(count[0], cap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const SiftKp k = kps[i];
+    for (int i0 = blockIdx.x * SIFT_RANK_T; i0 < n; i0 += gridDim.x * SIFT_RANK_T) {   // block-uniform loop: barriers inside
+        const int i = i0 + threadIdx.x;
+        SiftKp k = kps[min(i, n - 1)];
         int rank = 0;
-        for (int j = 0; j < n; ++j) rank += sift_before(kps[j], j, k, i);
-        sorted[rank] = k;
+        for (int j0 = 0; j0 < n; j0 += SIFT_RANK_T) {
+            const int m = min(SIFT_RANK_T, n - j0);
+            if ((int)threadIdx.x < m) tile[threadIdx.x] = kps[j0 + threadIdx.x];
+            __syncthreads();
+            if (i < n)
+                for (int j = 0; j < m; ++j) rank += sift_before(tile[j], j0 + j, k, i);
+            __syncthreads();
+        }
+        if (i < n) sorted[rank] = k;
     }
 }
 // Drop records that repeat (x, y, size, angle) of their predecessor, keep the order.  One CTA; chunks of blockDim.
@@ -382,6 +461,25 @@ sift_desc_kernel(SiftGeom G, const float *__restrict__ gauss, const SiftKp *__re
     }
 }
 
+// row pass src -> tmp, column pass tmp -> dst with kernel ki; the unrolled instantiation when the length is one of the scale space's
+int sift_blur(vo_ctx *ctx, dim3 grid, cudaStream_t st, const float *src, int w, int h, const SiftKernels &K, int ki, float *tmp, float *dst) {
+#define VO_SIFT_BLUR(N)                                                                  \
+    VO_LAUNCH(sift_blur_row_kernel<N>, grid, 128, st, src, w, h, K, ki, tmp);            \
+    VO_LAUNCH_CHECK(ctx);                                                                \
+    VO_LAUNCH(sift_blur_col_kernel<N>, grid, 128, st, tmp, w, h, K, ki, dst)
+    switch (K.ksize[ki]) {
+        case 11: VO_SIFT_BLUR(11); break;
+        case 13: VO_SIFT_BLUR(13); break;
+        case 17: VO_SIFT_BLUR(17); break;
+        case 21: VO_SIFT_BLUR(21); break;
+        case 27: VO_SIFT_BLUR(27); break;
+        default: VO_SIFT_BLUR(0); break;
+    }
+#undef VO_SIFT_BLUR
+    VO_LAUNCH_CHECK(ctx);
+    return VO_OK;
+}
+
 }  // namespace
 }  // namespace vo
 
@@ -392,14 +490,15 @@ struct vo_sift {
     vo::SiftKernels K;
     float *gauss, *dog, *tmp;
     vo::SiftKp *kps, *sorted, *uniq;
-    int32_t *counts;   // [0] raw count, [1] final count
+    int32_t *counts;   // [0] raw count, [1] final count, [2] candidates of the octave in flight
+    vo::SiftCand *cands;
 };
 
 extern "C" void vo_sift_destroy(vo_sift *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {s->gauss, s->dog, s->tmp, s->kps, s->sorted, s->uniq, s->counts};
+    void *ptrs[] = {s->gauss, s->dog, s->tmp, s->kps, s->sorted, s->uniq, s->counts, s->cands};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete s;
@@ -451,6 +550,7 @@ extern "C" int vo_sift_create(vo_ctx *ctx, const vo_sift_config *cfg, vo_sift **
     alloc((void **)&s->gauss, g_ofs * 4); alloc((void **)&s->dog, d_ofs * 4); alloc((void **)&s->tmp, (size_t)bw * bh * 4);
     alloc((void **)&s->kps, sizeof(SiftKp) * (size_t)s->cap); alloc((void **)&s->sorted, sizeof(SiftKp) * (size_t)s->cap);
     alloc((void **)&s->uniq, sizeof(SiftKp) * (size_t)s->cap); alloc((void **)&s->counts, sizeof(int32_t) * 4);
+    alloc((void **)&s->cands, sizeof(SiftCand) * (size_t)s->cap);
     if (e != cudaSuccess) {
         set_error("vo_sift_create: cudaMalloc -> %s", cudaGetErrorString(e));
         vo_sift_destroy(s);
@@ -475,10 +575,7 @@ extern "C" int vo_sift_extract(vo_sift *s, const uint8_t *image, int channels, f
     float *scratch = g00 + (size_t)o0.w * o0.h;
     VO_LAUNCH(sift_upsample_kernel, dim3(ceil_div(o0.w, 128), o0.h), 128, st, image, channels, s->W, s->H, scratch);
     VO_LAUNCH_CHECK(ctx);
-    VO_LAUNCH(sift_blur_row_kernel, dim3(ceil_div(o0.w, 128), o0.h), 128, st, scratch, o0.w, o0.h, s->K, 0, s->tmp);
-    VO_LAUNCH_CHECK(ctx);
-    VO_LAUNCH(sift_blur_col_kernel, dim3(ceil_div(o0.w, 128), o0.h), 128, st, s->tmp, o0.w, o0.h, s->K, 0, g00);
-    VO_LAUNCH_CHECK(ctx);
+    if (int rc = sift_blur(ctx, dim3(ceil_div(o0.w, 128), o0.h), st, scratch, o0.w, o0.h, s->K, 0, s->tmp, g00)) return rc;
     const int threshold = (int)floor(0.5 * 0.04 / SIFT_LAYERS * 255);
     for (int o = 0; o < G.n_oct; ++o) {
         const SiftOct &oc = G.o[o];
@@ -491,22 +588,22 @@ extern "C" int vo_sift_extract(vo_sift *s, const uint8_t *image, int channels, f
             VO_LAUNCH_CHECK(ctx);
         }
         for (int i = 1; i < SIFT_G; ++i) {
-            VO_LAUNCH(sift_blur_row_kernel, grid, 128, st, g + (i - 1) * plane, oc.w, oc.h, s->K, i, s->tmp);
-            VO_LAUNCH_CHECK(ctx);
-            VO_LAUNCH(sift_blur_col_kernel, grid, 128, st, s->tmp, oc.w, oc.h, s->K, i, g + i * plane);
-            VO_LAUNCH_CHECK(ctx);
+            if (int rc = sift_blur(ctx, grid, st, g + (i - 1) * plane, oc.w, oc.h, s->K, i, s->tmp, g + i * plane)) return rc;
         }
         VO_LAUNCH(sift_dog_kernel, dim3(ceil_div(oc.w, 128), SIFT_D * oc.h), 128, st, g, oc.w, oc.h, d);
         VO_LAUNCH_CHECK(ctx);
         if (oc.w > 2 * SIFT_BORDER && oc.h > 2 * SIFT_BORDER) {
-            VO_LAUNCH(sift_extrema_kernel, dim3(ceil_div(oc.w, 128), SIFT_LAYERS * oc.h), 128, st, d, g, oc.w, oc.h, o, threshold,
-                      s->kps, s->counts, s->cap);
+            VO_CUDA(cudaMemsetAsync(s->counts + 2, 0, sizeof(int32_t), st));
+            VO_LAUNCH(sift_extrema_kernel, dim3(ceil_div(oc.w, 128), SIFT_LAYERS * oc.h), 128, st, d, oc.w, oc.h, o, threshold,
+                      s->cands, s->counts + 2, s->cap);
+            VO_LAUNCH_CHECK(ctx);
+            VO_LAUNCH_BAR(sift_orient_kernel, 1184, 32, st, g, oc.w, oc.h, o, s->cands, s->counts + 2, s->cap, s->kps, s->counts, s->cap);
             VO_LAUNCH_CHECK(ctx);
         }
     }
     VO_LAUNCH(sift_rescale_kernel, 32, 256, st, s->kps, s->counts, s->cap);
     VO_LAUNCH_CHECK(ctx);
-    VO_LAUNCH(sift_rank_kernel, 64, 256, st, s->kps, s->counts, s->cap, s->sorted);
+    VO_LAUNCH_BAR(sift_rank_kernel, 64, SIFT_RANK_T, st, s->kps, s->counts, s->cap, s->sorted);
     VO_LAUNCH_CHECK(ctx);
     VO_LAUNCH_BAR(sift_unique_kernel, 1, 1024, st, s->sorted, s->counts, s->cap, s->uniq, s->counts + 1);
     VO_LAUNCH_CHECK(ctx);
