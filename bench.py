@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (descriptor kind, keypoints, hypotheses, matcher description, cpu matcher)
-    "c1": dict(kind="sift", n_kp=2000, n_hyp=512, pairs=256, chunk=256, shape="kitti", cpu_matcher="knn_ratio",
+    "c1": dict(kind="sift", n_kp=2000, n_hyp=512, pairs=512, chunk=256, shape="kitti", cpu_matcher="knn_ratio",
                desc="SIFT 2k kp, L2 kNN-2 + ratio 0.85, PnP-RANSAC 512 hyp, KITTI 1241x376"),
     "c2": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="hamming_mutual", e2e_sampled_frac=0.4,
                desc="ORB 5k kp, 256-bit Hamming mutual-NN, PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
@@ -45,7 +45,7 @@ WORKLOADS = {
     "c3": dict(kind="r2d2", n_kp=10000, n_hyp=4096, pairs=128, chunk=64, shape="kitti", cpu_matcher="r2d2",
                desc="R2D2 10k kp, cosine GEMM-argmin ratio+mutual, PnP-RANSAC 4096 hyp, KITTI 1241x376"),
     # the two multi-GPU configurations of BASELINE.json (per-GPU block of the sharded sequence; weak scaling)
-    "c4": dict(kind="sift", n_kp=20000, n_hyp=16384, pairs=32, chunk=32, shape="kitti", cpu_matcher="knn_ratio", unique=8,
+    "c4": dict(kind="sift", n_kp=20000, n_hyp=16384, pairs=64, chunk=32, shape="kitti", cpu_matcher="knn_ratio", unique=8,
                desc="SIFT 20k kp, L2 kNN-2 + ratio 0.85, PnP-RANSAC 16384 hyp, KITTI 1241x376"),
     "c5": dict(kind="r2d2", n_kp=50000, n_hyp=4096, pairs=8, chunk=8, shape="zed", cpu_matcher="r2d2", unique=4,
                desc="R2D2 50k kp, cosine GEMM-argmin ratio+mutual, PnP-RANSAC 4096 hyp, ZED-Mini-shaped 2208x1242"),
@@ -328,11 +328,16 @@ def run_ours(args, name):
     # R2D2 workloads: the reference never holds R2D2 descriptors on the host — its network runs on the GPU and Frame.desc stays a
     # CUDA tensor (R2D2.py:224-232) — so the reference-facing call gets device descriptors and host keypoints /
     # depth: that is `e2e`; the same run with the descriptors uploaded from host memory too is reported as e2e.all_from_host.
-    def measure_e2e(desc_on_device):
+    def measure_e2e(desc_on_device, desc_u8=False):
         src = {**host["_pinned"], "K": host["K"]}
+        run_cfg = cfg
         if desc_on_device:
             src["desc"] = seq.desc
-        runner = sequence.HostSequenceRunner(src, cfg, chunk=min(args.e2e_chunk or max(1, chunk // 2), P), device=dev, depth_mode=args.e2e_depth,
+        if desc_u8:   # SIFT values (integers 0..255) held as uint8: a quarter of the bytes, the same exact arithmetic on the device
+            src["desc"] = host["_pinned"]["desc"].to(torch.uint8).pin_memory()
+            run_cfg = sequence.PipelineConfig(n_hyp=wl["n_hyp"], norm_or_metric=ops.VO_NORM_L2_U8, mode=mc["mode"],
+                                              match_param=mc["match_param"], precision=0)
+        runner = sequence.HostSequenceRunner(src, run_cfg, chunk=min(args.e2e_chunk or max(1, chunk // 2), P), device=dev, depth_mode=args.e2e_depth,
                                              sampled_frac=args.e2e_sampled_frac if args.e2e_sampled_frac is not None else wl.get("e2e_sampled_frac", 0.4))
         tune = {}
         if args.e2e_depth == "hybrid" and args.e2e_sampled_frac is None:
@@ -381,6 +386,7 @@ def run_ours(args, name):
     r2d2_like = wl["kind"] == "r2d2"
     em = measure_e2e(desc_on_device=r2d2_like)
     em_host = measure_e2e(desc_on_device=False) if r2d2_like else None
+    em_u8 = measure_e2e(desc_on_device=False, desc_u8=True) if wl["kind"] == "sift" else None
     e2e_value, e2e_ms, Re, tune, e2e_same, h2d_pass, d2h_pass = em["value"], em["ms"], em["Re"], em["tune"], em["same"], em["h2d"], em["d2h"]
 
     if rank != 0:
@@ -572,6 +578,13 @@ def run_ours(args, name):
                                  "frames (descriptors, keypoints, depth maps) are in PINNED host memory when the timed region starts") +
                                 "; every frame crosses the bus once per pass, poses / status / inlier counts come back, host-side gating + "
                                 "pose chaining included",
+                "u8_descriptors": (None if em_u8 is None else
+                                   {"value": em_u8["value"], "frac_of_resident": em_u8["value"] / value, "h2d_bytes_per_step": int(em_u8["h2d"] * em_u8["Re"]),
+                                    "h2d_gbs_per_gpu": em_u8["h2d"] * em_u8["Re"] * args.steps / (em_u8["ms"] / 1e3) / 1e9,
+                                    "sampled_frac": em_u8["frac"], "equals_resident_bitwise": em_u8["same"],
+                                    "precondition": "as e2e, but the SIFT descriptors are held as uint8 in pinned host memory (OpenCV's SIFT "
+                                                    "descriptors are integers 0..255 stored as float32; vo_match_u8 with 128-byte rows / "
+                                                    "vo_pipeline_args.u8_bytes = 128 widens them on the device: identical matches and poses)"}),
                 "all_from_host": (None if em_host is None else
                                   {"value": em_host["value"], "frac_of_resident": em_host["value"] / value, "h2d_bytes_per_step": int(em_host["h2d"] * em_host["Re"]),
                                    "h2d_gbs_per_gpu": em_host["h2d"] * em_host["Re"] * args.steps / (em_host["ms"] / 1e3) / 1e9,

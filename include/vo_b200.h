@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VO_ABI_VERSION 1
+#define VO_ABI_VERSION 2   /* 2: vo_pipeline_args.u8_bytes, vo_pnp_ransac_ref, VO_NORM_HAMMING_TC, vo_orb_debug_read */
 
 #if defined(__GNUC__)
 #define VO_API __attribute__((visibility("default")))
@@ -243,6 +243,10 @@ typedef struct vo_pipeline_args {
     /* optional: depth already sampled at every reference keypoint (vo_sample_depth), float [B][n_stride];
      * when non-NULL it replaces the dense `depth` lookup */
     const float *depth_kp;
+    /* bytes per descriptor of the (ref_u8, cur_u8) pair: 0 or 32 = 256-bit descriptors; 128 = 128-d descriptors whose values are
+     * integers 0..255 held as uint8 (OpenCV SIFT: a quarter of the float32 bytes over the bus, same exact results) — with
+     * VO_NORM_L2_U8 and a rule without a column side (VO_MODE_RATIO / VO_MODE_NN) only */
+    int u8_bytes;
 } vo_pipeline_args;
 
 VO_API int vo_pipeline(vo_ctx *ctx, const vo_pipeline_args *args, void *stream);

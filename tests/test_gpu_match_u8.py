@@ -212,3 +212,29 @@ def test_tensor_core_hamming_ragged_batch(orc):
         assert np.array_equal(a.knn_idx[i, :nr].cpu().numpy(), t.knn_idx[i, :nr].cpu().numpy())
         assert np.array_equal(a.knn_val[i, :nr].cpu().numpy(), t.knn_val[i, :nr].cpu().numpy())
         assert np.array_equal(a.col_idx[i, :nc].cpu().numpy(), t.col_idx[i, :nc].cpu().numpy())
+
+
+def test_sift_values_as_uint8_equal_the_float32_path(golden):
+    """128-byte rows under VO_NORM_L2_U8 (OpenCV SIFT descriptors are integers 0..255: uint8 holds them exactly, a quarter of
+    the bytes over the bus): same 2-NN, same distances, same accepted pairs as the float32 matcher and as cv2.knnMatch."""
+    import torch
+    from vo_b200 import ops, synthetic
+    g = golden("match_f32_sift.npz")
+    ref, cur = g["ref"], g["cur"]
+    assert np.array_equal(ref, np.rint(ref)) and ref.min() >= 0 and ref.max() <= 255
+    f = ops.match_f32(_gpu(ref), _gpu(cur), ops.VO_METRIC_L2, ops.VO_MODE_RATIO, 0.85, precision=ops.VO_PREC_F16X1, want_knn="rows")
+    u = ops.match_u8(_gpu(ref.astype(np.uint8)), _gpu(cur.astype(np.uint8)), ops.VO_NORM_L2_U8, ops.VO_MODE_RATIO, 0.85, want_knn="rows")
+    assert np.array_equal(_pairs(f), _pairs(u)) and len(_pairs(u)) > 10
+    assert np.array_equal(f.knn_idx[0].cpu().numpy(), u.knn_idx[0].cpu().numpy())
+    assert np.array_equal(f.knn_val[0].cpu().numpy(), u.knn_val[0].cpu().numpy())
+    k = int(u.count[0])
+    assert np.array_equal(f.dist[0, :k].cpu().numpy(), u.dist[0, :k].cpu().numpy())
+    # ragged batch through the whole pipeline: identical poses
+    b = synthetic.make_batch(3, 2, n_kp=1300, kind="sift")
+    args = [_gpu(b[k]) for k in ("ref_kp", "cur_kp", "depth")]
+    pf = ops.pipeline(_gpu(b["ref_desc"]), _gpu(b["cur_desc"]), *args, b["K"], norm_or_metric=ops.VO_METRIC_L2, mode=ops.VO_MODE_RATIO,
+                      match_param=0.85, precision=ops.VO_PREC_F16X1, n_hyp=256)
+    pu = ops.pipeline(_gpu(b["ref_desc"].astype(np.uint8)), _gpu(b["cur_desc"].astype(np.uint8)), *args, b["K"],
+                      norm_or_metric=ops.VO_NORM_L2_U8, mode=ops.VO_MODE_RATIO, match_param=0.85, precision=0, n_hyp=256)
+    torch.cuda.synchronize()
+    assert np.array_equal(pf.T_rel.cpu().numpy(), pu.T_rel.cpu().numpy()) and np.array_equal(pf.n_matches.cpu().numpy(), pu.n_matches.cpu().numpy())

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvo_b200.so")
 
 # ---- constants mirrored from include/vo_b200.h ---------------------------------------------
-VO_ABI_VERSION = 1
+VO_ABI_VERSION = 2
 VO_OK, VO_ERR_ARG, VO_ERR_CUDA, VO_ERR_UNSUPPORTED = 0, -1, -2, -3
 VO_ST_OK, VO_ST_NO_MODEL, VO_ST_TOO_FEW_POINTS, VO_ST_KP_OUT_OF_IMAGE = 0, 1, 2, 4
 VO_NORM_HAMMING, VO_NORM_L2_U8, VO_NORM_HAMMING_TC = 0, 1, 2
@@ -51,6 +51,7 @@ class PipelineArgs(ctypes.Structure):
         ("T_rel", c_void_p), ("rt", c_void_p),
         ("n_matches", c_void_p), ("n_corr", c_void_p), ("n_inl", c_void_p), ("status", c_void_p),
         ("depth_kp", c_void_p),
+        ("u8_bytes", c_int),
     ]
 
 

@@ -217,7 +217,7 @@ int vo::pipeline_impl(vo_ctx *ctx, const vo_pipeline_args *a, void *stream, cons
     int32_t *hyp = (int32_t *)(ws + off_hyp);
 
     if (u8)
-        rc = vo_match_u8(ctx, a->ref_u8, a->cur_u8, B, a->n_stride, a->m_stride, a->n_ref, a->n_cur, 32,
+        rc = vo_match_u8(ctx, a->ref_u8, a->cur_u8, B, a->n_stride, a->m_stride, a->n_ref, a->n_cur, a->u8_bytes ? a->u8_bytes : 32,
                          a->norm_or_metric, a->mode, a->match_param, pairs, nullptr, a->n_matches, nullptr, stream);
     else
         rc = vo_match_f32(ctx, a->ref_f32, a->cur_f32, B, a->n_stride, a->m_stride, a->n_ref, a->n_cur, 128,

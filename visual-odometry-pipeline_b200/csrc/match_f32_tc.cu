@@ -159,31 +159,33 @@ prep16_kernel(const float *__restrict__ x, long long rows, __half *__restrict__ 
     }
 }
 
-// byte descriptors (32 per row, the reference's ORB semantics: BFMatcher NORM_L2 over byte values) as fp16 rows of 32
-// values; the matcher treats them as 128-d rows that are zero beyond the 32nd element (TMA out-of-bounds fill for B,
-// a bounds test in the A load): every value, product and partial sum is an exact integer, as for SIFT
+// byte descriptors as fp16 rows: ROW_BYTES = 32 (the reference's ORB semantics: BFMatcher NORM_L2 over byte values; the matcher
+// treats them as 128-d rows that are zero beyond the 32nd element — TMA out-of-bounds fill for B, a bounds test in the A load)
+// or 128 (SIFT descriptors shipped as uint8: they are integers 0..255, a quarter of the float32 bytes over the bus).  Every
+// value, product and partial sum is an exact integer, as for float32 SIFT.
+template <int ROW_BYTES>
 __global__ void __launch_bounds__(256)
 prep16_u8_kernel(const uint8_t *__restrict__ x, long long rows, __half *__restrict__ h16, float *__restrict__ norm2,
                  float *__restrict__ ext) {
-    // eight lanes per row (4 bytes each), four rows per warp, 32 rows per block
-    const int lane = threadIdx.x & 31, sub = lane & 7;
-    const long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 5) * 4 + (lane >> 3);
+    constexpr int LPR = ROW_BYTES / 4, RPW = 32 / LPR;   // lanes per row (4 bytes each), rows per warp
+    const int lane = threadIdx.x & 31, sub = lane % LPR;
+    const long long row = (long long)blockIdx.x * (8 * RPW) + (threadIdx.x >> 5) * RPW + lane / LPR;
     const bool ok = row < rows;
     float s = 0.f;
-    if (ok) {  // compact fp16 rows of 32 values: TMA zero-fills the other 96 dimensions of every box (out of bounds)
-        const uchar4 v = reinterpret_cast<const uchar4 *>(x)[row * 8 + sub];
+    if (ok) {  // compact fp16 rows of ROW_BYTES values
+        const uchar4 v = reinterpret_cast<const uchar4 *>(x)[row * LPR + sub];
         const __half2 p0 = __floats2half2_rn((float)v.x, (float)v.y), p1 = __floats2half2_rn((float)v.z, (float)v.w);
         uint2 w;
         w.x = *reinterpret_cast<const uint32_t *>(&p0);
         w.y = *reinterpret_cast<const uint32_t *>(&p1);
         s = (float)((int)v.x * v.x + (int)v.y * v.y + (int)v.z * v.z + (int)v.w * v.w);
-        reinterpret_cast<uint2 *>(h16)[row * 8 + sub] = w;
+        reinterpret_cast<uint2 *>(h16)[row * LPR + sub] = w;
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));  // integers < 2^21: exact
+    for (int o = LPR / 2; o > 0; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));  // integers < 2^24: exact
     if (!ok) return;
     if (sub == 0) norm2[row] = s;
-    if (ext) {
+    if (ext && sub < 8) {
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
         if (sub == 0) {
             const float n1 = to_tf32(s), n2 = to_tf32(__fsub_rn(s, n1));
@@ -1076,9 +1078,10 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
                  const int32_t *n_ref, const int32_t *n_cur, int metric, int passes, int need_cols,
                  vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey, const float **row_norm_out,
                  cudaStream_t st, int src_u8) {
-    // src_u8: ref / cur are 32-byte descriptors (uint8 [rows][32]); only the fp16 single pass without column side takes them
-    if (src_u8 && (passes != 16 || need_cols || metric != VO_METRIC_L2)) {
-        set_error("match_f32_tc: byte descriptors run the fp16 single pass (L2, no column arg-min) only");
+    // src_u8 = 32 / 128: ref / cur are byte descriptors (uint8 [rows][src_u8]) compared as byte values; only the fp16 single pass
+    // without column side takes them
+    if (src_u8 && (passes != 16 || need_cols || metric != VO_METRIC_L2 || (src_u8 != 32 && src_u8 != 128))) {
+        set_error("match_f32_tc: byte descriptors (32 or 128 per row) run the fp16 single pass (L2, no column arg-min) only");
         return VO_ERR_ARG;
     }
     if (!ctx->tc_ready) {
@@ -1100,7 +1103,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     int rc;
     const bool f16 = passes == 16, h16 = passes == 16 || passes == 48, three = passes == 3 || passes == 48;
     const size_t esz = h16 ? sizeof(__half) : sizeof(float);
-    const int row_elems = src_u8 ? 32 : TC_D;  // stored elements per descriptor row
+    const int row_elems = src_u8 ? src_u8 : TC_D;  // stored elements per descriptor row
     const size_t per_a = (size_t)rows_a * row_elems * esz, per_b = (size_t)rows_b * row_elems * esz;
     if ((rc = ws_get(ctx, WS_SPLIT_A, per_a * (three ? 2 : 1), (void **)&split_a))) return rc;
     const bool ext = !three && l2;  // B extension rows [rows_b][32] live behind B_hi
@@ -1120,9 +1123,15 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
         prep16x3_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, reinterpret_cast<__half *>(b_hi), reinterpret_cast<__half *>(b_lo), l2 ? col_norm : nullptr);
         VO_LAUNCH_CHECK(ctx);
     } else if (f16 && src_u8) {
-        prep16_u8_kernel<<<(unsigned)((rows_a + 31) / 32), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(ref), rows_a, reinterpret_cast<__half *>(a_hi), row_norm, nullptr);
-        VO_LAUNCH_CHECK(ctx);
-        prep16_u8_kernel<<<(unsigned)((rows_b + 31) / 32), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(cur), rows_b, reinterpret_cast<__half *>(b_hi), col_norm, b_ext);
+        if (src_u8 == 32) {
+            prep16_u8_kernel<32><<<(unsigned)((rows_a + 31) / 32), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(ref), rows_a, reinterpret_cast<__half *>(a_hi), row_norm, nullptr);
+            VO_LAUNCH_CHECK(ctx);
+            prep16_u8_kernel<32><<<(unsigned)((rows_b + 31) / 32), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(cur), rows_b, reinterpret_cast<__half *>(b_hi), col_norm, b_ext);
+        } else {
+            prep16_u8_kernel<128><<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(ref), rows_a, reinterpret_cast<__half *>(a_hi), row_norm, nullptr);
+            VO_LAUNCH_CHECK(ctx);
+            prep16_u8_kernel<128><<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(cur), rows_b, reinterpret_cast<__half *>(b_hi), col_norm, b_ext);
+        }
         VO_LAUNCH_CHECK(ctx);
     } else if (f16) {
         prep16_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, reinterpret_cast<__half *>(a_hi), l2 ? row_norm : nullptr, nullptr);

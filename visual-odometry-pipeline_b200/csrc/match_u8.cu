@@ -227,7 +227,8 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
                            void *stream) {
     using namespace vo;
     VO_REQUIRE(ctx, "vo_match_u8: null ctx");
-    VO_REQUIRE(bytes == 32, "vo_match_u8: only 32-byte (256-bit) descriptors are supported, got %d", bytes);
+    VO_REQUIRE(bytes == 32 || (bytes == 128 && norm == VO_NORM_L2_U8),
+               "vo_match_u8: 32-byte (256-bit) descriptors, or 128-byte descriptors under VO_NORM_L2_U8 (SIFT values as uint8), got %d", bytes);
     VO_REQUIRE(norm == VO_NORM_HAMMING || norm == VO_NORM_L2_U8 || norm == VO_NORM_HAMMING_TC, "vo_match_u8: bad norm %d", norm);
     VO_REQUIRE(mode >= VO_MODE_RATIO && mode <= VO_MODE_NN, "vo_match_u8: bad mode %d", mode);
     VO_REQUIRE(mode != VO_MODE_THRESH && mode != VO_MODE_THRESH_MUTUAL && mode != VO_MODE_RATIO_MUTUAL,
@@ -248,7 +249,8 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
     // pass SIFT uses, bytes widened to fp16 and zero-padded to 128 dimensions (3x the CUDA-core kernel: the pass is bound
     // by its row top-2 epilogue, not by the padded GEMM).  Same scores (exact integers), same tie rule, same finalize.
     const bool need_cols = mode == VO_MODE_MUTUAL || (knn && knn->col_idx);
-    if (norm == VO_NORM_L2_U8 && !need_cols && !getenv("VO_U8_L2_SIMT")) {
+    VO_REQUIRE(bytes == 32 || !need_cols, "vo_match_u8: 128-byte descriptors support the rules without a column side (ratio, NN)");
+    if (norm == VO_NORM_L2_U8 && !need_cols && (bytes == 128 || !getenv("VO_U8_L2_SIMT"))) {
         int rc;
         unsigned long long *colkey_tc;
         if ((rc = ws_get(ctx, WS_COLKEY, sizeof(unsigned long long) * (size_t)B * m_stride, (void **)&colkey_tc))) return rc;
@@ -256,7 +258,7 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
         const float *row_norm_tc = nullptr;
         int n_split_tc;
         if ((rc = match_f32_tc(ctx, reinterpret_cast<const float *>(ref), reinterpret_cast<const float *>(cur), B, n_stride,
-                               m_stride, n_ref, n_cur, VO_METRIC_L2, 16, 0, &part_tc, &n_split_tc, colkey_tc, &row_norm_tc, st, 1)))
+                               m_stride, n_ref, n_cur, VO_METRIC_L2, 16, 0, &part_tc, &n_split_tc, colkey_tc, &row_norm_tc, st, bytes)))
             return rc;
         return match_finalize(ctx, part_tc, n_split_tc, colkey_tc, B, n_stride, m_stride, n_ref, n_cur, SCORE_L2SQ_F32, mode,
                               ratio, row_norm_tc, out_pairs, out_dist, out_count, knn, nullptr, st);

@@ -351,6 +351,7 @@ def pipeline(ref_desc, cur_desc, ref_kp, cur_kp, depth, K, *, norm_or_metric, mo
     a.n_ref, a.n_cur = (n_ref.data_ptr() if n_ref is not None else None), (n_cur.data_ptr() if n_cur is not None else None)
     if ref_desc.dtype == torch.uint8:
         a.ref_u8, a.cur_u8 = ref_desc.data_ptr(), cur_desc.data_ptr()
+        a.u8_bytes = int(ref_desc.shape[2])          # 32: 256-bit descriptors; 128: SIFT values as uint8 (VO_NORM_L2_U8)
     elif ref_desc.dtype == torch.float32:
         a.ref_f32, a.cur_f32 = ref_desc.data_ptr(), cur_desc.data_ptr()
     else:
