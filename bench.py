@@ -315,6 +315,38 @@ def run_ours(args, name):
     ms = agree_max(ms)
     value = world * P * R * args.steps / (ms / 1e3)
 
+    # ---- matcher variants of the same workload, resident, same pairs, same R (reported beside the headline, never as it):
+    # c2: the Hamming distances on the tensor cores (bit-identical matches); c3 / c5: the split-fp16 form of the 3xTF32 GEMM
+    variants = {}
+    var_cfgs = {"orb": [("hamming_tc", dict(norm_or_metric=ops.VO_NORM_HAMMING_TC))] if not (wl.get("orb_l2") or wl.get("hamming_tc")) else [],
+                "r2d2": [("f16x3", dict(precision=ops.VO_PREC_F16X3))] if mc["precision"] == ops.VO_PREC_TF32X3 else []}.get(wl["kind"], [])
+    Tn_main = out.T_rel.cpu().numpy().copy()
+    for vname, override in ([] if args.no_variants else var_cfgs):
+        vcfg = sequence.PipelineConfig(n_hyp=wl["n_hyp"], **{**mc, **override})
+        vout = ops.PipelineBuffers(P, dev)
+
+        def vpass():
+            sequence.run_resident(seq, vcfg, pair0=rank * P, chunk=chunk, out=vout)
+            if world > 1:
+                sequence.all_gather_poses(vout.T_rel, vout.status, world)
+        for _ in range(2):
+            vpass()
+        barrier()
+        ops.profile_enable(True); ops.profile_collect()
+        e0.record()
+        for _ in range(args.steps * R):
+            vpass()
+        e1.record()
+        barrier()
+        vms = agree_max(e0.elapsed_time(e1))
+        vst = ops.profile_collect(); ops.profile_enable(False)
+        variants[vname] = {"value": world * P * R * args.steps / (vms / 1e3), "unit": "pairs/s", "timed_region_s": vms / 1e3,
+                           "match_ms_per_launch": vst["match"][0] / max(vst["match"][1], 1),
+                           "prep_ms_per_launch": vst["prep"][0] / max(vst["prep"][1], 1),
+                           "max_abs_pose_diff_vs_headline": float(np.abs(vout.T_rel.cpu().numpy() - Tn_main).max()),
+                           "same_status": bool(np.array_equal(vout.status.cpu().numpy(), out.status.cpu().numpy()))}
+        del vout
+
     # sanity of the work done inside the timed region (not a parity test: tests/ does that)
     st = out.status.cpu().numpy()
     ok_frac = float((st == 0).mean())
@@ -592,6 +624,7 @@ def run_ours(args, name):
                 "h2d_gbs_per_gpu": h2d_pass * Re * args.steps / (e2e_ms / 1e3) / 1e9},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "variants": variants or None,
         "roofline": roof,
         "kernels": kernels,
         "cpu_baseline": cpu,
@@ -629,6 +662,7 @@ def main():
     ap.add_argument("--precision", type=int, default=None)
     ap.add_argument("--cpu-pairs", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the matcher variants measured beside the headline (hamming_tc, f16x3)")
     ap.add_argument("--allow-no-clocks", action="store_true")
     args = ap.parse_args()
     rank, _, world = env_rank()

@@ -59,6 +59,18 @@ def test_device_loop_equals_host_policy(tmp_path, kind, extra, norm, mode, prec)
         assert np.abs(got - want).max() < 1e-9
         # and the trajectory is right in absolute terms
         assert np.linalg.norm(got[:, :3, 3] - gt[:, :3, 3], axis=1).max() < 0.15
+        # the keyframe decisions against the REFERENCE's loop (oracle/reference_vo.py: pinned pose for pose to the reference's own
+        # class, cv2 matcher + 3 x cv2.solvePnPRansac): the same frames become keyframes, up to one decision that sits on a
+        # threshold (inliers < 100 / common points < 200 / 1.5 m) and flips with the sampler
+        from oracle.reference_vo import ReferenceVO
+        matcher = {"orb": "hamming_mutual" if "hamming" in extra else "knn_ratio", "sift": "knn_ratio", "r2d2": "r2d2"}[kind]
+        ref = ReferenceVO(synthetic.KITTI_K, matcher=matcher)
+        ref_keys, ref_poses = [], []
+        for i, f in enumerate(frames):
+            ref_keys.append(ref.key[0] if i else 0)
+            ref_poses.append(ref.process_frame(f["kp"][:, :2] if kind == "r2d2" else f["kp"], f["desc"], f["depth"], i).copy())
+        assert (np.asarray(ref_keys) != info[:, 4]).sum() <= 1, (ref_keys, info[:, 4].tolist())
+        assert np.linalg.norm(got[:, :3, 3] - np.stack(ref_poses)[:, :3, 3], axis=1).max() < 0.05
     finally:
         os.chdir(cwd)
 
