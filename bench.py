@@ -224,6 +224,78 @@ def run_reference(args, name):
     }
 
 
+def measure_api_rate(wl, dev, n_frames=40):
+    """Frames/s through the REFERENCE-FACING API on one GPU: the drop-in VisualOdometry.process_frame (host keyframe policy, one
+    D2H round trip per frame, the reference's own PnP sampler = pnp_mode: reference) and the device-resident keyframe loop
+    (vo_seq_*, throughput sampler), on a short synthetic sequence of the workload's descriptor kind with precomputed features
+    (feature extraction is outside the metric)."""
+    import contextlib
+    import io
+    import tempfile
+    import torch
+    from vo_b200 import dropin, ops, synthetic, synthetic_sequence
+    from vo_b200.device_loop import DeviceLoop
+    kind = wl["kind"]
+    n_kp = min(wl["n_kp"], 10000)
+    frames, gt = synthetic_sequence.make_sequence(n_frames=n_frames, n_kp=n_kp, kind=kind, seed=3)
+    if kind == "r2d2":      # the reference's R2D2 keypoints are (x, y, scale) float32 rows, its descriptors CUDA tensors
+        for f in frames:
+            f["kp"] = np.concatenate([f["kp"], np.full((len(f["kp"]), 1), 32.0)], 1).astype(np.float32)
+            f["desc"] = torch.from_numpy(f["desc"]).to(dev)
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="vo_api_")
+    out = {"frames": n_frames, "keypoints_per_frame": n_kp}
+    try:
+        extra = "\norb_matcher: hamming_mutual\n" if (kind == "orb" and not wl.get("orb_l2")) else ""
+        vos = dropin.load(tmp, kind, extra)
+        feed = {}
+        vos.extract_features_and_desc = lambda img: feed["cur"]
+        img = np.zeros((synthetic.KITTI_WH[1], synthetic.KITTI_WH[0], 3), np.uint8)
+
+        def run_host():
+            np.random.seed(8214)
+            vo = vos.VisualOdometry(synthetic.KITTI_K, seq=0)
+            poses = []
+            for i, f in enumerate(frames):
+                feed["cur"] = (f["kp"], f["desc"])
+                poses.append(vo.process_frame(img, f["depth"], (100, 100), i).pose.copy())
+            torch.cuda.synchronize()
+            return np.stack(poses), vo
+        with contextlib.redirect_stdout(io.StringIO()):
+            run_host()
+            t0 = time.perf_counter()
+            poses, vo = run_host()
+            t_host = time.perf_counter() - t0
+        out["dropin_process_frame_fps"] = n_frames / t_host
+        out["dropin_pnp_mode"] = vo.pnp_mode
+        out["dropin_bad_pnp"] = int(vo.bad_pnp)
+        out["dropin_max_pos_err_m"] = float(np.linalg.norm(poses[:, :3, 3] - gt[:, :3, 3], axis=1).max())
+    finally:
+        os.chdir(cwd)
+    mc = matcher_cfg(kind, ops, wl)
+    pinned = [(torch.from_numpy(np.ascontiguousarray(f["kp"], dtype=np.float32)).pin_memory(),
+               f["desc"] if isinstance(f["desc"], torch.Tensor) else torch.from_numpy(f["desc"]).pin_memory(),
+               torch.from_numpy(f["depth"]).pin_memory()) for f in frames]
+
+    def run_dev():
+        loop = DeviceLoop(synthetic.KITTI_K, synthetic.KITTI_WH, n_kp, kind=kind, norm_or_metric=mc["norm_or_metric"], mode=mc["mode"],
+                          match_param=mc["match_param"] or 0.85, precision=mc["precision"] or None, n_hyp=min(wl["n_hyp"], 1024),
+                          kp_stride=3 if kind == "r2d2" else 2)
+        for i, (kp, d, z) in enumerate(pinned):
+            loop.push(kp, d, z, i)
+        res = loop.poses()
+        loop.close()
+        return res
+    run_dev()
+    t0 = time.perf_counter()
+    got, info = run_dev()
+    out["device_loop_fps"] = n_frames / (time.perf_counter() - t0)
+    out["device_loop_max_pos_err_m"] = float(np.linalg.norm(got[:, :3, 3] - gt[:, :3, 3], axis=1).max())
+    out["note"] = ("features precomputed; dropin = VisualOdometry.process_frame with the reference's keyframe policy on the host and its own "
+                   "PnP sampler on the GPU; device loop = vo_seq_push / vo_seq_read, one synchronisation per sequence")
+    return out
+
+
 def dtype_of(wl):
     if wl.get("orb_l2"):
         return "u8 -> fp16 (1x, exact on byte values) / f32+f64 PnP"
@@ -587,6 +659,12 @@ def run_ours(args, name):
     if clocks is not None and not clocks.get("samples") and not args.allow_no_clocks:
         raise SystemExit("bench.py: no nvidia-smi clock sample fell inside the timed region; the line would be unverifiable "
                          "(--allow-no-clocks to print it anyway)")
+    api = None
+    if world == 1 and not args.no_api_rate:
+        try:
+            api = measure_api_rate(wl, dev)
+        except Exception as e:  # informative block: never lose the headline line to it
+            api = {"error": repr(e)[:300]}
     line = {
         "metric": "frame-pairs/sec (match+PnP)", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -625,6 +703,7 @@ def run_ours(args, name):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "variants": variants or None,
+        "api_rate": api,
         "roofline": roof,
         "kernels": kernels,
         "cpu_baseline": cpu,
@@ -662,6 +741,7 @@ def main():
     ap.add_argument("--precision", type=int, default=None)
     ap.add_argument("--cpu-pairs", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-api-rate", action="store_true", help="skip the frames/s measurement through process_frame / the device loop")
     ap.add_argument("--no-variants", action="store_true", help="skip the matcher variants measured beside the headline (hamming_tc, f16x3)")
     ap.add_argument("--allow-no-clocks", action="store_true")
     args = ap.parse_args()

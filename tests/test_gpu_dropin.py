@@ -17,16 +17,9 @@ PKG = os.path.join(ROOT, "visual-odometry-pipeline_b200")
 
 def _load_dropin(tmp_path, extractor, extra=""):
     """Import the drop-in modules the way the reference is run: CWD holds config/vo_params.yaml."""
-    cfg = tmp_path / "config"
-    cfg.mkdir(exist_ok=True)
-    src = open(os.path.join(PKG, "config", "vo_params.yaml")).read().replace('feature_extractor: "orb"', f'feature_extractor: "{extractor}"')
-    (cfg / "vo_params.yaml").write_text(src + extra)
-    os.chdir(tmp_path)
-    if PKG not in sys.path:
-        sys.path.insert(0, PKG)
-    for name in ("VisualOdometry_Stereo", "vo_stereo_runner", "vo_runner", "feature_extractors.ORB", "feature_extractors.SIFT"):
-        sys.modules.pop(name, None)
-    return importlib.import_module("VisualOdometry_Stereo")
+    import vo_b200  # noqa: F401
+    from vo_b200 import dropin
+    return dropin.load(tmp_path, extractor, extra)
 
 
 @pytest.mark.parametrize("kind,extractor,extra,matcher", [
