@@ -1,8 +1,7 @@
 // Per-pixel / per-keypoint arithmetic of the ORB front-end (feature_extractors/ORB.py:8-21 -> cv2.ORB_create()
 // .detectAndCompute), written once for device code and compilable for the host: tests/test_host_math.py checks every
-// function bit for bit against the CPU restatement of the front-end, which is pinned against OpenCV.  The kernels that will call
-// these (pyramid, FAST map, retainBest, Harris, orientation, Gaussian, rBRIEF: DESIGN 8 item 7) are NOT built yet —
-// nothing in libvo_b200.so includes this header so far.
+// function bit for bit against the CPU restatement of the front-end, which is pinned against OpenCV.  The kernels that call
+// these (pyramid, FAST map, retainBest, Harris, orientation, Gaussian, rBRIEF) are csrc/orb.cu.
 //
 // Exactness rules: integer work is exact; fp32 work spells out every rounding (no contraction on either side: the
 // device uses __f*_rn intrinsics, the host build uses -ffp-contract=off); the two fused operations OpenCV itself

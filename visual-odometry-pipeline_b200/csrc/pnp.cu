@@ -792,34 +792,124 @@ __global__ void ref_table_kernel(int n, int iters, int32_t *__restrict__ table) 
     if (blockIdx.x == 0 && threadIdx.x == 0) refpnp::mwc_table(n, iters, table);
 }
 
-// one thread per (restart, iteration): the f64 EPnP solve is a long dependent chain with large local arrays; 32-thread
-// blocks spread the few hundred solves over the SMs
-__global__ void __launch_bounds__(32)
+// Cyclic Jacobi on a symmetric 12 x 12 matrix in shared memory, one warp: the rotations stay sequential (the order of
+// refpnp::jacobi_eig), but the 12 element pairs a rotation touches in its column phase, its row phase and in V are updated
+// by 12 lanes at once (lanes 12..23 rotate V while lanes 0..11 rotate the columns of A).  Every element sees the operations
+// of the serial loop in the same order: the result is bit-identical to jacobi_eig<12>.  Eigenvalues / vectors are then
+// sorted by lane 0 exactly as jacobi_eig does.
+__device__ void jacobi12_warp(double (*A)[12], double (*V)[12], double *d, int lane) {
+    for (int i = lane; i < 144; i += 32) V[i / 12][i % 12] = (i / 12 == i % 12) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < 12; ++i) {          // every lane sums in jacobi_eig's order: a warp-uniform decision
+            diag += A[i][i] * A[i][i];
+            for (int jj = i + 1; jj < 12; ++jj) off += A[i][jj] * A[i][jj];
+        }
+        if (off <= 1e-30 * diag || off == 0.0) break;
+        for (int p = 0; p < 11; ++p)
+            for (int q = p + 1; q < 12; ++q) {
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                __syncwarp();                   // all lanes have read A[p][p], A[q][q], A[p][q]
+                if (lane < 12) {
+                    const double akp = A[lane][p], akq = A[lane][q];
+                    A[lane][p] = c * akp - sn * akq;
+                    A[lane][q] = sn * akp + c * akq;
+                } else if (lane < 24) {
+                    const int k = lane - 12;
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + c * vkq;
+                }
+                __syncwarp();
+                if (lane < 12) {
+                    const double apk = A[p][lane], aqk = A[q][lane];
+                    A[p][lane] = c * apk - sn * aqk;
+                    A[q][lane] = sn * apk + c * aqk;
+                }
+                __syncwarp();
+            }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 0; i < 12; ++i) d[i] = A[i][i];
+        for (int i = 0; i < 11; ++i) {          // selection sort, descending (jacobi_eig)
+            int m = i;
+            for (int jj = i + 1; jj < 12; ++jj) m = (d[jj] > d[m]) ? jj : m;
+            if (m != i) {
+                const double td = d[i]; d[i] = d[m]; d[m] = td;
+                for (int k = 0; k < 12; ++k) { const double tv = V[k][i]; V[k][i] = V[k][m]; V[k][m] = tv; }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// one WARP per (restart, iteration): lane 0 prepares (control points, barycentrics, M^T M), the 12 x 12 eigen-decomposition runs
+// warp-wide in shared memory, and the three beta candidates (initialisation, five Gauss-Newton steps, orientation, error) run
+// on lanes 0, 1, 2 at once.  Same operations in the same order per element as the serial refpnp::epnp5: identical results.
+// (One thread per solve, the first version, took 1.05 ms per frame pair for the 300 solves — a chain of dependent f64
+// operations on local-memory arrays; the warp-wide Jacobi brought it to 0.56 ms.)
+constexpr int RP_WARPS = 4;
+__global__ void __launch_bounds__(32 * RP_WARPS)
 ref_epnp_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, const int32_t *__restrict__ boot, int n,
                 const int32_t *__restrict__ table, int restarts, int iters, IntrD kd, double *__restrict__ poses,
                 int32_t *__restrict__ valid) {
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= restarts * iters) return;
+    __shared__ double sA[RP_WARPS][12][12], sV[RP_WARPS][12][12], sd[RP_WARPS][12], sX[RP_WARPS][refpnp::EP_N][3], sv[RP_WARPS][4][12];
+    __shared__ refpnp::EpnpState sS[RP_WARPS];
+    __shared__ int s_mode[RP_WARPS];            // 0: repeated point (no model), 1: regular, 2: coplanar
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int id = blockIdx.x * RP_WARPS + w;
+    if (id >= restarts * iters) return;         // warp-uniform
     const int r = id / iters, h = id % iters;
-    double X[refpnp::EP_N][3], q[refpnp::EP_N][2];
-    int src[refpnp::EP_N];
-    bool repeated = false;
-    for (int j = 0; j < refpnp::EP_N; ++j) {
-        const int idx = boot[(size_t)r * n + table[h * refpnp::EP_N + j]];
-        for (int k = 0; k < j; ++k) repeated = repeated || (src[k] == idx);
-        src[j] = idx;
-        for (int k = 0; k < 3; ++k) X[j][k] = (double)xyz[(size_t)idx * 3 + k];
-        q[j][0] = (double)uv[(size_t)idx * 2];
-        q[j][1] = (double)uv[(size_t)idx * 2 + 1];
+    if (lane == 0) {
+        double q[refpnp::EP_N][2];
+        int src[refpnp::EP_N];
+        bool repeated = false;
+        for (int j = 0; j < refpnp::EP_N; ++j) {
+            const int idx = boot[(size_t)r * n + table[h * refpnp::EP_N + j]];
+            for (int k = 0; k < j; ++k) repeated = repeated || (src[k] == idx);
+            src[j] = idx;
+            for (int k = 0; k < 3; ++k) sX[w][j][k] = (double)xyz[(size_t)idx * 3 + k];
+            q[j][0] = (double)uv[(size_t)idx * 2];
+            q[j][1] = (double)uv[(size_t)idx * 2 + 1];
+        }
+        // The five sampled positions are distinct, but a bootstrap resample repeats points: a sample that holds the same
+        // correspondence twice has four distinct points, M^T M a four-dimensional null space, and what OpenCV's EPnP returns
+        // for it is arbitrary.  Such an iteration is spent without a model (0.7 % of the iterations at n = 1500) —
+        // deterministic, and the same in the oracle.
+        if (!repeated) refpnp::epnp5_prepare(sX[w], q, kd.fx, kd.fy, kd.cx, kd.cy, sS[w], sA[w]);
+        s_mode[w] = repeated ? 0 : (sS[w].planar ? 2 : 1);
     }
-    // The five sampled positions are distinct, but a bootstrap resample repeats points: a sample that holds the same
-    // correspondence twice has four distinct points, M^T M a four-dimensional null space, and what OpenCV's EPnP returns for
-    // it is arbitrary.  Such an iteration is spent without a model (0.7 % of the iterations at n = 1500) — deterministic, and
-    // the same in the oracle.
+    __syncwarp();
+    const int mode = s_mode[w];
+    if (mode == 1) jacobi12_warp(sA[w], sV[w], sd[w], lane);
+    if (lane == 0 && mode != 0) {
+        if (mode == 2) refpnp::epnp5_basis_planar(sA[w], sv[w]);
+        else refpnp::epnp5_basis_from_eig(sV[w], sv[w]);
+    }
+    __syncwarp();
+    // the three candidates (find_betas_approx_1 / _2 / _3 + Gauss-Newton + orientation) are independent: lanes 0, 1, 2
     refpnp::Pose p;
-    const bool ok = !repeated && refpnp::epnp5(X, q, kd.fx, kd.fy, kd.cx, kd.cy, p);
-    valid[id] = ok ? 1 : 0;
-    if (ok) {
+    double err = 0.0;
+    bool fin = false;
+    if (mode != 0 && lane < 3) fin = refpnp::epnp5_candidate(sX[w], sS[w], sv[w], lane, p, err);
+    const bool f1 = __shfl_sync(0xffffffffu, (int)fin, 1) != 0, f2 = __shfl_sync(0xffffffffu, (int)fin, 2) != 0;
+    const double e1 = __shfl_sync(0xffffffffu, err, 1), e2 = __shfl_sync(0xffffffffu, err, 2);
+    int pick = -1;                              // lowest error, the earlier candidate keeps ties (compute_pose)
+    if (lane == 0) {
+        double best = 0.0;
+        if (fin) { pick = 0; best = err; }
+        if (f1 && (pick < 0 || e1 < best)) { pick = 1; best = e1; }
+        if (f2 && (pick < 0 || e2 < best)) { pick = 2; best = e2; }
+        valid[id] = pick >= 0 ? 1 : 0;
+    }
+    pick = __shfl_sync(0xffffffffu, pick, 0);
+    if (lane == pick) {
         for (int k = 0; k < 9; ++k) poses[(size_t)id * 12 + k] = p.R[k];
         for (int k = 0; k < 3; ++k) poses[(size_t)id * 12 + 9 + k] = p.t[k];
     }
@@ -1065,7 +1155,7 @@ extern "C" int vo_pnp_ransac_ref(vo_ctx *ctx, const float *xyz, const float *uv,
         VO_PROF(ctx, st, VO_STAGE_P3P);
         ref_table_kernel<<<1, 32, 0, st>>>(n, iters, table);
         VO_LAUNCH_CHECK(ctx);
-        ref_epnp_kernel<<<ceil_div(total, 32), 32, 0, st>>>(xyz, uv, boot_idx, n, table, restarts, iters, kd, poses, valid);
+        ref_epnp_kernel<<<ceil_div(total, RP_WARPS), 32 * RP_WARPS, 0, st>>>(xyz, uv, boot_idx, n, table, restarts, iters, kd, poses, valid);
         VO_LAUNCH_CHECK(ctx);
         VO_PROF(ctx, st, VO_STAGE_SCORE);
         ref_score_kernel<<<ceil_div(total, 8), 256, 0, st>>>(xyz, uv, boot_idx, n, restarts, iters, kd, thr2, poses, valid, counts);

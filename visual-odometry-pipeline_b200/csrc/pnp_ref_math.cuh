@@ -182,24 +182,36 @@ struct Pose {
 // Follows epnp.cpp function by function (choose_control_points, compute_barycentric_coordinates, fill_M, compute_L_6x10,
 // compute_rho, find_betas_approx_{1,2,3}, gauss_newton, compute_R_and_t, reprojection_error).  Returns false when the
 // result is not finite.
-VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], double fu, double fv, double uc, double vc, Pose &out) {
+// Split in three so that the device can run the 12 x 12 eigen-decomposition warp-wide between the two serial parts
+// (csrc/pnp.cu ref_epnp_kernel); epnp5() below is the plain composition the host build and the tests use.
+struct EpnpState {
+    double us[EP_N][2], cws[4][3], al[EP_N][4], ks[3], cut, fu, fv, uc, vc;
+    bool planar;      // coplanar points: three effective control points (see epnp5_basis_planar)
+};
+
+// image points -> `us`, control points, barycentric coordinates, M^T M
+VO_RHDN void epnp5_prepare(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], double fu, double fv, double uc, double vc,
+                           EpnpState &S, double (&MtM)[12][12]) {
     constexpr int n = EP_N;
+    double (&us)[EP_N][2] = S.us;
+    double (&cws)[4][3] = S.cws;
+    double (&al)[EP_N][4] = S.al;
+    double (&ks)[3] = S.ks;
+    S.fu = fu; S.fv = fv; S.uc = uc; S.vc = vc;
     // solvePnP(EPNP) undistorts the image points first: normalised coordinates stored as float32 (no distortion: a pure
     // change of variables), which epnp::init_points maps back with fu, fv, uc, vc in double
-    double us[n][2];
     for (int i = 0; i < n; ++i) {
         const float xn = (float)((uv_in[i][0] - uc) * (1.0 / fu)), yn = (float)((uv_in[i][1] - vc) * (1.0 / fv));
         us[i][0] = (double)xn * fu + uc;
         us[i][1] = (double)yn * fv + vc;
     }
     // control points: centroid + principal directions scaled by sqrt(eigenvalue / n)
-    double cws[4][3];
     for (int j = 0; j < 3; ++j) {
         double s = 0.0;
         for (int i = 0; i < n; ++i) s += X[i][j];
         cws[0][j] = s / n;
     }
-    double axes[3][3], ks[3];                       // principal directions (orthonormal, sign-fixed) and their scales
+    double axes[3][3];                              // principal directions (orthonormal, sign-fixed); ks = their scales
     {
         double C[3][3], V[3][3], d[3];
         for (int a = 0; a < 3; ++a)
@@ -219,8 +231,9 @@ VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], d
     // barycentric coordinates: the control vectors are k_i * (orthonormal axis i), so the inverse of [c1-c0 c2-c0 c3-c0] is
     // axis_i / k_i row by row; a vanishing k_i (planar or collinear points) gives a zero row — the pseudo-inverse
     // cvInvert(CV_SVD) returns in epnp.cpp (singular values <= 2 eps * sum are dropped, SVD::backSubst)
-    double al[n][4];
     const double cut = 2.0 * 2.220446049250313e-16 * (ks[0] + ks[1] + ks[2]);
+    S.cut = cut;
+    S.planar = !(ks[2] > cut) && ks[1] > cut;
     {
         for (int i = 0; i < n; ++i) {
             const double p[3] = {X[i][0] - cws[0][0], X[i][1] - cws[0][1], X[i][2] - cws[0][2]};
@@ -228,8 +241,7 @@ VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], d
             al[i][0] = 1.0 - al[i][1] - al[i][2] - al[i][3];
         }
     }
-    // M^T M (12 x 12) accumulated row by row of M, then its eigenvectors
-    double MtM[12][12];
+    // M^T M (12 x 12) accumulated row by row of M
     for (int a = 0; a < 12; ++a)
         for (int b = 0; b < 12; ++b) MtM[a][b] = 0.0;
     for (int i = 0; i < n; ++i) {
@@ -241,29 +253,41 @@ VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], d
         for (int a = 0; a < 12; ++a)
             for (int b = 0; b < 12; ++b) MtM[a][b] += m1[a] * m1[b] + m2[a] * m2[b];
     }
-    double v[4][12];                    // v[0] = ut[11] ... v[3] = ut[8] of epnp.cpp
-    if (!(ks[2] > cut) && ks[1] > cut) {
-        // coplanar points: the fourth control point coincides with the centroid, its three columns of M vanish and e9, e10, e11
-        // span an exactly-null eigenspace (OpenCV gets an arbitrary basis of it from its SVD).  Canonical choice: those unit
-        // vectors as v[0..2], and the weakest direction of the 9 x 9 block of the three real control points as v[3]
-        double B[9][9], V9[9][9], d9[9];
-        for (int a = 0; a < 9; ++a)
-            for (int b = 0; b < 9; ++b) B[a][b] = MtM[a][b];
-        jacobi_eig<9>(B, V9, d9);
-        for (int i = 0; i < 4; ++i)
-            for (int k = 0; k < 12; ++k) v[i][k] = 0.0;
-        v[0][11] = 1.0; v[1][10] = 1.0; v[2][9] = 1.0;
-        for (int k = 0; k < 9; ++k) v[3][k] = V9[k][8];
-        fix_sign(v[3]);
-    } else {
-        double V[12][12], d[12];
-        jacobi_eig<12>(MtM, V, d);
-        for (int i = 0; i < 4; ++i)
-            for (int k = 0; k < 12; ++k) v[i][k] = V[k][11 - i];
-        canonical_null_basis(v[0], v[1]);
-        fix_sign(v[2]);
-        fix_sign(v[3]);
-    }
+}
+
+// v[0] = ut[11] ... v[3] = ut[8] of epnp.cpp from the eigenvectors of M^T M (columns of V, descending eigenvalues): the canonical
+// basis of the two-dimensional null space, sign-fixed partners
+VO_RHD void epnp5_basis_from_eig(const double (&V)[12][12], double (&v)[4][12]) {
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 12; ++k) v[i][k] = V[k][11 - i];
+    canonical_null_basis(v[0], v[1]);
+    fix_sign(v[2]);
+    fix_sign(v[3]);
+}
+// Coplanar points: the fourth control point coincides with the centroid, its three columns of M vanish and e9, e10, e11 span an
+// exactly-null eigenspace (OpenCV gets an arbitrary basis of it from its SVD).  Canonical choice: those unit vectors as
+// v[0..2], and the weakest direction of the 9 x 9 block of the three real control points as v[3].
+VO_RHDN void epnp5_basis_planar(const double (&MtM)[12][12], double (&v)[4][12]) {
+    double B[9][9], V9[9][9], d9[9];
+    for (int a = 0; a < 9; ++a)
+        for (int b = 0; b < 9; ++b) B[a][b] = MtM[a][b];
+    jacobi_eig<9>(B, V9, d9);
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 12; ++k) v[i][k] = 0.0;
+    v[0][11] = 1.0; v[1][10] = 1.0; v[2][9] = 1.0;
+    for (int k = 0; k < 9; ++k) v[3][k] = V9[k][8];
+    fix_sign(v[3]);
+}
+
+// One of the three candidates of compute_pose (cand = 0, 1, 2: find_betas_approx_1 / _2 / _3): the distance constraints L, rho,
+// the beta initialisation, five Gauss-Newton steps, absolute orientation, mean reprojection error.  Returns false when the result
+// is not finite.  The candidates are independent of each other: the device gives each its own lane.
+VO_RHDN bool epnp5_candidate(const double (&X)[EP_N][3], const EpnpState &S, const double (&v)[4][12], int cand, Pose &p, double &err_out) {
+    constexpr int n = EP_N;
+    const double (&us)[EP_N][2] = S.us;
+    const double (&cws)[4][3] = S.cws;
+    const double (&al)[EP_N][4] = S.al;
+    const double fu = S.fu, fv = S.fv, uc = S.uc, vc = S.vc;
     // L (6 x 10) and rho
     double L[6][10], rho[6];
     {
@@ -294,9 +318,7 @@ VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], d
             rho[i] = s;
         }
     }
-    double best_err = 0.0;
-    bool have = false;
-    for (int cand = 0; cand < 3; ++cand) {
+    {
         double be[4] = {0.0, 0.0, 0.0, 0.0};
         if (cand == 0) {                                     // find_betas_approx_1: B11 B12 B13 B14
             double A[6][4], b[6], x[4];
@@ -362,7 +384,6 @@ VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], d
         double Vq[4][4], dq[4];
         jacobi_eig<4>(Nq, Vq, dq);
         const double qw = Vq[0][0], qx = Vq[1][0], qy = Vq[2][0], qz = Vq[3][0];
-        Pose p;
         p.R[0] = qw * qw + qx * qx - qy * qy - qz * qz; p.R[1] = 2 * (qx * qy - qw * qz); p.R[2] = 2 * (qx * qz + qw * qy);
         p.R[3] = 2 * (qx * qy + qw * qz); p.R[4] = qw * qw - qx * qx + qy * qy - qz * qz; p.R[5] = 2 * (qy * qz - qw * qx);
         p.R[6] = 2 * (qx * qz - qw * qy); p.R[7] = 2 * (qy * qz + qw * qx); p.R[8] = qw * qw - qx * qx - qy * qy + qz * qz;
@@ -377,9 +398,35 @@ VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], d
         bool finite = err == err && err < 1e300;
         for (int k = 0; k < 9; ++k) finite = finite && p.R[k] == p.R[k];
         for (int k = 0; k < 3; ++k) finite = finite && p.t[k] == p.t[k] && fabs(p.t[k]) < 1e300;
-        if (finite && (!have || err < best_err)) { best_err = err; out = p; have = true; }   // strict <: the earlier candidate keeps ties
+        err_out = err;
+        return finite;
+    }
+}
+
+// the candidate with the lowest mean reprojection error (strict <: the earlier candidate keeps ties)
+VO_RHDN bool epnp5_finish(const double (&X)[EP_N][3], const EpnpState &S, const double (&v)[4][12], Pose &out) {
+    double best_err = 0.0;
+    bool have = false;
+    for (int cand = 0; cand < 3; ++cand) {
+        Pose p;
+        double err;
+        if (epnp5_candidate(X, S, v, cand, p, err) && (!have || err < best_err)) { best_err = err; out = p; have = true; }
     }
     return have;
+}
+
+VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], double fu, double fv, double uc, double vc, Pose &out) {
+    EpnpState S;
+    double MtM[12][12], v[4][12];
+    epnp5_prepare(X, uv_in, fu, fv, uc, vc, S, MtM);
+    if (S.planar) {
+        epnp5_basis_planar(MtM, v);
+    } else {
+        double V[12][12], d[12];
+        jacobi_eig<12>(MtM, V, d);
+        epnp5_basis_from_eig(V, v);
+    }
+    return epnp5_finish(X, S, v, out);
 }
 
 // ---- inlier rule of PnPRansacCallback::computeError + RANSACPointSetRegistrator::findInliers ----------------------------
