@@ -38,8 +38,9 @@ WORKLOADS = {
     # SURVEY D2) instead of the north-star's Hamming / mutual rule: an exact fp16 tensor-core pass
     "c2r": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="knn_ratio", orb_l2=True, e2e_sampled_frac=0.4,
                 desc="ORB 5k kp, reference rule: byte-wise L2 kNN-2 + ratio 0.85, PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
-    # c2 with the Hamming distances computed on the tensor cores (VO_NORM_HAMMING_TC: bits as fp16 0/1, K = 256 tcgen05 GEMM with the
-    # fused row / column arg-min epilogue): bit-identical matches (tests/test_gpu_match_u8.py), opt-in; c2 keeps XOR + POPC
+    # c2 with the Hamming distances computed on the tensor cores (VO_NORM_HAMMING_TC: bits as e4m3 -1 / +1, K = 256 tcgen05 kind::f8f6f4
+    # GEMM with the fused row top-2 epilogue, run in both directions): bit-identical matches (tests/test_gpu_match_u8.py), opt-in;
+    # c2 keeps XOR + POPC
     "c2tc": dict(kind="orb", n_kp=5000, n_hyp=1024, pairs=1000, chunk=250, shape="kitti", cpu_matcher="hamming_mutual", hamming_tc=True,
                  desc="ORB 5k kp, 256-bit Hamming mutual-NN on the tensor cores (opt-in, bit-identical to XOR+POPC), PnP-RANSAC 1024 hyp, 1000-pair sequence, KITTI 1241x376"),
     "c3": dict(kind="r2d2", n_kp=10000, n_hyp=4096, pairs=128, chunk=64, shape="kitti", cpu_matcher="r2d2",
@@ -300,7 +301,7 @@ def dtype_of(wl):
     if wl.get("orb_l2"):
         return "u8 -> fp16 (1x, exact on byte values) / f32+f64 PnP"
     if wl.get("hamming_tc"):
-        return "256 bits -> fp16 0/1, tcgen05 kind::f16 K=256 (exact integers) / f32+f64 PnP"
+        return "256 bits -> e4m3 -1/+1, tcgen05 kind::f8f6f4 K=256 (exact integers) / f32+f64 PnP"
     return {"orb": "u8 (XOR+POPC) / f32+f64 PnP", "sift": "fp16 (1x, exact on integer SIFT) / f32+f64 PnP",
             "r2d2": "tf32x3 / f32+f64 PnP"}[wl["kind"]]
 
@@ -518,12 +519,14 @@ def run_ours(args, name):
     elif wl.get("hamming_tc"):
         flops = pairs_per_launch * 2.0 * N * M * 256
         flops *= 2.0      # mutual rule: a second pass with the roles swapped supplies the column arg-min
-        roof = {"kernel": "match_f32_tc_kernel<fp16, K = 256> on 256-bit descriptors as -1 / +1 (tcgen05 kind::f16, fused row top-2; two passes for the mutual rule)",
-                "bound": "tensor", "achieved": flops / match_s / 1e12, "peak": bf16_peak, "unit": "TFLOP/s", "traffic": None,
-                "peak_source": f"dense bf16 cuBLAS burst peak of MEASURED_PEAKS.json ({peak_kind}); fp16 and bf16 share the rate",
+        roof = {"kernel": "match_f32_tc_kernel<e4m3, K = 256> on 256-bit descriptors as -1 / +1 (tcgen05 kind::f8f6f4, fused row top-2, persistent CTAs; two passes for the mutual rule)",
+                "bound": "tensor", "achieved": flops / match_s / 1e12, "peak": 2.0 * bf16_peak, "unit": "TFLOP/s", "traffic": None,
+                "peak_source": f"2 x the dense bf16 cuBLAS burst peak of MEASURED_PEAKS.json ({peak_kind}): kind::f8f6f4 issues at twice the kind::f16 rate; "
+                               "no fp8 GEMM peak was measured on this pool",
                 "issued_passes": 2, "algorithmic_flops": flops / 2.0, "distances_per_s": pairs_per_launch * float(N) * M / match_s,
                 "note": "a.b over -1 / +1 bit vectors = 256 - 2 Hamming: 2 x 256 FLOP per distance and pass, exact integers, no norms.  "
-                        "achieved counts both passes (the `match` stage covers both launches and the column-key merge)"}
+                        "achieved counts both passes (the `match` stage covers both launches and the column-key merge).  With e4m3 operands "
+                        "the row top-2 fold (ALU pipe), not the tensor pipe, bounds the pass: frac is structurally < 0.5"}
     elif wl["kind"] == "orb":
         alg_bytes = pairs_per_launch * (32.0 * (N + M) + 16.0 * N + 8.0 * M)      # descriptors + row partials + column keys
         roof = {"kernel": "match_u8_kernel (XOR+POPC Hamming, fused row/column arg-min)", "bound": "hbm",

@@ -28,13 +28,24 @@
 //    1  1xTF32      single tf32 pass, column norm as an extra K-step           integer-valued data, rules with a column side
 //   16  1xFP16      single fp16 pass (kind::f16, K = 16), 192-column tiles     integer-valued data: SIFT, ORB bytes (exact)
 //   48  3xFP16      x * 2^8 = hi + lo in fp16, three kind::f16 MMAs per 16 k   the 22 operand bits of 3xTF32 at twice the rate
-//  256  1xFP16/256  256-bit descriptors as 256-d rows of fp16 -1 / +1          a.b = 256 - 2 Hamming (exact), K = 256, no norms
+//    8  1xFP8/256   256-bit descriptors as 256-d rows of e4m3 -1 / +1         a.b = 256 - 2 Hamming (exact), kind::f8f6f4 (K = 32),
+//                                                                              K = 256, no norms (as fp16 rows: twice the bytes and MMAs)
 // The two fp16 modes use the all-warp epilogue (16 warps on every tile, accumulator released right after the TMEM read,
 // the four threads of a row share their filter threshold); tools/probe/mma_issue_probe.cu has the pipe rates.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
+
+#ifndef VO_TC_DBG
+#define VO_TC_DBG 0
+#endif
+// Work items (row-block pair x column split x frame pair) with at most this many column tiles run on the persistent form of the
+// fp16 / fp8 passes: at 11 tiles (2k x 2k) the per-CTA set-up and drain is as long as the tiles, at 105 (20k x 20k) it is 2 %
+// and the plain form's steady state is 6 % faster (B200: 2k +9 %, 5k +5 % / +2 %, 20k -6 % persistent vs plain).
+#ifndef VO_TC_PERSIST_MAX_TILES
+#define VO_TC_PERSIST_MAX_TILES 64
+#endif
 
 namespace vo {
 namespace {
@@ -58,8 +69,10 @@ constexpr int TC_NKB = TC_D / TC_KB;
 // three kind::tf32 MMAs per 8 k.  Tile geometry, ring and epilogue are those of 3xTF32.
 template <int PASSES>
 struct TcCfg {
-    static constexpr bool K256 = PASSES == 256;                   // fp16 single pass over 256-d rows (bit descriptors as -1 / +1)
-    static constexpr bool F16 = PASSES == 16 || K256;             // fp16 single pass (own epilogue)
+    static constexpr bool F8 = PASSES == 8;                       // e4m3 operands, tcgen05.mma.kind::f8f6f4 (128 k per 128-byte box)
+    static constexpr bool K256 = F8;                              // single pass over 256-d rows (bit descriptors as -1 / +1)
+    static constexpr bool F16 = PASSES == 16 || K256;             // fp16 / fp8 single pass (own epilogue)
+    static constexpr int KBOX = F8 ? 128 : 64;                    // k per box of the 16- and 8-bit passes
     static constexpr bool H16 = F16 || PASSES == 48;              // fp16 operands
     static constexpr bool THREE = PASSES == 3 || PASSES == 48;    // hi/lo split, three MMAs per k-step
     static constexpr bool ALLWARP_COLS = PASSES == 48;            // all-warp epilogue with the column side
@@ -196,20 +209,24 @@ prep16_u8_kernel(const uint8_t *__restrict__ x, long long rows, __half *__restri
     }
 }
 
-// 256-bit descriptors (VO_NORM_HAMMING_TC) as 256-d fp16 rows of -1 / +1: a.b = (#equal bits) - (#different bits) =
+// 256-bit descriptors (VO_NORM_HAMMING_TC) as 256-d rows of -1 / +1: a.b = (#equal bits) - (#different bits) =
 // 256 - 2 popcount(a xor b), an exact small integer in the fp32 accumulator, and no norm enters: the matcher's cosine
-// machinery (larger is closer) orders by Hamming distance.  One warp per descriptor, one byte (8 halves, 16 B) per lane.
+// machinery (larger is closer) orders by Hamming distance.  The values are e4m3 bytes (+1.0 = 0x38, -1.0 = 0xb8; as fp16
+// the pass moved twice the bytes and issued twice the MMAs: 5.40 -> 4.41 ms per 250 pairs of 5k x 5k): 256 B per
+// descriptor, one warp per descriptor, one byte of bits -> 8 bytes per lane.
 __global__ void __launch_bounds__(256)
-prep_bits_kernel(const uint8_t *__restrict__ x, long long rows, __half *__restrict__ h16) {
+prep_bits8_kernel(const uint8_t *__restrict__ x, long long rows, uint8_t *__restrict__ f8) {
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const uint32_t v = x[row * 32 + lane];
-    uint32_t w[4];
+    uint32_t w[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)   // fp16 +1.0 = 0x3c00, -1.0 = 0xbc00
-        w[i] = (((v >> (2 * i)) & 1u) ? 0x3c00u : 0xbc00u) | (((v >> (2 * i + 1)) & 1u) ? 0x3c000000u : 0xbc000000u);
-    *reinterpret_cast<uint4 *>(h16 + row * 256 + lane * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int i = 0; i < 2; ++i) {   // bit set -> sign clear
+        const uint32_t n = ~(v >> (4 * i));
+        w[i] = 0x38383838u | ((n & 1u) << 7) | ((n & 2u) << 14) | ((n & 4u) << 21) | ((n & 8u) << 28);
+    }
+    *reinterpret_cast<uint2 *>(f8 + row * 256 + lane * 8) = make_uint2(w[0], w[1]);
 }
 
 // Second pass of the tensor-core Hamming matcher (roles swapped: current-frame descriptors as rows): the row arg-max of every
@@ -381,17 +398,63 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
     }
 }
 
+// ---------------------------------------------------------------- A of the fp16 / fp8 single passes -> tensor memory
+// One thread's 128 bytes of A (src; zero where !have or past row_elems) -> 32 TMEM columns, arrival on bar_a; the warps of the
+// third column quarter (ones_warp) write the ones block of the norm extension.  wait_bar != 0: the loads are issued, then the
+// mbarrier is waited for (the accumulator of the previous item's last tile: every MMA that reads the old A has retired), then
+// the store happens.  Deliberately NOT inlined: it runs once per work item, and inlined into the tile loop its 32 registers
+// pushed the loop's invariants out of the register file (rematerialised per tile: the pass lost 15 %).
+template <bool EXT, bool F8>
+__device__ __noinline__ void tc_a_to_tmem(const uint8_t *src, bool have, int k0, int row_elems, bool a_warp, bool ones_warp,
+                                          uint32_t taddr_a, uint32_t taddr_ext, uint32_t bar_a, uint32_t wait_bar,
+                                          uint32_t wait_parity, int lane) {
+    constexpr int EPV = F8 ? 16 : 8;   // elements per 16-byte load
+    float v[32];
+    if (a_warp) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint4 x = (have && k0 + k * EPV < row_elems) ? __ldg(reinterpret_cast<const uint4 *>(src) + k) : make_uint4(0, 0, 0, 0);
+            uint32_t wd[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (EXT) {  // A scaled by 2 (exact): the accumulator holds 2 a.b - |b|^2
+                    const __half2 d = __hmul2(*reinterpret_cast<const __half2 *>(&wd[i]), __floats2half2_rn(2.0f, 2.0f));
+                    wd[i] = *reinterpret_cast<const uint32_t *>(&d);
+                }
+                v[4 * k + i] = __uint_as_float(wd[i]);
+            }
+        }
+    }
+    if (wait_bar) {
+        tc::mbar_wait(wait_bar, wait_parity);
+        tc::tc_fence_after();
+    }
+    if (a_warp) {
+        tc::tc_st32(taddr_a, v);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc::tc_fence_before();
+        if (lane == 0) tc::mbar_arrive(bar_a);
+    }
+    if (EXT && ones_warp) {  // constant, but rewritten with every A: its warps arrive on bar_a too
+        const float ones[8] = {1.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        tc::tc_st8(taddr_ext, ones);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc::tc_fence_before();
+        if (lane == 0) tc::mbar_arrive(bar_a);
+    }
+}
+
 // ---------------------------------------------------------------- main kernel
 // COLS = false drops the column arg-max (REDUX + ballot per column and warp, the per-tile merge and its barrier):
 // the ratio / threshold / plain-NN acceptance rules never read it.
-template <int PASSES, int METRIC, bool COLS>
+template <int PASSES, int METRIC, bool COLS, bool PERSIST_T = false>
 __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1)
 match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                     const float *__restrict__ a_hi, const float *__restrict__ a_lo, int n_stride, int m_stride,
                     const int32_t *__restrict__ n_ref, const int32_t *__restrict__ n_cur,
                     const float *__restrict__ row_norm, const float *__restrict__ col_norm, int n_split,
                     vo_row_partial *__restrict__ part, unsigned long long *__restrict__ colkey,
-                    long long *__restrict__ dbg, int pair_group, int row_elems) {
+                    long long *__restrict__ dbg, int pair_group, int row_elems, int lgrid_x, int n_pairs) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - smem_u32(smem_raw));
@@ -423,13 +486,41 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     const int t_begin = min(tiles_total, split * tiles_per_split);
     const int t_end = min(tiles_total, t_begin + tiles_per_split);
     const int n_tiles = t_end - t_begin;  // identical in both CTAs of the cluster (same pair, same split)
+    // The fp16 / fp8 single passes are PERSISTENT: the grid is one cluster per SM pair and every cluster walks the work items
+    // (row-block pair, column split, frame pair) w = cluster, cluster + #clusters, ... in the order the hardware would have
+    // handed out the CTAs of the logical grid (lgrid_x, n_split, n_pairs).  Barriers, the TMA ring and the two accumulators
+    // run on across items; only A is replaced (by the epilogue warps, once the last MMA of the previous item has retired).
+    // Per-CTA set-up / drain and the gap to the next CTA cost 14 k cycles against 27 tiles x 1.3 k at 5k x 5k (11 tiles at 2k x 2k).
+    // The other passes run one item per CTA, taken from blockIdx (the variables above).
+    constexpr bool PERSIST = PERSIST_T;
+    static_assert(!PERSIST || Cfg::F16, "only the fp16 / fp8 single passes have the item loop in their epilogue");
+    struct Item { int b, row0, split, N, M, t_begin, n_tiles; };
+    const int w_step = PERSIST ? (int)gridDim.x / TC_CLUSTER : 1;
+    const int w_first = PERSIST ? (int)blockIdx.x / TC_CLUSTER : 0;
+    const int w_end = PERSIST ? (lgrid_x / TC_CLUSTER) * n_split * n_pairs : 1;
+    auto item_at = [&](int w) {
+        Item I;
+        if (!PERSIST) { I.b = b; I.row0 = row0; I.split = split; I.N = N; I.M = M; I.t_begin = t_begin; I.n_tiles = n_tiles; return I; }
+        const int cx = lgrid_x / TC_CLUSTER;
+        I.b = w / (cx * n_split);
+        I.split = (w / cx) % n_split;
+        I.row0 = ((w % cx) * TC_CLUSTER + (int)(blockIdx.x % TC_CLUSTER)) * TC_BM;
+        I.N = n_ref ? min(n_ref[I.b], n_stride) : n_stride;
+        I.M = n_cur ? min(n_cur[I.b], m_stride) : m_stride;
+        const int tt = (I.M + BN - 1) / BN, tps = (tt + n_split - 1) / n_split;
+        I.t_begin = min(tt, I.split * tps);
+        I.n_tiles = min(tt, I.t_begin + tps) - I.t_begin;
+        return I;
+    };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_rank();
     // optional cycle accounting of CTA (0,0,0) for bring-up / tuning (dbg == nullptr in production)
-    const bool dbg_on = dbg != nullptr && rblock == 0 && blockIdx.y == 0 && b == 0;
+    // (compiled in with -DVO_TC_DBG=1 only — VO_TC_DEBUG / VO_TC_TRACE at run time then; the counters cost a dozen registers
+    // that the persistent fp16 / fp8 epilogue cannot spare.  Persistent kernels: CTA 0, over all its items.)
+    const bool dbg_on = VO_TC_DBG && dbg != nullptr && rblock == 0 && blockIdx.y == 0 && b == 0;
     const long long t_kernel0 = dbg_on ? clock64() : 0;
     // VO_TC_TRACE: every CTA leaves (clock64 at entry, clock64 at exit, SM id) behind: idle time between CTAs of one SM
-    const bool trace_on = dbg != nullptr && dbg[15] == 1;
+    const bool trace_on = VO_TC_DBG && dbg != nullptr && dbg[15] == 1;
     const long long t_trace0 = (trace_on && threadIdx.x == 0) ? clock64() : 0;
 #define TC_DBG_BEGIN() const long long _t0 = dbg_on ? clock64() : 0
 #define TC_DBG_END(slot) do { if (dbg_on) dbg_acc[slot] += clock64() - _t0; } while (0)
@@ -439,7 +530,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     constexpr bool F16 = Cfg::F16;
     constexpr bool H16 = Cfg::H16, THREE = Cfg::THREE, SCALED = PASSES == 48;
     constexpr bool EXT = !THREE && (METRIC == VO_METRIC_L2);
-    constexpr int NKB = H16 ? Cfg::KDIM / 64 : TC_NKB;                           // k boxes per tile (128 B of k each)
+    constexpr int NKB = H16 ? Cfg::KDIM / Cfg::KBOX : TC_NKB;                           // k boxes per tile (128 B of k each)
     constexpr int ITEMS = THREE ? 2 * NKB : (EXT ? NKB + 1 : NKB);               // B boxes streamed per tile
     const uint32_t s_b = base;
     float *scol_v = reinterpret_cast<float *>(smem + Cfg::OFF_SCOL);                      // [2 groups][2 bufs][4][BN]
@@ -460,7 +551,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             mbar_init(bar_full(s), 1);            // this CTA's producer arms it; TMA bytes complete it
             mbar_init(bar_empty(s), TC_CLUSTER);  // one commit from each CTA of the cluster
         }
-        mbar_init(bar_a, (THREE || Cfg::K256) ? 16 : (EXT ? 12 : 8));   // warps that store a part of A (or the ones block)
+        mbar_init(bar_a, THREE ? 16 : (EXT ? 12 : 8));   // warps that store a part of A (or the ones block)
         for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull(g), 1); mbar_init(bar_tempty(g), H16 ? 16 : 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -475,6 +566,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     cluster_sync_all();  // the peer's barriers exist before anything multicasts into this CTA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (dbg_on && threadIdx.x == 0) dbg[14] = clock64() - t_kernel0;   // set-up: barriers, TMEM, cluster rendezvous
 
     auto tile_of = [&](int lt) { return t_begin + lt; };
 
@@ -482,8 +574,10 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         // ===================== TMA producer =====================
         if (lane == 0) {
             int it = 0;
-            for (int lt = 0; lt < n_tiles; ++lt) {
-                const int brow = b * m_stride + tile_of(lt) * BN;
+            for (int w = w_first; w < w_end; w += w_step) {
+            const Item I = item_at(w);
+            for (int lt = 0; lt < I.n_tiles; ++lt) {
+                const int brow = I.b * m_stride + (I.t_begin + lt) * BN;
                 for (int item = 0; item < ITEMS; ++item, ++it) {
                     const int stage = it % STAGES;
                     const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
@@ -493,10 +587,11 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                         const bool is_ext = EXT && item == NKB;  // map_b_lo is the extension map in that mode
                         const int kb = is_ext ? 0 : (THREE ? (item >> 1) : item);
                         const bool is_lo = is_ext || (THREE && (item & 1));
-                        tma_load_2d_mc(s_b + stage * BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * (H16 ? 64 : TC_KB), brow,
+                        tma_load_2d_mc(s_b + stage * BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * (H16 ? Cfg::KBOX : TC_KB), brow,
                                        bar_full(stage), (uint16_t)((1u << TC_CLUSTER) - 1u));
                     }
                 }
+            }
             }
             if (dbg_on) dbg[4] = dbg_acc[0];
         }
@@ -504,14 +599,21 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         // ===================== MMA issuer =====================
         // The warp stays converged (all lanes wait on the barriers); one elected lane issues.  Descriptors are a
         // constant upper word plus (smem address >> 4): one integer add per MMA, nothing else on the issue path.
-        if (n_tiles > 0) {
-            mbar_wait(bar_a, 0);  // A is in tensor memory
+        {
+            uint32_t stage = 0, phase = 0, a_phase = 0;
+            long long mma_wait_full = 0, mma_wait_tempty = 0, mma_wait_a = 0;
+            int gt = 0;  // tiles issued so far, over all items: accumulator buffer and its phase
+            for (int w = w_first; w < w_end; w += w_step) {
+            const Item I = item_at(w);
+            if (I.n_tiles == 0) continue;
+            { const long long _t0 = dbg_on ? clock64() : 0;
+              mbar_wait(bar_a, a_phase);  // this item's A is in tensor memory
+              if (dbg_on) mma_wait_a += clock64() - _t0; }
+            a_phase ^= 1u;
             tc_fence_after();
-            uint32_t stage = 0, phase = 0;
-            long long mma_wait_full = 0, mma_wait_tempty = 0;
-            for (int lt = 0; lt < n_tiles; ++lt) {
-                const int buf = lt & 1;
-                const uint32_t use = (uint32_t)(lt >> 1);
+            for (int lt = 0; lt < I.n_tiles; ++lt, ++gt) {
+                const int buf = gt & 1;
+                const uint32_t use = (uint32_t)(gt >> 1);
                 { const long long _t0 = dbg_on ? clock64() : 0;
                   mbar_wait(bar_tempty(buf), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
                   if (dbg_on) mma_wait_tempty += clock64() - _t0; }
@@ -536,7 +638,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                         for (int k8 = 0; k8 < TC_KB / 8; ++k8) {
                             const uint64_t bdesc = ((uint64_t)TC_SDESC_HI << 32) | (uint64_t)(b_lo32 + k8 * 2);
                             const uint32_t ahi = a_hi_t + k8 * 8;
-                            if (F16) {  // 16 k per instruction: the same 32 B of B and 8 TMEM columns of A per step
+                            if (Cfg::F8) {  // 32 k per instruction: again 32 B of B and 8 TMEM columns of A per step
+                                tc_mma_f8_ts(d_tmem, ahi, bdesc, Cfg::IDESC16, (item | k8) ? 1u : 0u);  // e4m3 = format 0 as well
+                            } else if (F16) {  // 16 k per instruction: the same 32 B of B and 8 TMEM columns of A per step
                                 tc_mma_f16_ts(d_tmem, ahi, bdesc, Cfg::IDESC16, (item | k8) ? 1u : 0u);
                             } else if (H16) {  // split fp16: a_hi * b_lo on the lo boxes; a_lo * b_hi, a_hi * b_hi on the hi boxes
                                 if (is_lo) {
@@ -561,7 +665,8 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
-            if (dbg_on && lane == 0) { dbg[1] = mma_wait_full; dbg[2] = mma_wait_tempty; dbg[3] = clock64() - t_kernel0; dbg[11] = n_tiles; }
+            }
+            if (dbg_on && lane == 0) { dbg[1] = mma_wait_full; dbg[2] = mma_wait_tempty; dbg[3] = clock64() - t_kernel0; dbg[11] = gt; dbg[12] = mma_wait_a; }
         }
     } else {
         if constexpr (Cfg::F16) {
@@ -571,98 +676,151 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
         // at once, and only then folds them into its row's top-2: the accumulator is blocked for one TMEM read, not
         // for the fold (with two 8-warp groups the fold time of a tile sat on the critical path of its buffer).
         constexpr int QW = BN / 4;
+        const bool edbg = VO_TC_DBG >= 2 && dbg_on;   // the epilogue counters cost registers the fp16 / fp8 epilogue spills for
         static_assert(QW == 48, "three 16-column reads per thread");
         const int cq = warp >> 2;
         const int q = warp & 3;
-        const int row = row0 + q * 32 + lane;
-        const bool row_ok = row < N;
-        const bool partial_rows = row0 + TC_BM > N;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (n_tiles > 0 && cq < Cfg::KDIM / 64) {  // A -> tensor memory, once: 64 k (one 32-column chunk of packed halves) per warp
-            // row_elems < 128: compact rows (byte descriptors: 32 values), the missing dimensions are zero
-            const __half *src = reinterpret_cast<const __half *>(a_hi) + ((size_t)b * n_stride + min(row, n_stride - 1)) * row_elems + cq * 64;
-            const bool have = row < n_stride;
-            float v[32];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                uint4 x = (have && cq * 64 + k * 8 < row_elems) ? __ldg(reinterpret_cast<const uint4 *>(src) + k) : make_uint4(0, 0, 0, 0);
-                uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (EXT) {  // A scaled by 2 (exact): the accumulator holds 2 a.b - |b|^2
-                        const __half2 d = __hmul2(*reinterpret_cast<const __half2 *>(&w[i]), __floats2half2_rn(2.0f, 2.0f));
-                        w[i] = *reinterpret_cast<const uint32_t *>(&d);
+        const int rr = q * 32 + lane;  // row inside the CTA: index into the shared second-bests
+        const bool a_warp = cq < Cfg::KDIM / Cfg::KBOX;   // this warp carries 128 B of k (one 32-column chunk) of A into tensor memory
+        // A of an item: this thread's 128 bytes.  row_elems < 128: compact rows (byte descriptors: 32 values), the rest is zero.
+        auto a_src = [&](int ib, int irow0) {
+            const int row = irow0 + rr;
+            return reinterpret_cast<const uint8_t *>(a_hi) +
+                   (((size_t)ib * n_stride + min(row, n_stride - 1)) * row_elems + cq * Cfg::KBOX) * (Cfg::F8 ? 1 : 2);
+        };
+        auto a_put = [&](int ib, int irow0, uint32_t wait_bar, uint32_t wait_parity) {
+            tc_a_to_tmem<EXT, Cfg::F8>(a_src(ib, irow0), irow0 + rr < n_stride, cq * Cfg::KBOX, row_elems, a_warp, cq == 2,
+                                       lane_base + (uint32_t)(TMEM_A + cq * 32), lane_base + (uint32_t)TMEM_EXT, bar_a, wait_bar,
+                                       wait_parity, lane);
+        };
+        // Register budget: 576 threads leave 96 registers each, and 48 of them hold the tile slice during the fold — so nothing
+        // about the items stays live across the tile loop except (w, column count, first tile, tile count); whatever else is needed
+        // once per item (pair, split, row block; the next item for the hand-over) is decoded again from w where it is used.
+        int gt = 0;             // tiles consumed so far, over all items
+        bool a_stored = false;  // the current item's A went in during the previous item's last tile
+        long long t_between = edbg ? clock64() : 0;
+        for (int w = w_first; w < w_end; w += w_step) {
+            int M, n_t, tile0;
+            bool row_ok, partial_rows;
+            float na = 0.0f;
+            {
+                const Item I = item_at(w);
+                M = I.M; n_t = I.n_tiles; tile0 = I.t_begin;
+                row_ok = I.row0 + rr < I.N;
+                partial_rows = I.row0 + TC_BM > I.N;
+                if (METRIC == VO_METRIC_L2 && row_ok) na = row_norm[(size_t)I.b * n_stride + I.row0 + rr];
+                // every MMA of the earlier items has retired (their accumulators were all waited for below): A may be replaced
+                if (n_t > 0 && !a_stored) a_put(I.b, I.row0, 0u, 0u);
+            }
+            a_stored = false;
+            const bool has_next = PERSIST && w + w_step < w_end;
+            if (has_next && a_warp) {   // the next item's A towards L2 (128 B per thread): it is wanted at this item's last tile
+                const Item Nx = item_at(w + w_step);
+                if (Nx.n_tiles > 0 && Nx.row0 + rr < n_stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(a_src(Nx.b, Nx.row0)));
+            }
+            float s1 = -INFINITY, s2 = -INFINITY, thr = -INFINITY;
+            int32_t i1 = -1, i2 = -1;
+            if (edbg) dbg_acc[3] += clock64() - t_between;   // between the tile loops of consecutive items
+            // One tile: wait for its accumulator (unless the hand-over below already did), read it, fold it.
+            auto tile = [&](int lt, bool waited) {
+                const int buf = gt & 1;
+                const uint32_t use = (uint32_t)(gt >> 1);
+                const int col0 = (tile0 + lt) * BN + cq * QW;
+                const bool full_tile = (tile0 + lt) * BN + BN <= M;
+                if (!waited) {
+                    { const long long _t0 = edbg ? clock64() : 0; mbar_wait(bar_tfull(buf), use & 1u); if (edbg) dbg_acc[0] += clock64() - _t0; }
+                    tc_fence_after();
+                }
+                const long long _tc0 = edbg ? clock64() : 0;
+                const uint32_t taddr = lane_base + (uint32_t)(buf * BN + cq * QW);
+                // 48 columns per thread through 32 registers (four groups of 8): columns 0..31 are read; as the first two groups
+                // are folded, columns 32..47 are read into their registers (the reads fly during the next group's fold), and
+                // after the third group the accumulator is handed back — half a fold later than with 48 registers for the
+                // slice, which did not leave room for the item loop (96 per thread: 5 warps share a 16 K register file; a few
+                // spilled registers cost 10-40 % here, local memory has next to no L1 beside 220 KB of shared memory).
+                // With two accumulators the MMA thread has (2 x fold - MMA) cycles of slack per tile, more than this delay.
+                uint32_t g0[8], g1[8], g2[8], g3[8];
+                tc_ld8_issue(taddr, g0);
+                tc_ld8_issue(taddr + 8, g1);
+                tc_ld8_issue(taddr + 16, g2);
+                tc_ld8_issue(taddr + 24, g3);
+                {  // the other three column quarters' second-bests of this row (read while the TMEM loads fly)
+                    const float tau = fmaxf(fmaxf(srow2[((cq + 1) & 3) * TC_BM + rr], srow2[((cq + 2) & 3) * TC_BM + rr]),
+                                            srow2[((cq + 3) & 3) * TC_BM + rr]);
+                    thr = fmaxf(thr, row_threshold(s2, tau));
+                }
+                tc_ld_wait8(g0);
+                tc_ld_wait8(g1);
+                tc_ld_wait8(g2);
+                tc_ld_wait8(g3);
+                if (edbg) dbg_acc[1] += clock64() - _tc0;
+                const long long _tm0 = edbg ? clock64() : 0;
+#define TC_FOLD8(BUF, J0, MASKC, MASKR)                                                                                    \
+    {                                                                                                                      \
+        float v[8];                                                                                                        \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[i]);                                      \
+        epi_group8<METRIC, MASKC, MASKR, false, EXT>(v, col0 + (J0), M, row_ok, na, nullptr, false, lane, nullptr, nullptr, \
+                                                     s1, s2, i1, i2, thr);                                                  \
+    }
+#define TC_FOLD48(MASKC, MASKR)                                                                                            \
+    TC_FOLD8(g0, 0, MASKC, MASKR)                                                                                          \
+    tc_ld8_issue(taddr + 32, g0);                                                                                          \
+    TC_FOLD8(g1, 8, MASKC, MASKR)                                                                                          \
+    tc_ld8_issue(taddr + 40, g1);                                                                                          \
+    TC_FOLD8(g2, 16, MASKC, MASKR)                                                                                         \
+    tc_ld_wait8(g0);                                                                                                       \
+    tc_ld_wait8(g1);                                                                                                       \
+    tc_fence_before(); /* the whole tile slice has been read: hand the accumulator back */                                 \
+    if (lane == 0) mbar_arrive(bar_tempty(buf));                                                                           \
+    TC_FOLD8(g3, 24, MASKC, MASKR)                                                                                         \
+    TC_FOLD8(g0, 32, MASKC, MASKR)                                                                                         \
+    TC_FOLD8(g1, 40, MASKC, MASKR)
+                if (full_tile && !partial_rows) { TC_FOLD48(false, false) } else { TC_FOLD48(true, true) }
+#undef TC_FOLD48
+#undef TC_FOLD8
+                srow2[cq * TC_BM + rr] = s2;
+                if (edbg) dbg_acc[2] += clock64() - _tm0;
+                ++gt;
+            };
+            // all tiles but the last in a plain loop (the loop of the one-item-per-CTA kernel, and compiled like it); the last
+            // tile of an item, with the hand-over of A to the next item, stands apart
+            for (int lt = 0; lt < n_t - 1; ++lt) tile(lt, false);
+            if (n_t > 0) {
+                bool waited = false;
+                if (has_next) {
+                    // Once the last accumulator of the item is complete every MMA that reads this item's A has retired, so the
+                    // next item's A goes in first (its loads fly during the wait for that accumulator; the tile slice is not in
+                    // registers yet) and the tensor pipe restarts while this tile is still being folded.
+                    const Item Nx = item_at(w + w_step);
+                    if (Nx.n_tiles > 0) {   // warp-uniform (as is everything about an item)
+                        a_put(Nx.b, Nx.row0, bar_tfull(gt & 1), (uint32_t)(gt >> 1) & 1u);
+                        a_stored = waited = true;
                     }
-                    v[4 * k + i] = __uint_as_float(w[i]);
+                }
+                tile(n_t - 1, waited);
+            }
+            if (edbg) t_between = clock64();
+            if (METRIC == VO_METRIC_L2) {  // the deferred row norm (-inf stays -inf)
+                s1 = __fsub_rn(s1, na); s2 = __fsub_rn(s2, na);
+            }
+            {
+                const Item I = item_at(w);
+                if (I.row0 + rr < n_stride) {  // four column quarters: four partials per (row, split), merged by finalize
+                    vo_row_partial p;
+                    p.s1 = float_to_ordered(-s1); p.s2 = float_to_ordered(-s2);
+                    p.i1 = i1; p.i2 = i2;
+                    part[((size_t)I.b * (n_split * 4) + I.split * 4 + cq) * n_stride + I.row0 + rr] = p;
                 }
             }
-            tc_st32(lane_base + (uint32_t)(TMEM_A + cq * 32), v);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(bar_a);
-        }
-        if (EXT && n_tiles > 0 && cq == 2) {  // the ones block of A
-            const float ones[8] = {1.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            tc_st8(lane_base + (uint32_t)TMEM_EXT, ones);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(bar_a);
-        }
-        float s1 = -INFINITY, s2 = -INFINITY, thr = -INFINITY;
-        int32_t i1 = -1, i2 = -1;
-        const int rr = q * 32 + lane;  // row inside the CTA: index into the shared second-bests
-        const float na = (METRIC == VO_METRIC_L2 && row_ok) ? row_norm[(size_t)b * n_stride + row] : 0.0f;
-        for (int lt = 0; lt < n_tiles; ++lt) {
-            const int buf = lt & 1;
-            const uint32_t use = (uint32_t)(lt >> 1);
-            const int col0 = tile_of(lt) * BN + cq * QW;
-            const bool full_tile = tile_of(lt) * BN + BN <= M;
-            { TC_DBG_BEGIN(); mbar_wait(bar_tfull(buf), use & 1u); TC_DBG_END(0); }
-            tc_fence_after();
-            const long long _tc0 = dbg_on ? clock64() : 0;
-            const uint32_t taddr = lane_base + (uint32_t)(buf * BN + cq * QW);
-            uint32_t ra[16], rb[16], rc[16];
-            tc_ld16_issue(taddr, ra);
-            tc_ld16_issue(taddr + 16, rb);
-            tc_ld16_issue(taddr + 32, rc);
-            {  // the other three column quarters' second-bests of this row (read while the TMEM loads fly)
-                const float tau = fmaxf(fmaxf(srow2[((cq + 1) & 3) * TC_BM + rr], srow2[((cq + 2) & 3) * TC_BM + rr]),
-                                        srow2[((cq + 3) & 3) * TC_BM + rr]);
-                thr = fmaxf(thr, row_threshold(s2, tau));
+            if (has_next) {
+                // the shared second-bests belong to the item: clear the own slot (a quarter still inside this item then reads
+                // -inf, which only loosens its filter), and nobody starts the next item before every slot is clear
+                srow2[cq * TC_BM + rr] = -INFINITY;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
             }
-            tc_ld_wait16(ra);
-            tc_ld_wait16(rb);
-            tc_ld_wait16(rc);
-            tc_fence_before();  // the tile slice is in registers: hand the accumulator back before folding
-            if (lane == 0) mbar_arrive(bar_tempty(buf));
-            if (dbg_on) dbg_acc[1] += clock64() - _tc0;
-            const long long _tm0 = dbg_on ? clock64() : 0;
-#define TC_FOLD16(BUF, J0, MASKC, MASKR)                                                                                   \
-    _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                                                        \
-        float v[8];                                                                                                        \
-        _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[8 * u + i]);                              \
-        epi_group8<METRIC, MASKC, MASKR, false, EXT>(v, col0 + (J0) + 8 * u, M, row_ok, na, nullptr, false, lane, nullptr, \
-                                                     nullptr, s1, s2, i1, i2, thr);                                             \
-    }
-            if (full_tile && !partial_rows) {
-                TC_FOLD16(ra, 0, false, false) TC_FOLD16(rb, 16, false, false) TC_FOLD16(rc, 32, false, false)
-            } else {
-                TC_FOLD16(ra, 0, true, true) TC_FOLD16(rb, 16, true, true) TC_FOLD16(rc, 32, true, true)
-            }
-#undef TC_FOLD16
-            srow2[cq * TC_BM + rr] = s2;
-            if (dbg_on) dbg_acc[2] += clock64() - _tm0;
         }
-        if (dbg_on && q == 0 && lane == 0 && cq < 2) { dbg[5 + cq] = dbg_acc[0]; dbg[7 + cq] = dbg_acc[1]; dbg[9 + cq] = dbg_acc[2]; }
-        if (METRIC == VO_METRIC_L2) {  // the deferred row norm (-inf stays -inf)
-            s1 = __fsub_rn(s1, na); s2 = __fsub_rn(s2, na);
-        }
-        if (row < n_stride) {  // four column quarters: four partials per (row, split), merged by finalize
-            vo_row_partial p;
-            p.s1 = float_to_ordered(-s1); p.s2 = float_to_ordered(-s2);
-            p.i1 = i1; p.i2 = i2;
-            part[((size_t)b * (n_split * 4) + split * 4 + cq) * n_stride + row] = p;
-        }
+        if (edbg && q == 0 && lane == 0 && cq < 2) { dbg[5 + cq] = dbg_acc[0]; dbg[7 + cq] = dbg_acc[1]; dbg[9 + cq] = dbg_acc[2]; if (cq == 1) dbg[13] = dbg_acc[3]; }
         } else if constexpr (Cfg::ALLWARP_COLS) {
         // ===================== split-fp16 epilogue: all 16 warps on every tile, with the column side =====================
         // Same idea as the fp16 single pass: lane quarter q x column quarter cq (32 columns per thread), the tile slice
@@ -985,14 +1143,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 // [rows][row_elems] fp32 (or fp16 when `half`), box = 128 B of k x box_rows rows, SWIZZLE_128B
 int make_map(vo_ctx *ctx, CUtensorMap *map, const void *ptr, long long rows, int box_rows, int row_elems = TC_D,
-             bool half = false) {
+             bool half = false, bool bytes = false) {
     PFN_encodeTiled fn = (PFN_encodeTiled)ctx->encode_tiled;
-    const size_t esz = half ? 2 : 4;
+    const size_t esz = bytes ? 1 : (half ? 2 : 4);
     cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)row_elems * esz};
     cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
+    CUresult r = fn(map, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2, (void *)ptr, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1002,16 +1160,16 @@ int make_map(vo_ctx *ctx, CUtensorMap *map, const void *ptr, long long rows, int
     return VO_OK;
 }
 
-template <int PASSES, int METRIC, bool COLS>
-int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &bl, const float *a_hi, const float *a_lo,
-              int n_stride, int m_stride, const int32_t *n_ref, const int32_t *n_cur, const float *row_norm,
-              const float *col_norm, int n_split, vo_row_partial *part, unsigned long long *colkey, cudaStream_t st,
-              int row_elems = TC_D) {
-    auto kern = match_f32_tc_kernel<PASSES, METRIC, COLS>;
+template <int PASSES, int METRIC, bool COLS, bool PERSIST>
+int launch_tc_kern(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &bl, const float *a_hi, const float *a_lo,
+                   int n_stride, int m_stride, const int32_t *n_ref, const int32_t *n_cur, const float *row_norm,
+                   const float *col_norm, int n_split, vo_row_partial *part, unsigned long long *colkey, cudaStream_t st,
+                   int row_elems) {
+    auto kern = match_f32_tc_kernel<PASSES, METRIC, COLS, PERSIST>;
     long long *dbg = nullptr;
     const size_t n_ctas = (size_t)grid.x * grid.y * grid.z;
     const bool trace = getenv("VO_TC_TRACE") != nullptr;
-    if (getenv("VO_TC_DEBUG") || trace) {  // bring-up only: cycle accounting of CTA (0,0,0), printed after a sync
+    if (VO_TC_DBG && (getenv("VO_TC_DEBUG") || trace)) {  // bring-up only: cycle accounting of CTA (0,0,0), printed after a sync
         static long long *dbg_dev = nullptr;
         static size_t dbg_cap = 0;
         const size_t need = 16 + (trace ? 3 * n_ctas : 0);
@@ -1032,8 +1190,32 @@ int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &
     int pair_group = 1;
     if (TcCfg<PASSES>::ALLWARP_COLS && COLS && !getenv("VO_TC_NO_INTERLEAVE"))
         pair_group = (int)max(1ll, min(8ll, (64ll << 20) / ((long long)m_stride * TC_D * 4)));
-    kern<<<grid, TC_THREADS, TcCfg<PASSES>::SMEM_BYTES, st>>>(bh, bl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm,
-                                                  n_split, part, colkey, dbg, pair_group, row_elems);
+    dim3 launch_grid = grid;
+    if (PERSIST) {  // persistent: one cluster per SM pair (as many as can be resident), each walks the logical grid
+        static int max_clusters = 0;
+        if (max_clusters == 0) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(TC_CLUSTER * 64);
+            cfg.blockDim = dim3(TC_THREADS);
+            cfg.dynamicSmemBytes = TcCfg<PASSES>::SMEM_BYTES;
+            cudaLaunchAttribute at;
+            at.id = cudaLaunchAttributeClusterDimension;
+            at.val.clusterDim.x = TC_CLUSTER; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+            cfg.attrs = &at;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+                (void)cudaGetLastError();
+                n = ctx->sm_count / TC_CLUSTER;
+            }
+            max_clusters = n;
+        }
+        const long long items = (long long)(grid.x / TC_CLUSTER) * grid.y * grid.z;
+        const long long clusters = items < max_clusters ? items : (long long)max_clusters;
+        launch_grid = dim3((unsigned)(clusters * TC_CLUSTER), 1, 1);
+    }
+    kern<<<launch_grid, TC_THREADS, TcCfg<PASSES>::SMEM_BYTES, st>>>(bh, bl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm,
+                                                  n_split, part, colkey, dbg, pair_group, row_elems, (int)grid.x, (int)grid.z);
     VO_LAUNCH_CHECK(ctx);
     if (dbg && trace) {  // per SM: busy cycles of its CTAs and the idle cycles between one CTA's exit and the next one's entry
         VO_CUDA(cudaStreamSynchronize(st));
@@ -1066,10 +1248,27 @@ int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &
         VO_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr,
                 "[vo tc dbg] passes=%d tiles=%lld cta_cycles=%lld | mma: wait_full=%lld wait_tempty=%lld total=%lld | "
-                "producer wait_empty=%lld | epi g0: wait_tfull=%lld chunks=%lld merge=%lld | g1: wait_tfull=%lld chunks=%lld merge=%lld\n",
-                PASSES, h[11], h[0], h[1], h[2], h[3], h[4], h[5], h[7], h[9], h[6], h[8], h[10]);
+                "producer wait_empty=%lld | epi g0: wait_tfull=%lld chunks=%lld merge=%lld | g1: wait_tfull=%lld chunks=%lld merge=%lld | "
+                "mma wait_a=%lld, epi between items=%lld | set-up %lld | launch grid %u\n",
+                PASSES, h[11], h[0], h[1], h[2], h[3], h[4], h[5], h[7], h[9], h[6], h[8], h[10], h[12], h[13], h[14], launch_grid.x);
     }
     return VO_OK;
+}
+
+template <int PASSES, int METRIC, bool COLS>
+int launch_tc(vo_ctx *ctx, dim3 grid, const CUtensorMap &bh, const CUtensorMap &bl, const float *a_hi, const float *a_lo,
+              int n_stride, int m_stride, const int32_t *n_ref, const int32_t *n_cur, const float *row_norm,
+              const float *col_norm, int n_split, vo_row_partial *part, unsigned long long *colkey, cudaStream_t st,
+              int row_elems = TC_D) {
+#define TC_FWD ctx, grid, bh, bl, a_hi, a_lo, n_stride, m_stride, n_ref, n_cur, row_norm, col_norm, n_split, part, colkey, st, row_elems
+    if constexpr (TcCfg<PASSES>::F16) {
+        const int tiles_per_item = ceil_div(ceil_div(m_stride, TcCfg<PASSES>::BN), n_split);
+        const char *e = getenv("VO_TC_PERSIST");   // VO_TC_PERSIST=0 / 1 forces the plain / the persistent form (comparison runs)
+        const bool persist = e ? e[0] != '0' : tiles_per_item <= VO_TC_PERSIST_MAX_TILES;
+        if (persist) return launch_tc_kern<PASSES, METRIC, COLS, true>(TC_FWD);
+    }
+    return launch_tc_kern<PASSES, METRIC, COLS, false>(TC_FWD);
+#undef TC_FWD
 }
 
 }  // namespace
@@ -1174,10 +1373,10 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     return VO_OK;
 }
 
-// Tensor-core Hamming matcher (VO_NORM_HAMMING_TC): 256-bit descriptors -> fp16 rows of -1 / +1 (once per frame set), then the
-// fp16 single pass over K = 256 (row top-2, thread-private: with 16 MMAs of N = 192 per tile the pass is bound by the tensor
-// pipe, not by its epilogue) — once with the reference descriptors as rows, and, when the acceptance rule needs the column
-// arg-min (mutual nearest neighbours, raw column output), once more with the roles swapped.  Scores are exact integers.
+// Tensor-core Hamming matcher (VO_NORM_HAMMING_TC): 256-bit descriptors -> e4m3 rows of -1 / +1 (once per frame set), then the
+// single pass over K = 256 (8 kind::f8f6f4 MMAs of N = 192 per tile; row top-2, thread-private; with the e4m3 operands the
+// fold, not the tensor pipe, bounds it) — once with the reference descriptors as rows, and, when the acceptance rule needs the
+// column arg-min (mutual nearest neighbours, raw column output), once more with the roles swapped.  Scores are exact integers.
 int match_bits_tc(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, int n_stride, int m_stride, const int32_t *n_ref,
                   const int32_t *n_cur, int need_cols, vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey,
                   cudaStream_t st) {
@@ -1192,38 +1391,38 @@ int match_bits_tc(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, in
         ctx->encode_tiled = fn;
         ctx->tc_ready = 1;
     }
-    constexpr int KD = 256, BN = TcCfg<256>::BN;
+    constexpr int KD = 256, BN = TcCfg<8>::BN;
     const long long rows_a = (long long)B * n_stride, rows_b = (long long)B * m_stride;
-    __half *a16, *b16;
+    uint8_t *a8, *b8;
     int rc;
-    if ((rc = ws_get(ctx, WS_SPLIT_A, (size_t)rows_a * KD * sizeof(__half), (void **)&a16))) return rc;
-    if ((rc = ws_get(ctx, WS_SPLIT_B, (size_t)rows_b * KD * sizeof(__half), (void **)&b16))) return rc;
+    if ((rc = ws_get(ctx, WS_SPLIT_A, (size_t)rows_a * KD, (void **)&a8))) return rc;
+    if ((rc = ws_get(ctx, WS_SPLIT_B, (size_t)rows_b * KD, (void **)&b8))) return rc;
     VO_PROF(ctx, st, VO_STAGE_PREP);
-    prep_bits_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, a16);
+    prep_bits8_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, a8);
     VO_LAUNCH_CHECK(ctx);
-    prep_bits_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b16);
+    prep_bits8_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b8);
     VO_LAUNCH_CHECK(ctx);
 
-    auto pass = [&](const __half *A, const __half *Bm, int ns, int ms, const int32_t *na, const int32_t *nb, int slot,
+    auto pass = [&](const uint8_t *A, const uint8_t *Bm, int ns, int ms, const int32_t *na, const int32_t *nb, int slot,
                     vo_row_partial **part, int *n_split) -> int {
         CUtensorMap map;
         int r;
-        if ((r = make_map(ctx, &map, Bm, (long long)B * ms, BN, KD, true))) return r;
+        if ((r = make_map(ctx, &map, Bm, (long long)B * ms, BN, KD, false, true))) return r;
         const int row_blocks = ceil_div(ns, TC_BM);
         const int grid_x = ceil_div(row_blocks, TC_CLUSTER) * TC_CLUSTER;
         const int ns_split = pick_split(ctx, B, grid_x, ceil_div(ms, BN), 4);
         if ((r = ws_get(ctx, slot, sizeof(vo_row_partial) * (size_t)B * ns_split * 4 * ns, (void **)part))) return r;
         dim3 grid(grid_x, ns_split, B);
         *n_split = ns_split * 4;
-        return launch_tc<256, VO_METRIC_COSINE, false>(ctx, grid, map, map, reinterpret_cast<const float *>(A), nullptr, ns, ms, na, nb,
-                                                       nullptr, nullptr, ns_split, *part, nullptr, st, KD);
+        return launch_tc<8, VO_METRIC_COSINE, false>(ctx, grid, map, map, reinterpret_cast<const float *>(A), nullptr, ns, ms, na, nb,
+                                                     nullptr, nullptr, ns_split, *part, nullptr, st, KD);
     };
     VO_PROF(ctx, st, VO_STAGE_MATCH);
-    if ((rc = pass(a16, b16, n_stride, m_stride, n_ref, n_cur, WS_ROWPART, part_out, n_split_out))) return rc;
+    if ((rc = pass(a8, b8, n_stride, m_stride, n_ref, n_cur, WS_ROWPART, part_out, n_split_out))) return rc;
     if (need_cols) {
         vo_row_partial *part2;
         int n_split2;
-        if ((rc = pass(b16, a16, m_stride, n_stride, n_cur, n_ref, WS_ROWPART2, &part2, &n_split2))) return rc;
+        if ((rc = pass(b8, a8, m_stride, n_stride, n_cur, n_ref, WS_ROWPART2, &part2, &n_split2))) return rc;
         colkey_from_partials_kernel<<<dim3(ceil_div(m_stride, 256), B), 256, 0, st>>>(part2, n_split2, m_stride, n_cur, colkey);
         VO_LAUNCH_CHECK(ctx);
     }

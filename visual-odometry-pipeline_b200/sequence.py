@@ -139,20 +139,43 @@ class PipelineConfig:
                        n_hyp=n_hyp, seed=seed, thr_px=thr_px, min_inliers=min_inliers, refine_iters=refine_iters)
 
 
-def run_resident(batch, cfg, pair0=0, chunk=None, out=None):
-    """vo_pipeline over device-resident pairs, in chunks; returns a PipelineBuffers covering the whole block."""
+_LANE_STREAMS = {}
+
+
+def _lane_streams(device, lanes):
+    key = (torch.device(device).index, lanes)
+    if key not in _LANE_STREAMS:
+        _LANE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(lanes)]
+    return _LANE_STREAMS[key]
+
+
+def run_resident(batch, cfg, pair0=0, chunk=None, out=None, lanes=1):
+    """vo_pipeline over device-resident pairs, in chunks; returns a PipelineBuffers covering the whole block.
+    `lanes` > 1 issues the chunks round-robin on that many streams (one vo_ctx, i.e. one workspace, each), forked from and
+    joined to the current stream: the small-grid tail of one chunk (gather, P3P, score, refit — one CTA per pair) then
+    overlaps the next chunk's matcher instead of leaving most SMs idle.  Results do not depend on `lanes`."""
     B = batch.B
     chunk = chunk or B
-    out = out or ops.PipelineBuffers(B, batch.slice(0, 1).ref_desc.device)
-    for lo in range(0, B, chunk):
+    dev = batch.slice(0, 1).ref_desc.device
+    out = out or ops.PipelineBuffers(B, dev)
+    cur = torch.cuda.current_stream(dev)
+    streams = _lane_streams(dev, lanes) if lanes > 1 else [cur]
+    if lanes > 1:
+        for ls in streams:
+            ls.wait_stream(cur)
+    for i, lo in enumerate(range(0, B, chunk)):
         hi = min(B, lo + chunk)
         sub = batch.slice(lo, hi)
         view = ops.PipelineBuffers.__new__(ops.PipelineBuffers)
         view.T_rel, view.rt = out.T_rel[lo:hi], out.rt[lo:hi]
         view.n_matches, view.n_corr = out.n_matches[lo:hi], out.n_corr[lo:hi]
         view.n_inl, view.status = out.n_inl[lo:hi], out.status[lo:hi]
-        ops.pipeline(sub.ref_desc, sub.cur_desc, sub.ref_kp, sub.cur_kp, sub.depth, batch.K, pair0=pair0 + lo,
-                     out=view, **cfg.kw)
+        with torch.cuda.stream(streams[i % lanes]):
+            ops.pipeline(sub.ref_desc, sub.cur_desc, sub.ref_kp, sub.cur_kp, sub.depth, batch.K, pair0=pair0 + lo,
+                         out=view, lane=i % lanes, **cfg.kw)
+    if lanes > 1:
+        for ls in streams:
+            cur.wait_stream(ls)
     return out
 
 
