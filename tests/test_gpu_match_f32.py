@@ -231,3 +231,46 @@ def test_fp16_passes_random_shapes_vs_oracle(orc):
             s = orc.pair_scores_f64(ref, cur, [gc[col], cidx[col]], [col, col], orc.METRIC_COSINE)
             assert abs(s[0] - s[1]) <= REL_TIE * abs(s).max(), (n, m, col, s)
         assert np.allclose(r.knn_val[0].cpu().numpy()[:, 0], rval[:, 0], atol=2e-6, rtol=0), (n, m)
+
+
+@pytest.mark.parametrize("kind", ["sift_f16", "sift_tf32", "r2d2_tf32x3", "r2d2_f16x3", "bits_tc", "bits_l2", "sift_u8"])
+def test_consecutive_pairs_prepared_once_equal_separate_buffers(kind):
+    """Pairs of one frame sequence (cur = ref one frame on in memory: sequence.FrameSequence) take the path that prepares every
+    frame once (match_f32_tc / match_bits_tc, `chained`); the same descriptors in two separate buffers take the two-sided
+    path.  Same matches, distances and counts, bit for bit; ragged counts included."""
+    import torch
+    from vo_b200 import ops
+    rng = np.random.default_rng(11)
+    B, N = 5, 700 if kind != "sift_u8" else 512
+    n_ref = torch.tensor([N, N - 3, 650, N, 1], dtype=torch.int32, device="cuda")
+    n_cur = torch.tensor([N - 3, 650, N, 1, N], dtype=torch.int32, device="cuda")
+    perms = [rng.permutation(N) for _ in range(B + 1)]      # every frame: the same N features, shuffled and perturbed
+    if kind in ("bits_tc", "bits_l2"):
+        base = rng.integers(0, 256, (N, 32), dtype=np.uint8)
+        seq = torch.from_numpy(np.stack([base[p] ^ (rng.random((N, 32)) < 0.05).astype(np.uint8) for p in perms])).cuda()
+        norm, mode = (ops.VO_NORM_HAMMING_TC, ops.VO_MODE_MUTUAL) if kind == "bits_tc" else (ops.VO_NORM_L2_U8, ops.VO_MODE_RATIO)
+        call = lambda r, c: ops.match_u8(r, c, norm, mode, 0.85, n_ref=n_ref, n_cur=n_cur)
+    elif kind == "sift_u8":
+        base = rng.integers(0, 200, (N, 128))
+        seq = torch.from_numpy(np.stack([(base[p] + rng.integers(0, 8, (N, 128))).astype(np.uint8) for p in perms])).cuda()
+        call = lambda r, c: ops.match_u8(r, c, ops.VO_NORM_L2_U8, ops.VO_MODE_RATIO, 0.85, n_ref=n_ref, n_cur=n_cur)
+    elif kind.startswith("sift"):
+        base = rng.integers(0, 200, (N, 128))
+        seq = torch.from_numpy(np.stack([(base[p] + rng.integers(0, 8, (N, 128))).astype(np.float32) for p in perms])).cuda()
+        prec = ops.VO_PREC_F16X1 if kind == "sift_f16" else ops.VO_PREC_TF32X1
+        call = lambda r, c: ops.match_f32(r, c, ops.VO_METRIC_L2, ops.VO_MODE_RATIO, 0.85, prec, n_ref=n_ref, n_cur=n_cur)
+    else:
+        base = rng.standard_normal((N, 128))
+        d = np.stack([base[p] + 0.05 * rng.standard_normal((N, 128)) for p in perms]).astype(np.float32)
+        seq = torch.from_numpy(d / np.linalg.norm(d, axis=2, keepdims=True)).cuda()
+        prec = ops.VO_PREC_TF32X3 if kind == "r2d2_tf32x3" else ops.VO_PREC_F16X3
+        call = lambda r, c: ops.match_f32(r, c, ops.VO_METRIC_COSINE, ops.VO_MODE_RATIO_MUTUAL, 0.9, prec, n_ref=n_ref, n_cur=n_cur)
+    ref, cur = seq[:-1], seq[1:]
+    assert cur.data_ptr() == ref.data_ptr() + ref[0].numel() * ref.element_size()       # the chained layout
+    a = call(ref, cur)
+    b = call(ref.clone(), cur.clone())
+    torch.cuda.synchronize()
+    assert torch.equal(a.count, b.count) and int(a.count.sum()) > N
+    for i, c in enumerate(a.count.tolist()):                 # rows past count[b] are unspecified
+        assert torch.equal(a.pairs[i, :c], b.pairs[i, :c])
+        assert torch.equal(a.dist[i, :c].view(torch.int32), b.dist[i, :c].view(torch.int32))

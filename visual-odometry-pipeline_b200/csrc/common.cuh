@@ -138,8 +138,8 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
                  cudaStream_t st, int src_u8 = 0);
 // tensor-core Hamming (VO_NORM_HAMMING_TC): row partials of the 256-bit descriptors and, if need_cols, the column keys
 int match_bits_tc(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, int n_stride, int m_stride, const int32_t *n_ref,
-                  const int32_t *n_cur, int need_cols, vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey,
-                  cudaStream_t st);
+                  const int32_t *n_cur, int need_cols, int need_second, vo_row_partial **part_out, int *n_split_out,
+                  unsigned long long *colkey, cudaStream_t st);
 int pick_split(vo_ctx *ctx, int B, int row_blocks, int col_tiles, int min_tiles_per_split);
 int hypotheses_impl(vo_ctx *ctx, const int32_t *n_pts, int B, int H, uint64_t seed, int64_t pair0, const long long *pair0_dev,
                     int32_t *hyp, void *stream);

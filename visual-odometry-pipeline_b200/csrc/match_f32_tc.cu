@@ -30,6 +30,7 @@
 //   48  3xFP16      x * 2^8 = hi + lo in fp16, three kind::f16 MMAs per 16 k   the 22 operand bits of 3xTF32 at twice the rate
 //    8  1xFP8/256   256-bit descriptors as 256-d rows of e4m3 -1 / +1         a.b = 256 - 2 Hamming (exact), kind::f8f6f4 (K = 32),
 //                                                                              K = 256, no norms (as fp16 rows: twice the bytes and MMAs)
+//    9  the same, row arg-max only (no second best)                            mutual-NN rule without k-NN output; the swapped pass
 // The two fp16 modes use the all-warp epilogue (16 warps on every tile, accumulator released right after the TMEM read,
 // the four threads of a row share their filter threshold); tools/probe/mma_issue_probe.cu has the pipe rates.
 #include "common.cuh"
@@ -69,7 +70,8 @@ constexpr int TC_NKB = TC_D / TC_KB;
 // three kind::tf32 MMAs per 8 k.  Tile geometry, ring and epilogue are those of 3xTF32.
 template <int PASSES>
 struct TcCfg {
-    static constexpr bool F8 = PASSES == 8;                       // e4m3 operands, tcgen05.mma.kind::f8f6f4 (128 k per 128-byte box)
+    static constexpr bool F8 = PASSES == 8 || PASSES == 9;        // e4m3 operands, tcgen05.mma.kind::f8f6f4 (128 k per 128-byte box)
+    static constexpr bool TOP1 = PASSES == 9;                     // row arg-max only: the fold keeps (s1, i1), half the filter hits
     static constexpr bool K256 = F8;                              // single pass over 256-d rows (bit descriptors as -1 / +1)
     static constexpr bool F16 = PASSES == 16 || K256;             // fp16 / fp8 single pass (own epilogue)
     static constexpr int KBOX = F8 ? 128 : 64;                    // k per box of the 16- and 8-bit passes
@@ -317,7 +319,7 @@ __device__ __forceinline__ float row_threshold(float s2_own, float tau) {
 // the warp reaches `colthr`, a lower bound of what the warp's columns already hold in colkey (their best over the row
 // blocks seen so far, weakest column; >= keeps exact ties, which a lower row index may still win).  Slots of skipped
 // columns keep the zero ballot the caller wrote.  Needs row blocks of a pair that run at different times (pair_group).
-template <int METRIC, bool MASK_COLS, bool ROW_MASK, bool COLS, bool EXT, bool SCALED = false, bool COLFILT = false>
+template <int METRIC, bool MASK_COLS, bool ROW_MASK, bool COLS, bool EXT, bool SCALED = false, bool COLFILT = false, bool TOP1 = false>
 __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M, bool row_ok, float na,
                                            const float *__restrict__ cn, bool cn_vec, int lane, float *cv_out,
                                            uint32_t *cb_out, float &s1, float &s2, int32_t &i1, int32_t &i2, float &thr,
@@ -390,10 +392,20 @@ __device__ __forceinline__ void epi_group8(const float (&v)[8], int cbase, int M
 #pragma unroll
     for (int j0 = 0; j0 < 8; j0 += 4) {
         const float m4 = fmaxf(fmaxf(sc[j0], sc[j0 + 1]), fmaxf(sc[j0 + 2], sc[j0 + 3]));
-        if ((!ROW_MASK || row_ok) && m4 > thr) {  // thr >= s2: see row_threshold()
+        if ((!ROW_MASK || row_ok) && m4 > thr) {  // thr >= s2 (TOP1: >= s1): see row_threshold()
+            if (TOP1) {  // ascending columns: strict > keeps the lower column on ties
 #pragma unroll
-            for (int j = 0; j < 4; ++j) row_insert(sc[j0 + j], cbase + j0 + j, s1, s2, i1, i2);
-            thr = fmaxf(thr, s2);
+                for (int j = 0; j < 4; ++j) {
+                    const bool gt = sc[j0 + j] > s1;
+                    i1 = gt ? cbase + j0 + j : i1;
+                    s1 = gt ? sc[j0 + j] : s1;
+                }
+                thr = fmaxf(thr, s1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) row_insert(sc[j0 + j], cbase + j0 + j, s1, s2, i1, i2);
+                thr = fmaxf(thr, s2);
+            }
         }
     }
 }
@@ -748,7 +760,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                 {  // the other three column quarters' second-bests of this row (read while the TMEM loads fly)
                     const float tau = fmaxf(fmaxf(srow2[((cq + 1) & 3) * TC_BM + rr], srow2[((cq + 2) & 3) * TC_BM + rr]),
                                             srow2[((cq + 3) & 3) * TC_BM + rr]);
-                    thr = fmaxf(thr, row_threshold(s2, tau));
+                    thr = fmaxf(thr, row_threshold(Cfg::TOP1 ? s1 : s2, tau));   // TOP1: the slots hold running bests
                 }
                 tc_ld_wait8(g0);
                 tc_ld_wait8(g1);
@@ -760,8 +772,8 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
     {                                                                                                                      \
         float v[8];                                                                                                        \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(BUF[i]);                                      \
-        epi_group8<METRIC, MASKC, MASKR, false, EXT>(v, col0 + (J0), M, row_ok, na, nullptr, false, lane, nullptr, nullptr, \
-                                                     s1, s2, i1, i2, thr);                                                  \
+        epi_group8<METRIC, MASKC, MASKR, false, EXT, false, false, Cfg::TOP1>(v, col0 + (J0), M, row_ok, na, nullptr, false,  \
+                                                                              lane, nullptr, nullptr, s1, s2, i1, i2, thr); \
     }
 #define TC_FOLD48(MASKC, MASKR)                                                                                            \
     TC_FOLD8(g0, 0, MASKC, MASKR)                                                                                          \
@@ -779,7 +791,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                 if (full_tile && !partial_rows) { TC_FOLD48(false, false) } else { TC_FOLD48(true, true) }
 #undef TC_FOLD48
 #undef TC_FOLD8
-                srow2[cq * TC_BM + rr] = s2;
+                srow2[cq * TC_BM + rr] = Cfg::TOP1 ? s1 : s2;
                 if (edbg) dbg_acc[2] += clock64() - _tm0;
                 ++gt;
             };
@@ -1303,44 +1315,48 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     const bool f16 = passes == 16, h16 = passes == 16 || passes == 48, three = passes == 3 || passes == 48;
     const size_t esz = h16 ? sizeof(__half) : sizeof(float);
     const int row_elems = src_u8 ? src_u8 : TC_D;  // stored elements per descriptor row
-    const size_t per_a = (size_t)rows_a * row_elems * esz, per_b = (size_t)rows_b * row_elems * esz;
-    if ((rc = ws_get(ctx, WS_SPLIT_A, per_a * (three ? 2 : 1), (void **)&split_a))) return rc;
     const bool ext = !three && l2;  // B extension rows [rows_b][32] live behind B_hi
-    const size_t per_ext = (size_t)rows_b * TC_KB * sizeof(float);
-    if ((rc = ws_get(ctx, WS_SPLIT_B, per_b * (three ? 2 : 1) + (ext ? per_ext : 0), (void **)&split_b))) return rc;
+    // Consecutive pairs of one frame sequence (pair i = frames i, i + 1: what sequence.FrameSequence hands over, and what a VO run
+    // is): the current descriptors are the reference descriptors one frame on.  Then every frame is prepared ONCE — B + 1 frames
+    // instead of 2 B — and the B side of the matcher is the A side shifted by a frame (prep is 16 % of a 2k-keypoint SIFT step).
+    const size_t src_row_bytes = src_u8 ? (size_t)src_u8 : TC_D * sizeof(float);
+    const bool chained = n_stride == m_stride && (n_stride & 3) == 0 && B > 0 && !getenv("VO_NO_CHAIN_PREP") &&
+                         reinterpret_cast<const char *>(cur) == reinterpret_cast<const char *>(ref) + (size_t)n_stride * src_row_bytes;
+    const long long rows_p = chained ? rows_a + n_stride : rows_a;   // rows prepared on the A side
+    const size_t per_a = (size_t)rows_p * row_elems * esz, per_b = chained ? 0 : (size_t)rows_b * row_elems * esz;
+    if ((rc = ws_get(ctx, WS_SPLIT_A, per_a * (three ? 2 : 1), (void **)&split_a))) return rc;
+    const size_t per_ext = (size_t)(chained ? rows_p : rows_b) * TC_KB * sizeof(float);
+    if ((rc = ws_get(ctx, WS_SPLIT_B, per_b * (three ? 2 : 1) + (ext ? per_ext : 0) + 16, (void **)&split_b))) return rc;
     const long long rows_a4 = (rows_a + 3) & ~3ll;  // column norms start 16 B aligned (vector loads in the epilogue)
-    if ((rc = ws_get(ctx, WS_NORMS, sizeof(float) * (size_t)(rows_a4 + rows_b), (void **)&norms))) return rc;
+    if ((rc = ws_get(ctx, WS_NORMS, sizeof(float) * (size_t)(chained ? rows_p : rows_a4 + rows_b), (void **)&norms))) return rc;
+    const size_t shift = (size_t)n_stride * row_elems * esz;   // one frame of prepared rows, bytes (chained)
     float *a_hi = split_a, *a_lo = three ? reinterpret_cast<float *>(reinterpret_cast<char *>(split_a) + per_a) : nullptr;
-    float *b_hi = split_b, *b_lo = three ? reinterpret_cast<float *>(reinterpret_cast<char *>(split_b) + per_b) : nullptr;
-    float *b_ext = ext ? reinterpret_cast<float *>(reinterpret_cast<char *>(split_b) + per_b) : nullptr;
-    float *row_norm = norms, *col_norm = norms + rows_a4;
+    float *b_hi = chained ? reinterpret_cast<float *>(reinterpret_cast<char *>(a_hi) + shift) : split_b;
+    float *b_lo = !three ? nullptr : (chained ? reinterpret_cast<float *>(reinterpret_cast<char *>(a_lo) + shift)
+                                              : reinterpret_cast<float *>(reinterpret_cast<char *>(split_b) + per_b));
+    float *x_ext = ext ? reinterpret_cast<float *>(reinterpret_cast<char *>(split_b) + per_b * (three ? 2 : 1)) : nullptr;
+    float *b_ext = (ext && chained) ? x_ext + (size_t)n_stride * TC_KB : x_ext;
+    float *row_norm = norms, *col_norm = chained ? norms + n_stride : norms + rows_a4;
 
     VO_PROF(ctx, st, VO_STAGE_PREP);
-    if (passes == 48) {
-        prep16x3_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, reinterpret_cast<__half *>(a_hi), reinterpret_cast<__half *>(a_lo), l2 ? row_norm : nullptr);
-        VO_LAUNCH_CHECK(ctx);
-        prep16x3_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, reinterpret_cast<__half *>(b_hi), reinterpret_cast<__half *>(b_lo), l2 ? col_norm : nullptr);
-        VO_LAUNCH_CHECK(ctx);
-    } else if (f16 && src_u8) {
-        if (src_u8 == 32) {
-            prep16_u8_kernel<32><<<(unsigned)((rows_a + 31) / 32), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(ref), rows_a, reinterpret_cast<__half *>(a_hi), row_norm, nullptr);
-            VO_LAUNCH_CHECK(ctx);
-            prep16_u8_kernel<32><<<(unsigned)((rows_b + 31) / 32), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(cur), rows_b, reinterpret_cast<__half *>(b_hi), col_norm, b_ext);
-        } else {
-            prep16_u8_kernel<128><<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(ref), rows_a, reinterpret_cast<__half *>(a_hi), row_norm, nullptr);
-            VO_LAUNCH_CHECK(ctx);
-            prep16_u8_kernel<128><<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(cur), rows_b, reinterpret_cast<__half *>(b_hi), col_norm, b_ext);
-        }
-        VO_LAUNCH_CHECK(ctx);
-    } else if (f16) {
-        prep16_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, reinterpret_cast<__half *>(a_hi), l2 ? row_norm : nullptr, nullptr);
-        VO_LAUNCH_CHECK(ctx);
-        prep16_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, reinterpret_cast<__half *>(b_hi), l2 ? col_norm : nullptr, b_ext);
-        VO_LAUNCH_CHECK(ctx);
-    } else {
-        prep_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, a_hi, a_lo, l2 ? row_norm : nullptr, nullptr);
-        VO_LAUNCH_CHECK(ctx);
-        prep_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b_hi, b_lo, l2 ? col_norm : nullptr, b_ext);
+    // (side 0: reference rows — all prepared rows when chained, extension included; side 1: current rows, not run when chained)
+    for (int side = 0; side < (chained ? 1 : 2); ++side) {
+        const float *src = side ? cur : ref;
+        const long long rows = side ? rows_b : rows_p;
+        float *hi = side ? b_hi : a_hi, *lo = side ? b_lo : a_lo;
+        float *nrm = l2 ? (side ? col_norm : row_norm) : nullptr;
+        float *xe = (side || chained) ? x_ext : nullptr;
+        const unsigned g8 = (unsigned)((rows + 7) / 8);
+        if (passes == 48)
+            prep16x3_kernel<<<g8, 256, 0, st>>>(src, rows, reinterpret_cast<__half *>(hi), reinterpret_cast<__half *>(lo), nrm);
+        else if (f16 && src_u8 == 32)
+            prep16_u8_kernel<32><<<(unsigned)((rows + 31) / 32), 256, 0, st>>>(reinterpret_cast<const uint8_t *>(src), rows, reinterpret_cast<__half *>(hi), side ? col_norm : row_norm, xe);
+        else if (f16 && src_u8)
+            prep16_u8_kernel<128><<<g8, 256, 0, st>>>(reinterpret_cast<const uint8_t *>(src), rows, reinterpret_cast<__half *>(hi), side ? col_norm : row_norm, xe);
+        else if (f16)
+            prep16_kernel<<<g8, 256, 0, st>>>(src, rows, reinterpret_cast<__half *>(hi), nrm, xe);
+        else
+            prep_kernel<<<g8, 256, 0, st>>>(src, rows, hi, lo, nrm, xe);
         VO_LAUNCH_CHECK(ctx);
     }
 
@@ -1378,8 +1394,8 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
 // fold, not the tensor pipe, bounds it) — once with the reference descriptors as rows, and, when the acceptance rule needs the
 // column arg-min (mutual nearest neighbours, raw column output), once more with the roles swapped.  Scores are exact integers.
 int match_bits_tc(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, int n_stride, int m_stride, const int32_t *n_ref,
-                  const int32_t *n_cur, int need_cols, vo_row_partial **part_out, int *n_split_out, unsigned long long *colkey,
-                  cudaStream_t st) {
+                  const int32_t *n_cur, int need_cols, int need_second, vo_row_partial **part_out, int *n_split_out,
+                  unsigned long long *colkey, cudaStream_t st) {
     if (!ctx->tc_ready) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -1395,16 +1411,24 @@ int match_bits_tc(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, in
     const long long rows_a = (long long)B * n_stride, rows_b = (long long)B * m_stride;
     uint8_t *a8, *b8;
     int rc;
-    if ((rc = ws_get(ctx, WS_SPLIT_A, (size_t)rows_a * KD, (void **)&a8))) return rc;
-    if ((rc = ws_get(ctx, WS_SPLIT_B, (size_t)rows_b * KD, (void **)&b8))) return rc;
+    // consecutive pairs of one frame sequence (cur = ref one frame on): every frame is expanded once (see match_f32_tc)
+    const bool chained = n_stride == m_stride && B > 0 && !getenv("VO_NO_CHAIN_PREP") && cur == ref + (size_t)n_stride * 32;
+    const long long rows_p = chained ? rows_a + n_stride : rows_a;
+    if ((rc = ws_get(ctx, WS_SPLIT_A, (size_t)rows_p * KD, (void **)&a8))) return rc;
+    if (chained) b8 = a8 + (size_t)n_stride * KD;
+    else if ((rc = ws_get(ctx, WS_SPLIT_B, (size_t)rows_b * KD, (void **)&b8))) return rc;
     VO_PROF(ctx, st, VO_STAGE_PREP);
-    prep_bits8_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(ref, rows_a, a8);
+    prep_bits8_kernel<<<(unsigned)((rows_p + 7) / 8), 256, 0, st>>>(ref, rows_p, a8);
     VO_LAUNCH_CHECK(ctx);
-    prep_bits8_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b8);
-    VO_LAUNCH_CHECK(ctx);
+    if (!chained) {
+        prep_bits8_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(cur, rows_b, b8);
+        VO_LAUNCH_CHECK(ctx);
+    }
 
+    // second == false: the acceptance rule reads the row arg-max only (mutual NN without k-NN output; always so for the swapped
+    // pass) — the fold then keeps one (score, index) pair per row and its filter fires half as often
     auto pass = [&](const uint8_t *A, const uint8_t *Bm, int ns, int ms, const int32_t *na, const int32_t *nb, int slot,
-                    vo_row_partial **part, int *n_split) -> int {
+                    vo_row_partial **part, int *n_split, bool second) -> int {
         CUtensorMap map;
         int r;
         if ((r = make_map(ctx, &map, Bm, (long long)B * ms, BN, KD, false, true))) return r;
@@ -1414,15 +1438,18 @@ int match_bits_tc(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, in
         if ((r = ws_get(ctx, slot, sizeof(vo_row_partial) * (size_t)B * ns_split * 4 * ns, (void **)part))) return r;
         dim3 grid(grid_x, ns_split, B);
         *n_split = ns_split * 4;
-        return launch_tc<8, VO_METRIC_COSINE, false>(ctx, grid, map, map, reinterpret_cast<const float *>(A), nullptr, ns, ms, na, nb,
+        if (second)
+            return launch_tc<8, VO_METRIC_COSINE, false>(ctx, grid, map, map, reinterpret_cast<const float *>(A), nullptr, ns, ms, na, nb,
+                                                         nullptr, nullptr, ns_split, *part, nullptr, st, KD);
+        return launch_tc<9, VO_METRIC_COSINE, false>(ctx, grid, map, map, reinterpret_cast<const float *>(A), nullptr, ns, ms, na, nb,
                                                      nullptr, nullptr, ns_split, *part, nullptr, st, KD);
     };
     VO_PROF(ctx, st, VO_STAGE_MATCH);
-    if ((rc = pass(a8, b8, n_stride, m_stride, n_ref, n_cur, WS_ROWPART, part_out, n_split_out))) return rc;
+    if ((rc = pass(a8, b8, n_stride, m_stride, n_ref, n_cur, WS_ROWPART, part_out, n_split_out, need_second != 0))) return rc;
     if (need_cols) {
         vo_row_partial *part2;
         int n_split2;
-        if ((rc = pass(b8, a8, m_stride, n_stride, n_cur, n_ref, WS_ROWPART2, &part2, &n_split2))) return rc;
+        if ((rc = pass(b8, a8, m_stride, n_stride, n_cur, n_ref, WS_ROWPART2, &part2, &n_split2, false))) return rc;
         colkey_from_partials_kernel<<<dim3(ceil_div(m_stride, 256), B), 256, 0, st>>>(part2, n_split2, m_stride, n_cur, colkey);
         VO_LAUNCH_CHECK(ctx);
     }

@@ -264,7 +264,7 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
                               ratio, row_norm_tc, out_pairs, out_dist, out_count, knn, nullptr, st);
     }
     // Opt-in tensor-core Hamming (VO_NORM_HAMMING_TC; VO_NORM_HAMMING stays XOR + POPC, what the north-star prescribes): with the
-    // 256 bits as fp16 -1 / +1, a.b = 256 - 2 popcount(a xor b), so the fp16 single pass of the tcgen05 matcher over K = 256 orders
+    // 256 bits as e4m3 -1 / +1, a.b = 256 - 2 popcount(a xor b), so the single pass of the tcgen05 matcher over K = 256 orders
     // by Hamming distance (match_bits_tc, csrc/match_f32_tc.cu).  Exact integers throughout, same tie rules, same finalize:
     // results are bit-identical to the XOR + POPC kernel (tests/test_gpu_match_u8.py).
     if (norm == VO_NORM_HAMMING_TC) {
@@ -273,7 +273,10 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
         if ((rc = ws_get(ctx, WS_COLKEY, sizeof(unsigned long long) * (size_t)B * m_stride, (void **)&colkey_tc))) return rc;
         vo_row_partial *part_tc;
         int n_split_tc;
-        if ((rc = match_bits_tc(ctx, ref, cur, B, n_stride, m_stride, n_ref, n_cur, need_cols ? 1 : 0, &part_tc, &n_split_tc, colkey_tc, st)))
+        // the second best of a row is read by the ratio rule and by the k-NN output only
+        const bool need_second = mode == VO_MODE_RATIO || (knn && (knn->row_idx || knn->row_val));
+        if ((rc = match_bits_tc(ctx, ref, cur, B, n_stride, m_stride, n_ref, n_cur, need_cols ? 1 : 0, need_second ? 1 : 0, &part_tc,
+                                &n_split_tc, colkey_tc, st)))
             return rc;
         return match_finalize(ctx, part_tc, n_split_tc, colkey_tc, B, n_stride, m_stride, n_ref, n_cur, SCORE_HAMMING_F32, mode,
                               ratio, nullptr, out_pairs, out_dist, out_count, knn, nullptr, st);
