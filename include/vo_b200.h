@@ -51,7 +51,7 @@ extern "C" {
 /* byte descriptors (ORB) */
 #define VO_NORM_HAMMING 0 /* popcount(a xor b): cv2.NORM_HAMMING (north-star semantics)          */
 #define VO_NORM_L2_U8 1   /* sqrt(sum (a_k-b_k)^2) over byte VALUES: what ORB.py:8 really builds  */
-#define VO_NORM_HAMMING_TC 2 /* VO_NORM_HAMMING computed on the tensor cores (bits as fp16 -1/+1, K = 256 tcgen05 GEMM, exact integers;
+#define VO_NORM_HAMMING_TC 2 /* VO_NORM_HAMMING computed on the tensor cores (bits as e4m3 -1/+1, K = 256 tcgen05 kind::f8f6f4 GEMM, exact integers;
                                 a second pass with the roles swapped supplies the column arg-min): bit-identical results, opt-in;
                                 VO_NORM_HAMMING itself stays XOR + POPC */
 /* float descriptors */

@@ -169,7 +169,7 @@ def test_l2_bytes_tensor_core_pass_random_shapes(orc):
 
 @pytest.mark.parametrize("n,m", [(5000, 5000), (1237, 3001), (513, 255), (129, 700), (700, 1)])
 def test_tensor_core_hamming_is_bit_identical_to_xor_popc(orc, golden, n, m):
-    """VO_NORM_HAMMING_TC (bits as fp16 -1 / +1, K = 256 tcgen05 GEMM, row top-2; roles swapped for the column arg-min) against the XOR + POPC
+    """VO_NORM_HAMMING_TC (bits as e4m3 -1 / +1, K = 256 tcgen05 GEMM, row top-2 — or row arg-max only when nothing reads the second best; roles swapped for the column arg-min) against the XOR + POPC
     kernel and the CPU oracle: same neighbours, same distances, same column arg-min, same accepted pairs, every rule."""
     import torch
     from vo_b200 import ops, synthetic
