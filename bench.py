@@ -535,7 +535,7 @@ def run_ours(args, name):
                         "achieved counts both passes (the `match` stage covers both launches and the column-key merge).  With e4m3 operands "
                         "the row top-2 fold (ALU pipe), not the tensor pipe, bounds the pass: frac is structurally < 0.5"}
     elif wl["kind"] == "orb":
-        alg_bytes = pairs_per_launch * (32.0 * (N + M) + 16.0 * N + 8.0 * M)      # descriptors + row partials + column keys
+        alg_bytes = pairs_per_launch * (32.0 * (N + M) + 8.0 * N + 8.0 * M)       # descriptors + row bests (8 B: mutual rule) + column keys
         roof = {"kernel": "match_u8_kernel (XOR+POPC Hamming, fused row/column arg-min)", "bound": "hbm",
                 "achieved": alg_bytes / match_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "traffic": ncu_traffic("match_u8_kernel", pairs_per_launch), "algorithmic_bytes": alg_bytes,

@@ -162,6 +162,13 @@ enum ScoreKind {
     SCORE_L2SQ_U32 = 1,  // s = integer squared L2, dist = sqrtf((float)s)
     SCORE_L2SQ_F32 = 2,  // s = ordered key of fp32 squared L2, dist = sqrtf
     SCORE_NEGSIM_F32 = 3, // s = ordered key of -similarity, value = sim, dist = sqrtf(2-2 sim)
-    SCORE_HAMMING_F32 = 4 // s = ordered key of -(a.b) over -1 / +1 bit vectors = 2 Hamming - 256 (exact fp32): tensor-core Hamming
+    SCORE_HAMMING_F32 = 4, // s = ordered key of -(a.b) over -1 / +1 bit vectors = 2 Hamming - 256 (exact fp32): tensor-core Hamming
+    // flag, or-ed into the kind: the partials are 8-byte (s1, i1) pairs (vo_row_best) — written by the matchers when nothing
+    // reads a row's second best (mutual / plain-NN rules without k-NN output): half the bytes of the row side
+    SCORE_COMPACT_PARTIALS = 0x100
+};
+struct __align__(8) vo_row_best {
+    uint32_t s1;
+    int32_t i1;
 };
 }  // namespace vo

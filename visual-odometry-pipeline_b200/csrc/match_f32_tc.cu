@@ -235,7 +235,7 @@ prep_bits8_kernel(const uint8_t *__restrict__ x, long long rows, uint8_t *__rest
 // current descriptor IS the column arg-min of the first pass.  Merges the per-split partials (ties -> lower reference row,
 // the rule of the fused column arg-min) into the colkey format finalize reads: ordered(-score) << 32 | reference row.
 __global__ void __launch_bounds__(256)
-colkey_from_partials_kernel(const vo_row_partial *__restrict__ part, int n_split, int m_stride, const int32_t *__restrict__ n_cur,
+colkey_from_partials_kernel(const vo_row_best *__restrict__ part, int n_split, int m_stride, const int32_t *__restrict__ n_cur,
                             unsigned long long *__restrict__ colkey) {
     const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m_stride) return;
@@ -243,7 +243,7 @@ colkey_from_partials_kernel(const vo_row_partial *__restrict__ part, int n_split
     unsigned long long best = ~0ull;
     if (j < M)
         for (int sp = 0; sp < n_split; ++sp) {
-            const vo_row_partial p = part[((size_t)b * n_split + sp) * m_stride + j];
+            const vo_row_best p = part[((size_t)b * n_split + sp) * m_stride + j];   // the swapped pass keeps row bests only
             if (p.i1 >= 0) {
                 const unsigned long long key = ((unsigned long long)p.s1 << 32) | (unsigned long long)(uint32_t)p.i1;
                 best = key < best ? key : best;
@@ -819,10 +819,17 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
             {
                 const Item I = item_at(w);
                 if (I.row0 + rr < n_stride) {  // four column quarters: four partials per (row, split), merged by finalize
-                    vo_row_partial p;
-                    p.s1 = float_to_ordered(-s1); p.s2 = float_to_ordered(-s2);
-                    p.i1 = i1; p.i2 = i2;
-                    part[((size_t)I.b * (n_split * 4) + I.split * 4 + cq) * n_stride + I.row0 + rr] = p;
+                    const size_t at = ((size_t)I.b * (n_split * 4) + I.split * 4 + cq) * n_stride + I.row0 + rr;
+                    if (Cfg::TOP1) {  // 8-byte partials (SCORE_COMPACT_PARTIALS)
+                        vo_row_best q;
+                        q.s1 = float_to_ordered(-s1); q.i1 = i1;
+                        reinterpret_cast<vo_row_best *>(part)[at] = q;
+                    } else {
+                        vo_row_partial p;
+                        p.s1 = float_to_ordered(-s1); p.s2 = float_to_ordered(-s2);
+                        p.i1 = i1; p.i2 = i2;
+                        part[at] = p;
+                    }
                 }
             }
             if (has_next) {
@@ -1450,7 +1457,8 @@ int match_bits_tc(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, int B, in
         vo_row_partial *part2;
         int n_split2;
         if ((rc = pass(b8, a8, m_stride, n_stride, n_cur, n_ref, WS_ROWPART2, &part2, &n_split2, false))) return rc;
-        colkey_from_partials_kernel<<<dim3(ceil_div(m_stride, 256), B), 256, 0, st>>>(part2, n_split2, m_stride, n_cur, colkey);
+        colkey_from_partials_kernel<<<dim3(ceil_div(m_stride, 256), B), 256, 0, st>>>(reinterpret_cast<const vo_row_best *>(part2), n_split2,
+                                                                                      m_stride, n_cur, colkey);
         VO_LAUNCH_CHECK(ctx);
     }
     return VO_OK;

@@ -53,6 +53,8 @@ finalize_kernel(const vo_row_partial *__restrict__ part, int n_split, const unsi
                 float *__restrict__ out_dist, int32_t *__restrict__ chunk_count, int32_t *__restrict__ knn_row_idx,
                 float *__restrict__ knn_row_val, int32_t *__restrict__ knn_col_idx, uint8_t *__restrict__ near_tie,
                 int chunk_rows) {
+    const bool compact = (kind & SCORE_COMPACT_PARTIALS) != 0;
+    kind &= ~SCORE_COMPACT_PARTIALS;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int chunk0 = chunk * chunk_rows;
     const int N = n_ref ? min(n_ref[b], n_stride) : n_stride;
@@ -79,9 +81,15 @@ finalize_kernel(const vo_row_partial *__restrict__ part, int n_split, const unsi
         if (row < N) {
             uint32_t s1 = 0xffffffffu, s2 = 0xffffffffu;
             for (int sp = 0; sp < n_split; ++sp) {
-                vo_row_partial p = part[((size_t)b * n_split + sp) * n_stride + row];
-                top2_insert(p.s1, p.i1, s1, i1, s2, i2);
-                top2_insert(p.s2, p.i2, s1, i1, s2, i2);
+                const size_t at = ((size_t)b * n_split + sp) * n_stride + row;
+                if (compact) {
+                    const vo_row_best q = reinterpret_cast<const vo_row_best *>(part)[at];
+                    top2_insert(q.s1, q.i1, s1, i1, s2, i2);
+                } else {
+                    const vo_row_partial p = part[at];
+                    top2_insert(p.s1, p.i1, s1, i1, s2, i2);
+                    top2_insert(p.s2, p.i2, s1, i1, s2, i2);
+                }
             }
             const float rn = row_norm ? row_norm[(size_t)b * n_stride + row] : 0.f;
             if (i1 >= 0) v1 = score_value(kind, s1, rn);

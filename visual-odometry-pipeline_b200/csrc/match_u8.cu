@@ -197,7 +197,14 @@ match_u8_kernel(const uint8_t *__restrict__ ref, const uint8_t *__restrict__ cur
                 p.s1 = v ? s1[r] : 0xffffffffu; p.s2 = v ? s2[r] : 0xffffffffu;
                 p.i1 = v ? i1[r] : -1; p.i2 = v ? i2[r] : -1;
             }
-            part[((size_t)b * n_split + split) * n_stride + row] = p;
+            const size_t at = ((size_t)b * n_split + split) * n_stride + row;
+            if (SECOND) {
+                part[at] = p;
+            } else {  // nothing reads the second best: 8-byte partials (SCORE_COMPACT_PARTIALS)
+                vo_row_best q;
+                q.s1 = p.s1; q.i1 = p.i1;
+                reinterpret_cast<vo_row_best *>(part)[at] = q;
+            }
         }
     }
 }
@@ -278,8 +285,9 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
         if ((rc = match_bits_tc(ctx, ref, cur, B, n_stride, m_stride, n_ref, n_cur, need_cols ? 1 : 0, need_second ? 1 : 0, &part_tc,
                                 &n_split_tc, colkey_tc, st)))
             return rc;
-        return match_finalize(ctx, part_tc, n_split_tc, colkey_tc, B, n_stride, m_stride, n_ref, n_cur, SCORE_HAMMING_F32, mode,
-                              ratio, nullptr, out_pairs, out_dist, out_count, knn, nullptr, st);
+        return match_finalize(ctx, part_tc, n_split_tc, colkey_tc, B, n_stride, m_stride, n_ref, n_cur,
+                              SCORE_HAMMING_F32 | (need_second ? 0 : SCORE_COMPACT_PARTIALS), mode, ratio, nullptr, out_pairs, out_dist,
+                              out_count, knn, nullptr, st);
     }
     const int row_blocks = ceil_div(n_stride, U8_ROWS_CTA);
     // Column splits: every CTA costs the same, so pick the smallest split count whose CTA total fills the
@@ -320,6 +328,6 @@ extern "C" int vo_match_u8(vo_ctx *ctx, const uint8_t *ref, const uint8_t *cur, 
 #undef LAUNCH_U8
     VO_LAUNCH_CHECK(ctx);
     return match_finalize(ctx, part, n_split, colkey, B, n_stride, m_stride, n_ref, n_cur,
-                          norm == VO_NORM_HAMMING ? SCORE_HAMMING : SCORE_L2SQ_U32, mode, ratio, nullptr, out_pairs,
-                          out_dist, out_count, knn, nullptr, st);
+                          (norm == VO_NORM_HAMMING ? SCORE_HAMMING : SCORE_L2SQ_U32) | (second ? 0 : SCORE_COMPACT_PARTIALS), mode, ratio,
+                          nullptr, out_pairs, out_dist, out_count, knn, nullptr, st);
 }
