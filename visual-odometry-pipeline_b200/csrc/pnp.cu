@@ -788,10 +788,6 @@ namespace {
 
 constexpr int RP_MAX_RESTARTS = 8, RP_MAX_ITERS = 1024;
 
-__global__ void ref_table_kernel(int n, int iters, int32_t *__restrict__ table) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) refpnp::mwc_table(n, iters, table);
-}
-
 // Cyclic Jacobi on a symmetric 12 x 12 matrix in shared memory, one warp: the rotations stay sequential (the order of
 // refpnp::jacobi_eig), but the 12 element pairs a rotation touches in its column phase, its row phase and in V are updated
 // by 12 lanes at once (lanes 12..23 rotate V while lanes 0..11 rotate the columns of A).  Every element sees the operations
@@ -1153,8 +1149,14 @@ extern "C" int vo_pnp_ransac_ref(vo_ctx *ctx, const float *xyz, const float *uv,
         VO_CUDA(cudaMemsetAsync(counts, 0xff, sizeof(int32_t) * total, st));
     } else {
         VO_PROF(ctx, st, VO_STAGE_P3P);
-        ref_table_kernel<<<1, 32, 0, st>>>(n, iters, table);
-        VO_LAUNCH_CHECK(ctx);
+        // OpenCV's sample table is a function of the point count alone: built on the host (the same refpnp::mwc_table; the device
+        // kernel that did it took 87 us of the 470 us call, one thread stepping a multiply-with-carry generator) and copied in
+        // stream order — a pageable source is staged by the driver before cudaMemcpyAsync returns, so the array may die here
+        {
+            int32_t table_h[RP_MAX_ITERS * refpnp::EP_N];
+            refpnp::mwc_table(n, iters, table_h);
+            VO_CUDA(cudaMemcpyAsync(table, table_h, sizeof(int32_t) * (size_t)iters * refpnp::EP_N, cudaMemcpyHostToDevice, st));
+        }
         ref_epnp_kernel<<<ceil_div(total, RP_WARPS), 32 * RP_WARPS, 0, st>>>(xyz, uv, boot_idx, n, table, restarts, iters, kd, poses, valid);
         VO_LAUNCH_CHECK(ctx);
         VO_PROF(ctx, st, VO_STAGE_SCORE);
