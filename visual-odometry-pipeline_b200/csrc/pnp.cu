@@ -788,47 +788,51 @@ namespace {
 
 constexpr int RP_MAX_RESTARTS = 8, RP_MAX_ITERS = 1024;
 
-// Cyclic Jacobi on a symmetric 12 x 12 matrix in shared memory, one warp: the rotations stay sequential (the order of
-// refpnp::jacobi_eig), but the 12 element pairs a rotation touches in its column phase, its row phase and in V are updated
-// by 12 lanes at once (lanes 12..23 rotate V while lanes 0..11 rotate the columns of A).  Every element sees the operations
-// of the serial loop in the same order: the result is bit-identical to jacobi_eig<12>.  Eigenvalues / vectors are then
-// sorted by lane 0 exactly as jacobi_eig does.
-__device__ void jacobi12_warp(double (*A)[12], double (*V)[12], double *d, int lane) {
+// refpnp::jacobi_eig12_rr (parallel-order Jacobi on the symmetric 12 x 12 M^T M) by one warp on shared memory: lanes 0..5 take
+// the angles of the round's six disjoint pairs, then the 144 (pair, row, matrix) column updates and the 72 (pair, column) row
+// updates are dealt over the lanes.  Every element goes through the same operations as in the serial loop (the two phases make
+// them independent of the order of the pairs): bit-identical to it.  Eigenvalues / vectors are then sorted like jacobi_eig does.
+// (The cyclic-by-row order, one rotation after the other with only its 12-element updates in parallel, took 340-400 k cycles per
+// solve — 66 dependent f64 divide / square-root chains per sweep; this order has 11 per sweep.)
+__device__ void jacobi12_warp(double (*A)[12], double (*V)[12], double *d, double (*cs)[2], int lane) {
     for (int i = lane; i < 144; i += 32) V[i / 12][i % 12] = (i / 12 == i % 12) ? 1.0 : 0.0;
     __syncwarp();
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0.0, diag = 0.0;
-        for (int i = 0; i < 12; ++i) {          // every lane sums in jacobi_eig's order: a warp-uniform decision
+        for (int i = 0; i < 12; ++i) {          // every lane sums in jacobi_eig12_rr's order: a warp-uniform decision
             diag += A[i][i] * A[i][i];
             for (int jj = i + 1; jj < 12; ++jj) off += A[i][jj] * A[i][jj];
         }
         if (off <= 1e-30 * diag || off == 0.0) break;
-        for (int p = 0; p < 11; ++p)
-            for (int q = p + 1; q < 12; ++q) {
-                const double apq = A[p][q];
-                if (apq == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
-                __syncwarp();                   // all lanes have read A[p][p], A[q][q], A[p][q]
-                if (lane < 12) {
-                    const double akp = A[lane][p], akq = A[lane][q];
-                    A[lane][p] = c * akp - sn * akq;
-                    A[lane][q] = sn * akp + c * akq;
-                } else if (lane < 24) {
-                    const int k = lane - 12;
-                    const double vkp = V[k][p], vkq = V[k][q];
-                    V[k][p] = c * vkp - sn * vkq;
-                    V[k][q] = sn * vkp + c * vkq;
-                }
-                __syncwarp();
-                if (lane < 12) {
-                    const double apk = A[p][lane], aqk = A[q][lane];
-                    A[p][lane] = c * apk - sn * aqk;
-                    A[q][lane] = sn * apk + c * aqk;
-                }
-                __syncwarp();
+        for (int round = 0; round < 11; ++round) {
+            if (lane < 6) {
+                int p, q;
+                refpnp::jacobi12_pair(round, lane, p, q);
+                refpnp::jacobi12_angle(A[p][p], A[q][q], A[p][q], cs[lane][0], cs[lane][1]);
             }
+            __syncwarp();
+            for (int t = lane; t < 144; t += 32) {      // columns p, q: (pair k, row i) of A, then of V
+                const int k = (t % 72) / 12, i = t % 12;
+                int p, q;
+                refpnp::jacobi12_pair(round, k, p, q);
+                const double c = cs[k][0], sn = cs[k][1];
+                double (*Mx)[12] = t < 72 ? A : V;
+                const double akp = Mx[i][p], akq = Mx[i][q];
+                Mx[i][p] = c * akp - sn * akq;
+                Mx[i][q] = sn * akp + c * akq;
+            }
+            __syncwarp();
+            for (int t = lane; t < 72; t += 32) {       // rows p, q of A: (pair k, column j)
+                const int k = t / 12, j = t % 12;
+                int p, q;
+                refpnp::jacobi12_pair(round, k, p, q);
+                const double c = cs[k][0], sn = cs[k][1];
+                const double apk = A[p][j], aqk = A[q][j];
+                A[p][j] = c * apk - sn * aqk;
+                A[q][j] = sn * apk + c * aqk;
+            }
+            __syncwarp();
+        }
     }
     __syncwarp();
     if (lane == 0) {
@@ -858,6 +862,7 @@ ref_epnp_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, con
     __shared__ double sA[RP_WARPS][12][12], sV[RP_WARPS][12][12], sd[RP_WARPS][12], sX[RP_WARPS][refpnp::EP_N][3], sv[RP_WARPS][4][12];
     __shared__ refpnp::EpnpState sS[RP_WARPS];
     __shared__ int s_mode[RP_WARPS];            // 0: repeated point (no model), 1: regular, 2: coplanar
+    __shared__ double s_cs[RP_WARPS][6][2];     // the (cos, sin) of a Jacobi round's six rotations
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int id = blockIdx.x * RP_WARPS + w;
     if (id >= restarts * iters) return;         // warp-uniform
@@ -883,7 +888,7 @@ ref_epnp_kernel(const float *__restrict__ xyz, const float *__restrict__ uv, con
     }
     __syncwarp();
     const int mode = s_mode[w];
-    if (mode == 1) jacobi12_warp(sA[w], sV[w], sd[w], lane);
+    if (mode == 1) jacobi12_warp(sA[w], sV[w], sd[w], s_cs[w], lane);
     if (lane == 0 && mode != 0) {
         if (mode == 2) refpnp::epnp5_basis_planar(sA[w], sv[w]);
         else refpnp::epnp5_basis_from_eig(sV[w], sv[w]);

@@ -106,6 +106,70 @@ VO_RHDN void jacobi_eig(double (&A)[N][N], double (&V)[N][N], double (&d)[N]) {
     }
 }
 
+// The 12 x 12 case of EPnP in PARALLEL ORDER: a sweep is 11 rounds of 6 rotations on disjoint index pairs (round-robin
+// tournament: index 11 stays, the others rotate), and a round is applied in two phases — every pair's angle from the matrix as it
+// stands (disjoint pairs do not touch each other's a_pp, a_qq, a_pq), then all column updates A <- A J, V <- V J, then all row
+// updates A <- J^T A.  The phases make the arithmetic of every element independent of the order in which the six pairs are
+// visited, so a warp can do them side by side (pnp.cu: jacobi12_warp) and lands on the same bits as this serial loop.
+// Converges like the cyclic-by-row order (one sweep more at most); same stopping rule and sorting as jacobi_eig.
+VO_RHD void jacobi12_pair(int round, int k, int &p, int &q) {
+    const int a = (k == 0) ? 11 : (round + k) % 11, b = (k == 0) ? round : (round + 11 - k) % 11;
+    p = a < b ? a : b;
+    q = a < b ? b : a;
+}
+VO_RHD void jacobi12_angle(double app, double aqq, double apq, double &c, double &s) {
+    if (apq == 0.0) { c = 1.0; s = 0.0; return; }
+    const double theta = (aqq - app) / (2.0 * apq);
+    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    c = 1.0 / sqrt(t * t + 1.0);
+    s = t * c;
+}
+VO_RHDN void jacobi_eig12_rr(double (&A)[12][12], double (&V)[12][12], double (&d)[12]) {
+    for (int i = 0; i < 12; ++i) {
+        for (int j = 0; j < 12; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < 12; ++i) {
+            diag += A[i][i] * A[i][i];
+            for (int j = i + 1; j < 12; ++j) off += A[i][j] * A[i][j];
+        }
+        if (off <= 1e-30 * diag || off == 0.0) break;
+        for (int round = 0; round < 11; ++round) {
+            int P[6], Q[6];
+            double C[6], S[6];
+            for (int k = 0; k < 6; ++k) {
+                jacobi12_pair(round, k, P[k], Q[k]);
+                jacobi12_angle(A[P[k]][P[k]], A[Q[k]][Q[k]], A[P[k]][Q[k]], C[k], S[k]);
+            }
+            for (int k = 0; k < 6; ++k)
+                for (int i = 0; i < 12; ++i) {      // columns p, q of A and V
+                    const double akp = A[i][P[k]], akq = A[i][Q[k]];
+                    A[i][P[k]] = C[k] * akp - S[k] * akq;
+                    A[i][Q[k]] = S[k] * akp + C[k] * akq;
+                    const double vkp = V[i][P[k]], vkq = V[i][Q[k]];
+                    V[i][P[k]] = C[k] * vkp - S[k] * vkq;
+                    V[i][Q[k]] = S[k] * vkp + C[k] * vkq;
+                }
+            for (int k = 0; k < 6; ++k)
+                for (int j = 0; j < 12; ++j) {      // rows p, q of A
+                    const double apk = A[P[k]][j], aqk = A[Q[k]][j];
+                    A[P[k]][j] = C[k] * apk - S[k] * aqk;
+                    A[Q[k]][j] = S[k] * apk + C[k] * aqk;
+                }
+        }
+    }
+    for (int i = 0; i < 12; ++i) d[i] = A[i][i];
+    for (int i = 0; i < 11; ++i) {          // selection sort, descending
+        int m = i;
+        for (int j = i + 1; j < 12; ++j) m = (d[j] > d[m]) ? j : m;
+        if (m != i) {
+            const double td = d[i]; d[i] = d[m]; d[m] = td;
+            for (int k = 0; k < 12; ++k) { const double tv = V[k][i]; V[k][i] = V[k][m]; V[k][m] = tv; }
+        }
+    }
+}
+
 // Least squares min |A x - b| for an R x C system (R >= C) by Householder QR; a column that is numerically zero gets x = 0.
 template <int R, int C>
 VO_RHDN void lsq_qr(double (&A)[R][C], double (&b)[R], double (&x)[C]) {
@@ -423,7 +487,7 @@ VO_RHDN bool epnp5(const double (&X)[EP_N][3], const double (&uv_in)[EP_N][2], d
         epnp5_basis_planar(MtM, v);
     } else {
         double V[12][12], d[12];
-        jacobi_eig<12>(MtM, V, d);
+        jacobi_eig12_rr(MtM, V, d);
         epnp5_basis_from_eig(V, v);
     }
     return epnp5_finish(X, S, v, out);
