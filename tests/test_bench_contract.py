@@ -40,9 +40,9 @@ def test_reference_arm_is_silent_on_other_ranks():
 
 
 def test_committed_b200_line_has_the_roofline_and_clock_keys():
-    """The default line of this round as measured on a B200 (profiles/bench_default_r02h.json): the headline is workload c3 —
+    """The default line of this round as measured on a B200 (profiles/bench_default_r02j.json): the headline is workload c3 —
     the tcgen05 GEMM BASELINE.json's metric names — and the complete line of c2 rides in extra.c2."""
-    d = json.loads(open(os.path.join(ROOT, "profiles", "bench_default_r02h.json")).read().strip().splitlines()[-1])
+    d = json.loads(open(os.path.join(ROOT, "profiles", "bench_default_r02j.json")).read().strip().splitlines()[-1])
     for line, wl in ((d, "c3:"), (d["extra"]["c2"], "c2:")):
         assert BASE_KEYS <= set(line) and "impl" not in line
         assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["gpu_launches"] > 0
