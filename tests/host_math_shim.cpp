@@ -95,6 +95,18 @@ void hm_orb_rotate(float angle_deg, const int *pat, int n, int *ix, int *iy) {
 }
 // ---- reference-sampler PnP-RANSAC arithmetic (csrc/pnp_ref_math.cuh)
 void hm_ref_table(int n, int iters, int *out) { vo::refpnp::mwc_table(n, iters, out); }
+// the two Jacobi orders on the same symmetric 12 x 12 matrix (row-major): eigenvalues (descending) and eigenvectors (columns of V)
+void hm_jacobi12(const double *A_in, int parallel_order, double *V_out, double *d_out) {
+    double A[12][12], V[12][12], d[12];
+    for (int i = 0; i < 12; ++i)
+        for (int j = 0; j < 12; ++j) A[i][j] = A_in[12 * i + j];
+    if (parallel_order) vo::refpnp::jacobi_eig12_rr(A, V, d);
+    else vo::refpnp::jacobi_eig<12>(A, V, d);
+    for (int i = 0; i < 12; ++i) {
+        d_out[i] = d[i];
+        for (int j = 0; j < 12; ++j) V_out[12 * i + j] = V[i][j];
+    }
+}
 int hm_ref_epnp5(const double *X, const double *uv, const double *K, double *out) {
     double Xm[5][3], uvm[5][2];
     for (int i = 0; i < 5; ++i) {

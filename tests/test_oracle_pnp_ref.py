@@ -133,3 +133,33 @@ def test_restated_epnp_is_statistically_not_bitwise_the_opencv_minimal_solver():
         dn.append(abs(len(a[3]) - len(b[3])) / len(a[3]))
     print("refit pose difference, cv2 minimal solver vs restated EPnP: dt", np.round(dt, 5), "drvec", np.round(dr, 6), "d#inl", np.round(dn, 3))
     assert max(dt) < 2e-2 and max(dr) < 2e-3 and max(dn) < 0.25
+
+
+def test_parallel_order_jacobi_is_an_eigen_decomposition(hm):
+    """refpnp::jacobi_eig12_rr (rounds of six rotations on disjoint pairs, the order the GPU's warp-wide form runs) on matrices
+    shaped like EPnP's M^T M (symmetric positive semi-definite, rank 10, entries spanning many orders of magnitude): eigenvalues
+    equal numpy's and the cyclic-by-row order's to round-off, V is orthonormal, A V = V diag(d), and every pair of indices meets
+    exactly once per sweep."""
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        M = rng.standard_normal((10, 12)) * np.exp(rng.uniform(-6, 6, (1, 12)))
+        A = M.T @ M
+        V, d = np.zeros((12, 12)), np.zeros(12)
+        hm.hm_jacobi12(_p(np.ascontiguousarray(A)), 1, _p(V), _p(d))
+        Vc, dc = np.zeros((12, 12)), np.zeros(12)
+        hm.hm_jacobi12(_p(np.ascontiguousarray(A)), 0, _p(Vc), _p(dc))
+        w = np.linalg.eigvalsh(A)[::-1]
+        scale = w[0]
+        assert np.all(np.diff(d) <= 0)
+        assert np.abs(d - w).max() < 1e-12 * scale and np.abs(d - dc).max() < 1e-12 * scale
+        assert np.abs(V.T @ V - np.eye(12)).max() < 1e-13
+        assert np.abs(A @ V - V * d).max() < 1e-12 * scale
+        # the null space (two zero eigenvalues) is spanned by the same vectors in both orders
+        Pn, Pc = V[:, 10:] @ V[:, 10:].T, Vc[:, 10:] @ Vc[:, 10:].T
+        assert np.abs(Pn - Pc).max() < 1e-6
+    seen = set()
+    for r in range(11):                                     # the tournament schedule of jacobi12_pair
+        rnd = [(11, r)] + [((r + k) % 11, (r + 11 - k) % 11) for k in range(1, 6)]
+        assert len({i for pq in rnd for i in pq}) == 12      # six disjoint pairs
+        seen |= {tuple(sorted(pq)) for pq in rnd}
+    assert len(seen) == 66
