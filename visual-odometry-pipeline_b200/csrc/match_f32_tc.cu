@@ -56,6 +56,9 @@ constexpr int TC_BN = 128;      // columns per B tile (= accumulator columns), 3
 constexpr int TC_D = 128;       // descriptor length
 constexpr int TC_KB = 32;       // k elements per swizzle-128B row (32 fp32 = 128 B)
 constexpr int TC_NKB = TC_D / TC_KB;
+// the norm extension of the single passes (one more K-step: ones[128 x 8] * (-|b|^2 as three tf32 pieces, zeros)[8 x BN]) travels
+// as 8 floats = 32 B per column through a SWIZZLE_32B box — a quarter of the bytes of a 128-byte row
+constexpr int TC_EXT_K = 8;
 // Per-mode tile geometry.  3xTF32: 128-column tiles, 13-stage ring of 16 KB boxes, TMEM = acc0 0 | acc1 128 | A_hi 256 |
 // A_lo 384.  Single pass has no A_lo, so the accumulators can be wider: 160-column tiles (27 % fewer tcgen05.mma per
 // FLOP — the single-pass kernel is bound by the MMA-issuing thread, not by the pipe), 10-stage ring of 20 KB boxes,
@@ -139,7 +142,7 @@ prep_kernel(const float *__restrict__ x, long long rows, float *__restrict__ hi,
                 const float n3 = to_tf32(__fsub_rn(__fsub_rn(s, n1), n2));
                 e = make_float4(-n1, -n2, -n3, 0.f);
             }
-            if (lane < 8) reinterpret_cast<float4 *>(ext)[row * 8 + lane] = e;
+            if (lane < TC_EXT_K / 4) reinterpret_cast<float4 *>(ext)[row * (TC_EXT_K / 4) + lane] = e;
         }
     }
 }
@@ -169,7 +172,7 @@ prep16_kernel(const float *__restrict__ x, long long rows, __half *__restrict__ 
                 const float n3 = to_tf32(__fsub_rn(__fsub_rn(s, n1), n2));
                 e = make_float4(-n1, -n2, -n3, 0.f);
             }
-            if (lane < 8) reinterpret_cast<float4 *>(ext)[row * 8 + lane] = e;
+            if (lane < TC_EXT_K / 4) reinterpret_cast<float4 *>(ext)[row * (TC_EXT_K / 4) + lane] = e;
         }
     }
 }
@@ -200,14 +203,14 @@ prep16_u8_kernel(const uint8_t *__restrict__ x, long long rows, __half *__restri
     for (int o = LPR / 2; o > 0; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));  // integers < 2^24: exact
     if (!ok) return;
     if (sub == 0) norm2[row] = s;
-    if (ext && sub < 8) {
+    if (ext && sub < TC_EXT_K / 4) {
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
         if (sub == 0) {
             const float n1 = to_tf32(s), n2 = to_tf32(__fsub_rn(s, n1));
             const float n3 = to_tf32(__fsub_rn(__fsub_rn(s, n1), n2));
             e = make_float4(-n1, -n2, -n3, 0.f);
         }
-        reinterpret_cast<float4 *>(ext)[row * 8 + sub] = e;
+        reinterpret_cast<float4 *>(ext)[row * (TC_EXT_K / 4) + sub] = e;
     }
 }
 
@@ -594,9 +597,9 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                     const int stage = it % STAGES;
                     const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
                     { TC_DBG_BEGIN(); mbar_wait(bar_empty(stage), phase ^ 1u); TC_DBG_END(0); }  // both CTAs consumed the slot
-                    mbar_expect_tx(bar_full(stage), BLOCK_BYTES);  // bytes arrive by multicast, whoever issues
+                    const bool is_ext = EXT && item == NKB;  // map_b_lo is the extension map in that mode
+                    mbar_expect_tx(bar_full(stage), is_ext ? BN * TC_EXT_K * 4 : BLOCK_BYTES);  // bytes arrive by multicast, whoever issues
                     if ((uint32_t)(it & 1) == crank) {
-                        const bool is_ext = EXT && item == NKB;  // map_b_lo is the extension map in that mode
                         const int kb = is_ext ? 0 : (THREE ? (item >> 1) : item);
                         const bool is_lo = is_ext || (THREE && (item & 1));
                         tma_load_2d_mc(s_b + stage * BLOCK_BYTES, is_lo ? &map_b_lo : &map_b_hi, kb * (H16 ? Cfg::KBOX : TC_KB), brow,
@@ -643,7 +646,7 @@ match_f32_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_c
                         const uint32_t b_lo32 = (((s_b + stage * BLOCK_BYTES) & 0x3ffffu) >> 4) | (1u << 16);
                         const uint32_t a_hi_t = tmem_base + (uint32_t)(TMEM_A + kb * TC_KB);
                         if (EXT && item == NKB) {  // ones[128 x 8] * (-|b|^2 pieces)[8 x BN], always kind::tf32
-                            const uint64_t bdesc = ((uint64_t)TC_SDESC_HI << 32) | (uint64_t)b_lo32;
+                            const uint64_t bdesc = ((uint64_t)TC_SDESC_HI_32B << 32) | (uint64_t)b_lo32;
                             tc_mma_tf32_ts(d_tmem, tmem_base + (uint32_t)TMEM_EXT, bdesc, IDESC, 1u);
                         } else
 #pragma unroll
@@ -1162,15 +1165,15 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 // [rows][row_elems] fp32 (or fp16 when `half`), box = 128 B of k x box_rows rows, SWIZZLE_128B
 int make_map(vo_ctx *ctx, CUtensorMap *map, const void *ptr, long long rows, int box_rows, int row_elems = TC_D,
-             bool half = false, bool bytes = false) {
+             bool half = false, bool bytes = false, bool narrow = false) {
     PFN_encodeTiled fn = (PFN_encodeTiled)ctx->encode_tiled;
     const size_t esz = bytes ? 1 : (half ? 2 : 4);
     cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)row_elems * esz};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)((narrow ? 32 : 128) / esz), (cuuint32_t)box_rows};   // narrow: 32-byte rows, SWIZZLE_32B
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2, (void *)ptr, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, narrow ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -1332,7 +1335,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     const long long rows_p = chained ? rows_a + n_stride : rows_a;   // rows prepared on the A side
     const size_t per_a = (size_t)rows_p * row_elems * esz, per_b = chained ? 0 : (size_t)rows_b * row_elems * esz;
     if ((rc = ws_get(ctx, WS_SPLIT_A, per_a * (three ? 2 : 1), (void **)&split_a))) return rc;
-    const size_t per_ext = (size_t)(chained ? rows_p : rows_b) * TC_KB * sizeof(float);
+    const size_t per_ext = (size_t)(chained ? rows_p : rows_b) * TC_EXT_K * sizeof(float);
     if ((rc = ws_get(ctx, WS_SPLIT_B, per_b * (three ? 2 : 1) + (ext ? per_ext : 0) + 16, (void **)&split_b))) return rc;
     const long long rows_a4 = (rows_a + 3) & ~3ll;  // column norms start 16 B aligned (vector loads in the epilogue)
     if ((rc = ws_get(ctx, WS_NORMS, sizeof(float) * (size_t)(chained ? rows_p : rows_a4 + rows_b), (void **)&norms))) return rc;
@@ -1342,7 +1345,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     float *b_lo = !three ? nullptr : (chained ? reinterpret_cast<float *>(reinterpret_cast<char *>(a_lo) + shift)
                                               : reinterpret_cast<float *>(reinterpret_cast<char *>(split_b) + per_b));
     float *x_ext = ext ? reinterpret_cast<float *>(reinterpret_cast<char *>(split_b) + per_b * (three ? 2 : 1)) : nullptr;
-    float *b_ext = (ext && chained) ? x_ext + (size_t)n_stride * TC_KB : x_ext;
+    float *b_ext = (ext && chained) ? x_ext + (size_t)n_stride * TC_EXT_K : x_ext;
     float *row_norm = norms, *col_norm = chained ? norms + n_stride : norms + rows_a4;
 
     VO_PROF(ctx, st, VO_STAGE_PREP);
@@ -1370,7 +1373,7 @@ int match_f32_tc(vo_ctx *ctx, const float *ref, const float *cur, int B, int n_s
     CUtensorMap mbh, mbl;
     const int bn = three ? TcCfg<3>::BN : (f16 ? TcCfg<16>::BN : TcCfg<1>::BN);
     if ((rc = make_map(ctx, &mbh, b_hi, rows_b, bn, row_elems, h16))) return rc;
-    if (ext) rc = make_map(ctx, &mbl, b_ext, rows_b, bn, TC_KB);
+    if (ext) rc = make_map(ctx, &mbl, b_ext, rows_b, bn, TC_EXT_K, false, false, true);
     else rc = make_map(ctx, &mbl, three ? b_lo : b_hi, rows_b, bn, TC_D, h16);
     if (rc) return rc;
 

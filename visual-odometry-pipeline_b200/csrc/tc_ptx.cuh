@@ -177,6 +177,8 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 constexpr uint32_t TC_SDESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // upper word of make_sdesc()
+// the same for 32-byte rows under SWIZZLE_32B (layout 6): 8 rows x 32 B = 256 B between row groups
+constexpr uint32_t TC_SDESC_HI_32B = (uint32_t)(256 >> 4) | (1u << 14) | (6u << 29);
 
 // D[tmem] (+)= A[smem descriptor] * B[smem descriptor], tf32 inputs, fp32 accumulate
 __device__ __forceinline__ void tc_mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
